@@ -1,0 +1,320 @@
+"""CPU oracle for the TOAD attention-MIL hot path -- TEST INFRASTRUCTURE ONLY.
+
+This file is a numpy restatement of the arithmetic of the reference's
+``models/model_toad.py`` (mahmoodlab/TOAD).  It is the *checker* for the CUDA
+path in ``toad_b200/csrc``; nothing in the product path (``toad_b200/``,
+``models/``) may import it.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s cpu_baseline / ``--impl reference`` leg use it.
+
+Pinning: the reference ships no golden vectors or tests for this path
+(SURVEY.md section 4 / 8c), so the oracle is pinned against outputs of the
+unmodified reference module itself, generated in the authoring container by
+``tests/golden/make_golden.py`` (imports ``/root/reference``) and committed as
+``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks this file
+against every one of them (forward in fp32 and fp64, and the autograd
+gradients of the reference's training loss).
+
+Reference lines restated (all in /root/reference):
+  * Attn_Net_Gated.forward            models/model_toad.py:36-41
+  * TOAD_fc_mtl_concat.__init__       models/model_toad.py:54-75
+  * TOAD_fc_mtl_concat.forward        models/model_toad.py:90-116
+  * initialize_weights                utils/utils.py:150-154
+  * training loss 0.75*CE + 0.25*CE   utils/core_utils_mtl_concat.py:213-215
+
+Parameter naming follows the reference ``state_dict`` keys with
+``dropout=False`` (Sequential indices 0, 2, 4):
+  attention_net.0.{weight,bias}                   fc1   [512,1024],[512]
+  attention_net.2.{weight,bias}                   fc2   [512,512],[512]
+  attention_net.4.attention_a.0.{weight,bias}     Wa    [D,512],[D]
+  attention_net.4.attention_b.0.{weight,bias}     Wb    [D,512],[D]
+  attention_net.4.attention_c.{weight,bias}       Wc    [2,D],[2]
+  classifier.{weight,bias}                        [n_classes,513],[n_classes]
+  site_classifier.{weight,bias}                   [2,513],[2]
+"""
+from __future__ import annotations
+
+import numpy as np
+
+SIZE_DICT = {"small": [1024, 512, 256], "big": [1024, 512, 384]}  # model_toad.py:56
+
+PARAM_KEYS = [
+    "attention_net.0.weight", "attention_net.0.bias",
+    "attention_net.2.weight", "attention_net.2.bias",
+    "attention_net.4.attention_a.0.weight", "attention_net.4.attention_a.0.bias",
+    "attention_net.4.attention_b.0.weight", "attention_net.4.attention_b.0.bias",
+    "attention_net.4.attention_c.weight", "attention_net.4.attention_c.bias",
+    "classifier.weight", "classifier.bias",
+    "site_classifier.weight", "site_classifier.bias",
+]
+
+
+def param_shapes(size_arg: str = "big", n_classes: int = 2) -> dict:
+    """Shapes of the 14 parameter tensors (model_toad.py:56-73)."""
+    l0, l1, d = SIZE_DICT[size_arg]
+    return {
+        PARAM_KEYS[0]: (l1, l0), PARAM_KEYS[1]: (l1,),
+        PARAM_KEYS[2]: (l1, l1), PARAM_KEYS[3]: (l1,),
+        PARAM_KEYS[4]: (d, l1), PARAM_KEYS[5]: (d,),
+        PARAM_KEYS[6]: (d, l1), PARAM_KEYS[7]: (d,),
+        PARAM_KEYS[8]: (2, d), PARAM_KEYS[9]: (2,),
+        PARAM_KEYS[10]: (n_classes, l1 + 1), PARAM_KEYS[11]: (n_classes,),
+        PARAM_KEYS[12]: (2, l1 + 1), PARAM_KEYS[13]: (2,),
+    }
+
+
+def make_params(seed: int, size_arg: str = "big", n_classes: int = 18,
+                bias_std: float = 0.0) -> dict:
+    """Seeded synthetic parameters with the reference's init distribution.
+
+    utils/utils.py:150-154: xavier_normal_ on Linear weights
+    (std = sqrt(2/(fan_in+fan_out))), zero bias.  ``bias_std`` > 0 draws
+    non-zero biases instead so that tests exercise the bias adds.  numpy's
+    PCG64 stream is platform independent, so the same seed gives the same
+    parameters here and on the GPU box.
+    """
+    rng = np.random.default_rng(seed)
+    out = {}
+    for k, shp in param_shapes(size_arg, n_classes).items():
+        if len(shp) == 2:
+            std = np.sqrt(2.0 / (shp[0] + shp[1]))
+            out[k] = (rng.standard_normal(shp, dtype=np.float32) * np.float32(std)).astype(np.float32)
+        else:
+            out[k] = (rng.standard_normal(shp, dtype=np.float32) * np.float32(bias_std)).astype(np.float32)
+    return out
+
+
+def make_attn_params(seed: int, L: int = 1024, D: int = 256, n_tasks: int = 1) -> dict:
+    """Seeded parameters of a standalone Attn_Net_Gated (model_toad.py:19-34), non-zero biases."""
+    rng = np.random.default_rng(seed)
+
+    def w(*s):
+        return (rng.standard_normal(s, dtype=np.float32) * np.float32(np.sqrt(2.0 / sum(s)))).astype(np.float32)
+    return {"attention_a.0.weight": w(D, L), "attention_a.0.bias": w(D, 1)[:, 0],
+            "attention_b.0.weight": w(D, L), "attention_b.0.bias": w(D, 1)[:, 0],
+            "attention_c.weight": w(n_tasks, D), "attention_c.bias": w(n_tasks, 1)[:, 0]}
+
+
+def make_bag(seed: int, n_patches: int, width: int = 1024, kind: str = "randn") -> np.ndarray:
+    """Seeded synthetic bag of patch embeddings."""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n_patches, width), dtype=np.float32)
+    if kind == "relu":  # "realistic" post-ReLU, avg-pooled features are >= 0
+        x = np.maximum(x, 0) * np.float32(0.5)
+    return x
+
+
+# ----------------------------------------------------------------------------
+# forward
+# ----------------------------------------------------------------------------
+
+def _softmax_rows(a: np.ndarray) -> np.ndarray:
+    """F.softmax(A, dim=1): max-subtracted, model_toad.py:97."""
+    m = a.max(axis=1, keepdims=True)
+    e = np.exp(a - m)
+    return e / e.sum(axis=1, keepdims=True)
+
+
+def _sigmoid(z):
+    return 1.0 / (1.0 + np.exp(-z))
+
+
+def attn_net_gated_forward(x, wa, ba, wb, bb, wc, bc):
+    """Attn_Net_Gated.forward (model_toad.py:36-41) without dropout.
+
+    a = tanh(x Wa^T + ba); b = sigmoid(x Wb^T + bb); A = (a*b) Wc^T + bc.
+    Returns (A [N, n_tasks], a, b); the module itself returns (A, x).
+    """
+    a = np.tanh(x @ wa.T + ba)
+    b = _sigmoid(x @ wb.T + bb)
+    A = (a * b) @ wc.T + bc
+    return A, a, b
+
+
+def toad_forward(x: np.ndarray, sex: float, params: dict, dtype=np.float32,
+                 return_intermediates: bool = False) -> dict:
+    """TOAD_fc_mtl_concat.forward (model_toad.py:90-116), eval / dropout=False.
+
+    x [N,1024]; sex scalar 0/1.  Returns the reference's result dict
+    (logits, Y_prob, Y_hat, site_logits, site_prob, site_hat, A) plus
+    'features' (= M [2,513], model_toad.py:99,111) and, when asked, the
+    intermediates the backward needs.
+    """
+    p = {k: np.asarray(v, dtype=dtype) for k, v in params.items()}
+    x = np.asarray(x, dtype=dtype)
+    h1 = np.maximum(x @ p[PARAM_KEYS[0]].T + p[PARAM_KEYS[1]], 0)            # :59 fc1+ReLU
+    h = np.maximum(h1 @ p[PARAM_KEYS[2]].T + p[PARAM_KEYS[3]], 0)            # :62 fc2+ReLU
+    A, a, b = attn_net_gated_forward(h, p[PARAM_KEYS[4]], p[PARAM_KEYS[5]],
+                                     p[PARAM_KEYS[6]], p[PARAM_KEYS[7]],
+                                     p[PARAM_KEYS[8]], p[PARAM_KEYS[9]])     # :91
+    A_raw = np.ascontiguousarray(A.T)                                        # :92,96  [2,N]
+    P = _softmax_rows(A_raw)                                                 # :97
+    M = P @ h                                                                # :98  [2,512]
+    Mc = np.concatenate([M, np.full((2, 1), sex, dtype=dtype)], axis=1)      # :99  [2,513]
+    logits = Mc[0:1] @ p[PARAM_KEYS[10]].T + p[PARAM_KEYS[11]]               # :101
+    site_logits = Mc[1:2] @ p[PARAM_KEYS[12]].T + p[PARAM_KEYS[13]]          # :105
+    out = {
+        "features": Mc,
+        "logits": logits, "Y_prob": _softmax_rows(logits),                    # :103
+        "Y_hat": np.argmax(logits, axis=1).reshape(1, 1).astype(np.int64),    # :102
+        "site_logits": site_logits, "site_prob": _softmax_rows(site_logits),  # :107
+        "site_hat": np.argmax(site_logits, axis=1).reshape(1, 1).astype(np.int64),  # :106
+        "A": A_raw,                                                           # :116 (pre-softmax)
+    }
+    if return_intermediates:
+        out.update({"h1": h1, "h": h, "a": a, "b": b, "P": P})
+    return out
+
+
+def toad_attention_only(x, params, dtype=np.float32):
+    """forward(..., attention_only=True) -> A[0], raw task-0 scores (model_toad.py:92-94)."""
+    return toad_forward(x, 0.0, params, dtype)["A"][0]
+
+
+def cross_entropy(logits: np.ndarray, label: int) -> float:
+    """nn.CrossEntropyLoss on a [1,C] row (core_utils_mtl_concat.py:213-214)."""
+    z = logits[0] - logits[0].max()
+    return float(np.log(np.exp(z).sum()) - z[label])
+
+
+def toad_loss(out: dict, label: int, site: int) -> float:
+    """0.75*CE(logits,label) + 0.25*CE(site_logits,site) (core_utils_mtl_concat.py:215)."""
+    return 0.75 * cross_entropy(out["logits"], label) + 0.25 * cross_entropy(out["site_logits"], site)
+
+
+# ----------------------------------------------------------------------------
+# backward (what autograd computes for core_utils_mtl_concat.py:231)
+# ----------------------------------------------------------------------------
+
+def toad_backward(x, sex, params, label: int, site: int, dtype=np.float64,
+                  dlogits=None, dsite_logits=None) -> dict:
+    """Gradients of the training loss w.r.t. the 14 parameters.
+
+    If dlogits / dsite_logits are given they are used as the upstream
+    gradients of 'logits' / 'site_logits' instead of the CE loss gradients.
+    No gradient flows to x (features are leaf data, core_utils:201).
+    """
+    p = {k: np.asarray(v, dtype=dtype) for k, v in params.items()}
+    f = toad_forward(x, sex, params, dtype, return_intermediates=True)
+    x = np.asarray(x, dtype=dtype)
+    h1, h, a, b, P, Mc = f["h1"], f["h"], f["a"], f["b"], f["P"], f["features"]
+    if dlogits is None:
+        dlogits = f["Y_prob"].copy()
+        dlogits[0, label] -= 1.0
+        dlogits *= 0.75
+    if dsite_logits is None:
+        dsite_logits = f["site_prob"].copy()
+        dsite_logits[0, site] -= 1.0
+        dsite_logits *= 0.25
+    dlogits = np.asarray(dlogits, dtype=dtype).reshape(1, -1)
+    dsite_logits = np.asarray(dsite_logits, dtype=dtype).reshape(1, -1)
+    g = {}
+    g[PARAM_KEYS[10]] = dlogits.T @ Mc[0:1]
+    g[PARAM_KEYS[11]] = dlogits[0].copy()
+    g[PARAM_KEYS[12]] = dsite_logits.T @ Mc[1:2]
+    g[PARAM_KEYS[13]] = dsite_logits[0].copy()
+    dM = np.stack([(dlogits @ p[PARAM_KEYS[10]])[0, :-1],
+                   (dsite_logits @ p[PARAM_KEYS[12]])[0, :-1]])          # [2,512]
+    M = Mc[:, :-1]
+    # softmax backward: dA[t,n] = P[t,n] * (dM[t].h[n] - dM[t].M[t])
+    dP = dM @ h.T                                                       # [2,N]
+    dA = P * (dP - (dM * M).sum(axis=1, keepdims=True))                 # [2,N]
+    dh = P.T @ dM                                                       # pooling path [N,512]
+    gate = a * b
+    g[PARAM_KEYS[8]] = dA @ gate                                        # dWc [2,D]
+    g[PARAM_KEYS[9]] = dA.sum(axis=1)
+    dgate = dA.T @ p[PARAM_KEYS[8]]                                     # [N,D]
+    da_pre = dgate * b * (1.0 - a * a)
+    db_pre = dgate * a * b * (1.0 - b)
+    g[PARAM_KEYS[4]] = da_pre.T @ h
+    g[PARAM_KEYS[5]] = da_pre.sum(axis=0)
+    g[PARAM_KEYS[6]] = db_pre.T @ h
+    g[PARAM_KEYS[7]] = db_pre.sum(axis=0)
+    dh = dh + da_pre @ p[PARAM_KEYS[4]] + db_pre @ p[PARAM_KEYS[6]]
+    dz2 = dh * (h > 0)
+    g[PARAM_KEYS[2]] = dz2.T @ h1
+    g[PARAM_KEYS[3]] = dz2.sum(axis=0)
+    dz1 = (dz2 @ p[PARAM_KEYS[2]]) * (h1 > 0)
+    g[PARAM_KEYS[0]] = dz1.T @ x
+    g[PARAM_KEYS[1]] = dz1.sum(axis=0)
+    return g
+
+
+# ----------------------------------------------------------------------------
+# split-precision restatement: what the tcgen05 path computes
+# ----------------------------------------------------------------------------
+
+def bf16_round(v: np.ndarray) -> np.ndarray:
+    """Round-to-nearest-even fp32 -> bf16, returned as fp32 (cvt.rn.bf16.f32)."""
+    u = np.ascontiguousarray(v, dtype=np.float32).view(np.uint32)
+    r = ((u.astype(np.uint64) + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000).astype(np.uint32)
+    return r.view(np.float32)
+
+
+def split_bf16(v: np.ndarray):
+    """v ~= hi + lo with hi = bf16(v), lo = bf16(v - hi) (both exactly bf16)."""
+    v = np.asarray(v, dtype=np.float32)
+    hi = bf16_round(v)
+    lo = bf16_round(v - hi)
+    return hi, lo
+
+
+def linear_bf16x3(x_hi, x_lo, w_hi, w_lo):
+    """x_hi.w_hi + x_hi.w_lo + x_lo.w_hi with wide accumulation.
+
+    The tensor core multiplies bf16 pairs exactly and accumulates in fp32;
+    fp64 accumulation here stands for "fp32 accumulation in some order", so
+    the CUDA result agrees with this to fp32 summation error (~1e-6 rel),
+    while a wrong tile/descriptor shows up as O(1) differences.
+    """
+    xh, xl = x_hi.astype(np.float64), x_lo.astype(np.float64)
+    wh, wl = w_hi.astype(np.float64), w_lo.astype(np.float64)
+    return xh @ wh.T + xh @ wl.T + xl @ wh.T
+
+
+def toad_forward_bf16x3(x, sex, params) -> dict:
+    """The forward as the tcgen05 path orders it (3-pass split bf16, fp32 epilogues).
+
+    Intermediate activations h1 and h are carried between layers as
+    (hi, lo) bf16 pairs, exactly as the kernels store them; pooling uses
+    h = hi + lo.  Same result dict as ``toad_forward``.
+    """
+    p = params
+    f32 = np.float32
+    xh, xl = split_bf16(x)
+    w1h, w1l = split_bf16(p[PARAM_KEYS[0]])
+    z1 = (linear_bf16x3(xh, xl, w1h, w1l)).astype(f32) + p[PARAM_KEYS[1]]
+    h1h, h1l = split_bf16(np.maximum(z1, 0))
+    w2h, w2l = split_bf16(p[PARAM_KEYS[2]])
+    z2 = (linear_bf16x3(h1h, h1l, w2h, w2l)).astype(f32) + p[PARAM_KEYS[3]]
+    hh, hl = split_bf16(np.maximum(z2, 0))
+    wah, wal = split_bf16(p[PARAM_KEYS[4]])
+    wbh, wbl = split_bf16(p[PARAM_KEYS[6]])
+    za = linear_bf16x3(hh, hl, wah, wal).astype(f32) + p[PARAM_KEYS[5]]
+    zb = linear_bf16x3(hh, hl, wbh, wbl).astype(f32) + p[PARAM_KEYS[7]]
+    gate = (np.tanh(za.astype(np.float64)) * _sigmoid(zb.astype(np.float64))).astype(f32)
+    A = (gate.astype(np.float64) @ p[PARAM_KEYS[8]].astype(np.float64).T).astype(f32) + p[PARAM_KEYS[9]]
+    A_raw = np.ascontiguousarray(A.T)
+    P = _softmax_rows(A_raw.astype(np.float64))
+    h = hh.astype(np.float64) + hl.astype(np.float64)
+    M = (P @ h).astype(f32)
+    Mc = np.concatenate([M, np.full((2, 1), sex, dtype=f32)], axis=1)
+    logits = (Mc[0:1].astype(np.float64) @ p[PARAM_KEYS[10]].astype(np.float64).T).astype(f32) + p[PARAM_KEYS[11]]
+    site_logits = (Mc[1:2].astype(np.float64) @ p[PARAM_KEYS[12]].astype(np.float64).T).astype(f32) + p[PARAM_KEYS[13]]
+    return {
+        "features": Mc, "logits": logits, "Y_prob": _softmax_rows(logits),
+        "Y_hat": np.argmax(logits, axis=1).reshape(1, 1).astype(np.int64),
+        "site_logits": site_logits, "site_prob": _softmax_rows(site_logits),
+        "site_hat": np.argmax(site_logits, axis=1).reshape(1, 1).astype(np.int64),
+        "A": A_raw,
+    }
+
+
+def topk_indices(scores: np.ndarray, k: int):
+    """torch.topk(scores, k) order: descending value; ties -> lower index first.
+
+    Config 5: the reference has no heat-map code, the contract
+    is torch.topk over results['A'][t].
+    """
+    order = np.lexsort((np.arange(scores.size), -scores.astype(np.float64)))
+    idx = order[:k]
+    return scores[idx], idx.astype(np.int64)

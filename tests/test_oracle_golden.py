@@ -1,0 +1,113 @@
+"""Pin the numpy oracle against the reference's own outputs (tests/golden/*.npz).
+
+The golden files were produced by tests/golden/make_golden.py from the
+unmodified /root/reference module; here only the committed fixtures are read.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import toad_oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "toad_*.npz")))
+
+
+def load(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+def case_inputs(g):
+    params = O.make_params(int(g["meta_pseed"]), str(g["meta_size_arg"]), int(g["meta_n_classes"]),
+                           float(g["meta_bias_std"]))
+    x = O.make_bag(int(g["meta_xseed"]), int(g["meta_n"]), kind=str(g["meta_kind"]))
+    return params, x, float(g["meta_sex"])
+
+
+def test_cases_present():
+    assert len(CASES) >= 9
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_fp64_matches_reference(name):
+    g = load(name)
+    params, x, sex = case_inputs(g)
+    out = O.toad_forward(x, sex, params, dtype=np.float64)
+    for k in ("logits", "Y_prob", "site_logits", "site_prob", "features", "A"):
+        np.testing.assert_allclose(out[k], g["f64_" + k], rtol=1e-9, atol=1e-11, err_msg=k)
+    assert np.array_equal(out["Y_hat"], g["f64_Y_hat"]) and np.array_equal(out["site_hat"], g["f64_site_hat"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_fp32_matches_reference(name):
+    """fp32 oracle vs fp32 reference: same math, different BLAS summation order."""
+    g = load(name)
+    if int(g["meta_n"]) > 10000:
+        pytest.skip("fp32 numpy pass at 50k is covered by the fp64 test")
+    params, x, sex = case_inputs(g)
+    out = O.toad_forward(x, sex, params, dtype=np.float32)
+    for k in ("logits", "site_logits", "features"):
+        np.testing.assert_allclose(out[k], g["f32_" + k], rtol=2e-4, atol=2e-6, err_msg=k)
+    np.testing.assert_allclose(out["A"], g["f32_A"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(out["A"][0], g["f32_attention_only"], rtol=0, atol=2e-5)
+    assert np.array_equal(out["Y_hat"], g["f32_Y_hat"])
+
+
+@pytest.mark.parametrize("name", [c for c in CASES if "g64_classifier.bias__full" in load(c)])
+def test_backward_matches_reference_autograd(name):
+    g = load(name)
+    params, x, sex = case_inputs(g)
+    label, site = int(g["meta_label"]), int(g["meta_site"])
+    out = O.toad_forward(x, sex, params, dtype=np.float64)
+    assert abs(O.toad_loss(out, label, site) - float(g["f64_loss"])) < 1e-10
+    grads = O.toad_backward(x, sex, params, label, site, dtype=np.float64)
+    for k in O.PARAM_KEYS:
+        gk = grads[k]
+        if ("g64_%s__full" % k) in g:
+            np.testing.assert_allclose(gk, g["g64_%s__full" % k], rtol=1e-8, atol=1e-13, err_msg=k)
+        else:
+            np.testing.assert_allclose(gk[::37, ::41], g["g64_%s__sub" % k], rtol=1e-8, atol=1e-13, err_msg=k)
+            np.testing.assert_allclose(gk.sum(1), g["g64_%s__rowsum" % k], rtol=1e-7, atol=1e-12, err_msg=k)
+            np.testing.assert_allclose(gk.sum(0), g["g64_%s__colsum" % k], rtol=1e-7, atol=1e-12, err_msg=k)
+
+
+def test_attn_net_gated_default():
+    """Config 1: Attn_Net_Gated() defaults, 256x1024 bag (model_toad.py:19,36-41)."""
+    g = load("attn_gated_default_n256")
+    p = O.make_attn_params(int(g["meta_seed"]), int(g["meta_L"]), int(g["meta_D"]), int(g["meta_n_tasks"]))
+    x = O.make_bag(int(g["meta_seed"]) + 1, int(g["meta_n"]), width=int(g["meta_L"]))
+    assert bool(g["x_passthrough_equal"])
+    args = [p[k] for k in ("attention_a.0.weight", "attention_a.0.bias", "attention_b.0.weight",
+                           "attention_b.0.bias", "attention_c.weight", "attention_c.bias")]
+    A64, _, _ = O.attn_net_gated_forward(x.astype(np.float64), *[a.astype(np.float64) for a in args])
+    np.testing.assert_allclose(A64, g["f64_A"], rtol=1e-10, atol=1e-12)
+    A32, _, _ = O.attn_net_gated_forward(x, *args)
+    np.testing.assert_allclose(A32, g["f32_A"], rtol=0, atol=5e-6)
+
+
+@pytest.mark.parametrize("name", ["toad_big_n257", "toad_small_n300", "toad_big_n1000_relu"])
+def test_split_bf16x3_restatement_within_tolerance(name):
+    """The 3-pass split-bf16 ordering (what the tcgen05 kernels compute) meets the parity bar."""
+    g = load(name)
+    params, x, sex = case_inputs(g)
+    out = O.toad_forward_bf16x3(x, sex, params)
+    np.testing.assert_allclose(out["logits"], g["f64_logits"], rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(out["site_logits"], g["f64_site_logits"], rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(out["A"], g["f64_A"], rtol=0, atol=5e-5)
+    assert np.array_equal(out["Y_hat"], g["f64_Y_hat"])
+
+
+def test_split_bf16_is_exact_pair():
+    v = O.make_bag(3, 64)
+    hi, lo = O.split_bf16(v)
+    assert np.all((hi.view(np.uint32) & 0xFFFF) == 0) and np.all((lo.view(np.uint32) & 0xFFFF) == 0)
+    assert np.max(np.abs((hi.astype(np.float64) + lo) - v) / np.abs(v)) < 2.0 ** -16
+
+
+def test_topk_order():
+    s = np.array([0.5, 2.0, 2.0, -1.0, 3.0], dtype=np.float32)
+    v, i = O.topk_indices(s, 3)
+    assert i.tolist() == [4, 1, 2] and v.tolist() == [3.0, 2.0, 2.0]
