@@ -1,0 +1,171 @@
+/*
+ * toad_b200.h -- C ABI of libtoad_b200.so: the B200 (sm_100a) implementation of
+ * the attention-MIL hot path of mahmoodlab/TOAD.
+ *
+ * The reference has no FFI of its own (it is pure PyTorch); the boundary it
+ * offers is the nn.Module surface of models/model_toad.py.  Each entry point
+ * below replaces the ATen/cuBLAS call chain of one reference method and is
+ * what a ctypes binding in the reference's models/model_toad.py would call
+ * (see INTEGRATION.md):
+ *
+ *   toad_fwd              <- TOAD_fc_mtl_concat.forward        models/model_toad.py:90-116
+ *                            (TOAD_FLAG_ATTENTION_ONLY: the early return at :92-94)
+ *   toad_bwd              <- autograd of that forward under the training loss,
+ *                            utils/core_utils_mtl_concat.py:213-215,231
+ *   toad_attn_gated_fwd   <- Attn_Net_Gated.forward            models/model_toad.py:36-41
+ *   toad_topk             <- torch.topk over results['A'][t]   (SURVEY.md F6 / config 5;
+ *                            the k=1 uses at models/model_toad.py:102,106)
+ *   toad_linear_bf16x3    <- one nn.Linear(+ReLU), the building block (models/model_toad.py:59,62)
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers to fp32 (or int64 where stated),
+ *     row-major and contiguous; weights are [out_features, in_features] exactly
+ *     as nn.Linear stores them.  The library reads parameters in place.
+ *   - The caller owns every buffer, including the workspace (query its size
+ *     with the *_workspace_bytes function; 256-byte aligned).  The library
+ *     keeps no global mutable state and never frees caller memory.
+ *   - Every call is asynchronous on `stream`; no implicit synchronisation.
+ *   - Return 0 on success, a negative TOAD_ERR_* for argument errors, or a
+ *     positive cudaError_t.  No C++ exception crosses this boundary.
+ *   - There is no CPU fallback: without a CUDA device the calls fail.
+ */
+#ifndef TOAD_B200_H
+#define TOAD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TOAD_ABI_VERSION 1
+
+typedef void* toad_stream_t; /* cudaStream_t */
+
+enum {
+  TOAD_OK = 0,
+  TOAD_ERR_ARG = -1,         /* null pointer / bad size */
+  TOAD_ERR_WORKSPACE = -2,   /* workspace too small or misaligned */
+  TOAD_ERR_UNSUPPORTED = -3, /* dims outside what the kernels are built for */
+  TOAD_ERR_DRIVER = -4       /* could not obtain a driver entry point (TMA descriptor) */
+};
+
+/* forward flags */
+#define TOAD_FLAG_ATTENTION_ONLY 1u /* stop after the raw attention scores (model_toad.py:92-94) */
+#define TOAD_FLAG_SIMT_FP32 2u      /* fp32 CUDA-core GEMMs instead of the tcgen05 split-bf16 path */
+#define TOAD_FLAG_SAVE_ACTS 4u      /* also store h1,h,a,b (fp32) for toad_bwd */
+
+/* Layer widths of TOAD_fc_mtl_concat (model_toad.py:56): "big" = {1024,512,384}, "small" = {1024,512,256}. */
+typedef struct {
+  int32_t in_dim;    /* 1024 */
+  int32_t hid_dim;   /* 512  */
+  int32_t attn_dim;  /* 384 or 256 */
+  int32_t n_tasks;   /* 2 */
+  int32_t n_classes; /* rows of `classifier` */
+} toad_dims_t;
+
+/* The 14 parameter tensors, in state_dict order (model_toad.py:59-73). */
+typedef struct {
+  const float* w1;    /* attention_net.0.weight              [hid, in]   */
+  const float* b1;    /* attention_net.0.bias                [hid]       */
+  const float* w2;    /* attention_net.2.weight              [hid, hid]  */
+  const float* b2;    /* attention_net.2.bias                [hid]       */
+  const float* wa;    /* attention_net.4.attention_a.0.weight [D, hid]   */
+  const float* ba;    /* attention_net.4.attention_a.0.bias   [D]        */
+  const float* wb;    /* attention_net.4.attention_b.0.weight [D, hid]   */
+  const float* bb;    /* attention_net.4.attention_b.0.bias   [D]        */
+  const float* wc;    /* attention_net.4.attention_c.weight   [n_tasks, D] */
+  const float* bc;    /* attention_net.4.attention_c.bias     [n_tasks]  */
+  const float* wcls;  /* classifier.weight                   [n_classes, hid+1] */
+  const float* bcls;  /* classifier.bias                     [n_classes] */
+  const float* wsite; /* site_classifier.weight              [2, hid+1]  */
+  const float* bsite; /* site_classifier.bias                [2]         */
+} toad_params_t;
+
+/* Outputs of the forward = the reference's results_dict (model_toad.py:109-116). */
+typedef struct {
+  float* a_raw;        /* 'A'          [n_tasks, N]  pre-softmax scores, contiguous */
+  float* features;     /* 'features'   [n_tasks, hid+1]  (M with sex appended) */
+  float* logits;       /* 'logits'     [n_classes] */
+  float* y_prob;       /* 'Y_prob'     [n_classes] */
+  int64_t* y_hat;      /* 'Y_hat'      [1] */
+  float* site_logits;  /* 'site_logits'[2] */
+  float* site_prob;    /* 'site_prob'  [2] */
+  int64_t* site_hat;   /* 'site_hat'   [1] */
+  float* softmax_stats;/* [n_tasks][2] = (row max, sum of exp) of a_raw; needed by toad_bwd */
+} toad_fwd_out_t;
+
+/* Activations kept for the backward (TOAD_FLAG_SAVE_ACTS), fp32. */
+typedef struct {
+  float* h1; /* [N, hid] relu(fc1) */
+  float* h;  /* [N, hid] relu(fc2) */
+  float* a;  /* [N, D] tanh branch  */
+  float* b;  /* [N, D] sigmoid branch */
+} toad_saved_t;
+
+int toad_abi_version(void);
+const char* toad_error_string(int code);
+
+/* Number of fp32 elements of the flat parameter/gradient buffer and the offset of
+ * each of the 14 tensors in it (state_dict order); offsets[14] = total. */
+int toad_param_offsets(const toad_dims_t* dims, int64_t offsets[15]);
+
+int toad_fwd_workspace_bytes(const toad_dims_t* dims, int64_t n_patches, uint32_t flags, size_t* bytes);
+
+/* x: [N, in_dim]; sex: device float[1] (core_utils_mtl_concat.py:204).
+ * `saved` may be NULL unless TOAD_FLAG_SAVE_ACTS.  With TOAD_FLAG_ATTENTION_ONLY
+ * only out->a_raw is written. */
+int toad_fwd(const toad_dims_t* dims, const toad_params_t* params, const float* x, int64_t n_patches,
+             const float* sex, const toad_fwd_out_t* out, const toad_saved_t* saved, void* workspace,
+             size_t workspace_bytes, uint32_t flags, toad_stream_t stream);
+
+/* Per-stage device timing of toad_fwd (diagnostics; bench.py's roofline leg).  A profile handle
+ * owns CUDA events for up to max_calls forwards; toad_fwd_profiled records an event between the
+ * stages on `stream` (no synchronisation); toad_profile_read waits for the recorded events,
+ * returns the summed milliseconds per stage and the number of calls, and resets the handle.
+ * Stages: 0 weight split, 1 fc1 GEMM, 2 fc2 GEMM, 3 gated-attention GEMM(s), 4 pooling tail. */
+#define TOAD_N_STAGES 5
+int toad_profile_create(void** prof, int32_t max_calls);
+int toad_profile_destroy(void* prof);
+int toad_profile_read(void* prof, double stage_ms[TOAD_N_STAGES], int32_t* n_calls);
+int toad_fwd_profiled(const toad_dims_t* dims, const toad_params_t* params, const float* x, int64_t n_patches,
+                      const float* sex, const toad_fwd_out_t* out, const toad_saved_t* saved, void* workspace,
+                      size_t workspace_bytes, uint32_t flags, toad_stream_t stream, void* prof);
+
+int toad_bwd_workspace_bytes(const toad_dims_t* dims, int64_t n_patches, size_t* bytes);
+
+/* Gradients of sum(dlogits*logits) + sum(dsite_logits*site_logits) w.r.t. the 14
+ * parameters, written (not accumulated) into grad_flat in toad_param_offsets order.
+ * fwd_out / saved are the buffers the forward (with TOAD_FLAG_SAVE_ACTS) filled. */
+int toad_bwd(const toad_dims_t* dims, const toad_params_t* params, const float* x, int64_t n_patches,
+             const toad_fwd_out_t* fwd_out, const toad_saved_t* saved, const float* dlogits,
+             const float* dsite_logits, float* grad_flat, void* workspace, size_t workspace_bytes,
+             toad_stream_t stream);
+
+/* Standalone gated attention head: A[N, n_tasks] = Wc(tanh(Wa x + ba) * sigmoid(Wb x + bb)) + bc. */
+int toad_attn_gated_workspace_bytes(int32_t L, int32_t D, int32_t n_tasks, int64_t n, uint32_t flags, size_t* bytes);
+int toad_attn_gated_fwd(int32_t L, int32_t D, int32_t n_tasks, const float* wa, const float* ba,
+                        const float* wb, const float* bb, const float* wc, const float* bc,
+                        const float* x, int64_t n, float* A_out, void* workspace, size_t workspace_bytes,
+                        uint32_t flags, toad_stream_t stream);
+
+/* top-k of one score row: values descending, ties -> lower index first. */
+int toad_topk_workspace_bytes(int64_t n, int32_t k, size_t* bytes);
+int toad_topk(const float* scores, int64_t n, int32_t k, float* out_vals, int64_t* out_idx,
+              void* workspace, size_t workspace_bytes, toad_stream_t stream);
+
+/* y[M, N] = act(x[M, K] . w[N, K]^T + bias[N]) on the tcgen05 3-pass split-bf16 path.
+ * relu != 0 applies ReLU; bias may be NULL.  K % 64 == 0, N % 64 == 0.
+ * variant: bit 0 = feed x as pre-split (hi,lo) bf16 planes through TMA instead of converting
+ * fp32 rows in the kernel; bits 4-5 = force the N tile (1: 64, 2: 128, 3: 256; 0: largest that
+ * divides N).  Both paths give the same result; the knob exists so tests cover every tile shape. */
+int toad_linear_workspace_bytes(int64_t m, int32_t n, int32_t k, size_t* bytes);
+int toad_linear_bf16x3(const float* x, const float* w, const float* bias, float* y, int64_t m, int32_t n,
+                       int32_t k, int32_t relu, int32_t variant, void* workspace, size_t workspace_bytes,
+                       toad_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOAD_B200_H */

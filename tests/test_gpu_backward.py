@@ -1,0 +1,79 @@
+"""GPU parity of the backward: our autograd.Function (toad_bwd through the C ABI) vs the
+reference's autograd gradients (fp64 golden digests) under the training loss
+0.75*CE + 0.25*CE (utils/core_utils_mtl_concat.py:213-215)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import toad_oracle as O
+from tests.helpers import build_model, case_inputs, load_golden, to_np
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["toad_big_n1", "toad_big_n257", "toad_small_n300", "toad_big_n1000_relu"]
+
+
+def _grads(name, simt):
+    g = load_golden(name)
+    params, x, sex = case_inputs(g)
+    os.environ["TOAD_B200_SIMT"] = "1" if simt else "0"
+    try:
+        model = build_model(params, str(g["meta_size_arg"]), int(g["meta_n_classes"]))
+        model.train()
+        xd = torch.from_numpy(x).cuda()
+        sd = torch.tensor([sex], device="cuda")
+        r = model(xd, sd)
+        loss_fn = torch.nn.CrossEntropyLoss()
+        label = torch.tensor([int(g["meta_label"])], device="cuda")
+        site = torch.tensor([int(g["meta_site"])], device="cuda")
+        loss = 0.75 * loss_fn(r["logits"], label) + 0.25 * loss_fn(r["site_logits"], site)
+        loss.backward()
+        torch.cuda.synchronize()
+    finally:
+        os.environ["TOAD_B200_SIMT"] = "0"
+    return g, model, float(loss.item())
+
+
+@pytest.mark.parametrize("simt", [True, False])
+@pytest.mark.parametrize("name", CASES)
+def test_gradients_match_reference_autograd(name, simt):
+    g, model, loss = _grads(name, simt)
+    assert abs(loss - float(g["f64_loss"])) < 1e-3 * max(1.0, abs(float(g["f64_loss"])))
+    for k, prm in model.named_parameters():
+        assert prm.grad is not None, k
+        gk = to_np(prm.grad).astype(np.float64)
+        if ("g64_%s__full" % k) in g:
+            ref = g["g64_%s__full" % k]
+            scale = np.abs(ref).max() + 1e-12
+            assert np.abs(gk - ref).max() <= 2e-3 * scale, (k, np.abs(gk - ref).max(), scale)
+        else:
+            ref = g["g64_%s__sub" % k]
+            scale = np.abs(ref).max() + 1e-12
+            assert np.abs(gk[::37, ::41] - ref).max() <= 2e-3 * scale, k
+            rs, cs = g["g64_%s__rowsum" % k], g["g64_%s__colsum" % k]
+            assert np.abs(gk.sum(1) - rs).max() <= 2e-3 * (np.abs(rs).max() + 1e-12), k
+            assert np.abs(gk.sum(0) - cs).max() <= 2e-3 * (np.abs(cs).max() + 1e-12), k
+
+
+def test_optimizer_step_runs_like_the_reference_loop():
+    """The caller's contract (core_utils:206-234): real leaf fp32 parameters, Adam step, zero_grad."""
+    g = load_golden("toad_big_n257")
+    params, x, sex = case_inputs(g)
+    model = build_model(params, "big", 18)
+    model.train()
+    opt = torch.optim.Adam(filter(lambda p: p.requires_grad, model.parameters()), lr=1e-4, weight_decay=1e-5)
+    xd = torch.from_numpy(x).cuda()
+    sd = torch.tensor([sex], device="cuda")
+    loss_fn = torch.nn.CrossEntropyLoss()
+    losses = []
+    for _ in range(5):
+        r = model(xd, sd)
+        loss = 0.75 * loss_fn(r["logits"], torch.tensor([3], device="cuda")) + \
+            0.25 * loss_fn(r["site_logits"], torch.tensor([1], device="cuda"))
+        losses.append(loss.item())
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+    assert losses[-1] < losses[0]

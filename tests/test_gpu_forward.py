@@ -1,0 +1,158 @@
+"""GPU parity of the TOAD forward: our module (C ABI, sm_100a kernels) vs the reference's outputs.
+
+Golden = the unmodified reference run in fp64/fp32 (tests/golden/make_golden.py).  Tolerances are
+the north_star's: logits / attention within 1e-3 relative (fp32), top-k indices exact (up to
+reference-score ties).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import toad_oracle as O
+from tests.helpers import build_model, case_inputs, load_golden, rel_err, to_np, topk_sets_match
+
+pytestmark = pytest.mark.gpu
+
+SMALL = ["toad_big_n1", "toad_big_n2", "toad_big_n255", "toad_big_n256", "toad_big_n257",
+         "toad_small_n300", "toad_big_n1000_relu"]
+LARGE = ["toad_big_n10000", "toad_big_n50000"]
+
+
+def run_case(name, simt):
+    import os
+    g = load_golden(name)
+    params, x, sex = case_inputs(g)
+    os.environ["TOAD_B200_SIMT"] = "1" if simt else "0"
+    try:
+        model = build_model(params, str(g["meta_size_arg"]), int(g["meta_n_classes"]))
+        xd = torch.from_numpy(x).cuda()
+        sd = torch.tensor([sex], device="cuda")
+        with torch.no_grad():
+            out = model(xd, sd, return_features=True)
+            a_only = model(xd, sd, attention_only=True)
+        torch.cuda.synchronize()
+    finally:
+        os.environ["TOAD_B200_SIMT"] = "0"
+    return g, out, a_only
+
+
+def check_against_golden(g, out, a_only, n):
+    # logits / probabilities / pooled features: 1e-3 relative to the fp64 reference (with a small
+    # absolute floor for entries that happen to be ~0), and against the reference's own fp32 run.
+    for k in ("logits", "site_logits", "Y_prob", "site_prob", "features"):
+        ours = to_np(out[k])
+        ref64 = g["f64_" + k]
+        assert ours.shape == ref64.shape, k
+        np.testing.assert_allclose(ours, ref64, rtol=1e-3, atol=2e-6, err_msg=k)
+    A = to_np(out["A"])
+    assert A.shape == (2, n)
+    # attention scores: absolute 1e-4 (scores are O(0.1-1)); softmax weights 1e-3 relative
+    np.testing.assert_allclose(A, g["f64_A"], rtol=0, atol=1e-4)
+    P = np.exp(A.astype(np.float64) - A.max(axis=1, keepdims=True))
+    P /= P.sum(axis=1, keepdims=True)
+    P64 = np.exp(g["f64_A"] - g["f64_A"].max(axis=1, keepdims=True))
+    P64 /= P64.sum(axis=1, keepdims=True)
+    assert rel_err(P, P64) < 1e-3
+    assert np.array_equal(to_np(out["Y_hat"]), g["f64_Y_hat"])
+    assert np.array_equal(to_np(out["site_hat"]), g["f64_site_hat"])
+    assert out["Y_hat"].dtype == torch.int64 and tuple(out["Y_hat"].shape) == (1, 1)
+    assert tuple(out["logits"].shape) == (1, int(g["meta_n_classes"]))
+    # attention_only returns task-0 raw scores (model_toad.py:92-94)
+    np.testing.assert_array_equal(to_np(a_only), A[0])
+    for t in range(2):
+        for k in (1, 10, 100):
+            if k <= n:
+                assert topk_sets_match(A[t], g["f64_A"][t], k), (t, k)
+
+
+@pytest.mark.parametrize("name", SMALL + LARGE)
+def test_forward_tensorcore_path(name):
+    g, out, a_only = run_case(name, simt=False)
+    check_against_golden(g, out, a_only, int(g["meta_n"]))
+
+
+@pytest.mark.parametrize("name", SMALL + ["toad_big_n10000"])
+def test_forward_fp32_simt_path(name):
+    g, out, a_only = run_case(name, simt=True)
+    check_against_golden(g, out, a_only, int(g["meta_n"]))
+
+
+def test_tensorcore_matches_split_oracle_tightly():
+    """Against the oracle's restatement of the SAME split-bf16 ordering the kernel agrees to fp32
+    summation noise -- this separates 'kernel bug' from 'expected reordering error'."""
+    g = load_golden("toad_big_n257")
+    params, x, sex = case_inputs(g)
+    exp = O.toad_forward_bf16x3(x, sex, params)
+    _, out, _ = run_case("toad_big_n257", simt=False)
+    np.testing.assert_allclose(to_np(out["A"]), exp["A"], rtol=0, atol=3e-6)
+    np.testing.assert_allclose(to_np(out["logits"]), exp["logits"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(to_np(out["features"]), exp["features"], rtol=2e-5, atol=1e-6)
+
+
+def test_permutation_invariance_and_equivariance():
+    """Bag-order property (size independent): logits invariant, A equivariant under a row permutation."""
+    g = load_golden("toad_big_n10000")
+    params, x, sex = case_inputs(g)
+    model = build_model(params, "big", 18)
+    perm = np.random.default_rng(0).permutation(x.shape[0])
+    sd = torch.tensor([sex], device="cuda")
+    with torch.no_grad():
+        o1 = model(torch.from_numpy(x).cuda(), sd)
+        o2 = model(torch.from_numpy(x[perm]).cuda(), sd)
+    np.testing.assert_allclose(to_np(o1["logits"]), to_np(o2["logits"]), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(to_np(o1["A"])[:, perm], to_np(o2["A"]), rtol=0, atol=1e-6)
+
+
+def test_single_patch_softmax_weight_is_one():
+    """N=1: softmax weight 1, so features[t,:512] == h (SURVEY.md section 4 property)."""
+    g = load_golden("toad_big_n1")
+    params, x, sex = case_inputs(g)
+    f = O.toad_forward(x, sex, params, dtype=np.float64, return_intermediates=True)
+    _, out, _ = run_case("toad_big_n1", simt=False)
+    feats = to_np(out["features"])
+    np.testing.assert_allclose(feats[0, :512], f["h"][0], rtol=1e-3, atol=2e-6)
+    np.testing.assert_allclose(feats[1, :512], f["h"][0], rtol=1e-3, atol=2e-6)
+    assert feats[0, 512] == sex and feats[1, 512] == sex
+
+
+def test_duplicate_patches_tie():
+    """All patches identical: uniform attention, pooled vector equals the single patch embedding."""
+    g = load_golden("toad_big_n256")
+    params, x, sex = case_inputs(g)
+    xd = np.repeat(x[:1], 300, axis=0)
+    model = build_model(params, "big", 18)
+    with torch.no_grad():
+        o_many = model(torch.from_numpy(xd).cuda(), torch.tensor([sex], device="cuda"), return_features=True)
+        o_one = model(torch.from_numpy(x[:1].copy()).cuda(), torch.tensor([sex], device="cuda"), return_features=True)
+    A = to_np(o_many["A"])
+    assert np.all(A == A[:, :1])
+    np.testing.assert_allclose(to_np(o_many["features"]), to_np(o_one["features"]), rtol=1e-5, atol=1e-6)
+
+
+def test_repeatable_bitwise():
+    """Deterministic reductions: two runs give identical bits (reference sets cudnn deterministic, main:118-119)."""
+    g = load_golden("toad_big_n10000")
+    params, x, sex = case_inputs(g)
+    model = build_model(params, "big", 18)
+    xd = torch.from_numpy(x).cuda()
+    sd = torch.tensor([sex], device="cuda")
+    with torch.no_grad():
+        o1 = {k: v.clone() for k, v in model(xd, sd, return_features=True).items()}
+        o2 = model(xd, sd, return_features=True)
+    for k in o1:
+        assert torch.equal(o1[k], o2[k]), k
+
+
+def test_input_validation():
+    g = load_golden("toad_big_n2")
+    params, x, sex = case_inputs(g)
+    model = build_model(params, "big", 18)
+    sd = torch.tensor([sex], device="cuda")
+    with pytest.raises(ValueError):
+        model(torch.from_numpy(x), sd)                       # CPU tensor
+    with pytest.raises(ValueError):
+        model(torch.from_numpy(x).cuda().double(), sd)       # wrong dtype
+    with pytest.raises(ValueError):
+        model(torch.from_numpy(x).cuda()[:, :512], sd)       # wrong width / non-contiguous
+    with pytest.raises(ValueError):
+        model(torch.empty((0, 1024), device="cuda"), sd)     # empty bag

@@ -111,3 +111,17 @@ def test_topk_order():
     s = np.array([0.5, 2.0, 2.0, -1.0, 3.0], dtype=np.float32)
     v, i = O.topk_indices(s, 3)
     assert i.tolist() == [4, 1, 2] and v.tolist() == [3.0, 2.0, 2.0]
+
+
+@pytest.mark.parametrize("name", ["toad_big_n257", "toad_small_n300", "toad_big_n10000"])
+def test_torch_port_matches_reference_fp32(name):
+    """The functional-torch CPU port (bench baseline) reproduces the reference's own fp32 outputs."""
+    import torch
+    from oracle import toad_oracle_torch as OT
+    g = load(name)
+    params, x, sex = case_inputs(g)
+    out = OT.toad_forward(torch.from_numpy(x), torch.tensor([sex]), OT.to_torch_params(params), return_features=True)
+    for k in ("logits", "site_logits", "features", "Y_prob"):
+        np.testing.assert_allclose(out[k].numpy(), g["f32_" + k], rtol=1e-5, atol=1e-6, err_msg=k)
+    np.testing.assert_allclose(out["A"].numpy(), g["f32_A"], rtol=0, atol=5e-6)
+    assert np.array_equal(out["Y_hat"].numpy(), g["f32_Y_hat"])

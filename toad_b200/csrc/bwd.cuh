@@ -1,0 +1,149 @@
+// Backward of the TOAD forward: gradients of the 14 parameter tensors given the upstream
+// gradients of `logits` and `site_logits` (what autograd computes for
+// utils/core_utils_mtl_concat.py:231 on the graph of models/model_toad.py:90-107).
+// No gradient flows to the features x (leaf data, core_utils_mtl_concat.py:201).
+//
+// Small HBM-bound kernels live here; the five large contractions (2 dgrad, 3 wgrad) run on
+// the fp32 CUDA-core GEMM in sgemm_simt.cuh.  All cross-CTA sums are two-stage with a fixed
+// reduction order (deterministic).
+#pragma once
+#include "common.cuh"
+
+namespace toad {
+namespace bwd {
+
+constexpr int H = 512;
+constexpr int T = 2;
+
+// ---- heads: dW/db of classifier & site_classifier, dM[t] = dlogits_t . W_t[:, :H], sdot[t] = dM[t].M[t]
+__global__ void heads_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ dsite,
+                                 const float* __restrict__ features, const float* __restrict__ wcls,
+                                 const float* __restrict__ wsite, int n_classes, float* __restrict__ g_wcls,
+                                 float* __restrict__ g_bcls, float* __restrict__ g_wsite, float* __restrict__ g_bsite,
+                                 float* __restrict__ dM, float* __restrict__ sdot) {
+  __shared__ float s_part[2][32];
+  const int tid = threadIdx.x;  // 1024 threads
+  for (int i = tid; i < n_classes * (H + 1); i += blockDim.x)
+    g_wcls[i] = __ldg(dlogits + i / (H + 1)) * __ldg(features + i % (H + 1));
+  for (int i = tid; i < 2 * (H + 1); i += blockDim.x)
+    g_wsite[i] = __ldg(dsite + i / (H + 1)) * __ldg(features + (H + 1) + i % (H + 1));
+  if (tid < n_classes) g_bcls[tid] = dlogits[tid];
+  if (tid < 2) g_bsite[tid] = dsite[tid];
+  // dM: thread j < H -> task 0, H <= tid < 2H -> task 1
+  const int t = tid / H, j = tid % H;
+  float d = 0.f;
+  if (t == 0) {
+    for (int c = 0; c < n_classes; ++c) d = fmaf(__ldg(dlogits + c), __ldg(wcls + c * (H + 1) + j), d);
+  } else {
+    for (int c = 0; c < 2; ++c) d = fmaf(__ldg(dsite + c), __ldg(wsite + c * (H + 1) + j), d);
+  }
+  dM[tid] = d;
+  float prod = d * __ldg(features + t * (H + 1) + j);
+  prod = warp_sum(prod);
+  if ((tid & 31) == 0) s_part[t][(tid % H) >> 5] = prod;
+  __syncthreads();
+  if (tid < 2) {
+    float s = 0.f;
+    for (int w = 0; w < H / 32; ++w) s += s_part[tid][w];
+    sdot[tid] = s;
+  }
+}
+
+// ---- softmax-pooling backward per row: P[n,t], dA[n,t] = P (dM_t.h_n - sdot_t)   (warp per row)
+__global__ void pool_bwd_kernel(const float* __restrict__ h, const float* __restrict__ a_raw,
+                                const float* __restrict__ stats, const float* __restrict__ dM,
+                                const float* __restrict__ sdot, float* __restrict__ P, float* __restrict__ dA,
+                                int64_t N) {
+  __shared__ float s_dM[T * H];
+  for (int i = threadIdx.x; i < T * H; i += blockDim.x) s_dM[i] = dM[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); row < N;
+       row += static_cast<int64_t>(gridDim.x) * wpb) {
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = 4 * (lane + 32 * q);
+      const float4 v = ld_stream_f4(h + row * H + c);
+      d0 += v.x * s_dM[c] + v.y * s_dM[c + 1] + v.z * s_dM[c + 2] + v.w * s_dM[c + 3];
+      d1 += v.x * s_dM[H + c] + v.y * s_dM[H + c + 1] + v.z * s_dM[H + c + 2] + v.w * s_dM[H + c + 3];
+    }
+    d0 = warp_sum(d0);
+    d1 = warp_sum(d1);
+    if (lane < T) {
+      const float d = lane == 0 ? d0 : d1;
+      const float pr = expf(a_raw[static_cast<int64_t>(lane) * N + row] - stats[2 * lane]) / stats[2 * lane + 1];
+      P[row * T + lane] = pr;
+      dA[row * T + lane] = pr * (d - sdot[lane]);
+    }
+  }
+}
+
+// ---- gate backward: dab[n] = [da_pre | db_pre]; per-CTA partials of dWc, dba, dbb, dbc
+// block = D threads (thread j owns gate column j); partial layout per CTA: [dWc0[D] dWc1[D] dba[D] dbb[D] dbc[2]]
+__global__ void gate_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                const float* __restrict__ dA, const float* __restrict__ wc, float* __restrict__ dab,
+                                float* __restrict__ part, int64_t N, int D, int rows_per_block) {
+  const int j = threadIdx.x;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
+  int64_t r1 = r0 + rows_per_block;
+  if (r1 > N) r1 = N;
+  const float w0 = __ldg(wc + j), w1 = __ldg(wc + D + j);
+  float gw0 = 0.f, gw1 = 0.f, gba = 0.f, gbb = 0.f, gc0 = 0.f, gc1 = 0.f;
+  for (int64_t row = r0; row < r1; ++row) {
+    const float da0 = __ldg(dA + row * T), da1 = __ldg(dA + row * T + 1);
+    const float av = a[row * D + j], bv = b[row * D + j];
+    const float g = av * bv;
+    gw0 = fmaf(da0, g, gw0);
+    gw1 = fmaf(da1, g, gw1);
+    gc0 += da0;
+    gc1 += da1;
+    const float dg = da0 * w0 + da1 * w1;
+    const float dap = dg * bv * (1.f - av * av);
+    const float dbp = dg * av * bv * (1.f - bv);
+    dab[row * 2 * D + j] = dap;
+    dab[row * 2 * D + D + j] = dbp;
+    gba += dap;
+    gbb += dbp;
+  }
+  float* mine = part + static_cast<int64_t>(blockIdx.x) * (4 * D + 2);
+  mine[j] = gw0;
+  mine[D + j] = gw1;
+  mine[2 * D + j] = gba;
+  mine[3 * D + j] = gbb;
+  if (j == 0) { mine[4 * D] = gc0; mine[4 * D + 1] = gc1; }
+}
+
+// ---- column sums of a [N, C] matrix: per-CTA partials [gridDim.x][C] (thread per column)
+__global__ void colsum_kernel(const float* __restrict__ m, float* __restrict__ part, int64_t N, int C,
+                              int rows_per_block) {
+  const int c = threadIdx.x;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
+  int64_t r1 = r0 + rows_per_block;
+  if (r1 > N) r1 = N;
+  float s = 0.f;
+  for (int64_t row = r0; row < r1; ++row) s += m[row * C + c];
+  part[static_cast<int64_t>(blockIdx.x) * C + c] = s;
+}
+
+// out[i] = sum_z part[z*stride + i], fixed order
+__global__ void reduce_strided_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n,
+                                      int64_t stride, int splits) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += part[static_cast<int64_t>(z) * stride + i];
+  out[i] = s;
+}
+
+inline int launch_reduce_strided(const float* part, float* out, int64_t n, int64_t stride, int splits,
+                                 cudaStream_t stream) {
+  if (n <= 0) return 0;
+  reduce_strided_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(part, out, n, stride, splits);
+  TOAD_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace bwd
+}  // namespace toad

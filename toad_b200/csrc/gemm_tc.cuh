@@ -1,0 +1,511 @@
+// tcgen05 (5th-gen tensor core) GEMM with 3-pass split-bf16 operands, sm_100a.
+//
+//   D[M,N] = epilogue( A[M,K] . B[N,K]^T ),   A ~= A_hi + A_lo,  B ~= B_hi + B_lo  (bf16 pairs)
+//   A.B^T  ~= A_hi.B_hi + A_hi.B_lo + A_lo.B_hi      (fp32 accumulation in TMEM)
+//
+// This is the nn.Linear building block of the TOAD trunk (reference:
+// models/model_toad.py:59,62 fc layers and :37-38 the gated-attention pair), at
+// fp32-class accuracy (dropped terms are O(2^-16) relative per product).
+//
+// Structure (one persistent CTA per SM, 128 x BLOCK_N output tiles, K in 64-wide blocks):
+//   warp 0      TMA producer: B_hi/B_lo tiles (and A_hi/A_lo when A is already split)
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16)
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue: tcgen05.ld accumulator -> registers -> bias/activation -> global
+//   warps 8-11  (A_MODE 0 only) A converter: fp32 rows from global -> (hi,lo) bf16 pairs
+//               written straight into the 128B-swizzled UMMA operand layout
+// Pipelines: smem ring (full/empty mbarriers) between producer/converter and MMA, and a
+// 2-deep TMEM accumulator ring (tmem_full/tmem_empty) between MMA and epilogue, so the
+// epilogue of tile i overlaps the main loop of tile i+1.
+#pragma once
+#include "common.cuh"
+
+namespace toad {
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
+
+enum { EPI_LINEAR = 0, EPI_GATE = 1 };
+enum { A_F32 = 0, A_SPLIT = 1 };
+
+template <int BLOCK_N>
+struct Cfg {
+  static_assert(BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
+  static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  static constexpr int STAGES = BLOCK_N == 256 ? 2 : (BLOCK_N == 128 ? 3 : 4);
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator buffers (128/256/512: powers of 2)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + slack for 1024 B alignment
+};
+
+struct GemmTcParams {
+  // A operand when A_MODE == A_F32
+  const float* a_f32;
+  int64_t lda;
+  int64_t M;
+  int32_t N;
+  int32_t K;
+  // EPI_LINEAR
+  const float* bias;  // [N] or nullptr
+  int32_t relu;
+  float* out_f32;  // nullable
+  int64_t ld_f32;
+  __nv_bfloat16* out_hi;  // nullable (both or neither)
+  __nv_bfloat16* out_lo;
+  int64_t ld_split;
+  // EPI_GATE: tile columns [0,BLOCK_N/2) hold the tanh branch, [BLOCK_N/2,BLOCK_N) the sigmoid
+  // branch of gate columns j0 = n_tile*BLOCK_N/2 ...
+  const float* gate_ba;
+  const float* gate_bb;
+  const float* gate_wc;  // [ntasks, D]
+  int32_t gate_D;
+  int32_t gate_ntasks;  // 1..4
+  float* gate_part;     // [n_tiles][M][ntasks] partial scores (no bias)
+  float* gate_a;        // nullable [M, D]
+  float* gate_b;        // nullable [M, D]
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded spin: a protocol bug traps (launch error) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (spin == 1024) t0 = clock64();
+    if (spin > 1024 && (spin & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]; bf16 inputs, fp32 accumulate.
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive when all previously issued tcgen05.mma of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor: K-major operand, SWIZZLE_128B, rows of 128 B,
+// 8-row groups 1024 B apart (SBO), descriptor version 1 (Blackwell).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);  // start address        bits [0,14)
+  d |= static_cast<uint64_t>(1) << 16;                     // leading byte offset  bits [16,30) (unused for SW128 K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;             // stride byte offset   bits [32,46)
+  d |= static_cast<uint64_t>(1) << 46;                     // version = 1          bits [46,48)
+  d |= static_cast<uint64_t>(2) << 61;                     // SWIZZLE_128B         bits [61,64)
+  return d;
+}
+// Instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BLOCK_N.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK_N, int A_MODE, int EPI>
+__global__ void __launch_bounds__(A_MODE == A_F32 ? 384 : 256, 1)
+gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                   const GemmTcParams p) {
+  using C = Cfg<BLOCK_N>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full_b[STAGES];
+  __shared__ __align__(8) uint64_t bar_full_a[STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[STAGES];
+  __shared__ __align__(8) uint64_t bar_tmem_full[2];
+  __shared__ __align__(8) uint64_t bar_tmem_empty[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t tiles_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  const int m_tiles = static_cast<int>((p.M + BLOCK_M - 1) / BLOCK_M);
+  const int n_tiles = p.N / BLOCK_N;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = p.K / BLOCK_K;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&bar_full_b[s]), 1);
+      mbar_init(smem_u32(&bar_full_a[s]), 4);  // one arrive per converter warp
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&bar_tmem_full[a]), 1);
+      mbar_init(smem_u32(&bar_tmem_empty[a]), 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_b_hi);
+    prefetch_tmap(&tm_b_lo);
+    if (A_MODE == A_SPLIT) {
+      prefetch_tmap(&tm_a_hi);
+      prefetch_tmap(&tm_a_lo);
+    }
+  }
+  if (warp == 2) tmem_alloc(smem_u32(&tmem_slot), C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n0 = (tile % n_tiles) * BLOCK_N;
+        const int m0 = (tile / n_tiles) * BLOCK_M;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+          const uint32_t sa = tiles_base + stage * C::STAGE_BYTES;
+          const uint32_t fb = smem_u32(&bar_full_b[stage]);
+          mbar_expect_tx(fb, 2 * C::B_TILE_BYTES + (A_MODE == A_SPLIT ? 2 * A_TILE_BYTES : 0));
+          if (A_MODE == A_SPLIT) {
+            tma_load_2d(sa, &tm_a_hi, fb, kb * BLOCK_K, m0);
+            tma_load_2d(sa + A_TILE_BYTES, &tm_a_lo, fb, kb * BLOCK_K, m0);
+          }
+          tma_load_2d(sa + 2 * A_TILE_BYTES, &tm_b_hi, fb, kb * BLOCK_K, n0);
+          tma_load_2d(sa + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &tm_b_lo, fb, kb * BLOCK_K, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(smem_u32(&bar_tmem_empty[acc]), ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&bar_full_b[stage]), phase);
+          if (A_MODE == A_F32) mbar_wait(smem_u32(&bar_full_a[stage]), phase);
+          tc_fence_after();
+          const uint32_t sa = tiles_base + stage * C::STAGE_BYTES;
+          const uint64_t a_hi = make_kmajor_sw128_desc(sa);
+          const uint64_t a_lo = make_kmajor_sw128_desc(sa + A_TILE_BYTES);
+          const uint64_t b_hi = make_kmajor_sw128_desc(sa + 2 * A_TILE_BYTES);
+          const uint64_t b_lo = make_kmajor_sw128_desc(sa + 2 * A_TILE_BYTES + C::B_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);  // +32 B per K step
+            umma_bf16(d_tmem, a_hi + koff, b_hi + koff, idesc, (kb | k) != 0);
+          }
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);
+            umma_bf16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
+          }
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);
+            umma_bf16(d_tmem, a_lo + koff, b_hi + koff, idesc, 1);
+          }
+          umma_commit(smem_u32(&bar_empty[stage]));  // smem slot free once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(&bar_tmem_full[acc]));  // accumulator ready for the epilogue
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ epilogue
+    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int n_tile = tile % n_tiles;
+      const int n0 = n_tile * BLOCK_N;
+      const int m0 = (tile / n_tiles) * BLOCK_M;
+      const int acc = it & 1;
+      mbar_wait(smem_u32(&bar_tmem_full[acc]), (it >> 1) & 1);
+      tc_fence_after();
+      const int64_t row = static_cast<int64_t>(m0) + ew * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N;
+
+      if (EPI == EPI_LINEAR) {
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_row + c * 32, r);
+          tmem_ld_wait();
+          const int col0 = n0 + c * 32;
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float t = __uint_as_float(r[i]);
+            if (p.bias != nullptr) t += __ldg(p.bias + col0 + i);
+            if (p.relu) t = fmaxf(t, 0.0f);
+            v[i] = t;
+          }
+          if (row_ok) {
+            if (p.out_f32 != nullptr) {
+              float4* dst = reinterpret_cast<float4*>(p.out_f32 + row * p.ld_f32 + col0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+            if (p.out_hi != nullptr) {
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+              uint4* dh = reinterpret_cast<uint4*>(p.out_hi + row * p.ld_split + col0);
+              uint4* dl = reinterpret_cast<uint4*>(p.out_lo + row * p.ld_split + col0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                dh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                dl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+              }
+            }
+          }
+        }
+      } else {  // EPI_GATE
+        constexpr int HALF = BLOCK_N / 2;
+        const int j0 = n_tile * HALF;
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int c = 0; c < HALF / 32; ++c) {
+          uint32_t ra[32], rb[32];
+          tmem_ld32(t_row + c * 32, ra);
+          tmem_ld32(t_row + HALF + c * 32, rb);
+          tmem_ld_wait();
+          const int jc = j0 + c * 32;
+          float ga[32], gb[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            ga[i] = tanh_acc(__uint_as_float(ra[i]) + __ldg(p.gate_ba + jc + i));
+            gb[i] = sigmoid_acc(__uint_as_float(rb[i]) + __ldg(p.gate_bb + jc + i));
+            const float g = ga[i] * gb[i];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              if (t < p.gate_ntasks) s[t] = fmaf(g, __ldg(p.gate_wc + t * p.gate_D + jc + i), s[t]);
+          }
+          if (row_ok && p.gate_a != nullptr) {
+            float4* da = reinterpret_cast<float4*>(p.gate_a + row * p.gate_D + jc);
+            float4* db = reinterpret_cast<float4*>(p.gate_b + row * p.gate_D + jc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              da[i] = make_float4(ga[4 * i], ga[4 * i + 1], ga[4 * i + 2], ga[4 * i + 3]);
+              db[i] = make_float4(gb[4 * i], gb[4 * i + 1], gb[4 * i + 2], gb[4 * i + 3]);
+            }
+          }
+        }
+        if (row_ok) {
+          float* dst = p.gate_part + (static_cast<int64_t>(n_tile) * p.M + row) * p.gate_ntasks;
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            if (t < p.gate_ntasks) dst[t] = s[t];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[acc]));
+    }
+  } else if (A_MODE == A_F32 && warp >= 8) {
+    // ------------------------------------------------------------------ A converter
+    // Each half-warp streams one 256 B row segment (64 fp32) per load instruction; a thread
+    // turns its 4 floats into 4 (hi) + 4 (lo) bf16 = one 8 B store into each swizzled tile.
+    const int cw = warp - 8;
+    const int hw = lane >> 4, l16 = lane & 15;
+    const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                         static_cast<int>(gridDim.x);
+    const int64_t total = static_cast<int64_t>(my_tiles > 0 ? my_tiles : 0) * num_kb;
+    float4 cur[16], nxt[16];
+    auto issue = [&](int64_t g, float4(&buf)[16]) {
+      const int tile = blockIdx.x + static_cast<int>(g / num_kb) * gridDim.x;
+      const int kb = static_cast<int>(g % num_kb);
+      const int64_t m0 = static_cast<int64_t>(tile / n_tiles) * BLOCK_M;
+      const float* base = p.a_f32 + kb * BLOCK_K + l16 * 4;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int64_t row = m0 + cw * 32 + j * 2 + hw;
+        buf[j] = row < p.M ? ld_stream_f4(base + row * p.lda) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if (total > 0) issue(0, cur);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t g = 0; g < total; ++g) {
+      if (g + 1 < total) issue(g + 1, nxt);
+      mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+      const uint32_t sa = tiles_base + stage * C::STAGE_BYTES;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int r = cw * 32 + j * 2 + hw;
+        uint32_t h0, l0, h1, l1;
+        split2(cur[j].x, cur[j].y, h0, l0);
+        split2(cur[j].z, cur[j].w, h1, l1);
+        const uint32_t off = r * 128 + (((l16 >> 1) ^ (r & 7)) << 4) + ((l16 & 1) << 3);
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(sa + off), "r"(h0), "r"(h1) : "memory");
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(sa + A_TILE_BYTES + off), "r"(l0), "r"(l1) : "memory");
+      }
+      fence_proxy_async_smem();  // make generic-proxy smem writes visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_full_a[stage]));
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = []() -> PFN_encodeTiled {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    if (q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<PFN_encodeTiled>(f);
+  }();
+  return fn;
+}
+
+// Tensor map over a row-major bf16 matrix [rows, cols]; box = 64 columns x box_rows rows, 128B swizzle.
+inline int make_bf16_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (enc == nullptr) return TOAD_ERR_DRIVER;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BLOCK_K), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : TOAD_ERR_DRIVER;
+}
+
+inline int sm_count() {
+  static int n = []() {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+    return v;
+  }();
+  return n;
+}
+
+// A operand: fp32 (a_f32/lda in p) when A_MODE == A_F32, else the planes a_hi/a_lo [M, K] bf16.
+// B operand: planes b_hi/b_lo [N, K] bf16.
+template <int BLOCK_N, int A_MODE, int EPI>
+int launch_gemm(const GemmTcParams& p, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,
+                const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N>;
+  if (p.M <= 0) return 0;
+  if (p.K % BLOCK_K != 0 || p.N % BLOCK_N != 0 || p.K <= 0 || p.N <= 0) return TOAD_ERR_UNSUPPORTED;
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  TOAD_TRY(make_bf16_tmap(&tb_hi, b_hi, p.N, p.K, BLOCK_N));
+  TOAD_TRY(make_bf16_tmap(&tb_lo, b_lo, p.N, p.K, BLOCK_N));
+  if (A_MODE == A_SPLIT) {
+    TOAD_TRY(make_bf16_tmap(&ta_hi, a_hi, p.M, p.K, BLOCK_M));
+    TOAD_TRY(make_bf16_tmap(&ta_lo, a_lo, p.M, p.K, BLOCK_M));
+  } else {
+    ta_hi = tb_hi;
+    ta_lo = tb_lo;
+  }
+  auto kern = gemm_bf16x3_kernel<BLOCK_N, A_MODE, EPI>;
+  TOAD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  const int64_t m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int64_t tiles = m_tiles * (p.N / BLOCK_N);
+  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  kern<<<grid, A_MODE == A_F32 ? 384 : 256, C::SMEM_BYTES, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  TOAD_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace toad

@@ -1,0 +1,548 @@
+// extern "C" entry points of libtoad_b200.so (see include/toad_b200.h for the contract).
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "sgemm_simt.cuh"
+#include "tail.cuh"
+#include "bwd.cuh"
+#include "topk.cuh"
+#include <new>
+
+namespace {
+
+using namespace toad;
+typedef __nv_bfloat16 bf16;
+
+constexpr int kSMs = 148;       // B200; used only to size workspaces and tail grids
+constexpr int kGateHalf = 128;  // gate columns per EPI_GATE tile (BLOCK_N 256 / 2)
+
+struct Carver {
+  uint8_t* base;
+  size_t off;
+  explicit Carver(void* b) : base(static_cast<uint8_t*>(b)), off(0) {}
+  template <class T>
+  T* take(size_t count) {
+    off = align_up(off, 256);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+int check_dims(const toad_dims_t* d) {
+  if (d == nullptr) return TOAD_ERR_ARG;
+  if (d->hid_dim != tail::H || d->n_tasks != tail::T) return TOAD_ERR_UNSUPPORTED;
+  if (d->in_dim <= 0 || d->in_dim % 64 != 0) return TOAD_ERR_UNSUPPORTED;
+  if (d->attn_dim <= 0 || d->attn_dim % kGateHalf != 0 || d->attn_dim > 1024) return TOAD_ERR_UNSUPPORTED;
+  if (d->n_classes < 1 || d->n_classes > 1024) return TOAD_ERR_UNSUPPORTED;
+  return 0;
+}
+
+struct FwdWs {
+  unsigned int* ticket;
+  float* blk_part;
+  float* part;  // [n_parts][N][T]
+  int n_parts;
+  // tensor-core path
+  bf16 *w1_hi, *w1_lo, *w2_hi, *w2_lo, *wab_hi, *wab_lo, *h1_hi, *h1_lo, *h_hi, *h_lo;
+  // fp32 path (when the caller gave no `saved`)
+  float *h1, *h, *a, *b;
+  size_t bytes;
+};
+
+FwdWs carve_fwd(const toad_dims_t* d, int64_t n, uint32_t flags, void* base) {
+  FwdWs w{};
+  Carver c(base);
+  const int64_t Hd = d->hid_dim, D = d->attn_dim, L = d->in_dim;
+  w.ticket = c.take<unsigned int>(64);
+  w.blk_part = c.take<float>(static_cast<size_t>(tail::tail_blocks(n, kSMs)) * tail::PART_STRIDE);
+  const bool simt = (flags & TOAD_FLAG_SIMT_FP32) != 0;
+  w.n_parts = simt ? 1 : static_cast<int>(D / kGateHalf);
+  w.part = c.take<float>(static_cast<size_t>(w.n_parts) * n * d->n_tasks);
+  if (!simt) {
+    w.w1_hi = c.take<bf16>(Hd * L);  w.w1_lo = c.take<bf16>(Hd * L);
+    w.w2_hi = c.take<bf16>(Hd * Hd); w.w2_lo = c.take<bf16>(Hd * Hd);
+    w.wab_hi = c.take<bf16>(2 * D * Hd); w.wab_lo = c.take<bf16>(2 * D * Hd);
+    w.h1_hi = c.take<bf16>(n * Hd); w.h1_lo = c.take<bf16>(n * Hd);
+    w.h_hi = c.take<bf16>(n * Hd);  w.h_lo = c.take<bf16>(n * Hd);
+  } else if (!(flags & TOAD_FLAG_SAVE_ACTS)) {
+    w.h1 = c.take<float>(n * Hd); w.h = c.take<float>(n * Hd);
+    w.a = c.take<float>(n * D);   w.b = c.take<float>(n * D);
+  }
+  w.bytes = align_up(c.off, 256);
+  return w;
+}
+
+struct Prof {
+  cudaEvent_t* ev;  // [max_calls][TOAD_N_STAGES + 1]
+  int max_calls;
+  int n;
+};
+inline int prof_mark(Prof* p, int idx, cudaStream_t st) {
+  if (p == nullptr || p->n >= p->max_calls) return 0;
+  TOAD_CUDA_TRY(cudaEventRecord(p->ev[p->n * (TOAD_N_STAGES + 1) + idx], st));
+  return 0;
+}
+
+int check_ws(const void* ws, size_t have, size_t need) {
+  if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 255) != 0 || have < need) return TOAD_ERR_WORKSPACE;
+  return 0;
+}
+
+int run_tail(const toad_dims_t* d, const toad_params_t* P, int64_t n, const float* sex, const toad_fwd_out_t* out,
+             const FwdWs& w, const float* h_f32, const bf16* h_hi, const bf16* h_lo, bool attention_only,
+             cudaStream_t st) {
+  tail::TailParams t{};
+  t.part = w.part; t.n_parts = w.n_parts; t.bc = P->bc; t.a_raw = out->a_raw;
+  t.h_f32 = h_f32; t.h_hi = h_hi; t.h_lo = h_lo; t.N = n; t.sex = sex;
+  t.wcls = P->wcls; t.bcls = P->bcls; t.n_classes = d->n_classes; t.wsite = P->wsite; t.bsite = P->bsite;
+  t.features = out->features; t.logits = out->logits; t.y_prob = out->y_prob; t.y_hat = out->y_hat;
+  t.site_logits = out->site_logits; t.site_prob = out->site_prob; t.site_hat = out->site_hat;
+  t.stats = out->softmax_stats; t.blk_part = w.blk_part; t.ticket = w.ticket;
+  t.attention_only = attention_only ? 1 : 0;
+  return h_f32 ? tail::launch_tail<tail::H_F32>(t, kSMs, st) : tail::launch_tail<tail::H_SPLIT>(t, kSMs, st);
+}
+
+simt::SgemmParams linear_params(const float* x, int64_t ldx, const float* w, const float* bias, float* y, int64_t m,
+                                int n, int64_t k) {
+  simt::SgemmParams s{};
+  s.a = x; s.a_rs = ldx; s.a_ks = 1;
+  s.b = w; s.b_rs = k; s.b_ks = 1;
+  s.c = y; s.ldc = n; s.M = m; s.N = n; s.K = k; s.k_chunk = k; s.bias = bias;
+  return s;
+}
+
+}  // namespace
+
+extern "C" int toad_abi_version(void) { return TOAD_ABI_VERSION; }
+
+extern "C" const char* toad_error_string(int code) {
+  switch (code) {
+    case TOAD_OK: return "ok";
+    case TOAD_ERR_ARG: return "invalid argument (null pointer or bad size)";
+    case TOAD_ERR_WORKSPACE: return "workspace too small or not 256-byte aligned";
+    case TOAD_ERR_UNSUPPORTED: return "dimensions not supported by the sm_100a kernels";
+    case TOAD_ERR_DRIVER: return "could not obtain cuTensorMapEncodeTiled / encode a TMA descriptor";
+    default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "unknown error";
+  }
+}
+
+extern "C" int toad_param_offsets(const toad_dims_t* d, int64_t offsets[15]) {
+  if (d == nullptr || offsets == nullptr) return TOAD_ERR_ARG;
+  const int64_t L = d->in_dim, Hd = d->hid_dim, D = d->attn_dim, T = d->n_tasks, C = d->n_classes;
+  const int64_t sizes[14] = {Hd * L, Hd, Hd * Hd, Hd, D * Hd, D, D * Hd, D, T * D, T, C * (Hd + 1), C, 2 * (Hd + 1), 2};
+  int64_t o = 0;
+  for (int i = 0; i < 14; ++i) { offsets[i] = o; o += sizes[i]; }
+  offsets[14] = o;
+  return 0;
+}
+
+extern "C" int toad_fwd_workspace_bytes(const toad_dims_t* d, int64_t n, uint32_t flags, size_t* bytes) {
+  TOAD_TRY(check_dims(d));
+  if (bytes == nullptr || n <= 0) return TOAD_ERR_ARG;
+  *bytes = carve_fwd(d, n, flags, nullptr).bytes;
+  return 0;
+}
+
+static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t n, const float* sex,
+                    const toad_fwd_out_t* out, const toad_saved_t* saved, void* workspace, size_t workspace_bytes,
+                    uint32_t flags, toad_stream_t stream, Prof* prof) {
+  TOAD_TRY(check_dims(d));
+  if (P == nullptr || x == nullptr || out == nullptr || out->a_raw == nullptr || n <= 0) return TOAD_ERR_ARG;
+  const bool attn_only = (flags & TOAD_FLAG_ATTENTION_ONLY) != 0;
+  const bool save = (flags & TOAD_FLAG_SAVE_ACTS) != 0;
+  if (!attn_only && (sex == nullptr || out->features == nullptr || out->logits == nullptr || out->y_prob == nullptr ||
+                     out->y_hat == nullptr || out->site_logits == nullptr || out->site_prob == nullptr ||
+                     out->site_hat == nullptr || out->softmax_stats == nullptr))
+    return TOAD_ERR_ARG;
+  if (save && (saved == nullptr || !saved->h1 || !saved->h || !saved->a || !saved->b)) return TOAD_ERR_ARG;
+  FwdWs w = carve_fwd(d, n, flags, workspace);
+  TOAD_TRY(check_ws(workspace, workspace_bytes, w.bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Hd = d->hid_dim, D = d->attn_dim, L = d->in_dim;
+  TOAD_CUDA_TRY(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), st));
+
+  if (flags & TOAD_FLAG_SIMT_FP32) {
+    float* h1 = save ? saved->h1 : w.h1;
+    float* h = save ? saved->h : w.h;
+    float* a = save ? saved->a : w.a;
+    float* b = save ? saved->b : w.b;
+    TOAD_TRY(prof_mark(prof, 0, st));
+    TOAD_TRY(prof_mark(prof, 1, st));
+    TOAD_TRY((simt::launch_sgemm<true, true, simt::EPI_BIAS_RELU>(linear_params(x, L, P->w1, P->b1, h1, n, Hd, L), 1, st)));
+    TOAD_TRY(prof_mark(prof, 2, st));
+    TOAD_TRY((simt::launch_sgemm<true, true, simt::EPI_BIAS_RELU>(linear_params(h1, Hd, P->w2, P->b2, h, n, Hd, Hd), 1, st)));
+    TOAD_TRY(prof_mark(prof, 3, st));
+    TOAD_TRY((simt::launch_sgemm<true, true, simt::EPI_BIAS_TANH>(linear_params(h, Hd, P->wa, P->ba, a, n, D, Hd), 1, st)));
+    TOAD_TRY((simt::launch_sgemm<true, true, simt::EPI_BIAS_SIGMOID>(linear_params(h, Hd, P->wb, P->bb, b, n, D, Hd), 1, st)));
+    TOAD_TRY(tail::launch_attn_c(a, b, P->wc, w.part, n, D, d->n_tasks, st));
+    TOAD_TRY(prof_mark(prof, 4, st));
+    TOAD_TRY(run_tail(d, P, n, sex, out, w, h, nullptr, nullptr, attn_only, st));
+    TOAD_TRY(prof_mark(prof, 5, st));
+    if (prof != nullptr && prof->n < prof->max_calls) prof->n++;
+    return 0;
+  }
+
+  // ---- tensor-core path: split weights, three tcgen05 GEMMs with fused epilogues, tail
+  TOAD_TRY(prof_mark(prof, 0, st));
+  TOAD_TRY(tail::launch_split_planes(P->w1, w.w1_hi, w.w1_lo, static_cast<int64_t>(Hd) * L, st));
+  TOAD_TRY(tail::launch_split_planes(P->w2, w.w2_hi, w.w2_lo, static_cast<int64_t>(Hd) * Hd, st));
+  TOAD_TRY(tail::launch_split_gate_weights(P->wa, P->wb, w.wab_hi, w.wab_lo, D, Hd, kGateHalf, st));
+  TOAD_TRY(prof_mark(prof, 1, st));
+  {
+    tc::GemmTcParams g{};
+    g.a_f32 = x; g.lda = L; g.M = n; g.N = Hd; g.K = L; g.bias = P->b1; g.relu = 1;
+    g.out_f32 = save ? saved->h1 : nullptr; g.ld_f32 = Hd;
+    g.out_hi = w.h1_hi; g.out_lo = w.h1_lo; g.ld_split = Hd;
+    TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_LINEAR>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, st)));
+  }
+  TOAD_TRY(prof_mark(prof, 2, st));
+  {
+    tc::GemmTcParams g{};
+    g.M = n; g.N = Hd; g.K = Hd; g.bias = P->b2; g.relu = 1;
+    g.out_f32 = save ? saved->h : nullptr; g.ld_f32 = Hd;
+    g.out_hi = w.h_hi; g.out_lo = w.h_lo; g.ld_split = Hd;
+    TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR>(g, w.h1_hi, w.h1_lo, w.w2_hi, w.w2_lo, st)));
+  }
+  TOAD_TRY(prof_mark(prof, 3, st));
+  {
+    tc::GemmTcParams g{};
+    g.M = n; g.N = 2 * D; g.K = Hd;
+    g.gate_ba = P->ba; g.gate_bb = P->bb; g.gate_wc = P->wc; g.gate_D = D; g.gate_ntasks = d->n_tasks;
+    g.gate_part = w.part; g.gate_a = save ? saved->a : nullptr; g.gate_b = save ? saved->b : nullptr;
+    TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_GATE>(g, w.h_hi, w.h_lo, w.wab_hi, w.wab_lo, st)));
+  }
+  TOAD_TRY(prof_mark(prof, 4, st));
+  TOAD_TRY(run_tail(d, P, n, sex, out, w, nullptr, w.h_hi, w.h_lo, attn_only, st));
+  TOAD_TRY(prof_mark(prof, 5, st));
+  if (prof != nullptr && prof->n < prof->max_calls) prof->n++;
+  return 0;
+}
+
+extern "C" int toad_fwd(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t n, const float* sex,
+                        const toad_fwd_out_t* out, const toad_saved_t* saved, void* workspace, size_t workspace_bytes,
+                        uint32_t flags, toad_stream_t stream) {
+  return fwd_impl(d, P, x, n, sex, out, saved, workspace, workspace_bytes, flags, stream, nullptr);
+}
+
+extern "C" int toad_fwd_profiled(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t n,
+                                 const float* sex, const toad_fwd_out_t* out, const toad_saved_t* saved,
+                                 void* workspace, size_t workspace_bytes, uint32_t flags, toad_stream_t stream,
+                                 void* prof) {
+  return fwd_impl(d, P, x, n, sex, out, saved, workspace, workspace_bytes, flags, stream, static_cast<Prof*>(prof));
+}
+
+extern "C" int toad_profile_create(void** prof, int32_t max_calls) {
+  if (prof == nullptr || max_calls <= 0 || max_calls > 65536) return TOAD_ERR_ARG;
+  Prof* p = new (std::nothrow) Prof();
+  if (p == nullptr) return TOAD_ERR_ARG;
+  const int ne = max_calls * (TOAD_N_STAGES + 1);
+  p->ev = new (std::nothrow) cudaEvent_t[ne];
+  p->max_calls = max_calls;
+  p->n = 0;
+  if (p->ev == nullptr) { delete p; return TOAD_ERR_ARG; }
+  for (int i = 0; i < ne; ++i) {
+    cudaError_t e = cudaEventCreate(&p->ev[i]);
+    if (e != cudaSuccess) {
+      for (int j = 0; j < i; ++j) cudaEventDestroy(p->ev[j]);
+      delete[] p->ev;
+      delete p;
+      return static_cast<int>(e);
+    }
+  }
+  *prof = p;
+  return 0;
+}
+
+extern "C" int toad_profile_destroy(void* prof) {
+  Prof* p = static_cast<Prof*>(prof);
+  if (p == nullptr) return TOAD_ERR_ARG;
+  for (int i = 0; i < p->max_calls * (TOAD_N_STAGES + 1); ++i) cudaEventDestroy(p->ev[i]);
+  delete[] p->ev;
+  delete p;
+  return 0;
+}
+
+extern "C" int toad_profile_read(void* prof, double stage_ms[TOAD_N_STAGES], int32_t* n_calls) {
+  Prof* p = static_cast<Prof*>(prof);
+  if (p == nullptr || stage_ms == nullptr || n_calls == nullptr) return TOAD_ERR_ARG;
+  for (int s = 0; s < TOAD_N_STAGES; ++s) stage_ms[s] = 0.0;
+  for (int c = 0; c < p->n; ++c) {
+    cudaEvent_t* e = p->ev + c * (TOAD_N_STAGES + 1);
+    TOAD_CUDA_TRY(cudaEventSynchronize(e[TOAD_N_STAGES]));
+    for (int s = 0; s < TOAD_N_STAGES; ++s) {
+      float ms = 0.f;
+      TOAD_CUDA_TRY(cudaEventElapsedTime(&ms, e[s], e[s + 1]));
+      stage_ms[s] += ms;
+    }
+  }
+  *n_calls = p->n;
+  p->n = 0;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ backward
+namespace {
+struct BwdWs {
+  float *dM, *sdot, *P, *dA, *dab, *dz2, *dz1, *splitk, *gate_part, *col_part;
+  int splits, gate_blocks, col_blocks;
+  int64_t k_chunk;
+  size_t bytes;
+};
+BwdWs carve_bwd(const toad_dims_t* d, int64_t n, void* base) {
+  BwdWs w{};
+  Carver c(base);
+  const int64_t Hd = d->hid_dim, D = d->attn_dim, L = d->in_dim;
+  w.dM = c.take<float>(2 * Hd);
+  w.sdot = c.take<float>(64);
+  w.P = c.take<float>(n * 2);
+  w.dA = c.take<float>(n * 2);
+  w.dab = c.take<float>(n * 2 * D);
+  w.dz2 = c.take<float>(n * Hd);
+  w.dz1 = c.take<float>(n * Hd);
+  int64_t s = (n + 1023) / 1024;
+  if (s < 1) s = 1;
+  if (s > 32) s = 32;
+  w.splits = static_cast<int>(s);
+  w.k_chunk = ((n + s - 1) / s + 15) / 16 * 16;
+  int64_t big = Hd * L;
+  if (2 * D * Hd > big) big = 2 * D * Hd;
+  w.splitk = c.take<float>(static_cast<size_t>(w.splits) * big);
+  int64_t gb = (n + 127) / 128;
+  if (gb > 2 * kSMs) gb = 2 * kSMs;
+  w.gate_blocks = static_cast<int>(gb);
+  w.col_blocks = static_cast<int>(gb);
+  w.gate_part = c.take<float>(static_cast<size_t>(gb) * (4 * D + 2));
+  w.col_part = c.take<float>(static_cast<size_t>(gb) * Hd);
+  w.bytes = align_up(c.off, 256);
+  return w;
+}
+}  // namespace
+
+extern "C" int toad_bwd_workspace_bytes(const toad_dims_t* d, int64_t n, size_t* bytes) {
+  TOAD_TRY(check_dims(d));
+  if (bytes == nullptr || n <= 0) return TOAD_ERR_ARG;
+  *bytes = carve_bwd(d, n, nullptr).bytes;
+  return 0;
+}
+
+extern "C" int toad_bwd(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t n, const toad_fwd_out_t* fo,
+             const toad_saved_t* sv, const float* dlogits, const float* dsite, float* grad, void* workspace,
+             size_t workspace_bytes, toad_stream_t stream) {
+  TOAD_TRY(check_dims(d));
+  if (!P || !x || !fo || !sv || !dlogits || !dsite || !grad || n <= 0) return TOAD_ERR_ARG;
+  if (!fo->a_raw || !fo->features || !fo->softmax_stats || !sv->h1 || !sv->h || !sv->a || !sv->b) return TOAD_ERR_ARG;
+  BwdWs w = carve_bwd(d, n, workspace);
+  TOAD_TRY(check_ws(workspace, workspace_bytes, w.bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Hd = d->hid_dim, D = d->attn_dim, L = d->in_dim;
+  int64_t off[15];
+  toad_param_offsets(d, off);
+  float *g_w1 = grad + off[0], *g_b1 = grad + off[1], *g_w2 = grad + off[2], *g_b2 = grad + off[3];
+  float *g_wa = grad + off[4], *g_ba = grad + off[5], *g_wb = grad + off[6], *g_bb = grad + off[7];
+  float *g_wc = grad + off[8], *g_bc = grad + off[9], *g_wcls = grad + off[10], *g_bcls = grad + off[11];
+  float *g_wsite = grad + off[12], *g_bsite = grad + off[13];
+
+  // 1. heads -> dM, sdot ; 2. softmax-pooling backward -> P, dA
+  bwd::heads_bwd_kernel<<<1, 2 * bwd::H, 0, st>>>(dlogits, dsite, fo->features, P->wcls, P->wsite, d->n_classes, g_wcls,
+                                                   g_bcls, g_wsite, g_bsite, w.dM, w.sdot);
+  TOAD_CUDA_TRY(cudaGetLastError());
+  {
+    int64_t blocks = (n + 7) / 8;
+    if (blocks > 8 * kSMs) blocks = 8 * kSMs;
+    bwd::pool_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(sv->h, fo->a_raw, fo->softmax_stats, w.dM, w.sdot,
+                                                                         w.P, w.dA, n);
+    TOAD_CUDA_TRY(cudaGetLastError());
+  }
+  // 3. gate backward -> dab, partials of dWc/dba/dbb/dbc
+  {
+    const int rpb = static_cast<int>((n + w.gate_blocks - 1) / w.gate_blocks);
+    bwd::gate_bwd_kernel<<<w.gate_blocks, D, 0, st>>>(sv->a, sv->b, w.dA, P->wc, w.dab, w.gate_part, n, D, rpb);
+    TOAD_CUDA_TRY(cudaGetLastError());
+    const int64_t stride = 4 * D + 2;
+    TOAD_TRY(bwd::launch_reduce_strided(w.gate_part, g_wc, 2 * D, stride, w.gate_blocks, st));
+    TOAD_TRY(bwd::launch_reduce_strided(w.gate_part + 2 * D, g_ba, D, stride, w.gate_blocks, st));
+    TOAD_TRY(bwd::launch_reduce_strided(w.gate_part + 3 * D, g_bb, D, stride, w.gate_blocks, st));
+    TOAD_TRY(bwd::launch_reduce_strided(w.gate_part + 4 * D, g_bc, 2, stride, w.gate_blocks, st));
+  }
+  // 4. dWa | dWb = dab^T . h   (K = patches, split-K)
+  {
+    simt::SgemmParams s{};
+    s.a = w.dab; s.a_rs = 1; s.a_ks = 2 * D;
+    s.b = sv->h; s.b_rs = 1; s.b_ks = Hd;
+    s.c = w.splitk; s.ldc = Hd; s.M = 2 * D; s.N = Hd; s.K = n; s.k_chunk = w.k_chunk;
+    TOAD_TRY((simt::launch_sgemm<false, false, simt::EPI_STORE>(s, w.splits, st)));
+    const int64_t stride = static_cast<int64_t>(2) * D * Hd;
+    TOAD_TRY(bwd::launch_reduce_strided(w.splitk, g_wa, static_cast<int64_t>(D) * Hd, stride, w.splits, st));
+    TOAD_TRY(bwd::launch_reduce_strided(w.splitk + static_cast<int64_t>(D) * Hd, g_wb, static_cast<int64_t>(D) * Hd, stride, w.splits, st));
+  }
+  // 5. dz2 = (da_pre.Wa + db_pre.Wb + P0 dM0 + P1 dM1) * (h > 0)
+  {
+    simt::SgemmParams s{};
+    s.a = w.dab; s.a_rs = 2 * D; s.a_ks = 1;
+    s.b = P->wa; s.b_rs = 1; s.b_ks = Hd;
+    s.c = w.dz2; s.ldc = Hd; s.M = n; s.N = Hd; s.K = D; s.k_chunk = D;
+    TOAD_TRY((simt::launch_sgemm<true, false, simt::EPI_STORE>(s, 1, st)));
+    s.a = w.dab + D; s.b = P->wb;
+    s.accumulate = 1; s.mask = sv->h; s.ldmask = Hd;
+    s.p0 = w.P; s.p1 = w.P + 1; s.p_stride = 2; s.v0 = w.dM; s.v1 = w.dM + Hd;
+    TOAD_TRY((simt::launch_sgemm<true, false, simt::EPI_POOL_RELUMASK>(s, 1, st)));
+  }
+  // 6. db2, dW2 = dz2^T . h1
+  {
+    const int rpb = static_cast<int>((n + w.col_blocks - 1) / w.col_blocks);
+    bwd::colsum_kernel<<<w.col_blocks, Hd, 0, st>>>(w.dz2, w.col_part, n, Hd, rpb);
+    TOAD_CUDA_TRY(cudaGetLastError());
+    TOAD_TRY(bwd::launch_reduce_strided(w.col_part, g_b2, Hd, Hd, w.col_blocks, st));
+    simt::SgemmParams s{};
+    s.a = w.dz2; s.a_rs = 1; s.a_ks = Hd;
+    s.b = sv->h1; s.b_rs = 1; s.b_ks = Hd;
+    s.c = w.splitk; s.ldc = Hd; s.M = Hd; s.N = Hd; s.K = n; s.k_chunk = w.k_chunk;
+    TOAD_TRY((simt::launch_sgemm<false, false, simt::EPI_STORE>(s, w.splits, st)));
+    TOAD_TRY(bwd::launch_reduce_strided(w.splitk, g_w2, static_cast<int64_t>(Hd) * Hd, static_cast<int64_t>(Hd) * Hd, w.splits, st));
+  }
+  // 7. dz1 = (dz2 . W2) * (h1 > 0)
+  {
+    simt::SgemmParams s{};
+    s.a = w.dz2; s.a_rs = Hd; s.a_ks = 1;
+    s.b = P->w2; s.b_rs = 1; s.b_ks = Hd;
+    s.c = w.dz1; s.ldc = Hd; s.M = n; s.N = Hd; s.K = Hd; s.k_chunk = Hd;
+    s.mask = sv->h1; s.ldmask = Hd;
+    TOAD_TRY((simt::launch_sgemm<true, false, simt::EPI_RELUMASK>(s, 1, st)));
+  }
+  // 8. db1, dW1 = dz1^T . x
+  {
+    const int rpb = static_cast<int>((n + w.col_blocks - 1) / w.col_blocks);
+    bwd::colsum_kernel<<<w.col_blocks, Hd, 0, st>>>(w.dz1, w.col_part, n, Hd, rpb);
+    TOAD_CUDA_TRY(cudaGetLastError());
+    TOAD_TRY(bwd::launch_reduce_strided(w.col_part, g_b1, Hd, Hd, w.col_blocks, st));
+    simt::SgemmParams s{};
+    s.a = w.dz1; s.a_rs = 1; s.a_ks = Hd;
+    s.b = x; s.b_rs = 1; s.b_ks = L;
+    s.c = w.splitk; s.ldc = L; s.M = Hd; s.N = L; s.K = n; s.k_chunk = w.k_chunk;
+    TOAD_TRY((simt::launch_sgemm<false, false, simt::EPI_STORE>(s, w.splits, st)));
+    TOAD_TRY(bwd::launch_reduce_strided(w.splitk, g_w1, static_cast<int64_t>(Hd) * L, static_cast<int64_t>(Hd) * L, w.splits, st));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ Attn_Net_Gated
+namespace {
+struct AgWs {
+  bf16 *w_hi, *w_lo;
+  float *part, *a, *b;
+  int n_parts;
+  size_t bytes;
+};
+AgWs carve_ag(int L, int D, int nt, int64_t n, uint32_t flags, void* base) {
+  AgWs w{};
+  Carver c(base);
+  const bool simt = (flags & TOAD_FLAG_SIMT_FP32) != 0;
+  w.n_parts = simt ? 1 : D / kGateHalf;
+  w.part = c.take<float>(static_cast<size_t>(w.n_parts) * n * nt);
+  if (simt) {
+    w.a = c.take<float>(n * D);
+    w.b = c.take<float>(n * D);
+  } else {
+    w.w_hi = c.take<bf16>(static_cast<size_t>(2) * D * L);
+    w.w_lo = c.take<bf16>(static_cast<size_t>(2) * D * L);
+  }
+  w.bytes = align_up(c.off, 256);
+  return w;
+}
+int check_ag(int L, int D, int nt, int64_t n) {
+  if (n <= 0) return TOAD_ERR_ARG;
+  if (L <= 0 || L % 64 != 0 || D <= 0 || D % kGateHalf != 0 || nt < 1 || nt > 4) return TOAD_ERR_UNSUPPORTED;
+  return 0;
+}
+}  // namespace
+
+extern "C" int toad_attn_gated_workspace_bytes(int32_t L, int32_t D, int32_t nt, int64_t n, uint32_t flags, size_t* bytes) {
+  TOAD_TRY(check_ag(L, D, nt, n));
+  if (bytes == nullptr) return TOAD_ERR_ARG;
+  *bytes = carve_ag(L, D, nt, n, flags, nullptr).bytes;
+  return 0;
+}
+
+extern "C" int toad_attn_gated_fwd(int32_t L, int32_t D, int32_t nt, const float* wa, const float* ba, const float* wb,
+                        const float* bb, const float* wc, const float* bc, const float* x, int64_t n, float* A_out,
+                        void* workspace, size_t workspace_bytes, uint32_t flags, toad_stream_t stream) {
+  TOAD_TRY(check_ag(L, D, nt, n));
+  if (!wa || !ba || !wb || !bb || !wc || !bc || !x || !A_out) return TOAD_ERR_ARG;
+  AgWs w = carve_ag(L, D, nt, n, flags, workspace);
+  TOAD_TRY(check_ws(workspace, workspace_bytes, w.bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (flags & TOAD_FLAG_SIMT_FP32) {
+    TOAD_TRY((simt::launch_sgemm<true, true, simt::EPI_BIAS_TANH>(linear_params(x, L, wa, ba, w.a, n, D, L), 1, st)));
+    TOAD_TRY((simt::launch_sgemm<true, true, simt::EPI_BIAS_SIGMOID>(linear_params(x, L, wb, bb, w.b, n, D, L), 1, st)));
+    TOAD_TRY(tail::launch_attn_c(w.a, w.b, wc, w.part, n, D, nt, st));
+  } else {
+    TOAD_TRY(tail::launch_split_gate_weights(wa, wb, w.w_hi, w.w_lo, D, L, kGateHalf, st));
+    tc::GemmTcParams g{};
+    g.a_f32 = x; g.lda = L; g.M = n; g.N = 2 * D; g.K = L;
+    g.gate_ba = ba; g.gate_bb = bb; g.gate_wc = wc; g.gate_D = D; g.gate_ntasks = nt; g.gate_part = w.part;
+    TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_GATE>(g, nullptr, nullptr, w.w_hi, w.w_lo, st)));
+  }
+  return tail::launch_finish_scores(w.part, w.n_parts, bc, A_out, n, nt, st);
+}
+
+// ------------------------------------------------------------------------------------------ top-k
+extern "C" int toad_topk_workspace_bytes(int64_t n, int32_t k, size_t* bytes) {
+  if (bytes == nullptr || n <= 0 || k <= 0) return TOAD_ERR_ARG;
+  *bytes = 256;  // reserved; the current kernel needs no global scratch
+  return 0;
+}
+
+extern "C" int toad_topk(const float* scores, int64_t n, int32_t k, float* out_vals, int64_t* out_idx, void* workspace,
+              size_t workspace_bytes, toad_stream_t stream) {
+  (void)workspace; (void)workspace_bytes;
+  if (!scores || !out_vals || !out_idx || n <= 0 || k <= 0) return TOAD_ERR_ARG;
+  return topk::launch_topk(scores, n, k, out_vals, out_idx, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------ linear (test hook)
+namespace {
+struct LinWs { bf16 *w_hi, *w_lo, *x_hi, *x_lo; size_t bytes; };
+LinWs carve_lin(int64_t m, int n, int k, void* base) {
+  LinWs w{};
+  Carver c(base);
+  w.w_hi = c.take<bf16>(static_cast<size_t>(n) * k);
+  w.w_lo = c.take<bf16>(static_cast<size_t>(n) * k);
+  w.x_hi = c.take<bf16>(static_cast<size_t>(m) * k);
+  w.x_lo = c.take<bf16>(static_cast<size_t>(m) * k);
+  w.bytes = align_up(c.off, 256);
+  return w;
+}
+template <int BN>
+int run_linear(const tc::GemmTcParams& g, bool split_a, const LinWs& w, cudaStream_t st) {
+  if (split_a) return tc::launch_gemm<BN, tc::A_SPLIT, tc::EPI_LINEAR>(g, w.x_hi, w.x_lo, w.w_hi, w.w_lo, st);
+  return tc::launch_gemm<BN, tc::A_F32, tc::EPI_LINEAR>(g, nullptr, nullptr, w.w_hi, w.w_lo, st);
+}
+}  // namespace
+
+extern "C" int toad_linear_workspace_bytes(int64_t m, int32_t n, int32_t k, size_t* bytes) {
+  if (bytes == nullptr || m <= 0 || n <= 0 || k <= 0) return TOAD_ERR_ARG;
+  *bytes = carve_lin(m, n, k, nullptr).bytes;
+  return 0;
+}
+
+extern "C" int toad_linear_bf16x3(const float* x, const float* wgt, const float* bias, float* y, int64_t m, int32_t n, int32_t k,
+                       int32_t relu, int32_t variant, void* workspace, size_t workspace_bytes, toad_stream_t stream) {
+  if (!x || !wgt || !y || m <= 0 || n <= 0 || k <= 0) return TOAD_ERR_ARG;
+  if (k % 64 != 0 || n % 64 != 0) return TOAD_ERR_UNSUPPORTED;
+  LinWs w = carve_lin(m, n, k, workspace);
+  TOAD_TRY(check_ws(workspace, workspace_bytes, w.bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool split_a = (variant & 1) != 0;
+  int bn = (variant >> 4) & 3;
+  if (bn == 0) bn = (n % 256 == 0) ? 3 : (n % 128 == 0 ? 2 : 1);
+  const int BN = bn == 3 ? 256 : (bn == 2 ? 128 : 64);
+  if (n % BN != 0) return TOAD_ERR_UNSUPPORTED;
+  TOAD_TRY(tail::launch_split_planes(wgt, w.w_hi, w.w_lo, static_cast<int64_t>(n) * k, st));
+  if (split_a) TOAD_TRY(tail::launch_split_planes(x, w.x_hi, w.x_lo, m * k, st));
+  tc::GemmTcParams g{};
+  g.a_f32 = x; g.lda = k; g.M = m; g.N = n; g.K = k; g.bias = bias; g.relu = relu; g.out_f32 = y; g.ld_f32 = n;
+  if (BN == 256) return run_linear<256>(g, split_a, w, st);
+  if (BN == 128) return run_linear<128>(g, split_a, w, st);
+  return run_linear<64>(g, split_a, w, st);
+}
+

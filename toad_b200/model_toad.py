@@ -1,0 +1,189 @@
+"""Drop-in replacements for the reference's ``models/model_toad.py`` classes.
+
+Same constructor arguments, parameter names (``state_dict`` keys), ``relocate()``
+and ``forward()`` contract as mahmoodlab/TOAD ``models/model_toad.py:17-116``; the
+arithmetic runs in hand-written sm_100a kernels behind the C ABI
+(``include/toad_b200.h``).  The ``nn.Linear`` / ``nn.Sequential`` sub-modules exist
+only to own the parameters under the reference's names -- they are never called.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+
+
+def initialize_weights(module: nn.Module) -> None:
+    """xavier_normal_ weights, zero biases -- the reference's utils/utils.py:150-154."""
+    for m in module.modules():
+        if isinstance(m, nn.Linear):
+            nn.init.xavier_normal_(m.weight)
+            m.bias.data.zero_()
+
+
+def _default_flags() -> int:
+    # TOAD_B200_SIMT=1 selects the fp32 CUDA-core GEMMs (debug aid); default is the tcgen05 path.
+    return _lib.FLAG_SIMT_FP32 if os.environ.get("TOAD_B200_SIMT", "0") == "1" else 0
+
+
+class Attn_Net_Gated(nn.Module):
+    """Attention network with sigmoid gating (reference models/model_toad.py:17-41).
+
+    forward(x) -> (A [N, n_tasks], x) with x the same tensor object.
+    """
+
+    def __init__(self, L: int = 1024, D: int = 256, dropout: bool = False, n_tasks: int = 1):
+        super().__init__()
+        a: List[nn.Module] = [nn.Linear(L, D), nn.Tanh()]
+        b: List[nn.Module] = [nn.Linear(L, D), nn.Sigmoid()]
+        if dropout:
+            a.append(nn.Dropout(0.25))
+            b.append(nn.Dropout(0.25))
+        self.attention_a = nn.Sequential(*a)
+        self.attention_b = nn.Sequential(*b)
+        self.attention_c = nn.Linear(D, n_tasks)
+        self.dropout = bool(dropout)
+        self._ws = ops.Workspace()
+
+    def forward(self, x: torch.Tensor):
+        if self.dropout and self.training:
+            raise NotImplementedError("toad_b200: Dropout(0.25) in training mode is not implemented yet; "
+                                      "use dropout=False (the reference default) or .eval()")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("toad_b200: the standalone Attn_Net_Gated has no backward; run it under "
+                                      "torch.no_grad() (inside TOAD_fc_mtl_concat the fused backward is used)")
+        A = ops.attn_gated_fwd(x, self.attention_a[0].weight, self.attention_a[0].bias,
+                               self.attention_b[0].weight, self.attention_b[0].bias,
+                               self.attention_c.weight, self.attention_c.bias, self._ws, _default_flags())
+        return A, x
+
+
+class _ToadFunction(torch.autograd.Function):
+    """logits / site_logits with a hand-written backward (toad_bwd) for the 14 parameters."""
+
+    @staticmethod
+    def forward(ctx, module: "TOAD_fc_mtl_concat", h: torch.Tensor, sex: torch.Tensor, *params: torch.Tensor):
+        dims = module._dims
+        need_grad = any(ctx.needs_input_grad[3:])
+        flags = _default_flags()
+        saved = None
+        if need_grad:
+            flags |= _lib.FLAG_SAVE_ACTS
+            saved = ops.alloc_saved(dims, h.shape[0], h.device)
+        out = ops.toad_fwd(dims, params, h, sex, module._ws, flags, saved)
+        ctx.module = module
+        ctx.saved = saved
+        ctx.out = out
+        ctx.h = h
+        ctx.params = params
+        res = (out["logits"], out["site_logits"], out["y_prob"], out["y_hat"], out["site_prob"], out["site_hat"],
+               out["a_raw"], out["features"])
+        ctx.mark_non_differentiable(*res[2:])
+        return res
+
+    @staticmethod
+    def backward(ctx, dlogits, dsite_logits, *unused):
+        module = ctx.module
+        dims = module._dims
+        if ctx.saved is None:
+            raise RuntimeError("toad_b200: backward called but the forward ran without saved activations")
+        if dlogits is None:
+            dlogits = torch.zeros_like(ctx.out["logits"])
+        if dsite_logits is None:
+            dsite_logits = torch.zeros_like(ctx.out["site_logits"])
+        flat = ops.toad_bwd(dims, ctx.params, ctx.h, ctx.out, ctx.saved, dlogits, dsite_logits, module._ws_bwd)
+        off = ops.param_offsets(dims)
+        grads = tuple(flat[off[i]:off[i + 1]].view_as(p) if ctx.needs_input_grad[3 + i] else None
+                      for i, p in enumerate(ctx.params))
+        ctx.saved = None
+        return (None, None, None) + grads
+
+
+class TOAD_fc_mtl_concat(nn.Module):
+    """TOAD multi-task attention-MIL classifier (reference models/model_toad.py:53-116).
+
+    args: gate (only True is valid -- the reference's gate=False branch raises NameError,
+    model_toad.py:68), size_arg "big"|"small", dropout, n_classes.
+    """
+
+    def __init__(self, gate: bool = True, size_arg: str = "big", dropout: bool = False, n_classes: int = 2):
+        super().__init__()
+        self.size_dict = {"small": [1024, 512, 256], "big": [1024, 512, 384]}
+        size = self.size_dict[size_arg]
+        fc: List[nn.Module] = [nn.Linear(size[0], size[1]), nn.ReLU()]
+        if dropout:
+            fc.append(nn.Dropout(0.25))
+        fc.extend([nn.Linear(size[1], size[1]), nn.ReLU()])
+        if dropout:
+            fc.append(nn.Dropout(0.25))
+        if not gate:
+            raise NameError("name 'Attn_Net' is not defined")  # what the reference does (model_toad.py:68)
+        fc.append(Attn_Net_Gated(L=size[1], D=size[2], dropout=dropout, n_tasks=2))
+        self.attention_net = nn.Sequential(*fc)
+        self.classifier = nn.Linear(size[1] + 1, n_classes)
+        self.site_classifier = nn.Linear(size[1] + 1, 2)
+        initialize_weights(self)
+        self.dropout = bool(dropout)
+        self._dims = ops.make_dims(size[0], size[1], size[2], n_classes)
+        self._ws = ops.Workspace()
+        self._ws_bwd = ops.Workspace()
+        self._prof = None  # optional ops.Profile handle (bench.py roofline leg)
+
+    # -- parameters in C-ABI (= state_dict) order
+    def _param_list(self) -> List[torch.Tensor]:
+        fc1 = self.attention_net[0]
+        fc2 = self.attention_net[3 if self.dropout else 2]
+        gate = self.attention_net[-1]
+        return [fc1.weight, fc1.bias, fc2.weight, fc2.bias,
+                gate.attention_a[0].weight, gate.attention_a[0].bias,
+                gate.attention_b[0].weight, gate.attention_b[0].bias,
+                gate.attention_c.weight, gate.attention_c.bias,
+                self.classifier.weight, self.classifier.bias,
+                self.site_classifier.weight, self.site_classifier.bias]
+
+    def relocate(self) -> None:
+        """Move to the GPU (reference model_toad.py:77-88).
+
+        The reference wraps attention_net in nn.DataParallel and splits one bag across GPUs;
+        here one process drives one GPU and whole slides are sharded across ranks
+        (toad_b200.distributed), so this only moves parameters to the current CUDA device.
+        """
+        if not torch.cuda.is_available():
+            raise RuntimeError("toad_b200 needs a CUDA device (B200); there is no CPU path")
+        device = torch.device("cuda", torch.cuda.current_device())
+        self.attention_net = self.attention_net.to(device)
+        self.classifier = self.classifier.to(device)
+        self.site_classifier = self.site_classifier.to(device)
+
+    def forward(self, h: torch.Tensor, sex: torch.Tensor, return_features: bool = False,
+                attention_only: bool = False):
+        if self.dropout and self.training:
+            raise NotImplementedError("toad_b200: Dropout(0.25) in training mode is not implemented yet; "
+                                      "use dropout=False (the reference default) or .eval()")
+        params = self._param_list()
+        if attention_only:
+            out = ops.toad_fwd(self._dims, [p.detach() for p in params], h, sex, self._ws,
+                               _default_flags() | _lib.FLAG_ATTENTION_ONLY)
+            return out["a_raw"][0]
+        if not isinstance(sex, torch.Tensor):
+            raise ValueError("sex must be a tensor")
+        sex_f = sex.reshape(-1).to(device=h.device, dtype=torch.float32) if isinstance(h, torch.Tensor) and h.is_cuda else sex
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        if need_grad:
+            (logits, site_logits, y_prob, y_hat, site_prob, site_hat, a_raw, features) = _ToadFunction.apply(
+                self, h, sex_f, *params)
+        else:
+            out = ops.toad_fwd(self._dims, [p.detach() for p in params], h, sex_f, self._ws, _default_flags(),
+                               prof=self._prof)
+            logits, site_logits, y_prob, y_hat = out["logits"], out["site_logits"], out["y_prob"], out["y_hat"]
+            site_prob, site_hat, a_raw, features = out["site_prob"], out["site_hat"], out["a_raw"], out["features"]
+        results_dict: Dict[str, torch.Tensor] = {}
+        if return_features:
+            results_dict.update({"features": features})
+        results_dict.update({"logits": logits, "Y_prob": y_prob, "Y_hat": y_hat, "site_logits": site_logits,
+                             "site_prob": site_prob, "site_hat": site_hat, "A": a_raw})
+        return results_dict

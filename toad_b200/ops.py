@@ -1,0 +1,249 @@
+"""Host-side wrappers: torch tensors in, C-ABI calls on the current CUDA stream.
+
+PyTorch is used here only for device memory and streams; all arithmetic runs in
+libtoad_b200.so.  Every function raises (ValueError / ToadError) instead of
+falling back to another implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import Dims, FwdOut, Params, Saved
+
+PARAM_ORDER = ("w1", "b1", "w2", "b2", "wa", "ba", "wb", "bb", "wc", "bc", "wcls", "bcls", "wsite", "bsite")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check_dev_f32(t: torch.Tensor, name: str, shape: Optional[Sequence[int]] = None) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise ValueError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise ValueError("%s must be a CUDA tensor (toad_b200 has no CPU path)" % name)
+    if t.dtype != torch.float32:
+        raise ValueError("%s must be float32, got %s" % (name, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError("%s must have shape %s, got %s" % (name, tuple(shape), tuple(t.shape)))
+
+
+class Workspace:
+    """Grow-only 256-byte aligned device scratch buffer (caller-owned, per module / per stream)."""
+
+    def __init__(self) -> None:
+        self.buf: Optional[torch.Tensor] = None
+
+    def get(self, nbytes: int, device: torch.device) -> Tuple[int, int]:
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+        ptr = self.buf.data_ptr()
+        aligned = (ptr + 255) // 256 * 256
+        return aligned, self.buf.numel() - (aligned - ptr)
+
+
+def make_dims(in_dim: int, hid_dim: int, attn_dim: int, n_classes: int, n_tasks: int = 2) -> Dims:
+    return Dims(in_dim, hid_dim, attn_dim, n_tasks, n_classes)
+
+
+def param_offsets(dims: Dims):
+    off = (C.c_int64 * 15)()
+    _lib.check(_lib.load().toad_param_offsets(C.byref(dims), off), "toad_param_offsets")
+    return list(off)
+
+
+def _params_struct(dims: Dims, params: Sequence[torch.Tensor]) -> Params:
+    L, Hd, D, T, Cn = dims.in_dim, dims.hid_dim, dims.attn_dim, dims.n_tasks, dims.n_classes
+    shapes = [(Hd, L), (Hd,), (Hd, Hd), (Hd,), (D, Hd), (D,), (D, Hd), (D,), (T, D), (T,),
+              (Cn, Hd + 1), (Cn,), (2, Hd + 1), (2,)]
+    p = Params()
+    for name, t, shp in zip(PARAM_ORDER, params, shapes):
+        _check_dev_f32(t, name, shp)
+        setattr(p, name, t.data_ptr())
+    return p
+
+
+def alloc_fwd_out(dims: Dims, n: int, device: torch.device) -> Dict[str, torch.Tensor]:
+    f32 = dict(dtype=torch.float32, device=device)
+    return {
+        "a_raw": torch.empty((dims.n_tasks, n), **f32),
+        "features": torch.empty((dims.n_tasks, dims.hid_dim + 1), **f32),
+        "logits": torch.empty((1, dims.n_classes), **f32),
+        "y_prob": torch.empty((1, dims.n_classes), **f32),
+        "y_hat": torch.empty((1, 1), dtype=torch.int64, device=device),
+        "site_logits": torch.empty((1, 2), **f32),
+        "site_prob": torch.empty((1, 2), **f32),
+        "site_hat": torch.empty((1, 1), dtype=torch.int64, device=device),
+        "softmax_stats": torch.empty((dims.n_tasks, 2), **f32),
+    }
+
+
+def alloc_saved(dims: Dims, n: int, device: torch.device) -> Dict[str, torch.Tensor]:
+    f32 = dict(dtype=torch.float32, device=device)
+    return {"h1": torch.empty((n, dims.hid_dim), **f32), "h": torch.empty((n, dims.hid_dim), **f32),
+            "a": torch.empty((n, dims.attn_dim), **f32), "b": torch.empty((n, dims.attn_dim), **f32)}
+
+
+def _out_struct(out: Dict[str, torch.Tensor]) -> FwdOut:
+    o = FwdOut()
+    for k in ("a_raw", "features", "logits", "y_prob", "y_hat", "site_logits", "site_prob", "site_hat", "softmax_stats"):
+        setattr(o, k, out[k].data_ptr() if k in out and out[k] is not None else None)
+    return o
+
+
+def _saved_struct(saved: Dict[str, torch.Tensor]) -> Saved:
+    s = Saved()
+    for k in ("h1", "h", "a", "b"):
+        setattr(s, k, saved[k].data_ptr())
+    return s
+
+
+def toad_fwd(dims: Dims, params: Sequence[torch.Tensor], x: torch.Tensor, sex: torch.Tensor, ws: Workspace,
+             flags: int = 0, saved: Optional[Dict[str, torch.Tensor]] = None,
+             out: Optional[Dict[str, torch.Tensor]] = None, prof: Optional[int] = None) -> Dict[str, torch.Tensor]:
+    """One TOAD forward (models/model_toad.py:90-116) through the C ABI."""
+    lib = _lib.load()
+    _check_dev_f32(x, "h")
+    if x.dim() != 2 or x.shape[1] != dims.in_dim:
+        raise ValueError("h must be [N, %d], got %s" % (dims.in_dim, tuple(x.shape)))
+    n = x.shape[0]
+    if n < 1:
+        raise ValueError("empty bag: softmax over zero patches is undefined")
+    attn_only = bool(flags & _lib.FLAG_ATTENTION_ONLY)
+    if not attn_only:
+        _check_dev_f32(sex, "sex")
+        if sex.numel() != 1:
+            raise ValueError("sex must hold one value")
+    if out is None:
+        out = {"a_raw": torch.empty((dims.n_tasks, n), dtype=torch.float32, device=x.device)} if attn_only \
+            else alloc_fwd_out(dims, n, x.device)
+    p = _params_struct(dims, params)
+    nbytes = C.c_size_t()
+    _lib.check(lib.toad_fwd_workspace_bytes(C.byref(dims), n, flags, C.byref(nbytes)), "toad_fwd_workspace_bytes")
+    wptr, wsize = ws.get(nbytes.value, x.device)
+    o = _out_struct(out)
+    s = _saved_struct(saved) if saved is not None else None
+    args = [C.byref(dims), C.byref(p), x.data_ptr(), n, None if attn_only else sex.data_ptr(), C.byref(o),
+            C.byref(s) if s is not None else None, wptr, wsize, flags, _stream()]
+    if prof is None:
+        _lib.check(lib.toad_fwd(*args), "toad_fwd")
+    else:
+        _lib.check(lib.toad_fwd_profiled(*(args + [prof])), "toad_fwd_profiled")
+    return out
+
+
+def toad_bwd(dims: Dims, params: Sequence[torch.Tensor], x: torch.Tensor, out: Dict[str, torch.Tensor],
+             saved: Dict[str, torch.Tensor], dlogits: torch.Tensor, dsite_logits: torch.Tensor, ws: Workspace,
+             grad_flat: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Gradients of the 14 parameters as one flat fp32 buffer (toad_param_offsets order)."""
+    lib = _lib.load()
+    n = x.shape[0]
+    total = param_offsets(dims)[14]
+    if grad_flat is None:
+        grad_flat = torch.empty(total, dtype=torch.float32, device=x.device)
+    _check_dev_f32(grad_flat, "grad_flat", (total,))
+    dl = dlogits.reshape(-1).contiguous().float()
+    ds = dsite_logits.reshape(-1).contiguous().float()
+    _check_dev_f32(dl, "dlogits", (dims.n_classes,))
+    _check_dev_f32(ds, "dsite_logits", (2,))
+    p = _params_struct(dims, params)
+    nbytes = C.c_size_t()
+    _lib.check(lib.toad_bwd_workspace_bytes(C.byref(dims), n, C.byref(nbytes)), "toad_bwd_workspace_bytes")
+    wptr, wsize = ws.get(nbytes.value, x.device)
+    o = _out_struct(out)
+    s = _saved_struct(saved)
+    _lib.check(lib.toad_bwd(C.byref(dims), C.byref(p), x.data_ptr(), n, C.byref(o), C.byref(s), dl.data_ptr(),
+                            ds.data_ptr(), grad_flat.data_ptr(), wptr, wsize, _stream()), "toad_bwd")
+    return grad_flat
+
+
+def attn_gated_fwd(x: torch.Tensor, wa, ba, wb, bb, wc, bc, ws: Workspace, flags: int = 0) -> torch.Tensor:
+    """Attn_Net_Gated.forward (models/model_toad.py:36-41): A [N, n_tasks]."""
+    lib = _lib.load()
+    _check_dev_f32(x, "x")
+    if x.dim() != 2:
+        raise ValueError("x must be [N, L]")
+    n, L = x.shape
+    D, nt = wa.shape[0], wc.shape[0]
+    for t, name, shp in ((wa, "wa", (D, L)), (ba, "ba", (D,)), (wb, "wb", (D, L)), (bb, "bb", (D,)),
+                         (wc, "wc", (nt, D)), (bc, "bc", (nt,))):
+        _check_dev_f32(t, name, shp)
+    if n < 1:
+        raise ValueError("empty bag")
+    A = torch.empty((n, nt), dtype=torch.float32, device=x.device)
+    nbytes = C.c_size_t()
+    _lib.check(lib.toad_attn_gated_workspace_bytes(L, D, nt, n, flags, C.byref(nbytes)), "toad_attn_gated_workspace_bytes")
+    wptr, wsize = ws.get(nbytes.value, x.device)
+    _lib.check(lib.toad_attn_gated_fwd(L, D, nt, wa.data_ptr(), ba.data_ptr(), wb.data_ptr(), bb.data_ptr(),
+                                       wc.data_ptr(), bc.data_ptr(), x.data_ptr(), n, A.data_ptr(), wptr, wsize,
+                                       flags, _stream()), "toad_attn_gated_fwd")
+    return A
+
+
+def topk(scores: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(values, indices) of the k largest scores, values descending, ties -> lower index (torch.topk contract)."""
+    lib = _lib.load()
+    _check_dev_f32(scores, "scores")
+    if scores.dim() != 1:
+        raise ValueError("scores must be 1-D")
+    n = scores.shape[0]
+    if not (1 <= k <= n):
+        raise ValueError("k must be in [1, N]")
+    vals = torch.empty(k, dtype=torch.float32, device=scores.device)
+    idx = torch.empty(k, dtype=torch.int64, device=scores.device)
+    _lib.check(lib.toad_topk(scores.data_ptr(), n, k, vals.data_ptr(), idx.data_ptr(), None, 0, _stream()), "toad_topk")
+    return vals, idx
+
+
+def linear_bf16x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], relu: bool, ws: Workspace,
+                  variant: int = 0) -> torch.Tensor:
+    """y = act(x w^T + b) on the tcgen05 split-bf16 GEMM (test hook for the building block)."""
+    lib = _lib.load()
+    _check_dev_f32(x, "x")
+    _check_dev_f32(w, "w")
+    m, k = x.shape
+    n = w.shape[0]
+    if w.shape[1] != k:
+        raise ValueError("shape mismatch")
+    if bias is not None:
+        _check_dev_f32(bias, "bias", (n,))
+    y = torch.empty((m, n), dtype=torch.float32, device=x.device)
+    nbytes = C.c_size_t()
+    _lib.check(lib.toad_linear_workspace_bytes(m, n, k, C.byref(nbytes)), "toad_linear_workspace_bytes")
+    wptr, wsize = ws.get(nbytes.value, x.device)
+    _lib.check(lib.toad_linear_bf16x3(x.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                      y.data_ptr(), m, n, k, int(relu), variant, wptr, wsize, _stream()),
+               "toad_linear_bf16x3")
+    return y
+
+
+class Profile:
+    """Per-stage CUDA-event timing of toad_fwd (bench.py roofline leg)."""
+    STAGES = ("weight_split", "fc1_gemm", "fc2_gemm", "gate_gemm", "pool_tail")
+
+    def __init__(self, max_calls: int) -> None:
+        self.handle = C.c_void_p()
+        _lib.check(_lib.load().toad_profile_create(C.byref(self.handle), max_calls), "toad_profile_create")
+
+    def read(self):
+        ms = (C.c_double * 5)()
+        n = C.c_int32()
+        _lib.check(_lib.load().toad_profile_read(self.handle, ms, C.byref(n)), "toad_profile_read")
+        return dict(zip(self.STAGES, list(ms))), n.value
+
+    def close(self) -> None:
+        if self.handle:
+            _lib.load().toad_profile_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,71 @@
+"""Host->device streaming of slides for inference: pinned host bags are copied on a side stream
+into a small ring of device buffers while the previous slide computes (the reference does a
+blocking pageable `data.to(device)` per bag, utils/core_utils_mtl_concat.py:201).
+"""
+from __future__ import annotations
+
+from typing import Callable, Iterable, List, Optional, Tuple
+
+import torch
+
+
+class SlideStreamer:
+    """Runs `model(h, sex)` over an iterable of (pinned host bag [N,1024] fp32, sex float) pairs.
+
+    Device-side ring of `depth` buffers; H2D on a copy stream overlapped with compute; the small
+    result tensors of every slide are copied back to pinned host memory (D2H) on the compute stream.
+    """
+
+    def __init__(self, model, max_patches: int, width: int = 1024, depth: int = 2, device: Optional[torch.device] = None):
+        self.model = model
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.depth = depth
+        self.bufs = [torch.empty((max_patches, width), dtype=torch.float32, device=self.device) for _ in range(depth)]
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.copied = [torch.cuda.Event() for _ in range(depth)]
+        self.freed = [torch.cuda.Event() for _ in range(depth)]
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    @torch.no_grad()
+    def run(self, slides: Iterable[Tuple[torch.Tensor, float]],
+            sink: Optional[Callable[[int, dict], None]] = None) -> List[dict]:
+        compute = torch.cuda.current_stream(self.device)
+        results: List[dict] = []
+        pending = []
+        it = iter(slides)
+
+        def stage(slot: int, item):
+            bag, sex = item
+            n = bag.shape[0]
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(self.freed[slot])
+                self.bufs[slot][:n].copy_(bag, non_blocking=True)
+                self.copied[slot].record(self.copy_stream)
+            self.h2d_bytes += bag.numel() * 4
+            return (slot, n, sex)
+
+        for s in range(self.depth):
+            self.freed[s].record(compute)
+        nxt = next(it, None)
+        slot = 0
+        staged = stage(slot, nxt) if nxt is not None else None
+        i = 0
+        while staged is not None:
+            cur = staged
+            nxt = next(it, None)
+            staged = stage((cur[0] + 1) % self.depth, nxt) if nxt is not None else None
+            cslot, n, sex = cur
+            compute.wait_event(self.copied[cslot])
+            sex_t = torch.tensor([float(sex)], device=self.device)
+            out = self.model(self.bufs[cslot][:n], sex_t)
+            self.freed[cslot].record(compute)
+            host = {k: out[k].to("cpu", non_blocking=True) for k in ("logits", "Y_prob", "Y_hat", "site_prob", "site_hat")}
+            self.d2h_bytes += sum(v.numel() * v.element_size() for v in host.values())
+            if sink is not None:
+                sink(i, host)
+            else:
+                results.append(host)
+            i += 1
+        compute.synchronize()
+        return results

@@ -1,0 +1,210 @@
+"""First-contact GPU diagnostics: each step in its own process (a trapped kernel poisons the
+context), bounded by a timeout, results appended to gpurun_out/diag.jsonl, arrays dumped for
+offline analysis when something mismatches.
+
+    python tools/gpu_diag.py            # run all steps
+    python tools/gpu_diag.py --step X   # one step, in-process
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+import traceback
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "gpurun_out")
+os.makedirs(OUT, exist_ok=True)
+
+STEPS = ["lin_64_f32", "lin_64_split", "lin_128", "lin_256", "lin_multi", "attn_gated", "simt_fwd", "tc_fwd_small",
+         "tc_fwd_10k", "topk", "bwd_simt", "bwd_tc", "timing"]
+
+
+def log(rec):
+    with open(os.path.join(OUT, "diag.jsonl"), "a") as f:
+        f.write(json.dumps(rec) + "\n")
+    print(json.dumps(rec), flush=True)
+
+
+def lin(step, m, n, k, variant, dump=True):
+    import numpy as np
+    import torch
+    from oracle import toad_oracle as O
+    from toad_b200 import ops
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((m, k), dtype=np.float32)
+    w = (rng.standard_normal((n, k), dtype=np.float32) / np.float32(np.sqrt(k))).astype(np.float32)
+    ws = ops.Workspace()
+    y = ops.linear_bf16x3(torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda(), None, False, ws, variant)
+    torch.cuda.synchronize()
+    y = y.cpu().numpy()
+    xh, xl = O.split_bf16(x)
+    wh, wl = O.split_bf16(w)
+    exp = O.linear_bf16x3(xh, xl, wh, wl)
+    err = float(np.abs(y - exp).max())
+    rec = {"step": step, "m": m, "n": n, "k": k, "variant": variant, "max_abs_err": err,
+           "ok": bool(err < 1e-4), "y_absmax": float(np.abs(y).max()), "nan": bool(np.isnan(y).any())}
+    if not rec["ok"] and dump:
+        np.savez_compressed(os.path.join(OUT, step + ".npz"), y=y, exp=exp.astype(np.float32), x=x, w=w,
+                            hihi=(xh.astype(np.float64) @ wh.T.astype(np.float64)).astype(np.float32))
+    return rec
+
+
+def fwd_case(step, name, simt):
+    import numpy as np
+    import torch
+    from tests.helpers import build_model, case_inputs, load_golden, to_np
+    os.environ["TOAD_B200_SIMT"] = "1" if simt else "0"
+    g = load_golden(name)
+    params, x, sex = case_inputs(g)
+    model = build_model(params, str(g["meta_size_arg"]), int(g["meta_n_classes"]))
+    with torch.no_grad():
+        out = model(torch.from_numpy(x).cuda(), torch.tensor([sex], device="cuda"), return_features=True)
+    torch.cuda.synchronize()
+    rec = {"step": step, "case": name, "simt": simt}
+    for k in ("logits", "site_logits", "features", "A"):
+        o = to_np(out[k]).astype(np.float64)
+        r = g["f64_" + k]
+        rec["abs_" + k] = float(np.abs(o - r).max())
+        rec["rel_" + k] = float((np.abs(o - r) / np.maximum(np.abs(r), 1e-6)).max())
+    rec["ok"] = bool(rec["abs_A"] < 1e-4 and rec["rel_logits"] < 1e-3)
+    if not rec["ok"]:
+        np.savez_compressed(os.path.join(OUT, step + ".npz"), **{k: to_np(v) for k, v in out.items()})
+    return rec
+
+
+def bwd_case(step, simt):
+    from tests.test_gpu_backward import _grads
+    import numpy as np
+    from tests.helpers import to_np
+    g, model, loss = _grads("toad_big_n257", simt)
+    rec = {"step": step, "loss": loss, "loss_ref": float(g["f64_loss"])}
+    worst = 0.0
+    for k, prm in model.named_parameters():
+        gk = to_np(prm.grad).astype(np.float64)
+        if ("g64_%s__full" % k) in g:
+            ref = g["g64_%s__full" % k]
+            e = np.abs(gk - ref).max() / (np.abs(ref).max() + 1e-12)
+        else:
+            ref = g["g64_%s__sub" % k]
+            e = np.abs(gk[::37, ::41] - ref).max() / (np.abs(ref).max() + 1e-12)
+        rec["e_" + k] = float(e)
+        worst = max(worst, float(e))
+    rec["ok"] = bool(worst < 2e-3)
+    return rec
+
+
+def timing(step):
+    import numpy as np
+    import torch
+    from oracle import toad_oracle as O
+    from tests.helpers import build_model
+    from toad_b200 import ops, _lib
+    rec = {"step": step}
+    params = O.make_params(0, "big", 18)
+    model = build_model(params, "big", 18)
+    for n in (10000, 50000):
+        x = torch.randn(n, 1024, device="cuda")
+        sd = torch.tensor([1.0], device="cuda")
+        for simt in (False, True):
+            os.environ["TOAD_B200_SIMT"] = "1" if simt else "0"
+            prof = ops.Profile(16)
+            plist = [p.detach() for p in model._param_list()]
+            flags = _lib.FLAG_SIMT_FP32 if simt else 0
+            for _ in range(3):
+                ops.toad_fwd(model._dims, plist, x, sd, model._ws, flags)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            reps = 10
+            for _ in range(reps):
+                ops.toad_fwd(model._dims, plist, x, sd, model._ws, flags, prof=prof.handle)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / reps
+            stages, calls = prof.read()
+            rec["n%d_%s_ms" % (n, "simt" if simt else "tc")] = dt * 1e3
+            rec["n%d_%s_stages_ms" % (n, "simt" if simt else "tc")] = {k: v / max(calls, 1) for k, v in stages.items()}
+        os.environ["TOAD_B200_SIMT"] = "0"
+    rec["ok"] = True
+    return rec
+
+
+def run_step(step):
+    if step == "lin_64_f32":
+        return lin(step, 128, 64, 64, 0x10)
+    if step == "lin_64_split":
+        return lin(step, 128, 64, 64, 0x11)
+    if step == "lin_128":
+        return lin(step, 128, 128, 128, 0x20)
+    if step == "lin_256":
+        return lin(step, 256, 256, 256, 0x31)
+    if step == "lin_multi":
+        return lin(step, 40000, 512, 1024, 0x00, dump=False)
+    if step == "attn_gated":
+        import numpy as np
+        import torch
+        from oracle import toad_oracle as O
+        from models.model_toad import Attn_Net_Gated
+        from tests.helpers import load_golden, to_np
+        g = load_golden("attn_gated_default_n256")
+        p = O.make_attn_params(int(g["meta_seed"]), 1024, 256, 1)
+        x = O.make_bag(int(g["meta_seed"]) + 1, 256, width=1024)
+        net = Attn_Net_Gated()
+        net.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in p.items()})
+        net = net.cuda().eval()
+        with torch.no_grad():
+            A, _ = net(torch.from_numpy(x).cuda())
+        e = float(np.abs(to_np(A) - g["f64_A"]).max())
+        return {"step": step, "max_abs_err": e, "ok": bool(e < 1e-4)}
+    if step == "simt_fwd":
+        return fwd_case(step, "toad_big_n257", True)
+    if step == "tc_fwd_small":
+        return fwd_case(step, "toad_big_n257", False)
+    if step == "tc_fwd_10k":
+        return fwd_case(step, "toad_big_n10000", False)
+    if step == "topk":
+        import numpy as np
+        import torch
+        from oracle import toad_oracle as O
+        from toad_b200 import ops
+        s = O.make_bag(5, 200000, width=1)[:, 0].copy()
+        vals, idx = ops.topk(torch.from_numpy(s).cuda(), 1000)
+        ev, ei = O.topk_indices(s, 1000)
+        return {"step": step, "ok": bool(np.array_equal(idx.cpu().numpy(), ei) and np.array_equal(vals.cpu().numpy(), ev))}
+    if step == "bwd_simt":
+        return bwd_case(step, True)
+    if step == "bwd_tc":
+        return bwd_case(step, False)
+    if step == "timing":
+        return timing(step)
+    raise SystemExit("unknown step " + step)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--step")
+    ap.add_argument("--only", default="")
+    ap.add_argument("--timeout", type=int, default=120)
+    a = ap.parse_args()
+    if a.step:
+        try:
+            log(run_step(a.step))
+        except Exception as e:
+            log({"step": a.step, "ok": False, "error": repr(e), "tb": traceback.format_exc()[-1500:]})
+            sys.exit(1)
+        return
+    steps = [s for s in STEPS if not a.only or s in a.only.split(",")]
+    for s in steps:
+        t0 = time.time()
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--step", s], timeout=a.timeout,
+                               capture_output=True, text=True)
+            if r.returncode != 0:
+                log({"step": s, "ok": False, "rc": r.returncode, "stderr": r.stderr[-1500:], "secs": time.time() - t0})
+        except subprocess.TimeoutExpired:
+            log({"step": s, "ok": False, "error": "timeout", "secs": time.time() - t0})
+
+
+if __name__ == "__main__":
+    main()
