@@ -1,0 +1,95 @@
+"""The C-ABI library loads without a GPU, exports every symbol include/toad_b200.h declares, and
+its pure-host entry points (sizes, offsets, argument validation) behave.  No compute calls."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from toad_b200 import _lib, build
+    build.build()                     # nvcc cross-compiles for sm_100a without a GPU
+    return _lib.load()
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "toad_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(toad_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    from toad_b200 import _lib
+    names = header_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(_lib.EXPORTS) == names              # the binding covers exactly the header
+
+
+def test_abi_version_and_error_strings(lib):
+    assert lib.toad_abi_version() == 1
+    assert lib.toad_error_string(0) == b"ok"
+    assert b"workspace" in lib.toad_error_string(-2)
+    assert b"not supported" in lib.toad_error_string(-3)
+
+
+def test_param_offsets_match_state_dict_layout(lib):
+    from toad_b200 import ops
+    from models.model_toad import TOAD_fc_mtl_concat
+    for size_arg, n_classes in (("big", 18), ("small", 2)):
+        m = TOAD_fc_mtl_concat(size_arg=size_arg, n_classes=n_classes)
+        off = ops.param_offsets(m._dims)
+        sizes = [p.numel() for p in m._param_list()]
+        assert [off[i + 1] - off[i] for i in range(14)] == sizes
+        assert off[14] == sum(p.numel() for p in m.parameters())
+        # parameter order == state_dict order (the checkpoint-compatibility contract)
+        assert [p.data_ptr() for p in m._param_list()] == [v.data_ptr() for v in m.state_dict().values()]
+    assert ops.param_offsets(TOAD_fc_mtl_concat(n_classes=18)._dims)[14] == 1192490
+
+
+def test_state_dict_keys_are_the_references():
+    from models.model_toad import TOAD_fc_mtl_concat
+    from oracle.toad_oracle import PARAM_KEYS
+    assert list(TOAD_fc_mtl_concat(n_classes=18).state_dict().keys()) == PARAM_KEYS
+    keys_do = list(TOAD_fc_mtl_concat(dropout=True).state_dict().keys())
+    assert "attention_net.3.weight" in keys_do and "attention_net.6.attention_c.bias" in keys_do   # indices shift, as in the reference
+    with pytest.raises(NameError):
+        TOAD_fc_mtl_concat(gate=False)                # the reference's own behaviour (model_toad.py:68)
+
+
+def test_workspace_queries_and_argument_errors(lib):
+    from toad_b200._lib import Dims
+    d = Dims(1024, 512, 384, 2, 18)
+    n = C.c_size_t()
+    assert lib.toad_fwd_workspace_bytes(C.byref(d), 50000, 0, C.byref(n)) == 0
+    tc_bytes = n.value
+    assert lib.toad_fwd_workspace_bytes(C.byref(d), 50000, 2, C.byref(n)) == 0
+    assert 0 < tc_bytes < (1 << 30) and n.value > 0
+    assert lib.toad_bwd_workspace_bytes(C.byref(d), 50000, C.byref(n)) == 0 and n.value > 0
+    assert lib.toad_fwd_workspace_bytes(C.byref(d), 0, 0, C.byref(n)) == -1           # empty bag
+    assert lib.toad_fwd_workspace_bytes(None, 10, 0, C.byref(n)) == -1               # null dims
+    bad = Dims(1000, 512, 384, 2, 18)                                                # in_dim % 64 != 0
+    assert lib.toad_fwd_workspace_bytes(C.byref(bad), 10, 0, C.byref(n)) == -3
+    bad = Dims(1024, 256, 384, 2, 18)
+    assert lib.toad_fwd_workspace_bytes(C.byref(bad), 10, 0, C.byref(n)) == -3
+    assert lib.toad_fwd(C.byref(d), None, None, 10, None, None, None, None, 0, 0, None) == -1
+    assert lib.toad_topk(None, 10, 1, None, None, None, 0, None) == -1
+    assert lib.toad_linear_workspace_bytes(128, 64, 64, C.byref(n)) == 0 and n.value > 0
+    assert lib.toad_attn_gated_workspace_bytes(1024, 256, 1, 256, 0, C.byref(n)) == 0
+    assert lib.toad_attn_gated_workspace_bytes(1000, 256, 1, 256, 0, C.byref(n)) == -3
+
+
+def test_module_refuses_cpu_tensors():
+    import torch
+    from models.model_toad import TOAD_fc_mtl_concat
+    m = TOAD_fc_mtl_concat(n_classes=18).eval()
+    with pytest.raises(ValueError):
+        m(torch.randn(4, 1024), torch.tensor([1.0]))       # no CPU fallback
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            m.relocate()

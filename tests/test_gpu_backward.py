@@ -44,6 +44,11 @@ def test_gradients_match_reference_autograd(name, simt):
     for k, prm in model.named_parameters():
         assert prm.grad is not None, k
         gk = to_np(prm.grad).astype(np.float64)
+        if k.endswith("attention_c.bias"):
+            # softmax is shift invariant: the true gradient is exactly 0 (the reference holds ~1e-17
+            # of fp64 noise), so only an absolute bound is meaningful here.
+            assert np.abs(gk).max() < 1e-6, (k, gk)
+            continue
         if ("g64_%s__full" % k) in g:
             ref = g["g64_%s__full" % k]
             scale = np.abs(ref).max() + 1e-12
