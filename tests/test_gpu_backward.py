@@ -41,25 +41,24 @@ def _grads(name, simt):
 def test_gradients_match_reference_autograd(name, simt):
     g, model, loss = _grads(name, simt)
     assert abs(loss - float(g["f64_loss"])) < 1e-3 * max(1.0, abs(float(g["f64_loss"])))
+    # absolute floor: gradients that are exactly 0 in the reference (e.g. the whole gate branch when
+    # N == 1, or attention_c.bias always: softmax is shift invariant) come out as ~1e-9 noise here.
+    refs = {}
+    for k, _ in model.named_parameters():
+        refs[k] = g["g64_%s__full" % k] if ("g64_%s__full" % k) in g else g["g64_%s__sub" % k]
+    floor = 1e-6 * max(np.abs(r).max() for r in refs.values())
     for k, prm in model.named_parameters():
         assert prm.grad is not None, k
         gk = to_np(prm.grad).astype(np.float64)
-        if k.endswith("attention_c.bias"):
-            # softmax is shift invariant: the true gradient is exactly 0 (the reference holds ~1e-17
-            # of fp64 noise), so only an absolute bound is meaningful here.
-            assert np.abs(gk).max() < 1e-6, (k, gk)
-            continue
+        ref = refs[k]
+        tol = 2e-3 * np.abs(ref).max() + floor
         if ("g64_%s__full" % k) in g:
-            ref = g["g64_%s__full" % k]
-            scale = np.abs(ref).max() + 1e-12
-            assert np.abs(gk - ref).max() <= 2e-3 * scale, (k, np.abs(gk - ref).max(), scale)
+            assert np.abs(gk - ref).max() <= tol, (k, np.abs(gk - ref).max(), tol)
         else:
-            ref = g["g64_%s__sub" % k]
-            scale = np.abs(ref).max() + 1e-12
-            assert np.abs(gk[::37, ::41] - ref).max() <= 2e-3 * scale, k
+            assert np.abs(gk[::37, ::41] - ref).max() <= tol, (k, np.abs(gk[::37, ::41] - ref).max(), tol)
             rs, cs = g["g64_%s__rowsum" % k], g["g64_%s__colsum" % k]
-            assert np.abs(gk.sum(1) - rs).max() <= 2e-3 * (np.abs(rs).max() + 1e-12), k
-            assert np.abs(gk.sum(0) - cs).max() <= 2e-3 * (np.abs(cs).max() + 1e-12), k
+            assert np.abs(gk.sum(1) - rs).max() <= 2e-3 * np.abs(rs).max() + floor * gk.shape[1], k
+            assert np.abs(gk.sum(0) - cs).max() <= 2e-3 * np.abs(cs).max() + floor * gk.shape[0], k
 
 
 def test_optimizer_step_runs_like_the_reference_loop():

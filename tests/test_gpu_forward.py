@@ -77,6 +77,19 @@ def test_forward_fp32_simt_path(name):
     check_against_golden(g, out, a_only, int(g["meta_n"]))
 
 
+def test_forward_single_cta_tensorcore_variant():
+    """The cta_group::1 kernels (debug flag) give the same results as the default CTA-pair kernels."""
+    import os
+    os.environ["TOAD_B200_CG1"] = "1"
+    try:
+        g, out, a_only = run_case("toad_big_n10000", simt=False)
+    finally:
+        os.environ["TOAD_B200_CG1"] = "0"
+    check_against_golden(g, out, a_only, int(g["meta_n"]))
+    _, out2, _ = run_case("toad_big_n10000", simt=False)
+    np.testing.assert_allclose(to_np(out["A"]), to_np(out2["A"]), rtol=0, atol=2e-6)
+
+
 def test_tensorcore_matches_split_oracle_tightly():
     """Against the oracle's restatement of the SAME split-bf16 ordering the kernel agrees to fp32
     summation noise -- this separates 'kernel bug' from 'expected reordering error'."""

@@ -29,13 +29,17 @@ def _linear_case(m, n, k, relu, variant, seed=0):
     return to_np(y), exp_split, exp_true
 
 
-# variant = a_split | (tile << 4): tile 1 -> 64, 2 -> 128, 3 -> 256 columns
+# variant = a_split | (cta_pair << 1) | (tile << 4): tile 1 -> 64, 2 -> 128, 3 -> 256 columns
 @pytest.mark.parametrize("m,n,k,variant", [
     (128, 64, 64, 0x10), (128, 64, 64, 0x11),        # one tile, one K block, both A feeds
     (128, 128, 128, 0x20), (128, 256, 128, 0x30),
     (200, 256, 256, 0x31), (1, 64, 64, 0x10), (129, 128, 192, 0x21),
     (1000, 512, 1024, 0x30), (1000, 512, 512, 0x31), (777, 768, 512, 0x30),
     (5000, 256, 64, 0x20), (40000, 512, 1024, 0x00),  # multi-wave persistent schedule
+    # CTA pairs (cta_group::2): 256-row tiles, each CTA stages half of the weight tile
+    (256, 64, 64, 0x12), (256, 64, 64, 0x13), (256, 128, 128, 0x22), (256, 256, 256, 0x33),
+    (1, 256, 64, 0x32), (129, 256, 192, 0x33), (300, 512, 512, 0x32), (1000, 768, 512, 0x33),
+    (40000, 512, 1024, 0x02), (50000, 512, 512, 0x03),
 ])
 def test_linear_bf16x3(m, n, k, variant):
     y, exp_split, exp_true = _linear_case(m, n, k, relu=(m % 2 == 0), variant=variant)

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_PKG, "libtoad_b200.so")
 FLAG_ATTENTION_ONLY = 1
 FLAG_SIMT_FP32 = 2
 FLAG_SAVE_ACTS = 4
+FLAG_TC_SINGLE_CTA = 8
 
 EXPORTS = [
     "toad_abi_version", "toad_error_string", "toad_param_offsets",

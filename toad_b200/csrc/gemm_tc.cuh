@@ -31,12 +31,18 @@ constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
 enum { EPI_LINEAR = 0, EPI_GATE = 1 };
 enum { A_F32 = 0, A_SPLIT = 1 };
 
-template <int BLOCK_N>
+// CG = 1: one CTA per tile (UMMA M=128).  CG = 2: a CTA pair (cluster of 2, cta_group::2) shares one
+// 256 x BLOCK_N tile: each CTA stages its own 128 rows of A and HALF of the B tile, the leader CTA
+// issues UMMA M=256 reading both CTAs' shared memory, accumulators land in each CTA's own TMEM.
+// Halves the per-SM weight traffic (L2->smem and smem->tensor core) and frees room for a 3rd stage.
+template <int BLOCK_N, int CG = 1>
 struct Cfg {
   static_assert(BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
-  static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static_assert(CG == 1 || CG == 2, "CG");
+  static constexpr int B_ROWS = BLOCK_N / CG;  // B rows staged by one CTA
+  static constexpr int B_TILE_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-  static constexpr int STAGES = BLOCK_N == 256 ? 2 : (BLOCK_N == 128 ? 3 : 4);
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 6 ? 6 : (192 * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator buffers (128/256/512: powers of 2)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + slack for 1024 B alignment
 };
@@ -80,6 +86,20 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// arrive on the barrier at the same offset in CTA `rank` of this cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -109,37 +129,81 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+
+template <int CG>
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
+  if (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  } else {  // data to this CTA's smem, transaction bytes to the (cluster-mapped) leader barrier `bar`
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
 }
+template <int CG>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 // D[tmem] (+)= A[smem desc] . B[smem desc]; bf16 inputs, fp32 accumulate.
+template <int CG>
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
-// mbarrier arrive when all previously issued tcgen05.mma of this thread have completed.
+// mbarrier arrive (on every CTA of the pair for CG == 2) once all previously issued tcgen05.mma of this
+// thread have completed.
+template <int CG>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  if (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  } else {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask)
+                 : "memory");
+  }
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -166,21 +230,32 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                     // SWIZZLE_128B         bits [61,64)
   return d;
 }
-// Instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BLOCK_N.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int n) {
+// Instruction descriptor: D=f32, A=B=bf16, both K-major, M = 128*CG, N = BLOCK_N.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
-         (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
+         (static_cast<uint32_t>(m >> 4) << 24);
 }
+
+// sigmoid / tanh on the SFU (ex2.approx + rcp.approx): abs error ~2e-7, far below the score tolerance.
+__device__ __forceinline__ float fast_sigmoid(float z) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+__device__ __forceinline__ float fast_tanh(float z) { return fmaf(2.0f, fast_sigmoid(2.0f * z), -1.0f); }
 
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int BLOCK_N, int A_MODE, int EPI>
+constexpr int GATE_SMEM_FLOATS = 4 * 1024;  // ba | bb | wc rows (<= 2 tasks staged) for D <= 1024
+
+template <int BLOCK_N, int A_MODE, int EPI, int CG>
 __global__ void __launch_bounds__(A_MODE == A_F32 ? 384 : 256, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const GemmTcParams p) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, CG>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full_b[STAGES];
@@ -189,25 +264,31 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   __shared__ __align__(8) uint64_t bar_tmem_full[2];
   __shared__ __align__(8) uint64_t bar_tmem_empty[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ float s_gate[EPI == EPI_GATE ? GATE_SMEM_FLOATS : 1];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
   const uint32_t tiles_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
-  const int m_tiles = static_cast<int>((p.M + BLOCK_M - 1) / BLOCK_M);
+  // work units: (128*CG) x BLOCK_N tiles, n fastest; this CTA owns rows [m0, m0+128) of its unit
+  const int m_units = static_cast<int>((p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG));
   const int n_tiles = p.N / BLOCK_N;
-  const int num_tiles = m_tiles * n_tiles;
+  const int num_tiles = m_units * n_tiles;
   const int num_kb = p.K / BLOCK_K;
+  const int unit0 = blockIdx.x / CG;
+  const int unit_stride = gridDim.x / CG;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&bar_full_b[s]), 1);
-      mbar_init(smem_u32(&bar_full_a[s]), 4);  // one arrive per converter warp
+      mbar_init(smem_u32(&bar_full_b[s]), CG);      // producer of each CTA of the pair
+      mbar_init(smem_u32(&bar_full_a[s]), 4 * CG);  // one arrive per converter warp (both CTAs)
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&bar_tmem_full[a]), 1);
-      mbar_init(smem_u32(&bar_tmem_empty[a]), 4);  // one arrive per epilogue warp
+      mbar_init(smem_u32(&bar_tmem_empty[a]), 4 * CG);  // one arrive per epilogue warp (both CTAs)
     }
     fence_barrier_init();
   }
@@ -219,43 +300,62 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       prefetch_tmap(&tm_a_lo);
     }
   }
-  if (warp == 2) tmem_alloc(smem_u32(&tmem_slot), C::TMEM_COLS);
+  if (EPI == EPI_GATE) {  // stage the gate biases and (up to 2) score rows once per CTA
+    const int D = p.gate_D;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      s_gate[i] = __ldg(p.gate_ba + i);
+      s_gate[1024 + i] = __ldg(p.gate_bb + i);
+      s_gate[2048 + i] = __ldg(p.gate_wc + i);
+      s_gate[3072 + i] = p.gate_ntasks > 1 ? __ldg(p.gate_wc + D + i) : 0.f;
+    }
+  }
+  if (warp == 2) tmem_alloc<CG>(smem_u32(&tmem_slot), C::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // peer barriers initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n0 = (tile % n_tiles) * BLOCK_N;
-        const int m0 = (tile / n_tiles) * BLOCK_M;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+    // ------------------------------------------------------------------ TMA producer (all lanes loop, lane 0 issues)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+      const int n0 = (tile % n_tiles) * BLOCK_N + static_cast<int>(cta_rank) * C::B_ROWS;
+      const int m0 = (tile / n_tiles) * (BLOCK_M * CG) + static_cast<int>(cta_rank) * BLOCK_M;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+        if (lane == 0) {
           const uint32_t sa = tiles_base + stage * C::STAGE_BYTES;
-          const uint32_t fb = smem_u32(&bar_full_b[stage]);
-          mbar_expect_tx(fb, 2 * C::B_TILE_BYTES + (A_MODE == A_SPLIT ? 2 * A_TILE_BYTES : 0));
-          if (A_MODE == A_SPLIT) {
-            tma_load_2d(sa, &tm_a_hi, fb, kb * BLOCK_K, m0);
-            tma_load_2d(sa + A_TILE_BYTES, &tm_a_lo, fb, kb * BLOCK_K, m0);
+          const uint32_t fb_local = smem_u32(&bar_full_b[stage]);
+          const uint32_t bytes = 2 * C::B_TILE_BYTES + (A_MODE == A_SPLIT ? 2 * A_TILE_BYTES : 0);
+          uint32_t fb = fb_local;
+          if (CG == 1) {
+            mbar_expect_tx(fb_local, bytes);
+          } else {
+            fb = mapa_cluster(fb_local, 0);  // transaction bytes of both CTAs go to the leader's barrier
+            if (is_leader) mbar_expect_tx(fb_local, 2 * bytes);
+            else mbar_arrive_cluster(fb_local, 0);
           }
-          tma_load_2d(sa + 2 * A_TILE_BYTES, &tm_b_hi, fb, kb * BLOCK_K, n0);
-          tma_load_2d(sa + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &tm_b_lo, fb, kb * BLOCK_K, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (A_MODE == A_SPLIT) {
+            tma_load_2d<CG>(sa, &tm_a_hi, fb, kb * BLOCK_K, m0);
+            tma_load_2d<CG>(sa + A_TILE_BYTES, &tm_a_lo, fb, kb * BLOCK_K, m0);
+          }
+          tma_load_2d<CG>(sa + 2 * A_TILE_BYTES, &tm_b_hi, fb, kb * BLOCK_K, n0);
+          tma_load_2d<CG>(sa + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &tm_b_lo, fb, kb * BLOCK_K, n0);
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_N);
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (is_leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M * CG, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
         const int acc = it & 1;
         mbar_wait(smem_u32(&bar_tmem_empty[acc]), ((it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -264,40 +364,43 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           mbar_wait(smem_u32(&bar_full_b[stage]), phase);
           if (A_MODE == A_F32) mbar_wait(smem_u32(&bar_full_a[stage]), phase);
           tc_fence_after();
-          const uint32_t sa = tiles_base + stage * C::STAGE_BYTES;
-          const uint64_t a_hi = make_kmajor_sw128_desc(sa);
-          const uint64_t a_lo = make_kmajor_sw128_desc(sa + A_TILE_BYTES);
-          const uint64_t b_hi = make_kmajor_sw128_desc(sa + 2 * A_TILE_BYTES);
-          const uint64_t b_lo = make_kmajor_sw128_desc(sa + 2 * A_TILE_BYTES + C::B_TILE_BYTES);
+          if (lane == 0) {
+            const uint32_t sa = tiles_base + stage * C::STAGE_BYTES;
+            const uint64_t a_hi = make_kmajor_sw128_desc(sa);
+            const uint64_t a_lo = make_kmajor_sw128_desc(sa + A_TILE_BYTES);
+            const uint64_t b_hi = make_kmajor_sw128_desc(sa + 2 * A_TILE_BYTES);
+            const uint64_t b_lo = make_kmajor_sw128_desc(sa + 2 * A_TILE_BYTES + C::B_TILE_BYTES);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);  // +32 B per K step
-            umma_bf16(d_tmem, a_hi + koff, b_hi + koff, idesc, (kb | k) != 0);
-          }
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);  // +32 B per K step
+              umma_bf16<CG>(d_tmem, a_hi + koff, b_hi + koff, idesc, (kb | k) != 0);
+            }
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);
-            umma_bf16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
-          }
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);
+              umma_bf16<CG>(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
+            }
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);
-            umma_bf16(d_tmem, a_lo + koff, b_hi + koff, idesc, 1);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);
+              umma_bf16<CG>(d_tmem, a_lo + koff, b_hi + koff, idesc, 1);
+            }
+            umma_commit<CG>(smem_u32(&bar_empty[stage]));  // smem slot free (in both CTAs) once these MMAs retire
+            if (kb == num_kb - 1) umma_commit<CG>(smem_u32(&bar_tmem_full[acc]));  // accumulator ready
           }
-          umma_commit(smem_u32(&bar_empty[stage]));  // smem slot free once these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(smem_u32(&bar_tmem_full[acc]));  // accumulator ready for the epilogue
       }
     }
   } else if (warp >= 4 && warp < 8) {
     // ------------------------------------------------------------------ epilogue
     const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may access
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
       const int n_tile = tile % n_tiles;
       const int n0 = n_tile * BLOCK_N;
-      const int m0 = (tile / n_tiles) * BLOCK_M;
+      const int m0 = (tile / n_tiles) * (BLOCK_M * CG) + static_cast<int>(cta_rank) * BLOCK_M;
       const int acc = it & 1;
       mbar_wait(smem_u32(&bar_tmem_full[acc]), (it >> 1) & 1);
       tc_fence_after();
@@ -351,23 +454,28 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           tmem_ld32(t_row + HALF + c * 32, rb);
           tmem_ld_wait();
           const int jc = j0 + c * 32;
-          float ga[32], gb[32];
+          const bool save = row_ok && p.gate_a != nullptr;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            ga[i] = tanh_acc(__uint_as_float(ra[i]) + __ldg(p.gate_ba + jc + i));
-            gb[i] = sigmoid_acc(__uint_as_float(rb[i]) + __ldg(p.gate_bb + jc + i));
-            const float g = ga[i] * gb[i];
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-              if (t < p.gate_ntasks) s[t] = fmaf(g, __ldg(p.gate_wc + t * p.gate_D + jc + i), s[t]);
+            const float ga = fast_tanh(__uint_as_float(ra[i]) + s_gate[jc + i]);
+            const float gb = fast_sigmoid(__uint_as_float(rb[i]) + s_gate[1024 + jc + i]);
+            ra[i] = __float_as_uint(ga);
+            rb[i] = __float_as_uint(gb);
+            const float g = ga * gb;
+            s[0] = fmaf(g, s_gate[2048 + jc + i], s[0]);
+            s[1] = fmaf(g, s_gate[3072 + jc + i], s[1]);
+            if (p.gate_ntasks > 2) {  // rare: extra tasks read their score rows from global
+              s[2] = fmaf(g, __ldg(p.gate_wc + 2 * p.gate_D + jc + i), s[2]);
+              if (p.gate_ntasks > 3) s[3] = fmaf(g, __ldg(p.gate_wc + 3 * p.gate_D + jc + i), s[3]);
+            }
           }
-          if (row_ok && p.gate_a != nullptr) {
-            float4* da = reinterpret_cast<float4*>(p.gate_a + row * p.gate_D + jc);
-            float4* db = reinterpret_cast<float4*>(p.gate_b + row * p.gate_D + jc);
+          if (save) {
+            uint4* da = reinterpret_cast<uint4*>(p.gate_a + row * p.gate_D + jc);
+            uint4* db = reinterpret_cast<uint4*>(p.gate_b + row * p.gate_D + jc);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              da[i] = make_float4(ga[4 * i], ga[4 * i + 1], ga[4 * i + 2], ga[4 * i + 3]);
-              db[i] = make_float4(gb[4 * i], gb[4 * i + 1], gb[4 * i + 2], gb[4 * i + 3]);
+              da[i] = make_uint4(ra[4 * i], ra[4 * i + 1], ra[4 * i + 2], ra[4 * i + 3]);
+              db[i] = make_uint4(rb[4 * i], rb[4 * i + 1], rb[4 * i + 2], rb[4 * i + 3]);
             }
           }
         }
@@ -380,7 +488,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[acc]));
+      if (lane == 0) {
+        if (CG == 1) mbar_arrive(smem_u32(&bar_tmem_empty[acc]));
+        else mbar_arrive_cluster(smem_u32(&bar_tmem_empty[acc]), 0);
+      }
     }
   } else if (A_MODE == A_F32 && warp >= 8) {
     // ------------------------------------------------------------------ A converter
@@ -388,14 +499,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     // turns its 4 floats into 4 (hi) + 4 (lo) bf16 = one 8 B store into each swizzled tile.
     const int cw = warp - 8;
     const int hw = lane >> 4, l16 = lane & 15;
-    const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
-                         static_cast<int>(gridDim.x);
-    const int64_t total = static_cast<int64_t>(my_tiles > 0 ? my_tiles : 0) * num_kb;
+    const int my_tiles = unit0 < num_tiles ? (num_tiles - unit0 + unit_stride - 1) / unit_stride : 0;
+    const int64_t total = static_cast<int64_t>(my_tiles) * num_kb;
     float4 cur[16], nxt[16];
     auto issue = [&](int64_t g, float4(&buf)[16]) {
-      const int tile = blockIdx.x + static_cast<int>(g / num_kb) * gridDim.x;
+      const int tile = unit0 + static_cast<int>(g / num_kb) * unit_stride;
       const int kb = static_cast<int>(g % num_kb);
-      const int64_t m0 = static_cast<int64_t>(tile / n_tiles) * BLOCK_M;
+      const int64_t m0 = static_cast<int64_t>(tile / n_tiles) * (BLOCK_M * CG) + cta_rank * BLOCK_M;
       const float* base = p.a_f32 + kb * BLOCK_K + l16 * 4;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -422,7 +532,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       }
       fence_proxy_async_smem();  // make generic-proxy smem writes visible to the tensor core
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bar_full_a[stage]));
+      if (lane == 0) {
+        if (CG == 1) mbar_arrive(smem_u32(&bar_full_a[stage]));
+        else mbar_arrive_cluster(smem_u32(&bar_full_a[stage]), 0);
+      }
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
 #pragma unroll
       for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
@@ -431,9 +544,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the leader's MMAs read the peer's smem; nobody leaves early
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    tmem_dealloc<CG>(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -481,15 +595,16 @@ inline int sm_count() {
 
 // A operand: fp32 (a_f32/lda in p) when A_MODE == A_F32, else the planes a_hi/a_lo [M, K] bf16.
 // B operand: planes b_hi/b_lo [N, K] bf16.
-template <int BLOCK_N, int A_MODE, int EPI>
+template <int BLOCK_N, int A_MODE, int EPI, int CG = 1>
 int launch_gemm(const GemmTcParams& p, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,
                 const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, CG>;
   if (p.M <= 0) return 0;
   if (p.K % BLOCK_K != 0 || p.N % BLOCK_N != 0 || p.K <= 0 || p.N <= 0) return TOAD_ERR_UNSUPPORTED;
+  if (EPI == EPI_GATE && (p.gate_D > 1024 || p.gate_ntasks < 1 || p.gate_ntasks > 4)) return TOAD_ERR_UNSUPPORTED;
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
-  TOAD_TRY(make_bf16_tmap(&tb_hi, b_hi, p.N, p.K, BLOCK_N));
-  TOAD_TRY(make_bf16_tmap(&tb_lo, b_lo, p.N, p.K, BLOCK_N));
+  TOAD_TRY(make_bf16_tmap(&tb_hi, b_hi, p.N, p.K, C::B_ROWS));
+  TOAD_TRY(make_bf16_tmap(&tb_lo, b_lo, p.N, p.K, C::B_ROWS));
   if (A_MODE == A_SPLIT) {
     TOAD_TRY(make_bf16_tmap(&ta_hi, a_hi, p.M, p.K, BLOCK_M));
     TOAD_TRY(make_bf16_tmap(&ta_lo, a_lo, p.M, p.K, BLOCK_M));
@@ -497,12 +612,25 @@ int launch_gemm(const GemmTcParams& p, const __nv_bfloat16* a_hi, const __nv_bfl
     ta_hi = tb_hi;
     ta_lo = tb_lo;
   }
-  auto kern = gemm_bf16x3_kernel<BLOCK_N, A_MODE, EPI>;
+  auto kern = gemm_bf16x3_kernel<BLOCK_N, A_MODE, EPI, CG>;
   TOAD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-  const int64_t m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
-  const int64_t tiles = m_tiles * (p.N / BLOCK_N);
-  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
-  kern<<<grid, A_MODE == A_F32 ? 384 : 256, C::SMEM_BYTES, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  const int64_t m_units = (p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG);
+  const int64_t units = m_units * (p.N / BLOCK_N);
+  const int64_t max_units = sm_count() / CG;
+  const int grid = static_cast<int>(units < max_units ? units : max_units) * CG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(A_MODE == A_F32 ? 384 : 256);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CG > 1 ? 1 : 0;
+  TOAD_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, p));
   TOAD_CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -194,7 +194,15 @@ __global__ void __launch_bounds__(THREADS) pool_heads_kernel(const TailParams p)
   for (int c = tid; c < T * H; c += THREADS) {
     const int t = c / H, j = c % H;
     float s = 0.f;
-    for (int b = 0; b < nb; ++b) s = fmaf(s_scale[b * T + t], __ldcg(p.blk_part + static_cast<int64_t>(b) * PART_STRIDE + c), s);
+    int b = 0;
+    for (; b + 8 <= nb; b += 8) {  // 8 independent L2 loads in flight, summed in fixed order
+      float v8[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v8[u] = __ldcg(p.blk_part + static_cast<int64_t>(b + u) * PART_STRIDE + c);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s = fmaf(s_scale[(b + u) * T + t], v8[u], s);
+    }
+    for (; b < nb; ++b) s = fmaf(s_scale[b * T + t], __ldcg(p.blk_part + static_cast<int64_t>(b) * PART_STRIDE + c), s);
     const float v = s / s_l[t];
     s_feat[t * (H + 1) + j] = v;
     p.features[t * (H + 1) + j] = v;

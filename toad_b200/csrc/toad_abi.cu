@@ -183,6 +183,7 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
   }
 
   // ---- tensor-core path: split weights, three tcgen05 GEMMs with fused epilogues, tail
+  const bool cg1 = (flags & TOAD_FLAG_TC_SINGLE_CTA) != 0;
   TOAD_TRY(prof_mark(prof, 0, st));
   TOAD_TRY(tail::launch_split_planes(P->w1, w.w1_hi, w.w1_lo, static_cast<int64_t>(Hd) * L, st));
   TOAD_TRY(tail::launch_split_planes(P->w2, w.w2_hi, w.w2_lo, static_cast<int64_t>(Hd) * Hd, st));
@@ -193,7 +194,8 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
     g.a_f32 = x; g.lda = L; g.M = n; g.N = Hd; g.K = L; g.bias = P->b1; g.relu = 1;
     g.out_f32 = save ? saved->h1 : nullptr; g.ld_f32 = Hd;
     g.out_hi = w.h1_hi; g.out_lo = w.h1_lo; g.ld_split = Hd;
-    TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_LINEAR>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, st)));
+    if (cg1) TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_LINEAR, 1>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, st)));
+    else TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_LINEAR, 2>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, st)));
   }
   TOAD_TRY(prof_mark(prof, 2, st));
   {
@@ -201,7 +203,8 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
     g.M = n; g.N = Hd; g.K = Hd; g.bias = P->b2; g.relu = 1;
     g.out_f32 = save ? saved->h : nullptr; g.ld_f32 = Hd;
     g.out_hi = w.h_hi; g.out_lo = w.h_lo; g.ld_split = Hd;
-    TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR>(g, w.h1_hi, w.h1_lo, w.w2_hi, w.w2_lo, st)));
+    if (cg1) TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 1>(g, w.h1_hi, w.h1_lo, w.w2_hi, w.w2_lo, st)));
+    else TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, w.h1_hi, w.h1_lo, w.w2_hi, w.w2_lo, st)));
   }
   TOAD_TRY(prof_mark(prof, 3, st));
   {
@@ -209,7 +212,8 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
     g.M = n; g.N = 2 * D; g.K = Hd;
     g.gate_ba = P->ba; g.gate_bb = P->bb; g.gate_wc = P->wc; g.gate_D = D; g.gate_ntasks = d->n_tasks;
     g.gate_part = w.part; g.gate_a = save ? saved->a : nullptr; g.gate_b = save ? saved->b : nullptr;
-    TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_GATE>(g, w.h_hi, w.h_lo, w.wab_hi, w.wab_lo, st)));
+    if (cg1) TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_GATE, 1>(g, w.h_hi, w.h_lo, w.wab_hi, w.wab_lo, st)));
+    else TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_GATE, 2>(g, w.h_hi, w.h_lo, w.wab_hi, w.wab_lo, st)));
   }
   TOAD_TRY(prof_mark(prof, 4, st));
   TOAD_TRY(run_tail(d, P, n, sex, out, w, nullptr, w.h_hi, w.h_lo, attn_only, st));
@@ -480,7 +484,8 @@ extern "C" int toad_attn_gated_fwd(int32_t L, int32_t D, int32_t nt, const float
     tc::GemmTcParams g{};
     g.a_f32 = x; g.lda = L; g.M = n; g.N = 2 * D; g.K = L;
     g.gate_ba = ba; g.gate_bb = bb; g.gate_wc = wc; g.gate_D = D; g.gate_ntasks = nt; g.gate_part = w.part;
-    TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_GATE>(g, nullptr, nullptr, w.w_hi, w.w_lo, st)));
+    if (flags & TOAD_FLAG_TC_SINGLE_CTA) TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_GATE, 1>(g, nullptr, nullptr, w.w_hi, w.w_lo, st)));
+    else TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_GATE, 2>(g, nullptr, nullptr, w.w_hi, w.w_lo, st)));
   }
   return tail::launch_finish_scores(w.part, w.n_parts, bc, A_out, n, nt, st);
 }
@@ -512,10 +517,10 @@ LinWs carve_lin(int64_t m, int n, int k, void* base) {
   w.bytes = align_up(c.off, 256);
   return w;
 }
-template <int BN>
+template <int BN, int CG>
 int run_linear(const tc::GemmTcParams& g, bool split_a, const LinWs& w, cudaStream_t st) {
-  if (split_a) return tc::launch_gemm<BN, tc::A_SPLIT, tc::EPI_LINEAR>(g, w.x_hi, w.x_lo, w.w_hi, w.w_lo, st);
-  return tc::launch_gemm<BN, tc::A_F32, tc::EPI_LINEAR>(g, nullptr, nullptr, w.w_hi, w.w_lo, st);
+  if (split_a) return tc::launch_gemm<BN, tc::A_SPLIT, tc::EPI_LINEAR, CG>(g, w.x_hi, w.x_lo, w.w_hi, w.w_lo, st);
+  return tc::launch_gemm<BN, tc::A_F32, tc::EPI_LINEAR, CG>(g, nullptr, nullptr, w.w_hi, w.w_lo, st);
 }
 }  // namespace
 
@@ -541,8 +546,9 @@ extern "C" int toad_linear_bf16x3(const float* x, const float* wgt, const float*
   if (split_a) TOAD_TRY(tail::launch_split_planes(x, w.x_hi, w.x_lo, m * k, st));
   tc::GemmTcParams g{};
   g.a_f32 = x; g.lda = k; g.M = m; g.N = n; g.K = k; g.bias = bias; g.relu = relu; g.out_f32 = y; g.ld_f32 = n;
-  if (BN == 256) return run_linear<256>(g, split_a, w, st);
-  if (BN == 128) return run_linear<128>(g, split_a, w, st);
-  return run_linear<64>(g, split_a, w, st);
+  const bool pair = (variant & 2) != 0;  // cta_group::2 (CTA pair per 256-row tile)
+  if (BN == 256) return pair ? run_linear<256, 2>(g, split_a, w, st) : run_linear<256, 1>(g, split_a, w, st);
+  if (BN == 128) return pair ? run_linear<128, 2>(g, split_a, w, st) : run_linear<128, 1>(g, split_a, w, st);
+  return pair ? run_linear<64, 2>(g, split_a, w, st) : run_linear<64, 1>(g, split_a, w, st);
 }
 

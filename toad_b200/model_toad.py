@@ -26,8 +26,11 @@ def initialize_weights(module: nn.Module) -> None:
 
 
 def _default_flags() -> int:
-    # TOAD_B200_SIMT=1 selects the fp32 CUDA-core GEMMs (debug aid); default is the tcgen05 path.
-    return _lib.FLAG_SIMT_FP32 if os.environ.get("TOAD_B200_SIMT", "0") == "1" else 0
+    # TOAD_B200_SIMT=1 selects the fp32 CUDA-core GEMMs (debug aid); default is the tcgen05 CTA-pair path.
+    flags = _lib.FLAG_SIMT_FP32 if os.environ.get("TOAD_B200_SIMT", "0") == "1" else 0
+    if os.environ.get("TOAD_B200_CG1", "0") == "1":   # debug aid: cta_group::1 tensor-core kernels
+        flags |= _lib.FLAG_TC_SINGLE_CTA
+    return flags
 
 
 class Attn_Net_Gated(nn.Module):

@@ -18,8 +18,9 @@ sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "gpurun_out")
 os.makedirs(OUT, exist_ok=True)
 
-STEPS = ["lin_64_f32", "lin_64_split", "lin_128", "lin_256", "lin_multi", "attn_gated", "simt_fwd", "tc_fwd_small",
-         "tc_fwd_10k", "topk", "bwd_simt", "bwd_tc", "timing"]
+STEPS = ["lin_64_f32", "lin_64_split", "lin_128", "lin_256", "lin_multi", "pair_64_f32", "pair_64_split", "pair_256",
+         "pair_multi", "attn_gated", "simt_fwd", "tc_fwd_small", "tc_fwd_10k", "tc_fwd_10k_cg1", "topk", "bwd_simt",
+         "bwd_tc", "timing"]
 
 
 def log(rec):
@@ -108,11 +109,11 @@ def timing(step):
     for n in (10000, 50000):
         x = torch.randn(n, 1024, device="cuda")
         sd = torch.tensor([1.0], device="cuda")
-        for simt in (False, True):
-            os.environ["TOAD_B200_SIMT"] = "1" if simt else "0"
+        for mode in ("tc", "tc_cg1", "simt"):
+            simt = mode == "simt"
             prof = ops.Profile(16)
             plist = [p.detach() for p in model._param_list()]
-            flags = _lib.FLAG_SIMT_FP32 if simt else 0
+            flags = _lib.FLAG_SIMT_FP32 if simt else (_lib.FLAG_TC_SINGLE_CTA if mode == "tc_cg1" else 0)
             for _ in range(3):
                 ops.toad_fwd(model._dims, plist, x, sd, model._ws, flags)
             torch.cuda.synchronize()
@@ -123,9 +124,8 @@ def timing(step):
             torch.cuda.synchronize()
             dt = (time.perf_counter() - t0) / reps
             stages, calls = prof.read()
-            rec["n%d_%s_ms" % (n, "simt" if simt else "tc")] = dt * 1e3
-            rec["n%d_%s_stages_ms" % (n, "simt" if simt else "tc")] = {k: v / max(calls, 1) for k, v in stages.items()}
-        os.environ["TOAD_B200_SIMT"] = "0"
+            rec["n%d_%s_ms" % (n, mode)] = dt * 1e3
+            rec["n%d_%s_stages_ms" % (n, mode)] = {k: round(v / max(calls, 1), 4) for k, v in stages.items()}
     rec["ok"] = True
     return rec
 
@@ -141,6 +141,17 @@ def run_step(step):
         return lin(step, 256, 256, 256, 0x31)
     if step == "lin_multi":
         return lin(step, 40000, 512, 1024, 0x00, dump=False)
+    if step == "pair_64_f32":
+        return lin(step, 256, 64, 64, 0x12)
+    if step == "pair_64_split":
+        return lin(step, 256, 64, 64, 0x13)
+    if step == "pair_256":
+        return lin(step, 300, 256, 256, 0x33)
+    if step == "pair_multi":
+        return lin(step, 40000, 512, 1024, 0x02, dump=False)
+    if step == "tc_fwd_10k_cg1":
+        os.environ["TOAD_B200_CG1"] = "1"
+        return fwd_case(step, "toad_big_n10000", False)
     if step == "attn_gated":
         import numpy as np
         import torch
