@@ -19,7 +19,7 @@ constexpr int T = 2;            // n_tasks (model_toad.py:66)
 constexpr int THREADS = 512;    // 16 warps
 constexpr int WARPS = THREADS / 32;
 constexpr int MAX_CHUNK = 2048; // rows per CTA (scores cached in smem)
-constexpr int MAX_BLOCKS = 2048;
+constexpr int MAX_BLOCKS = 1024;   // (max,sum) staging of the merge fits s_score: 2*T*MAX_BLOCKS floats
 constexpr int PART_STRIDE = T * (H + 2);  // per-CTA partial: acc[T][H], then (m,l)[T]
 
 enum { H_F32 = 0, H_SPLIT = 1 };
@@ -167,23 +167,27 @@ __global__ void __launch_bounds__(THREADS) pool_heads_kernel(const TailParams p)
   if (s_ticket != gridDim.x - 1) return;
   __threadfence();
   const int nb = gridDim.x;
-  float* s_scale = &s_score[0][0];  // [nb][T], nb <= MAX_BLOCKS == MAX_CHUNK
+  // stage every CTA's (max, sum) pair in smem with parallel L2 loads, then two threads fold them
+  // serially from smem (fixed order, ~3k cycles) instead of chasing ~300 dependent L2 latencies.
+  float* s_scale = &s_score[0][0];  // [nb][T] max -> scale;  [nb][T] sums behind it (nb <= MAX_BLOCKS)
+  float* s_lb = s_scale + nb * T;
+  for (int i = tid; i < nb * T; i += THREADS) {
+    const int b = i / T, t = i % T;
+    s_scale[i] = __ldcg(p.blk_part + static_cast<int64_t>(b) * PART_STRIDE + T * H + 2 * t);
+    s_lb[i] = __ldcg(p.blk_part + static_cast<int64_t>(b) * PART_STRIDE + T * H + 2 * t + 1);
+  }
+  __syncthreads();
   if (tid < T) {
     float m = -INFINITY;
-    for (int b = 0; b < nb; ++b) m = fmaxf(m, __ldcg(p.blk_part + static_cast<int64_t>(b) * PART_STRIDE + T * H + 2 * tid));
+    for (int b = 0; b < nb; ++b) m = fmaxf(m, s_scale[b * T + tid]);
     s_m[tid] = m;
   }
   __syncthreads();
-  for (int i = tid; i < nb * T; i += THREADS) {
-    const int b = i / T, t = i % T;
-    const float mb = __ldcg(p.blk_part + static_cast<int64_t>(b) * PART_STRIDE + T * H + 2 * t);
-    s_scale[i] = expf(mb - s_m[t]);  // exp(-inf) = 0 for an empty CTA
-  }
+  for (int i = tid; i < nb * T; i += THREADS) s_scale[i] = expf(s_scale[i] - s_m[i % T]);  // exp(-inf) = 0: empty CTA
   __syncthreads();
   if (tid < T) {
     float l = 0.f;
-    for (int b = 0; b < nb; ++b)
-      l += s_scale[b * T + tid] * __ldcg(p.blk_part + static_cast<int64_t>(b) * PART_STRIDE + T * H + 2 * tid + 1);
+    for (int b = 0; b < nb; ++b) l = fmaf(s_scale[b * T + tid], s_lb[b * T + tid], l);
     s_l[tid] = l;
     p.stats[2 * tid] = s_m[tid];
     p.stats[2 * tid + 1] = l;
