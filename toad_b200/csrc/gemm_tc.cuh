@@ -44,7 +44,9 @@ struct Cfg {
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 6 ? 6 : (192 * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator buffers (128/256/512: powers of 2)
+  static constexpr int OUT_STAGE_BYTES = 2 * BLOCK_M * 128;  // (hi, lo) 128 x 64 bf16 staging tiles for the TMA store
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + slack for 1024 B alignment
+  static constexpr int SMEM_BYTES_LINEAR = SMEM_BYTES + OUT_STAGE_BYTES;
 };
 
 struct GemmTcParams {
@@ -153,6 +155,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         : "memory");
   }
 }
+// smem tile -> global through the tensor map (rows/cols beyond the tensor are clipped by the hardware)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -254,6 +267,7 @@ template <int BLOCK_N, int A_MODE, int EPI, int CG>
 __global__ void __launch_bounds__(A_MODE == A_F32 ? 384 : 256, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                   const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
                    const GemmTcParams p) {
   using C = Cfg<BLOCK_N, CG>;
   constexpr int STAGES = C::STAGES;
@@ -409,37 +423,61 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N;
 
       if (EPI == EPI_LINEAR) {
+        // 64 columns at a time: TMEM -> registers -> bias/ReLU -> (hi,lo) bf16 -> 128B-swizzled smem
+        // staging tile -> one TMA store per plane (full 128 B row segments, rows >= M clipped by TMA).
+        const uint32_t stage_hi = tiles_base + STAGES * C::STAGE_BYTES;
+        const uint32_t stage_lo = stage_hi + BLOCK_M * 128;
+        const int r_local = ew * 32 + lane;
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld32(t_row + c * 32, r);
+        for (int cc = 0; cc < BLOCK_N / 64; ++cc) {
+          uint32_t r[2][32];
+          tmem_ld32(t_row + cc * 64, r[0]);
+          tmem_ld32(t_row + cc * 64 + 32, r[1]);
           tmem_ld_wait();
-          const int col0 = n0 + c * 32;
-          float v[32];
+          const int col0 = n0 + cc * 64;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float t = __uint_as_float(r[i]);
-            if (p.bias != nullptr) t += __ldg(p.bias + col0 + i);
-            if (p.relu) t = fmaxf(t, 0.0f);
-            v[i] = t;
-          }
-          if (row_ok) {
-            if (p.out_f32 != nullptr) {
-              float4* dst = reinterpret_cast<float4*>(p.out_f32 + row * p.ld_f32 + col0);
+          for (int h = 0; h < 2; ++h) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            for (int i = 0; i < 32; ++i) {
+              float t = __uint_as_float(r[h][i]);
+              if (p.bias != nullptr) t += __ldg(p.bias + col0 + h * 32 + i);
+              if (p.relu) t = fmaxf(t, 0.0f);
+              r[h][i] = __float_as_uint(t);
             }
-            if (p.out_hi != nullptr) {
-              uint32_t hi[16], lo[16];
+          }
+          if (row_ok && p.out_f32 != nullptr) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out_f32 + row * p.ld_f32 + col0);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
-              uint4* dh = reinterpret_cast<uint4*>(p.out_hi + row * p.ld_split + col0);
-              uint4* dl = reinterpret_cast<uint4*>(p.out_lo + row * p.ld_split + col0);
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                dh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-                dl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+              for (int i = 0; i < 8; ++i)
+                dst[h * 8 + i] = make_uint4(r[h][4 * i], r[h][4 * i + 1], r[h][4 * i + 2], r[h][4 * i + 3]);
+          }
+          if (p.out_hi != nullptr) {
+            // staging buffer free again? (the previous TMA store must have finished READING it)
+            if (warp == 4 && lane == 0) tma_store_wait_read();
+            epi_barrier();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {  // 8 columns -> one 16 B chunk per plane
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  split2(__uint_as_float(r[h][8 * q + 2 * e]), __uint_as_float(r[h][8 * q + 2 * e + 1]), hi[e], lo[e]);
+                const uint32_t off = r_local * 128 + ((((h * 4 + q)) ^ (r_local & 7)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_hi + off), "r"(hi[0]), "r"(hi[1]),
+                             "r"(hi[2]), "r"(hi[3]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_lo + off), "r"(lo[0]), "r"(lo[1]),
+                             "r"(lo[2]), "r"(lo[3]) : "memory");
               }
+            }
+            fence_proxy_async_smem();
+            epi_barrier();
+            if (warp == 4 && lane == 0) {
+              tma_store_2d(&tm_o_hi, stage_hi, col0, m0);
+              tma_store_2d(&tm_o_lo, stage_lo, col0, m0);
+              tma_store_commit();
             }
           }
         }
@@ -542,6 +580,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     }
   }
 
+  if (EPI == EPI_LINEAR && warp == 4 && lane == 0) tma_store_wait_all();
   tc_fence_before();
   __syncthreads();
   if (CG == 2) cluster_sync_all();  // the leader's MMAs read the peer's smem; nobody leaves early
@@ -570,11 +609,13 @@ inline PFN_encodeTiled get_encode_fn() {
 }
 
 // Tensor map over a row-major bf16 matrix [rows, cols]; box = 64 columns x box_rows rows, 128B swizzle.
-inline int make_bf16_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int box_rows) {
+inline int make_bf16_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int box_rows,
+                          int64_t ld = 0) {
   PFN_encodeTiled enc = get_encode_fn();
   if (enc == nullptr) return TOAD_ERR_DRIVER;
+  if (ld == 0) ld = cols;
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(BLOCK_K), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
@@ -612,8 +653,15 @@ int launch_gemm(const GemmTcParams& p, const __nv_bfloat16* a_hi, const __nv_bfl
     ta_hi = tb_hi;
     ta_lo = tb_lo;
   }
+  CUtensorMap to_hi = tb_hi, to_lo = tb_lo;
+  if (EPI == EPI_LINEAR && p.out_hi != nullptr) {
+    if (p.out_lo == nullptr || p.ld_split % 8 != 0) return TOAD_ERR_ARG;
+    TOAD_TRY(make_bf16_tmap(&to_hi, p.out_hi, p.M, p.N, BLOCK_M, p.ld_split));
+    TOAD_TRY(make_bf16_tmap(&to_lo, p.out_lo, p.M, p.N, BLOCK_M, p.ld_split));
+  }
+  constexpr int kSmem = EPI == EPI_LINEAR ? C::SMEM_BYTES_LINEAR : C::SMEM_BYTES;
   auto kern = gemm_bf16x3_kernel<BLOCK_N, A_MODE, EPI, CG>;
-  TOAD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  TOAD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
   const int64_t m_units = (p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG);
   const int64_t units = m_units * (p.N / BLOCK_N);
   const int64_t max_units = sm_count() / CG;
@@ -621,7 +669,7 @@ int launch_gemm(const GemmTcParams& p, const __nv_bfloat16* a_hi, const __nv_bfl
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(A_MODE == A_F32 ? 384 : 256);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.dynamicSmemBytes = kSmem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -630,7 +678,7 @@ int launch_gemm(const GemmTcParams& p, const __nv_bfloat16* a_hi, const __nv_bfl
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CG > 1 ? 1 : 0;
-  TOAD_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, p));
+  TOAD_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, p));
   TOAD_CUDA_TRY(cudaGetLastError());
   return 0;
 }
