@@ -16,6 +16,7 @@
  *   toad_topk             <- torch.topk over results['A'][t]   (SURVEY.md F6 / config 5;
  *                            the k=1 uses at models/model_toad.py:102,106)
  *   toad_linear_bf16x3    <- one nn.Linear(+ReLU), the building block (models/model_toad.py:59,62)
+ *   toad_resnet_fwd       <- ResNet_Baseline.forward            models/resnet_custom.py:96-109
  *
  * Conventions
  *   - All pointers are DEVICE pointers to fp32 (or int64 where stated),
@@ -165,6 +166,22 @@ int toad_linear_workspace_bytes(int64_t m, int32_t n, int32_t k, size_t* bytes);
 int toad_linear_bf16x3(const float* x, const float* w, const float* bias, float* y, int64_t m, int32_t n,
                        int32_t k, int32_t relu, int32_t variant, void* workspace, size_t workspace_bytes,
                        toad_stream_t stream);
+
+/* ---- resnet50_baseline: ResNet-50 truncated after layer3 + global average pool, eval mode
+ * (models/resnet_custom.py:57-109; Bottleneck_Baseline :19-55).  BatchNorm (running statistics) is
+ * folded into the convolution weights by toad_resnet_prepare; activations are NHWC internally.
+ *
+ * tensors: HOST array of TOAD_RESNET_N_TENSORS device pointers (fp32), the module's state_dict in
+ * order with the `num_batches_tracked` entries skipped, i.e. for each of the 43 convolutions
+ * {conv.weight [Co,Ci,k,k], bn.weight, bn.bias, bn.running_mean, bn.running_var}.
+ * x: [B, 3, H, W] fp32 NCHW (H, W multiples of 16, H/4 and W/4 powers of two <= 128);  out: [B, 1024] fp32. */
+#define TOAD_RESNET_N_TENSORS 215
+int toad_resnet_prepared_bytes(size_t* bytes);
+int toad_resnet_prepare(const float* const* tensors, int32_t n_tensors, void* prepared, size_t prepared_bytes,
+                        toad_stream_t stream);
+int toad_resnet_workspace_bytes(int32_t batch, int32_t height, int32_t width, size_t* bytes);
+int toad_resnet_fwd(const void* prepared, const float* x, int32_t batch, int32_t height, int32_t width, float* out,
+                    void* workspace, size_t workspace_bytes, toad_stream_t stream);
 
 #ifdef __cplusplus
 }

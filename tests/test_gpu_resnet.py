@@ -1,0 +1,66 @@
+"""GPU parity of resnet50_baseline (models/resnet_custom.py) against reference-generated goldens.
+
+The trunk runs every convolution as a 3-pass split-bf16 tensor-core GEMM (fp32-class accuracy), so
+the tolerance is the same 1e-3 relative bar as the TOAD head (relative to the feature scale, since
+individual averaged features can be ~0)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import resnet_oracle as RO
+from tests.helpers import to_np
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "resnet_*.npz")))
+
+
+def build(params):
+    from models.resnet_custom import resnet50_baseline
+    m = resnet50_baseline(pretrained=False)
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v).copy()) for k, v in params.items()}, strict=True)
+    return m.cuda().eval()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_resnet_matches_reference(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    params = RO.make_params(int(z["meta_pseed"]))
+    x = RO.make_images(int(z["meta_xseed"]), int(z["meta_batch"]), int(z["meta_size"]))
+    model = build(params)
+    with torch.no_grad():
+        y = model(torch.from_numpy(x).cuda())
+    torch.cuda.synchronize()
+    y = to_np(y)
+    ref = z["f64_out"]
+    assert y.shape == ref.shape == (int(z["meta_batch"]), 1024)
+    scale = np.abs(ref).max()
+    assert np.abs(y - ref).max() <= 1e-3 * scale, (np.abs(y - ref).max(), scale)
+    np.testing.assert_allclose(y, ref, rtol=1e-2, atol=1e-3 * scale)
+
+
+def test_resnet_batch_independence_and_determinism():
+    """Each image's features do not depend on its batch neighbours; repeated runs are bit-identical."""
+    params = RO.make_params(1)
+    x = RO.make_images(9, 5, 64)
+    model = build(params)
+    xd = torch.from_numpy(x).cuda()
+    with torch.no_grad():
+        y_all = model(xd)
+        y_again = model(xd)
+        y_one = model(xd[3:4].contiguous())
+    assert torch.equal(y_all, y_again)
+    np.testing.assert_allclose(to_np(y_all[3:4]), to_np(y_one), rtol=1e-5, atol=1e-6)
+
+
+def test_resnet_refuses_train_mode_and_cpu():
+    from models.resnet_custom import resnet50_baseline
+    m = resnet50_baseline().cuda()
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 3, 64, 64, device="cuda"))       # constructed in train mode, like the reference
+    m.eval()
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 3, 64, 64))                       # CPU tensor: no fallback

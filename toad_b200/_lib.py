@@ -23,6 +23,7 @@ EXPORTS = [
     "toad_topk_workspace_bytes", "toad_topk",
     "toad_linear_workspace_bytes", "toad_linear_bf16x3",
     "toad_profile_create", "toad_profile_destroy", "toad_profile_read", "toad_fwd_profiled",
+    "toad_resnet_prepared_bytes", "toad_resnet_prepare", "toad_resnet_workspace_bytes", "toad_resnet_fwd",
 ]
 
 _f32p = C.c_void_p  # device pointers travel as integers
@@ -93,6 +94,11 @@ def load() -> C.CDLL:
     lib.toad_profile_create.argtypes = [C.POINTER(C.c_void_p), C.c_int32]
     lib.toad_profile_destroy.argtypes = [C.c_void_p]
     lib.toad_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
+    lib.toad_resnet_prepared_bytes.argtypes = [C.POINTER(C.c_size_t)]
+    lib.toad_resnet_prepare.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.toad_resnet_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
+    lib.toad_resnet_fwd.argtypes = [C.c_void_p, _f32p, C.c_int32, C.c_int32, C.c_int32, _f32p, C.c_void_p, C.c_size_t,
+                                    C.c_void_p]
     for name in EXPORTS:
         if name != "toad_error_string":
             getattr(lib, name).restype = C.c_int

@@ -29,7 +29,7 @@ constexpr int UMMA_K = 16;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
 
 enum { EPI_LINEAR = 0, EPI_GATE = 1 };
-enum { A_F32 = 0, A_SPLIT = 1 };
+enum { A_F32 = 0, A_SPLIT = 1, A_CONV = 2 };  // A_CONV: implicit-GEMM convolution over NHWC (hi,lo) planes
 
 // CG = 1: one CTA per tile (UMMA M=128).  CG = 2: a CTA pair (cluster of 2, cta_group::2) shares one
 // 256 x BLOCK_N tile: each CTA stages its own 128 rows of A and HALF of the B tile, the leader CTA
@@ -74,6 +74,19 @@ struct GemmTcParams {
   float* gate_part;     // [n_tiles][M][ntasks] partial scores (no bias)
   float* gate_a;        // nullable [M, D]
   float* gate_b;        // nullable [M, D]
+  // A_CONV: rows are output pixels (b, oh, ow) raster; K blocks walk (tap, 64-channel chunk); the A tile
+  // of one K block is one 4-D TMA box {64 ch, wb, hb, bb} of the NHWC input, shifted by the tap, with
+  // out-of-image pixels zero-filled by TMA (= the convolution's zero padding).
+  int32_t conv_kw;       // taps per filter row (1 or 3)
+  int32_t conv_cchunks;  // C_in / 64
+  int32_t conv_stride;   // 1 or 2 (encoded in the tensor map's elementStrides)
+  int32_t conv_pad;      // 0 or 1
+  int32_t conv_Wo;
+  int32_t conv_Ho;
+  // EPI_LINEAR residual: out = act(acc + bias + (res_hi + res_lo)), planes [M, ld_res]
+  const __nv_bfloat16* res_hi;
+  const __nv_bfloat16* res_lo;
+  int64_t ld_res;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -165,6 +178,22 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps
+
+template <int CG>
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  if (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+  }
+}
 
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -309,7 +338,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_b_hi);
     prefetch_tmap(&tm_b_lo);
-    if (A_MODE == A_SPLIT) {
+    if (A_MODE != A_F32) {
       prefetch_tmap(&tm_a_hi);
       prefetch_tmap(&tm_a_lo);
     }
@@ -342,7 +371,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         if (lane == 0) {
           const uint32_t sa = tiles_base + stage * C::STAGE_BYTES;
           const uint32_t fb_local = smem_u32(&bar_full_b[stage]);
-          const uint32_t bytes = 2 * C::B_TILE_BYTES + (A_MODE == A_SPLIT ? 2 * A_TILE_BYTES : 0);
+          const uint32_t bytes = 2 * C::B_TILE_BYTES + (A_MODE != A_F32 ? 2 * A_TILE_BYTES : 0);
           uint32_t fb = fb_local;
           if (CG == 1) {
             mbar_expect_tx(fb_local, bytes);
@@ -354,6 +383,16 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           if (A_MODE == A_SPLIT) {
             tma_load_2d<CG>(sa, &tm_a_hi, fb, kb * BLOCK_K, m0);
             tma_load_2d<CG>(sa + A_TILE_BYTES, &tm_a_lo, fb, kb * BLOCK_K, m0);
+          } else if (A_MODE == A_CONV) {
+            const int tap = kb / p.conv_cchunks, cc = kb - tap * p.conv_cchunks;
+            const int kh = tap / p.conv_kw, kw = tap - kh * p.conv_kw;
+            const int hw = p.conv_Ho * p.conv_Wo;
+            const int b0 = m0 / hw, pix = m0 - b0 * hw;
+            const int oh0 = pix / p.conv_Wo, ow0 = pix - oh0 * p.conv_Wo;
+            const int cw = ow0 * p.conv_stride + kw - p.conv_pad;
+            const int ch = oh0 * p.conv_stride + kh - p.conv_pad;
+            tma_load_4d<CG>(sa, &tm_a_hi, fb, cc * BLOCK_K, cw, ch, b0);
+            tma_load_4d<CG>(sa + A_TILE_BYTES, &tm_a_lo, fb, cc * BLOCK_K, cw, ch, b0);
           }
           tma_load_2d<CG>(sa + 2 * A_TILE_BYTES, &tm_b_hi, fb, kb * BLOCK_K, n0);
           tma_load_2d<CG>(sa + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &tm_b_lo, fb, kb * BLOCK_K, n0);
@@ -435,14 +474,27 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           tmem_ld32(t_row + cc * 64 + 32, r[1]);
           tmem_ld_wait();
           const int col0 = n0 + cc * 64;
+          const bool has_res = A_MODE != A_F32 && p.res_hi != nullptr && row_ok;  // residual only on plane-fed GEMMs
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float t = __uint_as_float(r[h][i]);
-              if (p.bias != nullptr) t += __ldg(p.bias + col0 + h * 32 + i);
-              if (p.relu) t = fmaxf(t, 0.0f);
-              r[h][i] = __float_as_uint(t);
+            for (int q = 0; q < 4; ++q) {
+              uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = make_uint4(0u, 0u, 0u, 0u);
+              if (has_res) {
+                vh = *reinterpret_cast<const uint4*>(p.res_hi + row * p.ld_res + col0 + h * 32 + q * 8);
+                vl = *reinterpret_cast<const uint4*>(p.res_lo + row * p.ld_res + col0 + h * 32 + q * 8);
+              }
+              const uint32_t uh[4] = {vh.x, vh.y, vh.z, vh.w}, ul[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int i = q * 8 + e;
+                float t = __uint_as_float(r[h][i]);
+                if (p.bias != nullptr) t += __ldg(p.bias + col0 + h * 32 + i);
+                const uint32_t wh = uh[e >> 1], wl = ul[e >> 1];
+                t += (e & 1) ? (bf16hi_to_f32(wh) + bf16hi_to_f32(wl)) : (bf16lo_to_f32(wh) + bf16lo_to_f32(wl));
+                if (p.relu) t = fmaxf(t, 0.0f);
+                r[h][i] = __float_as_uint(t);
+              }
             }
           }
           if (row_ok && p.out_f32 != nullptr) {
@@ -634,25 +686,36 @@ inline int sm_count() {
   return n;
 }
 
-// A operand: fp32 (a_f32/lda in p) when A_MODE == A_F32, else the planes a_hi/a_lo [M, K] bf16.
-// B operand: planes b_hi/b_lo [N, K] bf16.
-template <int BLOCK_N, int A_MODE, int EPI, int CG = 1>
-int launch_gemm(const GemmTcParams& p, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,
-                const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, cudaStream_t stream) {
+// 4-D tensor map over an NHWC bf16 plane [B, H, W, C]: box = 64 channels x (wb x hb x bb) pixels sampled with
+// `stride` in W and H (boxDim = pixels * stride, elementStrides = stride), 128B swizzle, zero OOB fill.
+inline int make_nhwc_tmap(CUtensorMap* map, const void* ptr, int64_t B, int64_t H, int64_t W, int64_t C, int wb, int hb,
+                          int bb, int stride) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (enc == nullptr) return TOAD_ERR_DRIVER;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
+                           static_cast<cuuint64_t>(H) * W * C * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(BLOCK_K), static_cast<cuuint32_t>(wb * stride),
+                       static_cast<cuuint32_t>(hb * stride), static_cast<cuuint32_t>(bb)};
+  cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : TOAD_ERR_DRIVER;
+}
+
+// Launch with ready-made A tensor maps (unused for A_F32).  B operand: planes b_hi/b_lo [N, K] bf16.
+template <int BLOCK_N, int A_MODE, int EPI, int CG>
+int launch_gemm_maps(const GemmTcParams& p, const CUtensorMap& ta_hi, const CUtensorMap& ta_lo,
+                     const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, cudaStream_t stream) {
   using C = Cfg<BLOCK_N, CG>;
   if (p.M <= 0) return 0;
   if (p.K % BLOCK_K != 0 || p.N % BLOCK_N != 0 || p.K <= 0 || p.N <= 0) return TOAD_ERR_UNSUPPORTED;
   if (EPI == EPI_GATE && (p.gate_D > 1024 || p.gate_ntasks < 1 || p.gate_ntasks > 4)) return TOAD_ERR_UNSUPPORTED;
-  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  CUtensorMap tb_hi, tb_lo;
   TOAD_TRY(make_bf16_tmap(&tb_hi, b_hi, p.N, p.K, C::B_ROWS));
   TOAD_TRY(make_bf16_tmap(&tb_lo, b_lo, p.N, p.K, C::B_ROWS));
-  if (A_MODE == A_SPLIT) {
-    TOAD_TRY(make_bf16_tmap(&ta_hi, a_hi, p.M, p.K, BLOCK_M));
-    TOAD_TRY(make_bf16_tmap(&ta_lo, a_lo, p.M, p.K, BLOCK_M));
-  } else {
-    ta_hi = tb_hi;
-    ta_lo = tb_lo;
-  }
   CUtensorMap to_hi = tb_hi, to_lo = tb_lo;
   if (EPI == EPI_LINEAR && p.out_hi != nullptr) {
     if (p.out_lo == nullptr || p.ld_split % 8 != 0) return TOAD_ERR_ARG;
@@ -681,6 +744,51 @@ int launch_gemm(const GemmTcParams& p, const __nv_bfloat16* a_hi, const __nv_bfl
   TOAD_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, p));
   TOAD_CUDA_TRY(cudaGetLastError());
   return 0;
+}
+
+// A operand: fp32 (a_f32/lda in p) when A_MODE == A_F32, else the planes a_hi/a_lo [M, K] bf16.
+template <int BLOCK_N, int A_MODE, int EPI, int CG = 1>
+int launch_gemm(const GemmTcParams& p, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,
+                const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, cudaStream_t stream) {
+  static_assert(A_MODE != A_CONV, "use launch_conv_gemm");
+  if (p.M <= 0) return 0;
+  CUtensorMap ta_hi, ta_lo;
+  if (A_MODE == A_SPLIT) {
+    if (p.K % BLOCK_K != 0 || p.K <= 0) return TOAD_ERR_UNSUPPORTED;
+    TOAD_TRY(make_bf16_tmap(&ta_hi, a_hi, p.M, p.K, BLOCK_M));
+    TOAD_TRY(make_bf16_tmap(&ta_lo, a_lo, p.M, p.K, BLOCK_M));
+  } else {
+    TOAD_TRY(make_bf16_tmap(&ta_hi, b_hi, p.N, p.K, 64));  // placeholders, never dereferenced
+    ta_lo = ta_hi;
+  }
+  return launch_gemm_maps<BLOCK_N, A_MODE, EPI, CG>(p, ta_hi, ta_lo, b_hi, b_lo, stream);
+}
+
+// Convolution as implicit GEMM: input planes NHWC [B, H, W, Cin] (hi, lo), weights [Cout, taps*Cin] with
+// K order (kh, kw, cin), output planes [B*Ho*Wo, Cout].  ksize in {1, 3}; stride in {1, 2}; pad = ksize/2.
+template <int BLOCK_N, int CG>
+int launch_conv_gemm(GemmTcParams p, const __nv_bfloat16* in_hi, const __nv_bfloat16* in_lo, int B, int H, int W,
+                     int Cin, int ksize, int stride, const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo,
+                     cudaStream_t stream) {
+  const int Ho = H / stride, Wo = W / stride;
+  if (Cin % BLOCK_K != 0 || (ksize != 1 && ksize != 3) || (stride != 1 && stride != 2)) return TOAD_ERR_UNSUPPORTED;
+  if (Wo > BLOCK_M || (Wo & (Wo - 1)) != 0 || (Ho & (Ho - 1)) != 0) return TOAD_ERR_UNSUPPORTED;
+  // 128 output pixels per tile = wb x hb x bb (full rows first, then rows, then images)
+  const int wb = Wo;
+  const int hb = (BLOCK_M / wb) < Ho ? (BLOCK_M / wb) : Ho;
+  const int bb = BLOCK_M / (wb * hb);
+  p.M = static_cast<int64_t>(B) * Ho * Wo;
+  p.K = ksize * ksize * Cin;
+  p.conv_kw = ksize;
+  p.conv_cchunks = Cin / BLOCK_K;
+  p.conv_stride = stride;
+  p.conv_pad = ksize / 2;
+  p.conv_Wo = Wo;
+  p.conv_Ho = Ho;
+  CUtensorMap ta_hi, ta_lo;
+  TOAD_TRY(make_nhwc_tmap(&ta_hi, in_hi, B, H, W, Cin, wb, hb, bb, stride));
+  TOAD_TRY(make_nhwc_tmap(&ta_lo, in_lo, B, H, W, Cin, wb, hb, bb, stride));
+  return launch_gemm_maps<BLOCK_N, A_CONV, EPI_LINEAR, CG>(p, ta_hi, ta_lo, w_hi, w_lo, stream);
 }
 
 }  // namespace tc

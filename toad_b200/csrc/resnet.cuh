@@ -1,0 +1,143 @@
+// Small kernels around the convolution GEMMs of the truncated ResNet-50 trunk
+// (reference models/resnet_custom.py:19-109, eval mode): BatchNorm folding + weight re-layout,
+// the 7x7/s2 stem's im2col, 3x3/s2 max-pool and the global average pool.  Activations live in
+// HBM as NHWC (hi, lo) bf16 planes -- the operand format of the tcgen05 split-bf16 GEMM -- so a
+// 1x1 convolution is a plain GEMM over the plane and a 3x3 one is 9 shifted TMA box loads.
+#pragma once
+#include "common.cuh"
+
+namespace toad {
+namespace resnet {
+
+// w [Co, Ci, KH, KW] fp32 + BN(gamma, beta, running_mean, running_var) ->
+//   planes [Co, Kpad] with K order (kh, kw, ci) (zero padded), bias[Co] = beta - mean * gamma / sqrt(var + eps)
+// (resnet_custom.py:38-47: conv (bias-free) followed by BatchNorm2d in eval mode).
+__global__ void fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, const float* __restrict__ mean,
+                                 const float* __restrict__ var, float eps, __nv_bfloat16* __restrict__ hi,
+                                 __nv_bfloat16* __restrict__ lo, float* __restrict__ bias, int Co, int Ci, int KH, int KW,
+                                 int Kpad) {
+  const int co = blockIdx.x;
+  const float scale = gamma[co] / sqrtf(var[co] + eps);
+  if (threadIdx.x == 0) bias[co] = beta[co] - mean[co] * scale;
+  const int K = KH * KW * Ci;
+  for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
+    float v = 0.f;
+    if (k < K) {
+      const int tap = k / Ci, ci = k % Ci;
+      const int kh = tap / KW, kw = tap % KW;
+      v = w[((static_cast<int64_t>(co) * Ci + ci) * KH + kh) * KW + kw] * scale;
+    }
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[static_cast<int64_t>(co) * Kpad + k] = h;
+    lo[static_cast<int64_t>(co) * Kpad + k] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// Stem im2col (conv1: 7x7, stride 2, pad 3, 3 input channels; resnet_custom.py:61,97).
+// x NCHW fp32 [B,3,H,W] -> planes [B*Ho*Wo, 192], column k = (kh*7 + kw)*3 + c (147 real, rest 0).
+// One thread produces 8 consecutive columns of one row (one 16 B store per plane).
+constexpr int STEM_K = 147, STEM_KPAD = 192;
+__global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                   __nv_bfloat16* __restrict__ lo, int B, int H, int W, int Ho, int Wo) {
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t total = static_cast<int64_t>(B) * Ho * Wo * (STEM_KPAD / 8);
+  if (gid >= total) return;
+  const int kg = static_cast<int>(gid % (STEM_KPAD / 8));
+  const int64_t row = gid / (STEM_KPAD / 8);
+  const int ow = static_cast<int>(row % Wo);
+  const int oh = static_cast<int>((row / Wo) % Ho);
+  const int b = static_cast<int>(row / (static_cast<int64_t>(Wo) * Ho));
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = kg * 8 + e;
+    float t = 0.f;
+    if (k < STEM_K) {
+      const int c = k % 3, tap = k / 3;
+      const int kh = tap / 7, kw = tap % 7;
+      const int ih = oh * 2 + kh - 3, iw = ow * 2 + kw - 3;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) t = __ldg(x + ((static_cast<int64_t>(b) * 3 + c) * H + ih) * W + iw);
+    }
+    v[e] = t;
+  }
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) split2(v[2 * e], v[2 * e + 1], h[e], l[e]);
+  *reinterpret_cast<uint4*>(hi + row * STEM_KPAD + kg * 8) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo + row * STEM_KPAD + kg * 8) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// MaxPool2d(3, stride 2, pad 1) on NHWC planes (resnet_custom.py:64,100).  Thread = (output pixel, 8 channels).
+__global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfloat16* __restrict__ in_lo,
+                                    __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int B, int H,
+                                    int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, CG8 = C / 8;
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t total = static_cast<int64_t>(B) * Ho * Wo * CG8;
+  if (gid >= total) return;
+  const int cg = static_cast<int>(gid % CG8);
+  const int64_t pix = gid / CG8;
+  const int ow = static_cast<int>(pix % Wo), oh = static_cast<int>((pix / Wo) % Ho);
+  const int b = static_cast<int>(pix / (static_cast<int64_t>(Wo) * Ho));
+  float m[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+  for (int kh = 0; kh < 3; ++kh) {
+    const int ih = oh * 2 + kh - 1;
+    if (ih < 0 || ih >= H) continue;
+    for (int kw = 0; kw < 3; ++kw) {
+      const int iw = ow * 2 + kw - 1;
+      if (iw < 0 || iw >= W) continue;
+      const int64_t off = ((static_cast<int64_t>(b) * H + ih) * W + iw) * C + cg * 8;
+      const uint4 vh = *reinterpret_cast<const uint4*>(in_hi + off);
+      const uint4 vl = *reinterpret_cast<const uint4*>(in_lo + off);
+      const uint32_t uh[4] = {vh.x, vh.y, vh.z, vh.w}, ul[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        m[2 * e] = fmaxf(m[2 * e], bf16lo_to_f32(uh[e]) + bf16lo_to_f32(ul[e]));
+        m[2 * e + 1] = fmaxf(m[2 * e + 1], bf16hi_to_f32(uh[e]) + bf16hi_to_f32(ul[e]));
+      }
+    }
+  }
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) split2(m[2 * e], m[2 * e + 1], h[e], l[e]);  // exact: m is one of the hi+lo inputs
+  const int64_t o = pix * C + cg * 8;
+  *reinterpret_cast<uint4*>(out_hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(out_lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// AdaptiveAvgPool2d(1) + view (resnet_custom.py:106-107): planes [B, HW, C] -> fp32 [B, C].
+// Block = (image, 256-channel slab); 8 pixel-groups x 32 lanes x 8 channels, fixed-order smem reduce.
+__global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfloat16* __restrict__ in_lo,
+                               float* __restrict__ out, int HW, int C) {
+  __shared__ float red[8][256];
+  const int b = blockIdx.x, c0 = blockIdx.y * 256;
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;  // 256 threads
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int p = grp; p < HW; p += 8) {
+    const int64_t off = (static_cast<int64_t>(b) * HW + p) * C + c0 + lane * 8;
+    const uint4 vh = *reinterpret_cast<const uint4*>(in_hi + off);
+    const uint4 vl = *reinterpret_cast<const uint4*>(in_lo + off);
+    const uint32_t uh[4] = {vh.x, vh.y, vh.z, vh.w}, ul[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      acc[2 * e] += bf16lo_to_f32(uh[e]) + bf16lo_to_f32(ul[e]);
+      acc[2 * e + 1] += bf16hi_to_f32(uh[e]) + bf16hi_to_f32(ul[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[grp][lane * 8 + e] = acc[e];
+  __syncthreads();
+  const int c = threadIdx.x;
+  float s = 0.f;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) s += red[g][c];
+  out[static_cast<int64_t>(b) * C + c0 + c] = s / static_cast<float>(HW);
+}
+
+}  // namespace resnet
+}  // namespace toad

@@ -5,6 +5,7 @@
 #include "tail.cuh"
 #include "bwd.cuh"
 #include "topk.cuh"
+#include "resnet.cuh"
 #include <new>
 
 namespace {
@@ -552,3 +553,205 @@ extern "C" int toad_linear_bf16x3(const float* x, const float* wgt, const float*
   return pair ? run_linear<64, 2>(g, split_a, w, st) : run_linear<64, 1>(g, split_a, w, st);
 }
 
+
+// ------------------------------------------------------------------------------------------ ResNet-50 trunk
+namespace {
+
+struct ConvSpec { int cin, cout, k, stride; };
+
+// the 43 convolutions in state_dict order (resnet_custom.py:57-94 with layers [3,4,6])
+int build_specs(ConvSpec* specs) {
+  int n = 0;
+  specs[n++] = {3, 64, 7, 2};
+  int inplanes = 64;
+  const int planes[3] = {64, 128, 256}, blocks[3] = {3, 4, 6}, strides[3] = {1, 2, 2};
+  for (int l = 0; l < 3; ++l) {
+    for (int i = 0; i < blocks[l]; ++i) {
+      const int s = i == 0 ? strides[l] : 1;
+      specs[n++] = {inplanes, planes[l], 1, 1};
+      specs[n++] = {planes[l], planes[l], 3, s};
+      specs[n++] = {planes[l], planes[l] * 4, 1, 1};
+      if (i == 0) specs[n++] = {inplanes, planes[l] * 4, 1, s};  // downsample
+      inplanes = planes[l] * 4;
+    }
+  }
+  return n;  // 43
+}
+
+inline int kpad_of(const ConvSpec& c) {
+  const int k = c.k * c.k * c.cin;
+  return (k + 63) / 64 * 64;
+}
+
+struct PreparedConv { bf16* hi; bf16* lo; float* bias; };
+struct Prepared { PreparedConv conv[43]; size_t bytes; };
+
+Prepared carve_prepared(void* base) {
+  Prepared p{};
+  Carver c(base);
+  ConvSpec specs[43];
+  build_specs(specs);
+  for (int i = 0; i < 43; ++i) {
+    const size_t n = static_cast<size_t>(specs[i].cout) * kpad_of(specs[i]);
+    p.conv[i].hi = c.take<bf16>(n);
+    p.conv[i].lo = c.take<bf16>(n);
+    p.conv[i].bias = c.take<float>(specs[i].cout);
+  }
+  p.bytes = align_up(c.off, 256);
+  return p;
+}
+
+struct ResWs {
+  bf16 *col_hi, *col_lo, *stem_hi, *stem_lo;
+  bf16 *buf_hi[5], *buf_lo[5];
+  int stem_chunk;
+  size_t bytes;
+};
+
+ResWs carve_resnet(int B, int H, int W, void* base) {
+  ResWs w{};
+  Carver c(base);
+  const int64_t H1 = H / 2, W1 = W / 2, H2 = H / 4, W2 = W / 4;
+  w.stem_chunk = B < 64 ? B : 64;
+  const size_t col = static_cast<size_t>(w.stem_chunk) * H1 * W1 * resnet::STEM_KPAD;
+  w.col_hi = c.take<bf16>(col);
+  w.col_lo = c.take<bf16>(col);
+  const size_t stem = static_cast<size_t>(B) * H1 * W1 * 64;
+  w.stem_hi = c.take<bf16>(stem);
+  w.stem_lo = c.take<bf16>(stem);
+  const size_t act = static_cast<size_t>(B) * H2 * W2 * 256;
+  for (int i = 0; i < 5; ++i) {
+    w.buf_hi[i] = c.take<bf16>(act);
+    w.buf_lo[i] = c.take<bf16>(act);
+  }
+  w.bytes = align_up(c.off, 256);
+  return w;
+}
+
+int check_resnet_shape(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return TOAD_ERR_ARG;
+  if (H % 16 != 0 || W % 16 != 0) return TOAD_ERR_UNSUPPORTED;
+  const int H2 = H / 4, W2 = W / 4;
+  if (W2 > 128 || (W2 & (W2 - 1)) != 0 || (H2 & (H2 - 1)) != 0 || W2 < 4 || H2 < 4) return TOAD_ERR_UNSUPPORTED;
+  return 0;
+}
+
+// out planes [M, Cout] = act(conv(in) + bias (+ residual)); in: NHWC planes [B, H, W, Cin]
+int run_conv(const ConvSpec& cs, const PreparedConv& pc, const bf16* in_hi, const bf16* in_lo, int B, int H, int W,
+             bf16* out_hi, bf16* out_lo, const bf16* res_hi, const bf16* res_lo, bool relu, cudaStream_t st) {
+  tc::GemmTcParams g{};
+  g.N = cs.cout;
+  g.bias = pc.bias;
+  g.relu = relu ? 1 : 0;
+  g.out_hi = out_hi; g.out_lo = out_lo; g.ld_split = cs.cout;
+  g.res_hi = res_hi; g.res_lo = res_lo; g.ld_res = cs.cout;
+  if (cs.k == 1 && cs.stride == 1) {  // plain GEMM over the NHWC plane
+    g.M = static_cast<int64_t>(B) * H * W;
+    g.K = cs.cin;
+    if (cs.cout % 256 == 0) return tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, in_hi, in_lo, pc.hi, pc.lo, st);
+    if (cs.cout % 128 == 0) return tc::launch_gemm<128, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, in_hi, in_lo, pc.hi, pc.lo, st);
+    return tc::launch_gemm<64, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, in_hi, in_lo, pc.hi, pc.lo, st);
+  }
+  if (cs.cout % 256 == 0) return tc::launch_conv_gemm<256, 2>(g, in_hi, in_lo, B, H, W, cs.cin, cs.k, cs.stride, pc.hi, pc.lo, st);
+  if (cs.cout % 128 == 0) return tc::launch_conv_gemm<128, 2>(g, in_hi, in_lo, B, H, W, cs.cin, cs.k, cs.stride, pc.hi, pc.lo, st);
+  return tc::launch_conv_gemm<64, 2>(g, in_hi, in_lo, B, H, W, cs.cin, cs.k, cs.stride, pc.hi, pc.lo, st);
+}
+
+}  // namespace
+
+extern "C" int toad_resnet_prepared_bytes(size_t* bytes) {
+  if (bytes == nullptr) return TOAD_ERR_ARG;
+  *bytes = carve_prepared(nullptr).bytes;
+  return 0;
+}
+
+extern "C" int toad_resnet_prepare(const float* const* tensors, int32_t n_tensors, void* prepared, size_t prepared_bytes,
+                                   toad_stream_t stream) {
+  if (tensors == nullptr || n_tensors != TOAD_RESNET_N_TENSORS) return TOAD_ERR_ARG;
+  for (int i = 0; i < n_tensors; ++i)
+    if (tensors[i] == nullptr) return TOAD_ERR_ARG;
+  Prepared P = carve_prepared(prepared);
+  TOAD_TRY(check_ws(prepared, prepared_bytes, P.bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ConvSpec specs[43];
+  build_specs(specs);
+  for (int i = 0; i < 43; ++i) {
+    const float* const* t = tensors + 5 * i;
+    resnet::fold_conv_kernel<<<specs[i].cout, 256, 0, st>>>(t[0], t[1], t[2], t[3], t[4], 1e-5f, P.conv[i].hi, P.conv[i].lo,
+                                                          P.conv[i].bias, specs[i].cout, specs[i].cin, specs[i].k,
+                                                          specs[i].k, kpad_of(specs[i]));
+    TOAD_CUDA_TRY(cudaGetLastError());
+  }
+  return 0;
+}
+
+extern "C" int toad_resnet_workspace_bytes(int32_t B, int32_t H, int32_t W, size_t* bytes) {
+  TOAD_TRY(check_resnet_shape(B, H, W));
+  if (bytes == nullptr) return TOAD_ERR_ARG;
+  *bytes = carve_resnet(B, H, W, nullptr).bytes;
+  return 0;
+}
+
+extern "C" int toad_resnet_fwd(const void* prepared, const float* x, int32_t B, int32_t H, int32_t W, float* out,
+                               void* workspace, size_t workspace_bytes, toad_stream_t stream) {
+  TOAD_TRY(check_resnet_shape(B, H, W));
+  if (prepared == nullptr || x == nullptr || out == nullptr) return TOAD_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(prepared) & 255) != 0) return TOAD_ERR_WORKSPACE;
+  Prepared P = carve_prepared(const_cast<void*>(prepared));
+  ResWs w = carve_resnet(B, H, W, workspace);
+  TOAD_TRY(check_ws(workspace, workspace_bytes, w.bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ConvSpec specs[43];
+  build_specs(specs);
+  const int H1 = H / 2, W1 = W / 2, H2 = H / 4, W2 = W / 4;
+
+  // ---- stem: conv1 7x7/s2 (im2col + GEMM) + BN + ReLU, in chunks of images (resnet_custom.py:97-99)
+  for (int b0 = 0; b0 < B; b0 += w.stem_chunk) {
+    const int nb = (B - b0) < w.stem_chunk ? (B - b0) : w.stem_chunk;
+    const int64_t rows = static_cast<int64_t>(nb) * H1 * W1;
+    const int64_t threads = rows * (resnet::STEM_KPAD / 8);
+    resnet::stem_im2col_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
+        x + static_cast<int64_t>(b0) * 3 * H * W, w.col_hi, w.col_lo, nb, H, W, H1, W1);
+    TOAD_CUDA_TRY(cudaGetLastError());
+    tc::GemmTcParams g{};
+    g.M = rows; g.N = 64; g.K = resnet::STEM_KPAD; g.bias = P.conv[0].bias; g.relu = 1;
+    g.out_hi = w.stem_hi + static_cast<int64_t>(b0) * H1 * W1 * 64;
+    g.out_lo = w.stem_lo + static_cast<int64_t>(b0) * H1 * W1 * 64;
+    g.ld_split = 64;
+    TOAD_TRY((tc::launch_gemm<64, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, w.col_hi, w.col_lo, P.conv[0].hi, P.conv[0].lo, st)));
+  }
+  // ---- maxpool 3x3/s2 (resnet_custom.py:100)
+  int cur = 0;  // buffer holding the block input
+  {
+    const int64_t threads = static_cast<int64_t>(B) * H2 * W2 * (64 / 8);
+    resnet::maxpool3x3s2_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
+        w.stem_hi, w.stem_lo, w.buf_hi[cur], w.buf_lo[cur], B, H1, W1, 64);
+    TOAD_CUDA_TRY(cudaGetLastError());
+  }
+  // ---- layer1..layer3: bottleneck blocks (resnet_custom.py:35-55)
+  int ci = 1, h = H2, wd = W2;
+  const int blocks[3] = {3, 4, 6};
+  for (int l = 0; l < 3; ++l) {
+    for (int i = 0; i < blocks[l]; ++i) {
+      const ConvSpec &c1 = specs[ci], &c2 = specs[ci + 1], &c3 = specs[ci + 2];
+      const bool has_ds = i == 0;
+      const int t1 = (cur + 1) % 5, t2 = (cur + 2) % 5, r = (cur + 3) % 5, y = (cur + 4) % 5;
+      const int ho = h / c2.stride, wo = wd / c2.stride;
+      TOAD_TRY(run_conv(c1, P.conv[ci], w.buf_hi[cur], w.buf_lo[cur], B, h, wd, w.buf_hi[t1], w.buf_lo[t1], nullptr, nullptr, true, st));
+      TOAD_TRY(run_conv(c2, P.conv[ci + 1], w.buf_hi[t1], w.buf_lo[t1], B, h, wd, w.buf_hi[t2], w.buf_lo[t2], nullptr, nullptr, true, st));
+      const bf16 *res_hi = w.buf_hi[cur], *res_lo = w.buf_lo[cur];
+      if (has_ds) {
+        TOAD_TRY(run_conv(specs[ci + 3], P.conv[ci + 3], w.buf_hi[cur], w.buf_lo[cur], B, h, wd, w.buf_hi[r], w.buf_lo[r], nullptr, nullptr, false, st));
+        res_hi = w.buf_hi[r]; res_lo = w.buf_lo[r];
+      }
+      TOAD_TRY(run_conv(c3, P.conv[ci + 2], w.buf_hi[t2], w.buf_lo[t2], B, ho, wo, w.buf_hi[y], w.buf_lo[y], res_hi, res_lo, true, st));
+      cur = y;
+      h = ho; wd = wo;
+      ci += has_ds ? 4 : 3;
+    }
+  }
+  // ---- global average pool + flatten (resnet_custom.py:106-107)
+  resnet::avgpool_kernel<<<dim3(B, 1024 / 256), 256, 0, st>>>(w.buf_hi[cur], w.buf_lo[cur], out, h * wd, 1024);
+  TOAD_CUDA_TRY(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,139 @@
+"""Drop-in replacement for the reference's ``models/resnet_custom.py`` (mahmoodlab/TOAD).
+
+``resnet50_baseline(pretrained=False)`` builds the same module tree as the reference
+(``ResNet_Baseline(Bottleneck_Baseline, [3, 4, 6, 3])``, truncated after layer3, so the
+``state_dict`` keys are torchvision's resnet50 names) but ``forward`` runs the whole trunk in
+hand-written sm_100a kernels behind the C ABI (``toad_resnet_fwd``): BatchNorm folded into the
+weights, NHWC (hi, lo) bf16 activations, every convolution a tcgen05 split-bf16 (implicit) GEMM
+with bias / residual / ReLU fused in the epilogue.  Only eval mode (running statistics) is
+implemented -- the reference's use is offline feature extraction.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+import torch.utils.model_zoo as model_zoo
+
+from . import _lib, ops
+
+__all__ = ["ResNet_Baseline", "Bottleneck_Baseline", "resnet50_baseline", "load_pretrained_weights"]
+
+model_urls = {  # resnet_custom.py:11-17
+    "resnet18": "https://download.pytorch.org/models/resnet18-5c106cde.pth",
+    "resnet34": "https://download.pytorch.org/models/resnet34-333f7ec4.pth",
+    "resnet50": "https://download.pytorch.org/models/resnet50-19c8e357.pth",
+    "resnet101": "https://download.pytorch.org/models/resnet101-5d3b4d8f.pth",
+    "resnet152": "https://download.pytorch.org/models/resnet152-b121ed2d.pth",
+}
+
+
+class Bottleneck_Baseline(nn.Module):
+    """Parameter container with the reference's layout (resnet_custom.py:19-34); never called."""
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, kernel_size=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, kernel_size=3, stride=stride, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * self.expansion, kernel_size=1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * self.expansion)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+        self.stride = stride
+
+
+class ResNet_Baseline(nn.Module):
+    """resnet_custom.py:57-109.  `layers[3]` is ignored exactly as in the reference (no layer4 / fc)."""
+
+    def __init__(self, block, layers):
+        self.inplanes = 64
+        super().__init__()
+        self.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+        self.layer1 = self._make_layer(block, 64, layers[0])
+        self.layer2 = self._make_layer(block, 128, layers[1], stride=2)
+        self.layer3 = self._make_layer(block, 256, layers[2], stride=2)
+        self.avgpool = nn.AdaptiveAvgPool2d(1)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+        if list(layers[:3]) != [3, 4, 6] or block is not Bottleneck_Baseline:
+            raise NotImplementedError("toad_b200 implements the resnet50_baseline configuration ([3, 4, 6, 3] bottlenecks)")
+        self._prepared = None
+        self._prepared_key = None
+        self._ws = ops.Workspace()
+
+    def _make_layer(self, block, planes, blocks, stride=1):
+        downsample = None
+        if stride != 1 or self.inplanes != planes * block.expansion:
+            downsample = nn.Sequential(
+                nn.Conv2d(self.inplanes, planes * block.expansion, kernel_size=1, stride=stride, bias=False),
+                nn.BatchNorm2d(planes * block.expansion),
+            )
+        layers = [block(self.inplanes, planes, stride, downsample)]
+        self.inplanes = planes * block.expansion
+        for _ in range(1, blocks):
+            layers.append(block(self.inplanes, planes))
+        return nn.Sequential(*layers)
+
+    # -- tensors in state_dict order without num_batches_tracked (the C ABI's `tensors` array)
+    def _tensor_list(self):
+        return [v for k, v in self.state_dict(keep_vars=True).items() if not k.endswith("num_batches_tracked")]
+
+    def _prepare(self, device):
+        lib = _lib.load()
+        tensors = self._tensor_list()
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        if self._prepared is not None and key == self._prepared_key and self._prepared.device == device:
+            return
+        for t in tensors:
+            ops._check_dev_f32(t, "resnet parameter")
+        nbytes = C.c_size_t()
+        _lib.check(lib.toad_resnet_prepared_bytes(C.byref(nbytes)), "toad_resnet_prepared_bytes")
+        buf = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=device)
+        arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+        ptr = (buf.data_ptr() + 255) // 256 * 256
+        _lib.check(lib.toad_resnet_prepare(arr, len(tensors), ptr, nbytes.value, ops._stream()), "toad_resnet_prepare")
+        self._prepared, self._prepared_key, self._prepared_ptr, self._prepared_bytes = buf, key, ptr, nbytes.value
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.training:
+            raise NotImplementedError("toad_b200: resnet50_baseline runs in eval mode only (BatchNorm running "
+                                      "statistics are folded into the convolutions); call .eval() first")
+        ops._check_dev_f32(x, "x")
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError("x must be [B, 3, H, W], got %s" % (tuple(x.shape),))
+        lib = _lib.load()
+        self._prepare(x.device)
+        B, _, H, W = x.shape
+        out = torch.empty((B, 1024), dtype=torch.float32, device=x.device)
+        nbytes = C.c_size_t()
+        _lib.check(lib.toad_resnet_workspace_bytes(B, H, W, C.byref(nbytes)), "toad_resnet_workspace_bytes")
+        wptr, wsize = self._ws.get(nbytes.value, x.device)
+        _lib.check(lib.toad_resnet_fwd(self._prepared_ptr, x.data_ptr(), B, H, W, out.data_ptr(), wptr, wsize,
+                                       ops._stream()), "toad_resnet_fwd")
+        return out
+
+
+def resnet50_baseline(pretrained: bool = False) -> ResNet_Baseline:
+    """Modified ResNet-50 truncated after layer3 (resnet_custom.py:111-119)."""
+    model = ResNet_Baseline(Bottleneck_Baseline, [3, 4, 6, 3])
+    if pretrained:
+        model = load_pretrained_weights(model, "resnet50")
+    return model
+
+
+def load_pretrained_weights(model, name):
+    """resnet_custom.py:121-124 (needs network access, like the reference)."""
+    pretrained_dict = model_zoo.load_url(model_urls[name])
+    model.load_state_dict(pretrained_dict, strict=False)
+    return model

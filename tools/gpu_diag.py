@@ -20,7 +20,7 @@ os.makedirs(OUT, exist_ok=True)
 
 STEPS = ["lin_64_f32", "lin_64_split", "lin_128", "lin_256", "lin_multi", "pair_64_f32", "pair_64_split", "pair_256",
          "pair_multi", "attn_gated", "simt_fwd", "tc_fwd_small", "tc_fwd_10k", "tc_fwd_10k_cg1", "topk", "bwd_simt",
-         "bwd_tc", "timing"]
+         "bwd_tc", "timing", "lin_timing", "resnet_s64", "resnet_s256", "resnet_timing"]
 
 
 def log(rec):
@@ -189,6 +189,67 @@ def run_step(step):
         return bwd_case(step, False)
     if step == "timing":
         return timing(step)
+    if step == "lin_timing":
+        import torch
+        from toad_b200 import ops
+        rec = {"step": step, "ok": True}
+        ws = ops.Workspace()
+        for (m, n, k) in ((50000, 512, 1024), (50000, 512, 512), (50000, 768, 512)):
+            x = torch.randn(m, k, device="cuda")
+            w = torch.randn(n, k, device="cuda") / k ** 0.5
+            b = torch.zeros(n, device="cuda")
+            for variant in (0x00, 0x01, 0x02, 0x03):
+                for _ in range(3):
+                    ops.linear_bf16x3(x, w, b, True, ws, variant)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(10):
+                    ops.linear_bf16x3(x, w, b, True, ws, variant)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 10
+                rec["m%d_n%d_k%d_v%d_ms" % (m, n, k, variant)] = round(ms, 4)
+        return rec
+    if step in ("resnet_s64", "resnet_s256"):
+        import numpy as np
+        import torch
+        from oracle import resnet_oracle as RO
+        from tests.test_gpu_resnet import build
+        name = "resnet_b2_s64" if step == "resnet_s64" else "resnet_b2_s256"
+        z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+        params = RO.make_params(int(z["meta_pseed"]))
+        x = RO.make_images(int(z["meta_xseed"]), int(z["meta_batch"]), int(z["meta_size"]))
+        model = build(params)
+        with torch.no_grad():
+            y = model(torch.from_numpy(x).cuda()).cpu().numpy()
+        ref = z["f64_out"]
+        err = float(np.abs(y - ref).max())
+        rec = {"step": step, "max_abs_err": err, "scale": float(np.abs(ref).max()), "nan": bool(np.isnan(y).any())}
+        rec["ok"] = bool(err <= 1e-3 * rec["scale"])
+        if not rec["ok"]:
+            np.savez_compressed(os.path.join(OUT, step + ".npz"), y=y, ref=ref)
+        return rec
+    if step == "resnet_timing":
+        import torch
+        from oracle import resnet_oracle as RO
+        from tests.test_gpu_resnet import build
+        model = build(RO.make_params(1))
+        rec = {"step": step, "ok": True}
+        for B in (64, 256):
+            x = torch.randn(B, 3, 256, 256, device="cuda")
+            with torch.no_grad():
+                model(x)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    model(x)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            rec["b%d_ms" % B] = round(ms, 3)
+            rec["b%d_patches_per_s" % B] = round(B / ms * 1e3, 1)
+        return rec
     raise SystemExit("unknown step " + step)
 
 
