@@ -56,6 +56,7 @@ enum {
 #define TOAD_FLAG_ATTENTION_ONLY 1u /* stop after the raw attention scores (model_toad.py:92-94) */
 #define TOAD_FLAG_SIMT_FP32 2u      /* fp32 CUDA-core GEMMs instead of the tcgen05 split-bf16 path */
 #define TOAD_FLAG_SAVE_ACTS 4u      /* also store h1,h,a,b (fp32) for toad_bwd */
+#define TOAD_FLAG_DROPOUT 16u        /* training-mode nn.Dropout on h1, h, a, b (model_toad.py:27-29,60-64); needs `saved` */
 #define TOAD_FLAG_TC_SINGLE_CTA 8u  /* tcgen05 GEMMs with cta_group::1 (one CTA per 128-row tile) instead of CTA pairs */
 
 /* Layer widths of TOAD_fc_mtl_concat (model_toad.py:56): "big" = {1024,512,384}, "small" = {1024,512,256}. */
@@ -98,13 +99,22 @@ typedef struct {
   float* softmax_stats;/* [n_tasks][2] = (row max, sum of exp) of a_raw; needed by toad_bwd */
 } toad_fwd_out_t;
 
-/* Activations kept for the backward (TOAD_FLAG_SAVE_ACTS), fp32. */
+/* Activations kept for the backward (TOAD_FLAG_SAVE_ACTS), fp32, as the next layer saw them
+ * (i.e. after dropout when TOAD_FLAG_DROPOUT is set), plus the dropout configuration: element i of
+ * activation L in {1: h1, 2: h, 3: a, 4: b} is kept iff toad_dropout_hash(seed, L, i) >= p * 2^32 and
+ * kept values are scaled by 1/(1-p).  The mask is a pure function of (seed, L, i): bitwise parity with
+ * torch's Philox stream is impossible, distributional parity is what holds. */
 typedef struct {
   float* h1; /* [N, hid] relu(fc1) */
   float* h;  /* [N, hid] relu(fc2) */
   float* a;  /* [N, D] tanh branch  */
   float* b;  /* [N, D] sigmoid branch */
+  uint64_t dropout_seed;
+  float dropout_p; /* 0.25 in the reference; used only with TOAD_FLAG_DROPOUT (forward) / when > 0 (backward) */
 } toad_saved_t;
+
+/* The mask hash (host-callable, for tests): high 32 bits of splitmix64(seed, layer, index). */
+uint32_t toad_dropout_hash(uint64_t seed, uint32_t layer, uint64_t index);
 
 int toad_abi_version(void);
 const char* toad_error_string(int code);

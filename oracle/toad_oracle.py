@@ -130,8 +130,33 @@ def attn_net_gated_forward(x, wa, ba, wb, bb, wc, bc):
     return A, a, b
 
 
+def dropout_hash(seed: int, layer: int, idx: np.ndarray) -> np.ndarray:
+    """High 32 bits of splitmix64(seed + golden*(idx+1) + layer*c): the mask hash of the CUDA path
+    (toad_b200/csrc/common.cuh:dropout_hash), in wrapping uint64 numpy arithmetic."""
+    with np.errstate(over="ignore"):
+        z = (np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * (idx.astype(np.uint64) + np.uint64(1))
+             + np.uint64(layer) * np.uint64(0xD1B54A32D192ED03))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(32)).astype(np.uint32)
+
+
+def dropout_multipliers(seed: int, p: float, n: int, hid: int, d: int) -> dict:
+    """nn.Dropout(p) multipliers (0 or 1/(1-p)) for the four dropped activations of the training
+    forward (reference models/model_toad.py:27-29,60-64): layer 1 = h1 [n,hid], 2 = h [n,hid],
+    3 = a [n,d], 4 = b [n,d]; element index = row*width + col."""
+    thresh = np.uint32(min(int(p * 4294967296.0), 0xFFFFFFFF))
+    out = {}
+    for layer, width in ((1, hid), (2, hid), (3, d), (4, d)):
+        idx = np.arange(n * width, dtype=np.uint64)
+        keep = dropout_hash(seed, layer, idx) >= thresh
+        out[layer] = (keep.astype(np.float64) / (1.0 - p)).reshape(n, width)
+    return out
+
+
 def toad_forward(x: np.ndarray, sex: float, params: dict, dtype=np.float32,
-                 return_intermediates: bool = False) -> dict:
+                 return_intermediates: bool = False, masks: dict = None) -> dict:
     """TOAD_fc_mtl_concat.forward (model_toad.py:90-116), eval / dropout=False.
 
     x [N,1024]; sex scalar 0/1.  Returns the reference's result dict
@@ -141,11 +166,13 @@ def toad_forward(x: np.ndarray, sex: float, params: dict, dtype=np.float32,
     """
     p = {k: np.asarray(v, dtype=dtype) for k, v in params.items()}
     x = np.asarray(x, dtype=dtype)
-    h1 = np.maximum(x @ p[PARAM_KEYS[0]].T + p[PARAM_KEYS[1]], 0)            # :59 fc1+ReLU
-    h = np.maximum(h1 @ p[PARAM_KEYS[2]].T + p[PARAM_KEYS[3]], 0)            # :62 fc2+ReLU
-    A, a, b = attn_net_gated_forward(h, p[PARAM_KEYS[4]], p[PARAM_KEYS[5]],
-                                     p[PARAM_KEYS[6]], p[PARAM_KEYS[7]],
-                                     p[PARAM_KEYS[8]], p[PARAM_KEYS[9]])     # :91
+    one = dtype(1.0)
+    m = {k: (np.asarray(v, dtype=dtype) if masks is not None else one) for k, v in (masks or {1: 1, 2: 1, 3: 1, 4: 1}).items()}
+    h1 = np.maximum(x @ p[PARAM_KEYS[0]].T + p[PARAM_KEYS[1]], 0) * m[1]     # :59-61 fc1+ReLU(+Dropout)
+    h = np.maximum(h1 @ p[PARAM_KEYS[2]].T + p[PARAM_KEYS[3]], 0) * m[2]     # :62-64 fc2+ReLU(+Dropout)
+    a = np.tanh(h @ p[PARAM_KEYS[4]].T + p[PARAM_KEYS[5]]) * m[3]            # :37 (+Dropout :28)
+    b = _sigmoid(h @ p[PARAM_KEYS[6]].T + p[PARAM_KEYS[7]]) * m[4]           # :38 (+Dropout :29)
+    A = (a * b) @ p[PARAM_KEYS[8]].T + p[PARAM_KEYS[9]]                      # :39-40
     A_raw = np.ascontiguousarray(A.T)                                        # :92,96  [2,N]
     P = _softmax_rows(A_raw)                                                 # :97
     M = P @ h                                                                # :98  [2,512]
@@ -161,7 +188,7 @@ def toad_forward(x: np.ndarray, sex: float, params: dict, dtype=np.float32,
         "A": A_raw,                                                           # :116 (pre-softmax)
     }
     if return_intermediates:
-        out.update({"h1": h1, "h": h, "a": a, "b": b, "P": P})
+        out.update({"h1": h1, "h": h, "a": a, "b": b, "P": P, "masks": m})
     return out
 
 
@@ -186,7 +213,7 @@ def toad_loss(out: dict, label: int, site: int) -> float:
 # ----------------------------------------------------------------------------
 
 def toad_backward(x, sex, params, label: int, site: int, dtype=np.float64,
-                  dlogits=None, dsite_logits=None) -> dict:
+                  dlogits=None, dsite_logits=None, masks: dict = None) -> dict:
     """Gradients of the training loss w.r.t. the 14 parameters.
 
     If dlogits / dsite_logits are given they are used as the upstream
@@ -194,9 +221,10 @@ def toad_backward(x, sex, params, label: int, site: int, dtype=np.float64,
     No gradient flows to x (features are leaf data, core_utils:201).
     """
     p = {k: np.asarray(v, dtype=dtype) for k, v in params.items()}
-    f = toad_forward(x, sex, params, dtype, return_intermediates=True)
+    f = toad_forward(x, sex, params, dtype, return_intermediates=True, masks=masks)
     x = np.asarray(x, dtype=dtype)
-    h1, h, a, b, P, Mc = f["h1"], f["h"], f["a"], f["b"], f["P"], f["features"]
+    h1, h, a, b, P, Mc = f["h1"], f["h"], f["a"], f["b"], f["P"], f["features"]   # post-dropout values
+    m = f["masks"]
     if dlogits is None:
         dlogits = f["Y_prob"].copy()
         dlogits[0, label] -= 1.0
@@ -223,17 +251,21 @@ def toad_backward(x, sex, params, label: int, site: int, dtype=np.float64,
     g[PARAM_KEYS[8]] = dA @ gate                                        # dWc [2,D]
     g[PARAM_KEYS[9]] = dA.sum(axis=1)
     dgate = dA.T @ p[PARAM_KEYS[8]]                                     # [N,D]
-    da_pre = dgate * b * (1.0 - a * a)
-    db_pre = dgate * a * b * (1.0 - b)
+    # a = tanh(.)*m3, b = sigmoid(.)*m4 with m in {0, 1/keep}: d tanh = 1 - tanh^2, d sigmoid = s(1-s)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = np.where(m[3] != 0, a / np.where(m[3] != 0, m[3], 1), 0.0)
+        sg = np.where(m[4] != 0, b / np.where(m[4] != 0, m[4], 1), 0.0)
+    da_pre = dgate * b * m[3] * (1.0 - t * t)
+    db_pre = dgate * a * m[4] * sg * (1.0 - sg)
     g[PARAM_KEYS[4]] = da_pre.T @ h
     g[PARAM_KEYS[5]] = da_pre.sum(axis=0)
     g[PARAM_KEYS[6]] = db_pre.T @ h
     g[PARAM_KEYS[7]] = db_pre.sum(axis=0)
     dh = dh + da_pre @ p[PARAM_KEYS[4]] + db_pre @ p[PARAM_KEYS[6]]
-    dz2 = dh * (h > 0)
+    dz2 = dh * (h > 0) * m[2]
     g[PARAM_KEYS[2]] = dz2.T @ h1
     g[PARAM_KEYS[3]] = dz2.sum(axis=0)
-    dz1 = (dz2 @ p[PARAM_KEYS[2]]) * (h1 > 0)
+    dz1 = (dz2 @ p[PARAM_KEYS[2]]) * (h1 > 0) * m[1]
     g[PARAM_KEYS[0]] = dz1.T @ x
     g[PARAM_KEYS[1]] = dz1.sum(axis=0)
     return g

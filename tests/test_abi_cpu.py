@@ -93,3 +93,15 @@ def test_module_refuses_cpu_tensors():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):
             m.relocate()
+
+
+def test_dropout_hash_matches_oracle(lib):
+    """The mask hash is host-callable: pin the numpy restatement used by the GPU dropout tests."""
+    import numpy as np
+    from oracle import toad_oracle as O
+    idx = np.array([0, 1, 2, 511, 512, 12345, 2 ** 33 + 5, 2 ** 40 + 7], dtype=np.uint64)
+    for seed, layer in ((0, 1), (987654321, 3), (2 ** 62 - 1, 4)):
+        ours = [lib.toad_dropout_hash(seed, layer, int(i)) for i in idx]
+        assert O.dropout_hash(seed, layer, idx).tolist() == ours
+    m = O.dropout_multipliers(42, 0.25, 64, 512, 256)
+    assert abs((m[1] == 0).mean() - 0.25) < 0.02 and set(np.unique(m[3])) == {0.0, 1.0 / 0.75}

@@ -15,9 +15,10 @@ FLAG_ATTENTION_ONLY = 1
 FLAG_SIMT_FP32 = 2
 FLAG_SAVE_ACTS = 4
 FLAG_TC_SINGLE_CTA = 8
+FLAG_DROPOUT = 16
 
 EXPORTS = [
-    "toad_abi_version", "toad_error_string", "toad_param_offsets",
+    "toad_abi_version", "toad_error_string", "toad_param_offsets", "toad_dropout_hash",
     "toad_fwd_workspace_bytes", "toad_fwd", "toad_bwd_workspace_bytes", "toad_bwd",
     "toad_attn_gated_workspace_bytes", "toad_attn_gated_fwd",
     "toad_topk_workspace_bytes", "toad_topk",
@@ -45,7 +46,7 @@ class FwdOut(C.Structure):
 
 
 class Saved(C.Structure):
-    _fields_ = [(n, _f32p) for n in ("h1", "h", "a", "b")]
+    _fields_ = [(n, _f32p) for n in ("h1", "h", "a", "b")] + [("dropout_seed", C.c_uint64), ("dropout_p", C.c_float)]
 
 
 class ToadError(RuntimeError):
@@ -99,9 +100,11 @@ def load() -> C.CDLL:
     lib.toad_resnet_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
     lib.toad_resnet_fwd.argtypes = [C.c_void_p, _f32p, C.c_int32, C.c_int32, C.c_int32, _f32p, C.c_void_p, C.c_size_t,
                                     C.c_void_p]
+    lib.toad_dropout_hash.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64]
     for name in EXPORTS:
-        if name != "toad_error_string":
+        if name not in ("toad_error_string", "toad_dropout_hash"):
             getattr(lib, name).restype = C.c_int
+    lib.toad_dropout_hash.restype = C.c_uint32
     if lib.toad_abi_version() != 1:
         raise ToadError("libtoad_b200.so ABI version %d, expected 1" % lib.toad_abi_version())
     _lib = lib

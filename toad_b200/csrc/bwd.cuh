@@ -84,7 +84,9 @@ __global__ void pool_bwd_kernel(const float* __restrict__ h, const float* __rest
 // block = D threads (thread j owns gate column j); partial layout per CTA: [dWc0[D] dWc1[D] dba[D] dbb[D] dbc[2]]
 __global__ void gate_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                 const float* __restrict__ dA, const float* __restrict__ wc, float* __restrict__ dab,
-                                float* __restrict__ part, int64_t N, int D, int rows_per_block) {
+                                float* __restrict__ part, int64_t N, int D, int rows_per_block, float keep) {
+  // a, b are the saved POST-dropout activations (a_post = a*mask/keep); keep == 1 without dropout.
+  const float inv_keep = 1.f / keep;
   const int j = threadIdx.x;
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
   int64_t r1 = r0 + rows_per_block;
@@ -100,8 +102,9 @@ __global__ void gate_bwd_kernel(const float* __restrict__ a, const float* __rest
     gc0 += da0;
     gc1 += da1;
     const float dg = da0 * w0 + da1 * w1;
-    const float dap = dg * bv * (1.f - av * av);
-    const float dbp = dg * av * bv * (1.f - bv);
+    const float a_pre = av * keep;  // tanh output where kept (0 where dropped: no gradient there)
+    const float dap = (keep < 1.f && av == 0.f) ? 0.f : dg * bv * (1.f - a_pre * a_pre) * inv_keep;
+    const float dbp = dg * av * bv * (1.f - bv * keep);
     dab[row * 2 * D + j] = dap;
     dab[row * 2 * D + D + j] = dbp;
     gba += dap;

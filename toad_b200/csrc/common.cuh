@@ -43,6 +43,27 @@ __device__ __forceinline__ float bf16hi_to_f32(uint32_t packed) { return __uint_
 __device__ __forceinline__ float sigmoid_acc(float z) { return 1.0f / (1.0f + expf(-z)); }
 __device__ __forceinline__ float tanh_acc(float z) { return tanhf(z); }
 
+// Counter-based dropout mask (training, nn.Dropout(0.25), reference models/model_toad.py:27-29,60-64):
+// keep element `idx` of activation `layer` iff splitmix64(seed, layer, idx) >> 32 >= thresh, thresh = p * 2^32.
+// Stateless, so forward and tests regenerate the same mask from (seed, layer, idx).
+struct DropoutCfg {
+  unsigned long long seed;
+  uint32_t thresh;  // 0 = dropout off
+  float scale;      // 1 / (1 - p)
+};
+__host__ __device__ __forceinline__ uint32_t dropout_hash(unsigned long long seed, uint32_t layer, unsigned long long idx) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (idx + 1ull) + static_cast<unsigned long long>(layer) * 0xD1B54A32D192ED03ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return static_cast<uint32_t>(z >> 32);
+}
+__device__ __forceinline__ float dropout_apply(const DropoutCfg& d, uint32_t layer, unsigned long long idx, float v) {
+  if (d.thresh == 0u) return v;
+  return dropout_hash(d.seed, layer, idx) >= d.thresh ? v * d.scale : 0.f;
+}
+enum { DROP_H1 = 1, DROP_H = 2, DROP_A = 3, DROP_B = 4 };
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

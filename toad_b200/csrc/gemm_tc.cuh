@@ -87,6 +87,10 @@ struct GemmTcParams {
   const __nv_bfloat16* res_hi;
   const __nv_bfloat16* res_lo;
   int64_t ld_res;
+  // training-mode dropout on the epilogue's activation: EPI_LINEAR uses drop_layer with element index
+  // row*N + col; EPI_GATE uses DROP_A / DROP_B with index row*D + gate column.
+  DropoutCfg drop;
+  uint32_t drop_layer;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -493,6 +497,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 const uint32_t wh = uh[e >> 1], wl = ul[e >> 1];
                 t += (e & 1) ? (bf16hi_to_f32(wh) + bf16hi_to_f32(wl)) : (bf16lo_to_f32(wh) + bf16lo_to_f32(wl));
                 if (p.relu) t = fmaxf(t, 0.0f);
+                if (p.drop.thresh != 0u)
+                  t = dropout_apply(p.drop, p.drop_layer, static_cast<unsigned long long>(row) * p.N + col0 + h * 32 + i, t);
                 r[h][i] = __float_as_uint(t);
               }
             }
@@ -547,8 +553,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           const bool save = row_ok && p.gate_a != nullptr;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float ga = fast_tanh(__uint_as_float(ra[i]) + s_gate[jc + i]);
-            const float gb = fast_sigmoid(__uint_as_float(rb[i]) + s_gate[1024 + jc + i]);
+            float ga = fast_tanh(__uint_as_float(ra[i]) + s_gate[jc + i]);
+            float gb = fast_sigmoid(__uint_as_float(rb[i]) + s_gate[1024 + jc + i]);
+            if (p.drop.thresh != 0u) {
+              const unsigned long long di = static_cast<unsigned long long>(row) * p.gate_D + jc + i;
+              ga = dropout_apply(p.drop, DROP_A, di, ga);
+              gb = dropout_apply(p.drop, DROP_B, di, gb);
+            }
             ra[i] = __float_as_uint(ga);
             rb[i] = __float_as_uint(gb);
             const float g = ga * gb;

@@ -34,6 +34,9 @@ struct SgemmParams {
   int64_t p_stride;
   const float* v0; const float* v1;  // [N]
   int32_t accumulate;   // EPI_RELUMASK/POOL: add existing c before masking
+  float out_scale;      // EPI_RELUMASK/POOL: multiply the masked result (1/(1-p) when the mask tensor is post-dropout); 0 -> 1
+  DropoutCfg drop;      // EPI_BIAS_RELU/TANH/SIGMOID: dropout on the activation (element index m*N + n)
+  uint32_t drop_layer;
 };
 
 constexpr int BM = 128, BN = 128, BK = 16, TM = 8, TN = 8, NTHREADS = 256;
@@ -130,12 +133,15 @@ __global__ void __launch_bounds__(NTHREADS) sgemm_kernel(const SgemmParams p) {
       if (EPI == EPI_BIAS_RELU) v = fmaxf(v + __ldg(p.bias + gn), 0.f);
       else if (EPI == EPI_BIAS_TANH) v = tanh_acc(v + __ldg(p.bias + gn));
       else if (EPI == EPI_BIAS_SIGMOID) v = sigmoid_acc(v + __ldg(p.bias + gn));
+      if (EPI == EPI_BIAS_RELU || EPI == EPI_BIAS_TANH || EPI == EPI_BIAS_SIGMOID)
+        v = dropout_apply(p.drop, p.drop_layer, static_cast<unsigned long long>(gm) * p.N + gn, v);
       else if (EPI == EPI_BIAS) v = v + (p.bias ? __ldg(p.bias + gn) : 0.f);
       else if (EPI == EPI_RELUMASK || EPI == EPI_POOL_RELUMASK) {
         if (p.accumulate) v += cbase[gm * p.ldc + gn];
         if (EPI == EPI_POOL_RELUMASK)
           v += __ldg(p.p0 + gm * p.p_stride) * __ldg(p.v0 + gn) + __ldg(p.p1 + gm * p.p_stride) * __ldg(p.v1 + gn);
         v = (__ldg(p.mask + gm * p.ldmask + gn) > 0.f) ? v : 0.f;
+        if (p.out_scale != 0.f) v *= p.out_scale;
       }
       cbase[gm * p.ldc + gn] = v;
     }

@@ -84,6 +84,17 @@ inline int prof_mark(Prof* p, int idx, cudaStream_t st) {
   return 0;
 }
 
+DropoutCfg make_drop(const toad_saved_t* sv, uint32_t flags) {
+  DropoutCfg d{};
+  if ((flags & TOAD_FLAG_DROPOUT) && sv != nullptr && sv->dropout_p > 0.f) {
+    d.seed = sv->dropout_seed;
+    const double t = static_cast<double>(sv->dropout_p) * 4294967296.0;
+    d.thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(t);
+    d.scale = 1.0f / (1.0f - sv->dropout_p);
+  }
+  return d;
+}
+
 int check_ws(const void* ws, size_t have, size_t need) {
   if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 255) != 0 || have < need) return TOAD_ERR_WORKSPACE;
   return 0;
@@ -115,6 +126,10 @@ simt::SgemmParams linear_params(const float* x, int64_t ldx, const float* w, con
 }  // namespace
 
 extern "C" int toad_abi_version(void) { return TOAD_ABI_VERSION; }
+
+extern "C" uint32_t toad_dropout_hash(uint64_t seed, uint32_t layer, uint64_t index) {
+  return dropout_hash(seed, layer, index);
+}
 
 extern "C" const char* toad_error_string(int code) {
   switch (code) {
@@ -156,6 +171,8 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
                      out->site_hat == nullptr || out->softmax_stats == nullptr))
     return TOAD_ERR_ARG;
   if (save && (saved == nullptr || !saved->h1 || !saved->h || !saved->a || !saved->b)) return TOAD_ERR_ARG;
+  if ((flags & TOAD_FLAG_DROPOUT) && (!save || saved->dropout_p < 0.f || saved->dropout_p >= 1.f)) return TOAD_ERR_ARG;
+  const DropoutCfg drop = make_drop(saved, flags);
   FwdWs w = carve_fwd(d, n, flags, workspace);
   TOAD_TRY(check_ws(workspace, workspace_bytes, w.bytes));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -169,12 +186,13 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
     float* b = save ? saved->b : w.b;
     TOAD_TRY(prof_mark(prof, 0, st));
     TOAD_TRY(prof_mark(prof, 1, st));
-    TOAD_TRY((simt::launch_sgemm<true, true, simt::EPI_BIAS_RELU>(linear_params(x, L, P->w1, P->b1, h1, n, Hd, L), 1, st)));
+    auto with_drop = [&](simt::SgemmParams s, uint32_t layer) { s.drop = drop; s.drop_layer = layer; return s; };
+    TOAD_TRY((simt::launch_sgemm<true, true, simt::EPI_BIAS_RELU>(with_drop(linear_params(x, L, P->w1, P->b1, h1, n, Hd, L), DROP_H1), 1, st)));
     TOAD_TRY(prof_mark(prof, 2, st));
-    TOAD_TRY((simt::launch_sgemm<true, true, simt::EPI_BIAS_RELU>(linear_params(h1, Hd, P->w2, P->b2, h, n, Hd, Hd), 1, st)));
+    TOAD_TRY((simt::launch_sgemm<true, true, simt::EPI_BIAS_RELU>(with_drop(linear_params(h1, Hd, P->w2, P->b2, h, n, Hd, Hd), DROP_H), 1, st)));
     TOAD_TRY(prof_mark(prof, 3, st));
-    TOAD_TRY((simt::launch_sgemm<true, true, simt::EPI_BIAS_TANH>(linear_params(h, Hd, P->wa, P->ba, a, n, D, Hd), 1, st)));
-    TOAD_TRY((simt::launch_sgemm<true, true, simt::EPI_BIAS_SIGMOID>(linear_params(h, Hd, P->wb, P->bb, b, n, D, Hd), 1, st)));
+    TOAD_TRY((simt::launch_sgemm<true, true, simt::EPI_BIAS_TANH>(with_drop(linear_params(h, Hd, P->wa, P->ba, a, n, D, Hd), DROP_A), 1, st)));
+    TOAD_TRY((simt::launch_sgemm<true, true, simt::EPI_BIAS_SIGMOID>(with_drop(linear_params(h, Hd, P->wb, P->bb, b, n, D, Hd), DROP_B), 1, st)));
     TOAD_TRY(tail::launch_attn_c(a, b, P->wc, w.part, n, D, d->n_tasks, st));
     TOAD_TRY(prof_mark(prof, 4, st));
     TOAD_TRY(run_tail(d, P, n, sex, out, w, h, nullptr, nullptr, attn_only, st));
@@ -193,6 +211,7 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
   {
     tc::GemmTcParams g{};
     g.a_f32 = x; g.lda = L; g.M = n; g.N = Hd; g.K = L; g.bias = P->b1; g.relu = 1;
+    g.drop = drop; g.drop_layer = DROP_H1;
     g.out_f32 = save ? saved->h1 : nullptr; g.ld_f32 = Hd;
     g.out_hi = w.h1_hi; g.out_lo = w.h1_lo; g.ld_split = Hd;
     if (cg1) TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_LINEAR, 1>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, st)));
@@ -202,6 +221,7 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
   {
     tc::GemmTcParams g{};
     g.M = n; g.N = Hd; g.K = Hd; g.bias = P->b2; g.relu = 1;
+    g.drop = drop; g.drop_layer = DROP_H;
     g.out_f32 = save ? saved->h : nullptr; g.ld_f32 = Hd;
     g.out_hi = w.h_hi; g.out_lo = w.h_lo; g.ld_split = Hd;
     if (cg1) TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 1>(g, w.h1_hi, w.h1_lo, w.w2_hi, w.w2_lo, st)));
@@ -213,6 +233,7 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
     g.M = n; g.N = 2 * D; g.K = Hd;
     g.gate_ba = P->ba; g.gate_bb = P->bb; g.gate_wc = P->wc; g.gate_D = D; g.gate_ntasks = d->n_tasks;
     g.gate_part = w.part; g.gate_a = save ? saved->a : nullptr; g.gate_b = save ? saved->b : nullptr;
+    g.drop = drop;
     if (cg1) TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_GATE, 1>(g, w.h_hi, w.h_lo, w.wab_hi, w.wab_lo, st)));
     else TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_GATE, 2>(g, w.h_hi, w.h_lo, w.wab_hi, w.wab_lo, st)));
   }
@@ -340,6 +361,9 @@ extern "C" int toad_bwd(const toad_dims_t* d, const toad_params_t* P, const floa
   TOAD_TRY(check_ws(workspace, workspace_bytes, w.bytes));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int Hd = d->hid_dim, D = d->attn_dim, L = d->in_dim;
+  if (sv->dropout_p < 0.f || sv->dropout_p >= 1.f) return TOAD_ERR_ARG;
+  const float keep = 1.0f - sv->dropout_p;  // saved activations are post-dropout: undo / re-apply the 1/keep scale
+  const float inv_keep = 1.0f / keep;
   int64_t off[15];
   toad_param_offsets(d, off);
   float *g_w1 = grad + off[0], *g_b1 = grad + off[1], *g_w2 = grad + off[2], *g_b2 = grad + off[3];
@@ -361,7 +385,7 @@ extern "C" int toad_bwd(const toad_dims_t* d, const toad_params_t* P, const floa
   // 3. gate backward -> dab, partials of dWc/dba/dbb/dbc
   {
     const int rpb = static_cast<int>((n + w.gate_blocks - 1) / w.gate_blocks);
-    bwd::gate_bwd_kernel<<<w.gate_blocks, D, 0, st>>>(sv->a, sv->b, w.dA, P->wc, w.dab, w.gate_part, n, D, rpb);
+    bwd::gate_bwd_kernel<<<w.gate_blocks, D, 0, st>>>(sv->a, sv->b, w.dA, P->wc, w.dab, w.gate_part, n, D, rpb, keep);
     TOAD_CUDA_TRY(cudaGetLastError());
     const int64_t stride = 4 * D + 2;
     TOAD_TRY(bwd::launch_reduce_strided(w.gate_part, g_wc, 2 * D, stride, w.gate_blocks, st));
@@ -388,7 +412,7 @@ extern "C" int toad_bwd(const toad_dims_t* d, const toad_params_t* P, const floa
     s.c = w.dz2; s.ldc = Hd; s.M = n; s.N = Hd; s.K = D; s.k_chunk = D;
     TOAD_TRY((simt::launch_sgemm<true, false, simt::EPI_STORE>(s, 1, st)));
     s.a = w.dab + D; s.b = P->wb;
-    s.accumulate = 1; s.mask = sv->h; s.ldmask = Hd;
+    s.accumulate = 1; s.mask = sv->h; s.ldmask = Hd; s.out_scale = inv_keep;
     s.p0 = w.P; s.p1 = w.P + 1; s.p_stride = 2; s.v0 = w.dM; s.v1 = w.dM + Hd;
     TOAD_TRY((simt::launch_sgemm<true, false, simt::EPI_POOL_RELUMASK>(s, 1, st)));
   }
@@ -411,7 +435,7 @@ extern "C" int toad_bwd(const toad_dims_t* d, const toad_params_t* P, const floa
     s.a = w.dz2; s.a_rs = Hd; s.a_ks = 1;
     s.b = P->w2; s.b_rs = 1; s.b_ks = Hd;
     s.c = w.dz1; s.ldc = Hd; s.M = n; s.N = Hd; s.K = Hd; s.k_chunk = Hd;
-    s.mask = sv->h1; s.ldmask = Hd;
+    s.mask = sv->h1; s.ldmask = Hd; s.out_scale = inv_keep;
     TOAD_TRY((simt::launch_sgemm<true, false, simt::EPI_RELUMASK>(s, 1, st)));
   }
   // 8. db1, dW1 = dz1^T . x

@@ -74,9 +74,15 @@ class _ToadFunction(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad[3:])
         flags = _default_flags()
         saved = None
-        if need_grad:
+        if need_grad or module._dropout_active():
             flags |= _lib.FLAG_SAVE_ACTS
             saved = ops.alloc_saved(dims, h.shape[0], h.device)
+            if module._dropout_active():
+                # nn.Dropout(0.25) x4 (model_toad.py:27-29,60-64): a fresh mask per forward, drawn from
+                # torch's CPU generator so torch.manual_seed() makes training runs repeatable.
+                flags |= _lib.FLAG_DROPOUT
+                saved["dropout_seed"] = int(torch.randint(0, 2 ** 62, (1,)).item())
+                saved["dropout_p"] = 0.25
         out = ops.toad_fwd(dims, params, h, sex, module._ws, flags, saved)
         ctx.module = module
         ctx.saved = saved
@@ -162,11 +168,11 @@ class TOAD_fc_mtl_concat(nn.Module):
         self.classifier = self.classifier.to(device)
         self.site_classifier = self.site_classifier.to(device)
 
+    def _dropout_active(self) -> bool:
+        return self.dropout and self.training
+
     def forward(self, h: torch.Tensor, sex: torch.Tensor, return_features: bool = False,
                 attention_only: bool = False):
-        if self.dropout and self.training:
-            raise NotImplementedError("toad_b200: Dropout(0.25) in training mode is not implemented yet; "
-                                      "use dropout=False (the reference default) or .eval()")
         params = self._param_list()
         if attention_only:
             out = ops.toad_fwd(self._dims, [p.detach() for p in params], h, sex, self._ws,
@@ -176,7 +182,7 @@ class TOAD_fc_mtl_concat(nn.Module):
             raise ValueError("sex must be a tensor")
         sex_f = sex.reshape(-1).to(device=h.device, dtype=torch.float32) if isinstance(h, torch.Tensor) and h.is_cuda else sex
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        if need_grad:
+        if need_grad or self._dropout_active():
             (logits, site_logits, y_prob, y_hat, site_prob, site_hat, a_raw, features) = _ToadFunction.apply(
                 self, h, sex_f, *params)
         else:

@@ -101,6 +101,8 @@ def _saved_struct(saved: Dict[str, torch.Tensor]) -> Saved:
     s = Saved()
     for k in ("h1", "h", "a", "b"):
         setattr(s, k, saved[k].data_ptr())
+    s.dropout_seed = int(saved.get("dropout_seed", 0))
+    s.dropout_p = float(saved.get("dropout_p", 0.0))
     return s
 
 
