@@ -57,7 +57,8 @@ enum {
 #define TOAD_FLAG_SIMT_FP32 2u      /* fp32 CUDA-core GEMMs instead of the tcgen05 split-bf16 path */
 #define TOAD_FLAG_SAVE_ACTS 4u      /* also store h1,h,a,b (fp32) for toad_bwd */
 #define TOAD_FLAG_DROPOUT 16u        /* training-mode nn.Dropout on h1, h, a, b (model_toad.py:27-29,60-64); needs `saved` */
-#define TOAD_FLAG_TC_SINGLE_CTA 8u  /* tcgen05 GEMMs with cta_group::1 (one CTA per 128-row tile) instead of CTA pairs */
+#define TOAD_FLAG_TC_SINGLE_CTA 8u  /* debug: every tcgen05 GEMM with cta_group::1 (one CTA per 128-row tile) */
+#define TOAD_FLAG_TC_PAIR_ALL 32u   /* debug: every tcgen05 GEMM as CTA pairs (cta_group::2), including the fp32-fed fc1 */
 
 /* Layer widths of TOAD_fc_mtl_concat (model_toad.py:56): "big" = {1024,512,384}, "small" = {1024,512,256}. */
 typedef struct {

@@ -51,7 +51,9 @@ def test_gradients_match_reference_autograd(name, simt):
         assert prm.grad is not None, k
         gk = to_np(prm.grad).astype(np.float64)
         ref = refs[k]
-        tol = 2e-3 * np.abs(ref).max() + floor
+        # fp32 path: 2e-3.  Tensor-core forward: its ~1e-5 activation differences flip a handful of ReLU
+        # masks (|z| < 1e-5), each moving a bias gradient by one |dz| ~ 1e-4 * max -> allow 1e-2 there.
+        tol = (2e-3 if simt else 1e-2) * np.abs(ref).max() + floor
         if ("g64_%s__full" % k) in g:
             assert np.abs(gk - ref).max() <= tol, (k, np.abs(gk - ref).max(), tol)
         else:

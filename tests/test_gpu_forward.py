@@ -90,6 +90,12 @@ def test_forward_single_cta_tensorcore_variant():
     check_against_golden(g, out, a_only, int(g["meta_n"]))
     _, out2, _ = run_case("toad_big_n10000", simt=False)
     np.testing.assert_allclose(to_np(out["A"]), to_np(out2["A"]), rtol=0, atol=2e-6)
+    os.environ["TOAD_B200_CG2"] = "1"
+    try:
+        _, out3, _ = run_case("toad_big_n10000", simt=False)
+    finally:
+        os.environ["TOAD_B200_CG2"] = "0"
+    np.testing.assert_allclose(to_np(out3["A"]), to_np(out2["A"]), rtol=0, atol=2e-6)
 
 
 def test_tensorcore_matches_split_oracle_tightly():

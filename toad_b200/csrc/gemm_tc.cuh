@@ -12,8 +12,8 @@
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16)
 //   warp 2      TMEM allocator
 //   warps 4-7   epilogue: tcgen05.ld accumulator -> registers -> bias/activation -> global
-//   warps 8-11  (A_MODE 0 only) A converter: fp32 rows from global -> (hi,lo) bf16 pairs
-//               written straight into the 128B-swizzled UMMA operand layout
+//   warps 8-15  (A_MODE 0 only) A converter: fp32 rows from global -> (hi,lo) bf16 pairs written
+//               straight into the 128B-swizzled UMMA operand layout, loads two K blocks ahead
 // Pipelines: smem ring (full/empty mbarriers) between producer/converter and MMA, and a
 // 2-deep TMEM accumulator ring (tmem_full/tmem_empty) between MMA and epilogue, so the
 // epilogue of tile i overlaps the main loop of tile i+1.
@@ -297,7 +297,7 @@ __device__ __forceinline__ float fast_tanh(float z) { return fmaf(2.0f, fast_sig
 constexpr int GATE_SMEM_FLOATS = 4 * 1024;  // ba | bb | wc rows (<= 2 tasks staged) for D <= 1024
 
 template <int BLOCK_N, int A_MODE, int EPI, int CG>
-__global__ void __launch_bounds__(A_MODE == A_F32 ? 384 : 256, 1)
+__global__ void __launch_bounds__(A_MODE == A_F32 ? 512 : 256, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
@@ -330,7 +330,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&bar_full_b[s]), CG);      // producer of each CTA of the pair
-      mbar_init(smem_u32(&bar_full_a[s]), 4 * CG);  // one arrive per converter warp (both CTAs)
+      mbar_init(smem_u32(&bar_full_a[s]), 8 * CG);  // one arrive per converter warp (8 per CTA)
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -473,56 +473,51 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         const int r_local = ew * 32 + lane;
 #pragma unroll 1
         for (int cc = 0; cc < BLOCK_N / 64; ++cc) {
-          uint32_t r[2][32];
-          tmem_ld32(t_row + cc * 64, r[0]);
-          tmem_ld32(t_row + cc * 64 + 32, r[1]);
-          tmem_ld_wait();
-          const int col0 = n0 + cc * 64;
-          const bool has_res = A_MODE != A_F32 && p.res_hi != nullptr && row_ok;  // residual only on plane-fed GEMMs
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          if (p.out_hi != nullptr) {
+            // staging buffer free again? (the previous TMA store must have finished READING it)
+            if (warp == 4 && lane == 0) tma_store_wait_read();
+            epi_barrier();
+          }
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {  // two 32-column halves of the 64-column chunk
+            uint32_t r[32];
+            tmem_ld32(t_row + cc * 64 + h * 32, r);
+            tmem_ld_wait();
+            const int col0 = n0 + cc * 64 + h * 32;
+            const bool has_res = A_MODE != A_F32 && p.res_hi != nullptr && row_ok;  // residual only on plane-fed GEMMs
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = make_uint4(0u, 0u, 0u, 0u);
               if (has_res) {
-                vh = *reinterpret_cast<const uint4*>(p.res_hi + row * p.ld_res + col0 + h * 32 + q * 8);
-                vl = *reinterpret_cast<const uint4*>(p.res_lo + row * p.ld_res + col0 + h * 32 + q * 8);
+                vh = *reinterpret_cast<const uint4*>(p.res_hi + row * p.ld_res + col0 + q * 8);
+                vl = *reinterpret_cast<const uint4*>(p.res_lo + row * p.ld_res + col0 + q * 8);
               }
               const uint32_t uh[4] = {vh.x, vh.y, vh.z, vh.w}, ul[4] = {vl.x, vl.y, vl.z, vl.w};
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 const int i = q * 8 + e;
-                float t = __uint_as_float(r[h][i]);
-                if (p.bias != nullptr) t += __ldg(p.bias + col0 + h * 32 + i);
+                float t = __uint_as_float(r[i]);
+                if (p.bias != nullptr) t += __ldg(p.bias + col0 + i);
                 const uint32_t wh = uh[e >> 1], wl = ul[e >> 1];
                 t += (e & 1) ? (bf16hi_to_f32(wh) + bf16hi_to_f32(wl)) : (bf16lo_to_f32(wh) + bf16lo_to_f32(wl));
                 if (p.relu) t = fmaxf(t, 0.0f);
                 if (p.drop.thresh != 0u)
-                  t = dropout_apply(p.drop, p.drop_layer, static_cast<unsigned long long>(row) * p.N + col0 + h * 32 + i, t);
-                r[h][i] = __float_as_uint(t);
+                  t = dropout_apply(p.drop, p.drop_layer, static_cast<unsigned long long>(row) * p.N + col0 + i, t);
+                r[i] = __float_as_uint(t);
               }
             }
-          }
-          if (row_ok && p.out_f32 != nullptr) {
-            uint4* dst = reinterpret_cast<uint4*>(p.out_f32 + row * p.ld_f32 + col0);
+            if (row_ok && p.out_f32 != nullptr) {
+              uint4* dst = reinterpret_cast<uint4*>(p.out_f32 + row * p.ld_f32 + col0);
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                dst[h * 8 + i] = make_uint4(r[h][4 * i], r[h][4 * i + 1], r[h][4 * i + 2], r[h][4 * i + 3]);
-          }
-          if (p.out_hi != nullptr) {
-            // staging buffer free again? (the previous TMA store must have finished READING it)
-            if (warp == 4 && lane == 0) tma_store_wait_read();
-            epi_barrier();
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
+              for (int i = 0; i < 8; ++i) dst[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+            }
+            if (p.out_hi != nullptr) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {  // 8 columns -> one 16 B chunk per plane
                 uint32_t hi[4], lo[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
-                  split2(__uint_as_float(r[h][8 * q + 2 * e]), __uint_as_float(r[h][8 * q + 2 * e + 1]), hi[e], lo[e]);
+                  split2(__uint_as_float(r[8 * q + 2 * e]), __uint_as_float(r[8 * q + 2 * e + 1]), hi[e], lo[e]);
                 const uint32_t off = r_local * 128 + ((((h * 4 + q)) ^ (r_local & 7)) << 4);
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_hi + off), "r"(hi[0]), "r"(hi[1]),
                              "r"(hi[2]), "r"(hi[3]) : "memory");
@@ -530,11 +525,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                              "r"(lo[2]), "r"(lo[3]) : "memory");
               }
             }
+          }
+          if (p.out_hi != nullptr) {
             fence_proxy_async_smem();
             epi_barrier();
             if (warp == 4 && lane == 0) {
-              tma_store_2d(&tm_o_hi, stage_hi, col0, m0);
-              tma_store_2d(&tm_o_lo, stage_lo, col0, m0);
+              tma_store_2d(&tm_o_hi, stage_hi, n0 + cc * 64, m0);
+              tma_store_2d(&tm_o_lo, stage_lo, n0 + cc * 64, m0);
               tma_store_commit();
             }
           }
@@ -595,35 +592,34 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       }
     }
   } else if (A_MODE == A_F32 && warp >= 8) {
-    // ------------------------------------------------------------------ A converter
-    // Each half-warp streams one 256 B row segment (64 fp32) per load instruction; a thread
-    // turns its 4 floats into 4 (hi) + 4 (lo) bf16 = one 8 B store into each swizzled tile.
-    const int cw = warp - 8;
+    // ------------------------------------------------------------------ A converter (8 warps)
+    // Each half-warp streams one 256 B row segment (64 fp32) per load instruction; a thread turns its
+    // 4 floats into 4 (hi) + 4 (lo) bf16 = one 8 B store into each swizzled tile.  Global loads run
+    // TWO K blocks ahead of the conversion (3 rotating register buffers) to cover HBM latency.
+    const int cw = warp - 8;  // 0..7: rows cw*16 .. cw*16+15 of the tile
     const int hw = lane >> 4, l16 = lane & 15;
     const int my_tiles = unit0 < num_tiles ? (num_tiles - unit0 + unit_stride - 1) / unit_stride : 0;
     const int64_t total = static_cast<int64_t>(my_tiles) * num_kb;
-    float4 cur[16], nxt[16];
-    auto issue = [&](int64_t g, float4(&buf)[16]) {
+    float4 buf0[8], buf1[8], buf2[8];
+    auto issue = [&](int64_t g, float4(&buf)[8]) {
       const int tile = unit0 + static_cast<int>(g / num_kb) * unit_stride;
       const int kb = static_cast<int>(g % num_kb);
       const int64_t m0 = static_cast<int64_t>(tile / n_tiles) * (BLOCK_M * CG) + cta_rank * BLOCK_M;
       const float* base = p.a_f32 + kb * BLOCK_K + l16 * 4;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int64_t row = m0 + cw * 32 + j * 2 + hw;
+      for (int j = 0; j < 8; ++j) {
+        const int64_t row = m0 + cw * 16 + j * 2 + hw;
         buf[j] = row < p.M ? ld_stream_f4(base + row * p.lda) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    if (total > 0) issue(0, cur);
     int stage = 0;
     uint32_t phase = 0;
-    for (int64_t g = 0; g < total; ++g) {
-      if (g + 1 < total) issue(g + 1, nxt);
+    auto convert = [&](float4(&cur)[8]) {
       mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
       const uint32_t sa = tiles_base + stage * C::STAGE_BYTES;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int r = cw * 32 + j * 2 + hw;
+      for (int j = 0; j < 8; ++j) {
+        const int r = cw * 16 + j * 2 + hw;
         uint32_t h0, l0, h1, l1;
         split2(cur[j].x, cur[j].y, h0, l0);
         split2(cur[j].z, cur[j].w, h1, l1);
@@ -638,8 +634,18 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         else mbar_arrive_cluster(smem_u32(&bar_full_a[stage]), 0);
       }
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
+    };
+    if (total > 0) issue(0, buf0);
+    if (total > 1) issue(1, buf1);
+    for (int64_t g = 0; g < total; g += 3) {
+      if (g + 2 < total) issue(g + 2, buf2);
+      convert(buf0);
+      if (g + 1 >= total) break;
+      if (g + 3 < total) issue(g + 3, buf0);
+      convert(buf1);
+      if (g + 2 >= total) break;
+      if (g + 4 < total) issue(g + 4, buf1);
+      convert(buf2);
     }
   }
 
@@ -742,7 +748,7 @@ int launch_gemm_maps(const GemmTcParams& p, const CUtensorMap& ta_hi, const CUte
   const int grid = static_cast<int>(units < max_units ? units : max_units) * CG;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
-  cfg.blockDim = dim3(A_MODE == A_F32 ? 384 : 256);
+  cfg.blockDim = dim3(A_MODE == A_F32 ? 512 : 256);
   cfg.dynamicSmemBytes = kSmem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

@@ -193,23 +193,49 @@ __global__ void __launch_bounds__(THREADS) pool_heads_kernel(const TailParams p)
     p.stats[2 * tid + 1] = l;
   }
   __syncthreads();
-  float* s_feat = dsm;  // [T][H+1]
+  // weighted sum of the per-CTA accumulators: 2 thread groups x 256 float4 columns, 8 independent
+  // 16 B L2 loads in flight per thread, partial sums combined in fixed order through smem.
+  float* s_feat = dsm;                 // [T][H+1]
+  float4* s_half = reinterpret_cast<float4*>(dsm + 2048);  // [2][256] float4 scratch (dsm is 64 KB)
   const float sexv = __ldg(p.sex);
-  for (int c = tid; c < T * H; c += THREADS) {
-    const int t = c / H, j = c % H;
-    float s = 0.f;
-    int b = 0;
-    for (; b + 8 <= nb; b += 8) {  // 8 independent L2 loads in flight, summed in fixed order
-      float v8[8];
+  {
+    const int c4 = tid & 255, bg = tid >> 8;
+    const int t = c4 >> 7;  // 128 float4 per task
+    const int bper = (nb + 1) / 2;
+    const int b0 = bg * bper, b1 = (b0 + bper) < nb ? (b0 + bper) : nb;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int b = b0;
+    for (; b + 8 <= b1; b += 8) {
+      float4 v8[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v8[u] = __ldcg(p.blk_part + static_cast<int64_t>(b + u) * PART_STRIDE + c);
+      for (int u = 0; u < 8; ++u)
+        v8[u] = __ldcg(reinterpret_cast<const float4*>(p.blk_part + static_cast<int64_t>(b + u) * PART_STRIDE) + c4);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) s = fmaf(s_scale[(b + u) * T + t], v8[u], s);
+      for (int u = 0; u < 8; ++u) {
+        const float sc = s_scale[(b + u) * T + t];
+        acc.x = fmaf(sc, v8[u].x, acc.x); acc.y = fmaf(sc, v8[u].y, acc.y);
+        acc.z = fmaf(sc, v8[u].z, acc.z); acc.w = fmaf(sc, v8[u].w, acc.w);
+      }
     }
-    for (; b < nb; ++b) s = fmaf(s_scale[b * T + t], __ldcg(p.blk_part + static_cast<int64_t>(b) * PART_STRIDE + c), s);
-    const float v = s / s_l[t];
-    s_feat[t * (H + 1) + j] = v;
-    p.features[t * (H + 1) + j] = v;
+    for (; b < b1; ++b) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(p.blk_part + static_cast<int64_t>(b) * PART_STRIDE) + c4);
+      const float sc = s_scale[b * T + t];
+      acc.x = fmaf(sc, v.x, acc.x); acc.y = fmaf(sc, v.y, acc.y);
+      acc.z = fmaf(sc, v.z, acc.z); acc.w = fmaf(sc, v.w, acc.w);
+    }
+    s_half[bg * 256 + c4] = acc;
+  }
+  __syncthreads();
+  if (tid < 256) {
+    const float4 a0 = s_half[tid], a1 = s_half[256 + tid];
+    const int t = tid >> 7, j = (tid & 127) * 4;
+    const float inv = 1.0f / s_l[t];
+    const float v[4] = {(a0.x + a1.x) * inv, (a0.y + a1.y) * inv, (a0.z + a1.z) * inv, (a0.w + a1.w) * inv};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      s_feat[t * (H + 1) + j + e] = v[e];
+      p.features[t * (H + 1) + j + e] = v[e];
+    }
   }
   if (tid < T) {
     s_feat[tid * (H + 1) + H] = sexv;

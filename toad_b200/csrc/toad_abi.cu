@@ -202,7 +202,11 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
   }
 
   // ---- tensor-core path: split weights, three tcgen05 GEMMs with fused epilogues, tail
+  // CTA-pair (cta_group::2) vs single-CTA tiles.  Default: measured best per kernel -- the fp32-fed fc1
+  // runs single-CTA (its converter warps are the limiter, pairing only adds remote-arrive latency), the
+  // TMA-fed fc2 / gate GEMMs run as CTA pairs.  The two debug flags force one shape everywhere.
   const bool cg1 = (flags & TOAD_FLAG_TC_SINGLE_CTA) != 0;
+  const bool fc1_pair = (flags & TOAD_FLAG_TC_PAIR_ALL) != 0;
   TOAD_TRY(prof_mark(prof, 0, st));
   TOAD_TRY(tail::launch_split_planes(P->w1, w.w1_hi, w.w1_lo, static_cast<int64_t>(Hd) * L, st));
   TOAD_TRY(tail::launch_split_planes(P->w2, w.w2_hi, w.w2_lo, static_cast<int64_t>(Hd) * Hd, st));
@@ -214,7 +218,7 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
     g.drop = drop; g.drop_layer = DROP_H1;
     g.out_f32 = save ? saved->h1 : nullptr; g.ld_f32 = Hd;
     g.out_hi = w.h1_hi; g.out_lo = w.h1_lo; g.ld_split = Hd;
-    if (cg1) TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_LINEAR, 1>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, st)));
+    if (!fc1_pair) TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_LINEAR, 1>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, st)));
     else TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_LINEAR, 2>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, st)));
   }
   TOAD_TRY(prof_mark(prof, 2, st));

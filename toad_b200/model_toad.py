@@ -30,6 +30,8 @@ def _default_flags() -> int:
     flags = _lib.FLAG_SIMT_FP32 if os.environ.get("TOAD_B200_SIMT", "0") == "1" else 0
     if os.environ.get("TOAD_B200_CG1", "0") == "1":   # debug aid: cta_group::1 tensor-core kernels
         flags |= _lib.FLAG_TC_SINGLE_CTA
+    if os.environ.get("TOAD_B200_CG2", "0") == "1":   # debug aid: CTA pairs everywhere
+        flags |= _lib.FLAG_TC_PAIR_ALL
     return flags
 
 

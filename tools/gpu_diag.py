@@ -109,11 +109,11 @@ def timing(step):
     for n in (10000, 50000):
         x = torch.randn(n, 1024, device="cuda")
         sd = torch.tensor([1.0], device="cuda")
-        for mode in ("tc", "tc_cg1", "simt"):
+        for mode in ("tc", "tc_cg1", "tc_cg2", "simt"):
             simt = mode == "simt"
             prof = ops.Profile(16)
             plist = [p.detach() for p in model._param_list()]
-            flags = _lib.FLAG_SIMT_FP32 if simt else (_lib.FLAG_TC_SINGLE_CTA if mode == "tc_cg1" else 0)
+            flags = _lib.FLAG_SIMT_FP32 if simt else {"tc_cg1": _lib.FLAG_TC_SINGLE_CTA, "tc_cg2": _lib.FLAG_TC_PAIR_ALL}.get(mode, 0)
             for _ in range(3):
                 ops.toad_fwd(model._dims, plist, x, sd, model._ws, flags)
             torch.cuda.synchronize()
