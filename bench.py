@@ -241,6 +241,8 @@ def run_ours(args):
                          "forward_hbm_gbs": BYTES_PER_PATCH * n / (whole_ms * 1e-3) / 1e9 if whole_ms > 0 else None,
                          "hbm_peak_gbs": pk["hbm_gbs"]},
         }
+        if world == 1 and not args.no_resnet:
+            line["resnet50_baseline"] = resnet_leg(dev)
         if world == 1 and not args.no_cpu_baseline:
             rate, done, cores, total = cpu_reference_rate(n, 40, 1, budget_s=15.0)
             line["cpu_baseline"] = {"value": rate, "unit": "slides/s", "cores": cores, "kind": "port",
@@ -252,6 +254,35 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def resnet_leg(dev):
+    """Secondary number (config 3): resnet50_baseline feature extraction, synthetic 3x256x256 patches."""
+    import torch
+    from models.resnet_custom import resnet50_baseline
+    torch.manual_seed(1)
+    model = resnet50_baseline(pretrained=False).to(dev).eval()
+    B = 256
+    x = torch.randn(B, 3, 256, 256, device=dev)
+    with torch.no_grad():
+        for _ in range(2):
+            model(x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        reps = 4
+        for _ in range(reps):
+            model(x)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    pps = B / ms * 1e3
+    tf = 8.562671616e9 * pps / 1e12
+    pk = peaks()
+    return {"patches_per_s": pps, "batch": B, "ms_per_batch": ms, "algorithmic_tflops": tf,
+            "executed_tflops": 3 * tf, "executed_frac_of_bf16_peak": 3 * tf / pk["bf16_tflops"],
+            "note": "BN-folded implicit-GEMM convs on the split-bf16 tcgen05 kernel (3 tensor passes per FLOP), "
+                    "8.563 GFLOP/patch (SURVEY.md R3); kaiming-init weights, eval mode"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -261,6 +292,7 @@ def main():
     ap.add_argument("--n-patches", type=int, default=N_PATCHES)
     ap.add_argument("--slides-per-step", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-resnet", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

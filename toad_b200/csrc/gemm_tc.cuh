@@ -501,10 +501,14 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 const uint32_t wh = uh[e >> 1], wl = ul[e >> 1];
                 t += (e & 1) ? (bf16hi_to_f32(wh) + bf16hi_to_f32(wl)) : (bf16lo_to_f32(wh) + bf16lo_to_f32(wl));
                 if (p.relu) t = fmaxf(t, 0.0f);
-                if (p.drop.thresh != 0u)
-                  t = dropout_apply(p.drop, p.drop_layer, static_cast<unsigned long long>(row) * p.N + col0 + i, t);
                 r[i] = __float_as_uint(t);
               }
+            }
+            if (p.drop.thresh != 0u) {  // training only: one big uniform branch, never predicated into the hot path
+              const unsigned long long e0 = static_cast<unsigned long long>(row) * p.N + col0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                r[i] = __float_as_uint(dropout_apply(p.drop, p.drop_layer, e0 + i, __uint_as_float(r[i])));
             }
             if (row_ok && p.out_f32 != nullptr) {
               uint4* dst = reinterpret_cast<uint4*>(p.out_f32 + row * p.ld_f32 + col0);
@@ -550,16 +554,20 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           const bool save = row_ok && p.gate_a != nullptr;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            float ga = fast_tanh(__uint_as_float(ra[i]) + s_gate[jc + i]);
-            float gb = fast_sigmoid(__uint_as_float(rb[i]) + s_gate[1024 + jc + i]);
-            if (p.drop.thresh != 0u) {
-              const unsigned long long di = static_cast<unsigned long long>(row) * p.gate_D + jc + i;
-              ga = dropout_apply(p.drop, DROP_A, di, ga);
-              gb = dropout_apply(p.drop, DROP_B, di, gb);
+            ra[i] = __float_as_uint(fast_tanh(__uint_as_float(ra[i]) + s_gate[jc + i]));
+            rb[i] = __float_as_uint(fast_sigmoid(__uint_as_float(rb[i]) + s_gate[1024 + jc + i]));
+          }
+          if (p.drop.thresh != 0u) {  // training only: one big uniform branch (see EPI_LINEAR)
+            const unsigned long long e0 = static_cast<unsigned long long>(row) * p.gate_D + jc;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              ra[i] = __float_as_uint(dropout_apply(p.drop, DROP_A, e0 + i, __uint_as_float(ra[i])));
+              rb[i] = __float_as_uint(dropout_apply(p.drop, DROP_B, e0 + i, __uint_as_float(rb[i])));
             }
-            ra[i] = __float_as_uint(ga);
-            rb[i] = __float_as_uint(gb);
-            const float g = ga * gb;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float g = __uint_as_float(ra[i]) * __uint_as_float(rb[i]);
             s[0] = fmaf(g, s_gate[2048 + jc + i], s[0]);
             s[1] = fmaf(g, s_gate[3072 + jc + i], s[1]);
             if (p.gate_ntasks > 2) {  // rare: extra tasks read their score rows from global
