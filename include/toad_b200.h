@@ -58,6 +58,7 @@ enum {
 #define TOAD_FLAG_SAVE_ACTS 4u      /* also store h1,h,a,b (fp32) for toad_bwd */
 #define TOAD_FLAG_DROPOUT 16u        /* training-mode nn.Dropout on h1, h, a, b (model_toad.py:27-29,60-64); needs `saved` */
 #define TOAD_FLAG_TC_SINGLE_CTA 8u  /* debug: every tcgen05 GEMM with cta_group::1 (one CTA per 128-row tile) */
+#define TOAD_FLAG_FC2_WIDE 64u      /* debug: fc2 on 256 x 512 pair tiles like fc1 */
 #define TOAD_FLAG_TC_PAIR_ALL 32u   /* debug: every tcgen05 GEMM as CTA pairs (cta_group::2), including the fp32-fed fc1 */
 
 /* Layer widths of TOAD_fc_mtl_concat (model_toad.py:56): "big" = {1024,512,384}, "small" = {1024,512,256}. */
@@ -171,7 +172,7 @@ int toad_topk(const float* scores, int64_t n, int32_t k, float* out_vals, int64_
 /* y[M, N] = act(x[M, K] . w[N, K]^T + bias[N]) on the tcgen05 3-pass split-bf16 path.
  * relu != 0 applies ReLU; bias may be NULL.  K % 64 == 0, N % 64 == 0.
  * variant: bit 0 = feed x as pre-split (hi,lo) bf16 planes through TMA instead of converting
- * fp32 rows in the kernel; bit 1 = CTA pairs (cta_group::2, 256-row tiles); bits 4-5 = force the N tile (1: 64, 2: 128, 3: 256; 0: largest that
+ * fp32 rows in the kernel; bit 1 = CTA pairs (cta_group::2, 256-row tiles); bit 6 = 512-wide tiles (with bit 1); bits 4-5 = force the N tile (1: 64, 2: 128, 3: 256; 0: largest that
  * divides N).  Both paths give the same result; the knob exists so tests cover every tile shape. */
 int toad_linear_workspace_bytes(int64_t m, int32_t n, int32_t k, size_t* bytes);
 int toad_linear_bf16x3(const float* x, const float* w, const float* bias, float* y, int64_t m, int32_t n,

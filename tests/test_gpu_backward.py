@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import toad_oracle as O
-from tests.helpers import build_model, case_inputs, load_golden, to_np
+from tests.helpers import build_model, case_inputs, grads_close, load_golden, to_np
 
 pytestmark = pytest.mark.gpu
 
@@ -51,19 +51,16 @@ def test_gradients_match_reference_autograd(name, simt):
         assert prm.grad is not None, k
         gk = to_np(prm.grad).astype(np.float64)
         ref = refs[k]
-        # fp32 path: 2e-3.  Tensor-core forward: its ~1e-5 activation differences flip a handful of ReLU
-        # masks (|z| < 1e-5), each moving a bias gradient by one |dz| ~ 1e-4 * max -> allow 1e-2 there.
-        tol = (2e-3 if simt else 1e-2) * np.abs(ref).max() + floor
-        if ("g64_%s__full" % k) in g:
-            assert np.abs(gk - ref).max() <= tol, (k, np.abs(gk - ref).max(), tol)
-        else:
-            assert np.abs(gk[::37, ::41] - ref).max() <= tol, (k, np.abs(gk[::37, ::41] - ref).max(), tol)
-            # Row/column sums add ~1000 entries coherently, so the few ReLU-mask flips caused by the
-            # forward's ~1e-5 activation differences (a whole x row enters or leaves a dW row) show up
-            # here at the 1e-2 level while every entry stays within tolerance; a wrong kernel gives O(1).
+        sub = gk if ("g64_%s__full" % k) in g else gk[::37, ::41]
+        ok, err, tol = grads_close(sub, ref, 2e-3, floor, robust=not simt)
+        assert ok, (k, err, tol)
+        if ("g64_%s__full" % k) not in g:
+            # Row/column sums add ~1000 entries coherently, so a ReLU-mask flip (see grads_close) shows up at
+            # the 1e-2 level on the tensor-core path; a wrong kernel gives O(1).
             rs, cs = g["g64_%s__rowsum" % k], g["g64_%s__colsum" % k]
-            assert np.abs(gk.sum(1) - rs).max() <= 2e-2 * np.abs(rs).max() + floor * gk.shape[1], k
-            assert np.abs(gk.sum(0) - cs).max() <= 2e-2 * np.abs(cs).max() + floor * gk.shape[0], k
+            rel = 2e-3 if simt else 5e-2
+            assert np.abs(gk.sum(1) - rs).max() <= rel * np.abs(rs).max() + floor * gk.shape[1], k
+            assert np.abs(gk.sum(0) - cs).max() <= rel * np.abs(cs).max() + floor * gk.shape[0], k
 
 
 def test_optimizer_step_runs_like_the_reference_loop():

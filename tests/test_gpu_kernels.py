@@ -40,6 +40,9 @@ def _linear_case(m, n, k, relu, variant, seed=0):
     (256, 64, 64, 0x12), (256, 64, 64, 0x13), (256, 128, 128, 0x22), (256, 256, 256, 0x33),
     (1, 256, 64, 0x32), (129, 256, 192, 0x33), (300, 512, 512, 0x32), (1000, 768, 512, 0x33),
     (40000, 512, 1024, 0x02), (50000, 512, 512, 0x03),
+    # 512-wide pair tiles (two UMMA halves share one staged A tile; single TMEM accumulator)
+    (256, 512, 64, 0x42), (300, 512, 128, 0x43), (1, 512, 64, 0x42), (1000, 1024, 256, 0x43),
+    (50000, 512, 1024, 0x42), (40000, 512, 512, 0x43),
 ])
 def test_linear_bf16x3(m, n, k, variant):
     y, exp_split, exp_true = _linear_case(m, n, k, relu=(m % 2 == 0), variant=variant)

@@ -37,13 +37,21 @@ enum { A_F32 = 0, A_SPLIT = 1, A_CONV = 2 };  // A_CONV: implicit-GEMM convoluti
 // Halves the per-SM weight traffic (L2->smem and smem->tensor core) and frees room for a 3rd stage.
 template <int BLOCK_N, int CG = 1>
 struct Cfg {
-  static_assert(BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
+  static_assert(BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256 || BLOCK_N == 512, "BLOCK_N");
   static_assert(CG == 1 || CG == 2, "CG");
-  static constexpr int B_ROWS = BLOCK_N / CG;  // B rows staged by one CTA
+  static_assert(BLOCK_N < 512 || CG == 2, "512-wide tiles are CTA-pair only");
+  // BLOCK_N = 512 ("wide"): two UMMA N=256 halves per K step sharing ONE staged A tile, so a row tile's A
+  // operand is loaded / converted once for all 512 output columns.  The accumulator then fills TMEM
+  // (512 columns): a single accumulator buffer, the epilogue no longer overlaps the next main loop.
+  static constexpr int N_SUB = BLOCK_N == 512 ? 2 : 1;
+  static constexpr int UMMA_N = BLOCK_N / N_SUB;
+  static constexpr int ACC_STAGES = BLOCK_N == 512 ? 1 : 2;
+  static constexpr int B_ROWS = BLOCK_N / CG;        // B rows staged by one CTA (N_SUB sub-tiles of B_SUB_ROWS)
+  static constexpr int B_SUB_ROWS = UMMA_N / CG;     // rows of one sub-tile staged by one CTA
   static constexpr int B_TILE_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 6 ? 6 : (192 * 1024) / STAGE_BYTES;
-  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator buffers (128/256/512: powers of 2)
+  static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // accumulator ring (128/256/512: powers of 2)
   static constexpr int OUT_STAGE_BYTES = 2 * BLOCK_M * 128;  // (hi, lo) 128 x 64 bf16 staging tiles for the TMA store
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + slack for 1024 B alignment
   static constexpr int SMEM_BYTES_LINEAR = SMEM_BYTES + OUT_STAGE_BYTES;
@@ -303,6 +311,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                    const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
                    const GemmTcParams p) {
   using C = Cfg<BLOCK_N, CG>;
+  static_assert(EPI != EPI_GATE || BLOCK_N <= 256, "the gate epilogue pairs two 128-column halves of a 256-wide tile");
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full_b[STAGES];
@@ -368,7 +377,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
-      const int n0 = (tile % n_tiles) * BLOCK_N + static_cast<int>(cta_rank) * C::B_ROWS;
+      const int n0 = (tile % n_tiles) * BLOCK_N + static_cast<int>(cta_rank) * C::B_SUB_ROWS;
       const int m0 = (tile / n_tiles) * (BLOCK_M * CG) + static_cast<int>(cta_rank) * BLOCK_M;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
@@ -398,8 +407,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             tma_load_4d<CG>(sa, &tm_a_hi, fb, cc * BLOCK_K, cw, ch, b0);
             tma_load_4d<CG>(sa + A_TILE_BYTES, &tm_a_lo, fb, cc * BLOCK_K, cw, ch, b0);
           }
-          tma_load_2d<CG>(sa + 2 * A_TILE_BYTES, &tm_b_hi, fb, kb * BLOCK_K, n0);
-          tma_load_2d<CG>(sa + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &tm_b_lo, fb, kb * BLOCK_K, n0);
+#pragma unroll
+          for (int hs = 0; hs < C::N_SUB; ++hs) {  // sub-tile hs = rows [n0 + hs*UMMA_N, +B_SUB_ROWS) of this CTA's share
+            const uint32_t so = hs * (C::B_SUB_ROWS * 128);
+            tma_load_2d<CG>(sa + 2 * A_TILE_BYTES + so, &tm_b_hi, fb, kb * BLOCK_K, n0 + hs * C::UMMA_N);
+            tma_load_2d<CG>(sa + 2 * A_TILE_BYTES + C::B_TILE_BYTES + so, &tm_b_lo, fb, kb * BLOCK_K, n0 + hs * C::UMMA_N);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -408,15 +421,15 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (is_leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M * CG, BLOCK_N);
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M * CG, C::UMMA_N);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
-        const int acc = it & 1;
-        mbar_wait(smem_u32(&bar_tmem_empty[acc]), ((it >> 1) & 1) ^ 1);
+        const int acc = it % C::ACC_STAGES;
+        mbar_wait(smem_u32(&bar_tmem_empty[acc]), ((it / C::ACC_STAGES) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        const uint32_t d_tmem0 = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(smem_u32(&bar_full_b[stage]), phase);
           if (A_MODE == A_F32) mbar_wait(smem_u32(&bar_full_a[stage]), phase);
@@ -425,22 +438,27 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             const uint32_t sa = tiles_base + stage * C::STAGE_BYTES;
             const uint64_t a_hi = make_kmajor_sw128_desc(sa);
             const uint64_t a_lo = make_kmajor_sw128_desc(sa + A_TILE_BYTES);
-            const uint64_t b_hi = make_kmajor_sw128_desc(sa + 2 * A_TILE_BYTES);
-            const uint64_t b_lo = make_kmajor_sw128_desc(sa + 2 * A_TILE_BYTES + C::B_TILE_BYTES);
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);  // +32 B per K step
-              umma_bf16<CG>(d_tmem, a_hi + koff, b_hi + koff, idesc, (kb | k) != 0);
-            }
+            for (int hs = 0; hs < C::N_SUB; ++hs) {
+              const uint32_t so = hs * (C::B_SUB_ROWS * 128);
+              const uint64_t b_hi = make_kmajor_sw128_desc(sa + 2 * A_TILE_BYTES + so);
+              const uint64_t b_lo = make_kmajor_sw128_desc(sa + 2 * A_TILE_BYTES + C::B_TILE_BYTES + so);
+              const uint32_t d_tmem = d_tmem0 + hs * C::UMMA_N;
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);
-              umma_bf16<CG>(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
-            }
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);  // +32 B per K step
+                umma_bf16<CG>(d_tmem, a_hi + koff, b_hi + koff, idesc, (kb | k) != 0);
+              }
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);
-              umma_bf16<CG>(d_tmem, a_lo + koff, b_hi + koff, idesc, 1);
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);
+                umma_bf16<CG>(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
+              }
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);
+                umma_bf16<CG>(d_tmem, a_lo + koff, b_hi + koff, idesc, 1);
+              }
             }
             umma_commit<CG>(smem_u32(&bar_empty[stage]));  // smem slot free (in both CTAs) once these MMAs retire
             if (kb == num_kb - 1) umma_commit<CG>(smem_u32(&bar_tmem_full[acc]));  // accumulator ready
@@ -458,8 +476,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       const int n_tile = tile % n_tiles;
       const int n0 = n_tile * BLOCK_N;
       const int m0 = (tile / n_tiles) * (BLOCK_M * CG) + static_cast<int>(cta_rank) * BLOCK_M;
-      const int acc = it & 1;
-      mbar_wait(smem_u32(&bar_tmem_full[acc]), (it >> 1) & 1);
+      const int acc = it % C::ACC_STAGES;
+      mbar_wait(smem_u32(&bar_tmem_full[acc]), (it / C::ACC_STAGES) & 1);
       tc_fence_after();
       const int64_t row = static_cast<int64_t>(m0) + ew * 32 + lane;
       const bool row_ok = row < p.M;
@@ -643,17 +661,29 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       }
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     };
-    if (total > 0) issue(0, buf0);
-    if (total > 1) issue(1, buf1);
-    for (int64_t g = 0; g < total; g += 3) {
-      if (g + 2 < total) issue(g + 2, buf2);
-      convert(buf0);
-      if (g + 1 >= total) break;
-      if (g + 3 < total) issue(g + 3, buf0);
-      convert(buf1);
-      if (g + 2 >= total) break;
-      if (g + 4 < total) issue(g + 4, buf1);
-      convert(buf2);
+    if (C::N_SUB == 2) {
+      // wide tiles: a K block carries twice the MMA time, one block of look-ahead covers the same latency
+      if (total > 0) issue(0, buf0);
+      for (int64_t g = 0; g < total; g += 2) {
+        if (g + 1 < total) issue(g + 1, buf1);
+        convert(buf0);
+        if (g + 1 >= total) break;
+        if (g + 2 < total) issue(g + 2, buf0);
+        convert(buf1);
+      }
+    } else {
+      if (total > 0) issue(0, buf0);
+      if (total > 1) issue(1, buf1);
+      for (int64_t g = 0; g < total; g += 3) {
+        if (g + 2 < total) issue(g + 2, buf2);
+        convert(buf0);
+        if (g + 1 >= total) break;
+        if (g + 3 < total) issue(g + 3, buf0);
+        convert(buf1);
+        if (g + 2 >= total) break;
+        if (g + 4 < total) issue(g + 4, buf1);
+        convert(buf2);
+      }
     }
   }
 
@@ -739,8 +769,8 @@ int launch_gemm_maps(const GemmTcParams& p, const CUtensorMap& ta_hi, const CUte
   if (p.K % BLOCK_K != 0 || p.N % BLOCK_N != 0 || p.K <= 0 || p.N <= 0) return TOAD_ERR_UNSUPPORTED;
   if (EPI == EPI_GATE && (p.gate_D > 1024 || p.gate_ntasks < 1 || p.gate_ntasks > 4)) return TOAD_ERR_UNSUPPORTED;
   CUtensorMap tb_hi, tb_lo;
-  TOAD_TRY(make_bf16_tmap(&tb_hi, b_hi, p.N, p.K, C::B_ROWS));
-  TOAD_TRY(make_bf16_tmap(&tb_lo, b_lo, p.N, p.K, C::B_ROWS));
+  TOAD_TRY(make_bf16_tmap(&tb_hi, b_hi, p.N, p.K, C::B_SUB_ROWS));
+  TOAD_TRY(make_bf16_tmap(&tb_lo, b_lo, p.N, p.K, C::B_SUB_ROWS));
   CUtensorMap to_hi = tb_hi, to_lo = tb_lo;
   if (EPI == EPI_LINEAR && p.out_hi != nullptr) {
     if (p.out_lo == nullptr || p.ld_split % 8 != 0) return TOAD_ERR_ARG;

@@ -202,9 +202,10 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
   }
 
   // ---- tensor-core path: split weights, three tcgen05 GEMMs with fused epilogues, tail
-  // CTA-pair (cta_group::2) vs single-CTA tiles.  Default: measured best per kernel -- the fp32-fed fc1
-  // runs single-CTA (its converter warps are the limiter, pairing only adds remote-arrive latency), the
-  // TMA-fed fc2 / gate GEMMs run as CTA pairs.  The two debug flags force one shape everywhere.
+  // Tile shapes.  Default: fc1 (fp32-fed) runs as CTA pairs on 256 x 512 tiles -- the whole hidden width in
+  // one tile, so every x row is read and converted exactly once --, fc2 / gate as CTA pairs on 256 x 256
+  // tiles.  Debug flags: SINGLE_CTA = 128 x 256 cta_group::1 tiles everywhere, PAIR_ALL = 256 x 256 pairs
+  // everywhere.
   const bool cg1 = (flags & TOAD_FLAG_TC_SINGLE_CTA) != 0;
   const bool fc1_pair = (flags & TOAD_FLAG_TC_PAIR_ALL) != 0;
   TOAD_TRY(prof_mark(prof, 0, st));
@@ -218,8 +219,9 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
     g.drop = drop; g.drop_layer = DROP_H1;
     g.out_f32 = save ? saved->h1 : nullptr; g.ld_f32 = Hd;
     g.out_hi = w.h1_hi; g.out_lo = w.h1_lo; g.ld_split = Hd;
-    if (!fc1_pair) TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_LINEAR, 1>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, st)));
-    else TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_LINEAR, 2>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, st)));
+    if (cg1) TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_LINEAR, 1>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, st)));
+    else if (fc1_pair) TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_LINEAR, 2>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, st)));
+    else TOAD_TRY((tc::launch_gemm<512, tc::A_F32, tc::EPI_LINEAR, 2>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, st)));
   }
   TOAD_TRY(prof_mark(prof, 2, st));
   {
@@ -229,6 +231,7 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
     g.out_f32 = save ? saved->h : nullptr; g.ld_f32 = Hd;
     g.out_hi = w.h_hi; g.out_lo = w.h_lo; g.ld_split = Hd;
     if (cg1) TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 1>(g, w.h1_hi, w.h1_lo, w.w2_hi, w.w2_lo, st)));
+    else if (flags & TOAD_FLAG_FC2_WIDE) TOAD_TRY((tc::launch_gemm<512, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, w.h1_hi, w.h1_lo, w.w2_hi, w.w2_lo, st)));
     else TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, w.h1_hi, w.h1_lo, w.w2_hi, w.w2_lo, st)));
   }
   TOAD_TRY(prof_mark(prof, 3, st));
@@ -576,6 +579,10 @@ extern "C" int toad_linear_bf16x3(const float* x, const float* wgt, const float*
   tc::GemmTcParams g{};
   g.a_f32 = x; g.lda = k; g.M = m; g.N = n; g.K = k; g.bias = bias; g.relu = relu; g.out_f32 = y; g.ld_f32 = n;
   const bool pair = (variant & 2) != 0;  // cta_group::2 (CTA pair per 256-row tile)
+  if (variant & 0x40) {              // 512-wide tiles (pairs only)
+    if (!pair || n % 512 != 0) return TOAD_ERR_UNSUPPORTED;
+    return run_linear<512, 2>(g, split_a, w, st);
+  }
   if (BN == 256) return pair ? run_linear<256, 2>(g, split_a, w, st) : run_linear<256, 1>(g, split_a, w, st);
   if (BN == 128) return pair ? run_linear<128, 2>(g, split_a, w, st) : run_linear<128, 1>(g, split_a, w, st);
   return pair ? run_linear<64, 2>(g, split_a, w, st) : run_linear<64, 1>(g, split_a, w, st);

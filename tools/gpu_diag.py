@@ -19,7 +19,7 @@ OUT = os.path.join(ROOT, "gpurun_out")
 os.makedirs(OUT, exist_ok=True)
 
 STEPS = ["lin_64_f32", "lin_64_split", "lin_128", "lin_256", "lin_multi", "pair_64_f32", "pair_64_split", "pair_256",
-         "pair_multi", "attn_gated", "simt_fwd", "tc_fwd_small", "tc_fwd_10k", "tc_fwd_10k_cg1", "topk", "bwd_simt",
+         "pair_multi", "wide_small", "wide_multi", "attn_gated", "simt_fwd", "tc_fwd_small", "tc_fwd_10k", "tc_fwd_10k_cg1", "topk", "bwd_simt",
          "bwd_tc", "timing", "lin_timing", "resnet_s64", "resnet_s256", "resnet_timing"]
 
 
@@ -149,6 +149,10 @@ def run_step(step):
         return lin(step, 300, 256, 256, 0x33)
     if step == "pair_multi":
         return lin(step, 40000, 512, 1024, 0x02, dump=False)
+    if step == "wide_small":
+        return lin(step, 300, 512, 128, 0x42)
+    if step == "wide_multi":
+        return lin(step, 50000, 512, 1024, 0x42, dump=False)
     if step == "tc_fwd_10k_cg1":
         os.environ["TOAD_B200_CG1"] = "1"
         return fwd_case(step, "toad_big_n10000", False)
