@@ -11,9 +11,9 @@
 //   warp 0      TMA producer: B_hi/B_lo tiles (and A_hi/A_lo when A is already split)
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16)
 //   warp 2      TMEM allocator
-//   warps 4-7   epilogue: tcgen05.ld accumulator -> registers -> bias/activation -> global
-//   warps 8-15  (A_MODE 0 only) A converter: fp32 rows from global -> (hi,lo) bf16 pairs written
-//               straight into the 128B-swizzled UMMA operand layout, loads two K blocks ahead
+//   warps 4-11  epilogue: tcgen05.ld accumulator -> registers -> bias/activation -> smem staging -> TMA store
+//   warps 12-19 (A_MODE 0 only) A converter: fp32 rows from global -> (hi,lo) bf16 pairs written
+//               straight into the 128B-swizzled UMMA operand layout, loads one K block ahead
 // Pipelines: smem ring (full/empty mbarriers) between producer/converter and MMA, and a
 // 2-deep TMEM accumulator ring (tmem_full/tmem_empty) between MMA and epilogue, so the
 // epilogue of tile i overlaps the main loop of tile i+1.
@@ -79,7 +79,7 @@ struct GemmTcParams {
   const float* gate_wc;  // [ntasks, D]
   int32_t gate_D;
   int32_t gate_ntasks;  // 1..4
-  float* gate_part;     // [n_tiles][M][ntasks] partial scores (no bias)
+  float* gate_part;     // [2 * n_tiles][M][ntasks] partial scores (no bias): one per (tile, epilogue warp set)
   float* gate_a;        // nullable [M, D]
   float* gate_b;        // nullable [M, D]
   // A_CONV: rows are output pixels (b, oh, ow) raster; K blocks walk (tap, 64-channel chunk); the A tile
@@ -189,7 +189,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the 8 epilogue warps
 
 template <int CG>
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
@@ -305,7 +305,7 @@ __device__ __forceinline__ float fast_tanh(float z) { return fmaf(2.0f, fast_sig
 constexpr int GATE_SMEM_FLOATS = 4 * 1024;  // ba | bb | wc rows (<= 2 tasks staged) for D <= 1024
 
 template <int BLOCK_N, int A_MODE, int EPI, int CG>
-__global__ void __launch_bounds__(A_MODE == A_F32 ? 512 : 256, 1)
+__global__ void __launch_bounds__(A_MODE == A_F32 ? 640 : 384, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
@@ -344,7 +344,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&bar_tmem_full[a]), 1);
-      mbar_init(smem_u32(&bar_tmem_empty[a]), 4 * CG);  // one arrive per epilogue warp (both CTAs)
+      mbar_init(smem_u32(&bar_tmem_empty[a]), 8 * CG);  // one arrive per epilogue warp (8 per CTA)
     }
     fence_barrier_init();
   }
@@ -468,9 +468,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ------------------------------------------------------------------ epilogue
-    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may access
+  } else if (warp >= 4 && warp < 12) {
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    // warp -> (TMEM lane quarter ew = warp % 4, column half eh): the two warps of a lane quarter split every
+    // 64-column chunk into its two 32-column halves.
+    const int ew = (warp - 4) & 3;  // == warp % 4: the TMEM lane quarter this warp may access
+    const int eh = (warp - 4) >> 2;
     int it = 0;
     for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
       const int n_tile = tile % n_tiles;
@@ -496,8 +499,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             if (warp == 4 && lane == 0) tma_store_wait_read();
             epi_barrier();
           }
-#pragma unroll 1
-          for (int h = 0; h < 2; ++h) {  // two 32-column halves of the 64-column chunk
+          {
+            const int h = eh;  // this warp's 32-column half of the 64-column chunk
             uint32_t r[32];
             tmem_ld32(t_row + cc * 64 + h * 32, r);
             tmem_ld_wait();
@@ -563,7 +566,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         const int j0 = n_tile * HALF;
         float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-        for (int c = 0; c < HALF / 32; ++c) {
+        for (int c = eh; c < HALF / 32; c += 2) {  // the two warps of a lane quarter alternate 32-column chunks
           uint32_t ra[32], rb[32];
           tmem_ld32(t_row + c * 32, ra);
           tmem_ld32(t_row + HALF + c * 32, rb);
@@ -604,7 +607,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           }
         }
         if (row_ok) {
-          float* dst = p.gate_part + (static_cast<int64_t>(n_tile) * p.M + row) * p.gate_ntasks;
+          float* dst = p.gate_part + (static_cast<int64_t>(n_tile * 2 + eh) * p.M + row) * p.gate_ntasks;
 #pragma unroll
           for (int t = 0; t < 4; ++t)
             if (t < p.gate_ntasks) dst[t] = s[t];
@@ -617,16 +620,15 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         else mbar_arrive_cluster(smem_u32(&bar_tmem_empty[acc]), 0);
       }
     }
-  } else if (A_MODE == A_F32 && warp >= 8) {
+  } else if (A_MODE == A_F32 && warp >= 12) {
     // ------------------------------------------------------------------ A converter (8 warps)
     // Each half-warp streams one 256 B row segment (64 fp32) per load instruction; a thread turns its
-    // 4 floats into 4 (hi) + 4 (lo) bf16 = one 8 B store into each swizzled tile.  Global loads run
-    // TWO K blocks ahead of the conversion (3 rotating register buffers) to cover HBM latency.
-    const int cw = warp - 8;  // 0..7: rows cw*16 .. cw*16+15 of the tile
+    // 4 floats into 4 (hi) + 4 (lo) bf16 = one 8 B store into each swizzled tile.
+    const int cw = warp - 12;  // 0..7: rows cw*16 .. cw*16+15 of the tile
     const int hw = lane >> 4, l16 = lane & 15;
     const int my_tiles = unit0 < num_tiles ? (num_tiles - unit0 + unit_stride - 1) / unit_stride : 0;
     const int64_t total = static_cast<int64_t>(my_tiles) * num_kb;
-    float4 buf0[8], buf1[8], buf2[8];
+    float4 buf0[8], buf1[8];
     auto issue = [&](int64_t g, float4(&buf)[8]) {
       const int tile = unit0 + static_cast<int>(g / num_kb) * unit_stride;
       const int kb = static_cast<int>(g % num_kb);
@@ -661,29 +663,14 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       }
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     };
-    if (C::N_SUB == 2) {
-      // wide tiles: a K block carries twice the MMA time, one block of look-ahead covers the same latency
-      if (total > 0) issue(0, buf0);
-      for (int64_t g = 0; g < total; g += 2) {
-        if (g + 1 < total) issue(g + 1, buf1);
-        convert(buf0);
-        if (g + 1 >= total) break;
-        if (g + 2 < total) issue(g + 2, buf0);
-        convert(buf1);
-      }
-    } else {
-      if (total > 0) issue(0, buf0);
-      if (total > 1) issue(1, buf1);
-      for (int64_t g = 0; g < total; g += 3) {
-        if (g + 2 < total) issue(g + 2, buf2);
-        convert(buf0);
-        if (g + 1 >= total) break;
-        if (g + 3 < total) issue(g + 3, buf0);
-        convert(buf1);
-        if (g + 2 >= total) break;
-        if (g + 4 < total) issue(g + 4, buf1);
-        convert(buf2);
-      }
+    // loads run one K block ahead of the conversion (two rotating register buffers)
+    if (total > 0) issue(0, buf0);
+    for (int64_t g = 0; g < total; g += 2) {
+      if (g + 1 < total) issue(g + 1, buf1);
+      convert(buf0);
+      if (g + 1 >= total) break;
+      if (g + 2 < total) issue(g + 2, buf0);
+      convert(buf1);
     }
   }
 
@@ -786,7 +773,7 @@ int launch_gemm_maps(const GemmTcParams& p, const CUtensorMap& ta_hi, const CUte
   const int grid = static_cast<int>(units < max_units ? units : max_units) * CG;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
-  cfg.blockDim = dim3(A_MODE == A_F32 ? 512 : 256);
+  cfg.blockDim = dim3(A_MODE == A_F32 ? 640 : 384);
   cfg.dynamicSmemBytes = kSmem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

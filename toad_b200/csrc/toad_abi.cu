@@ -57,7 +57,7 @@ FwdWs carve_fwd(const toad_dims_t* d, int64_t n, uint32_t flags, void* base) {
   w.ticket = c.take<unsigned int>(64);
   w.blk_part = c.take<float>(static_cast<size_t>(tail::tail_blocks(n, kSMs)) * tail::PART_STRIDE);
   const bool simt = (flags & TOAD_FLAG_SIMT_FP32) != 0;
-  w.n_parts = simt ? 1 : static_cast<int>(D / kGateHalf);
+  w.n_parts = simt ? 1 : 2 * static_cast<int>(D / kGateHalf);  // (tile, epilogue warp set) partials
   w.part = c.take<float>(static_cast<size_t>(w.n_parts) * n * d->n_tasks);
   if (!simt) {
     w.w1_hi = c.take<bf16>(Hd * L);  w.w1_lo = c.take<bf16>(Hd * L);
@@ -473,7 +473,7 @@ AgWs carve_ag(int L, int D, int nt, int64_t n, uint32_t flags, void* base) {
   AgWs w{};
   Carver c(base);
   const bool simt = (flags & TOAD_FLAG_SIMT_FP32) != 0;
-  w.n_parts = simt ? 1 : D / kGateHalf;
+  w.n_parts = simt ? 1 : 2 * (D / kGateHalf);
   w.part = c.take<float>(static_cast<size_t>(w.n_parts) * n * nt);
   if (simt) {
     w.a = c.take<float>(n * D);
