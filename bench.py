@@ -241,6 +241,8 @@ def run_ours(args):
                          "forward_hbm_gbs": BYTES_PER_PATCH * n / (whole_ms * 1e-3) / 1e9 if whole_ms > 0 else None,
                          "hbm_peak_gbs": pk["hbm_gbs"]},
         }
+        if world == 1:
+            line["eager_gpu_baseline"] = eager_gpu_leg(dev, n)
         if world == 1 and not args.no_resnet:
             line["resnet50_baseline"] = resnet_leg(dev)
         if world == 1 and not args.no_cpu_baseline:
@@ -252,6 +254,34 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def eager_gpu_leg(dev, n):
+    """Secondary bar: the reference's own ATen op sequence (oracle torch port) run
+    eagerly on the SAME GPU -- cuBLAS fp32 SGEMMs + elementwise kernels, what the unmodified reference
+    module does on a B200.  A baseline, not part of the product path."""
+    import torch
+    from oracle import toad_oracle as O
+    from oracle import toad_oracle_torch as OT
+    params = {k: v.to(dev) for k, v in OT.to_torch_params(O.make_params(0, "big", 18)).items()}
+    x = torch.randn(n, WIDTH, device=dev)
+    sex = torch.ones(1, device=dev)
+    out = {}
+    for tf32 in (False, True):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        for _ in range(3):
+            OT.toad_forward(x, sex, params)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            OT.toad_forward(x, sex, params)
+        e1.record()
+        torch.cuda.synchronize()
+        out["slides_per_s_tf32" if tf32 else "slides_per_s_fp32"] = 10 / (e0.elapsed_time(e1) / 1e3)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    out["note"] = "torch eager on the same B200: fp32 = the reference's default (allow_tf32 off); tf32 = single-pass TF32, which fails the 1e-3 parity bar (SURVEY F4)"
+    return out
 
 
 def resnet_leg(dev):
