@@ -40,37 +40,63 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML every 5 ms
+    (nvidia_ml_py), falling back to polling nvidia-smi."""
+
+    HW_SLOWDOWN, SW_POWER_CAP, SW_THERMAL, HW_THERMAL = 0x8, 0x4, 0x20, 0x40
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.sm = []
+        self.max_mhz = None
+        self.reason_bits = 0
+        self.source = None
         self.stop_flag = threading.Event()
 
     def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+            while not self.stop_flag.is_set():
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                try:
+                    self.reason_bits |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    self.reason_bits |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.stop_flag.wait(0.005)
+            return
+        except Exception:
+            pass
+        self.source = "nvidia-smi"
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        bits = [self.HW_SLOWDOWN, self.HW_THERMAL, self.SW_THERMAL, self.SW_POWER_CAP]
         while not self.stop_flag.is_set():
             try:
                 r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
                                     "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                parts = [s.strip() for s in r.stdout.strip().split(",")]
+                parts = [x.strip() for x in r.stdout.strip().split(",")]
                 if len(parts) >= 6:
-                    self.samples.append(parts)
+                    self.sm.append(float(parts[0]))
+                    self.max_mhz = float(parts[1])
+                    for i, b in enumerate(bits):
+                        if parts[2 + i].lower().startswith("active"):
+                            self.reason_bits |= b
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05)
 
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"], "samples": 0}
+        names = [(self.HW_SLOWDOWN, "hw_slowdown"), (self.HW_THERMAL, "hw_thermal_slowdown"),
+                 (self.SW_THERMAL, "sw_thermal_slowdown"), (self.SW_POWER_CAP, "sw_power_cap")]
+        return {"sm_mhz": statistics.median(self.sm), "sm_min_mhz": min(self.sm), "sm_max_mhz": self.max_mhz,
+                "reasons": [n for b, n in names if self.reason_bits & b], "samples": len(self.sm), "source": self.source}
 
 
 def cpu_reference_rate(n_patches: int, steps: int, warmup: int, budget_s: float):

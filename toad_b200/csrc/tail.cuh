@@ -16,7 +16,7 @@ namespace tail {
 
 constexpr int H = 512;          // hid_dim (model_toad.py:56, both size_args)
 constexpr int T = 2;            // n_tasks (model_toad.py:66)
-constexpr int THREADS = 512;    // 16 warps
+constexpr int THREADS = 1024;   // 32 warps, one CTA per SM
 constexpr int WARPS = THREADS / 32;
 constexpr int MAX_CHUNK = 2048; // rows per CTA (scores cached in smem)
 constexpr int MAX_BLOCKS = 1024;   // (max,sum) staging of the merge fits s_score: 2*T*MAX_BLOCKS floats
@@ -45,7 +45,7 @@ struct TailParams {
 };
 
 inline int tail_blocks(int64_t n, int sms) {
-  int64_t b = 2 * static_cast<int64_t>(sms);
+  int64_t b = static_cast<int64_t>(sms);  // one 1024-thread CTA per SM: fewer partials for the final merge
   const int64_t need = (n + MAX_CHUNK - 1) / MAX_CHUNK;
   if (b < need) b = need;
   const int64_t most = (n + 31) / 32;  // at least 32 rows per CTA
@@ -196,12 +196,12 @@ __global__ void __launch_bounds__(THREADS) pool_heads_kernel(const TailParams p)
   // weighted sum of the per-CTA accumulators: 2 thread groups x 256 float4 columns, 8 independent
   // 16 B L2 loads in flight per thread, partial sums combined in fixed order through smem.
   float* s_feat = dsm;                 // [T][H+1]
-  float4* s_half = reinterpret_cast<float4*>(dsm + 2048);  // [2][256] float4 scratch (dsm is 64 KB)
+  float4* s_half = reinterpret_cast<float4*>(dsm + 4096);  // [4][256] float4 scratch (dsm is 128 KB)
   const float sexv = __ldg(p.sex);
   {
-    const int c4 = tid & 255, bg = tid >> 8;
+    const int c4 = tid & 255, bg = tid >> 8;  // 4 partial-groups x 256 float4 columns
     const int t = c4 >> 7;  // 128 float4 per task
-    const int bper = (nb + 1) / 2;
+    const int bper = (nb + 3) / 4;
     const int b0 = bg * bper, b1 = (b0 + bper) < nb ? (b0 + bper) : nb;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int b = b0;
@@ -227,10 +227,11 @@ __global__ void __launch_bounds__(THREADS) pool_heads_kernel(const TailParams p)
   }
   __syncthreads();
   if (tid < 256) {
-    const float4 a0 = s_half[tid], a1 = s_half[256 + tid];
+    const float4 a0 = s_half[tid], a1 = s_half[256 + tid], a2 = s_half[512 + tid], a3 = s_half[768 + tid];
     const int t = tid >> 7, j = (tid & 127) * 4;
     const float inv = 1.0f / s_l[t];
-    const float v[4] = {(a0.x + a1.x) * inv, (a0.y + a1.y) * inv, (a0.z + a1.z) * inv, (a0.w + a1.w) * inv};
+    const float v[4] = {(((a0.x + a1.x) + a2.x) + a3.x) * inv, (((a0.y + a1.y) + a2.y) + a3.y) * inv,
+                        (((a0.z + a1.z) + a2.z) + a3.z) * inv, (((a0.w + a1.w) + a2.w) + a3.w) * inv};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       s_feat[t * (H + 1) + j + e] = v[e];
@@ -249,8 +250,12 @@ __global__ void __launch_bounds__(THREADS) pool_heads_kernel(const TailParams p)
     const bool is_site = o >= p.n_classes;
     const float* w = is_site ? p.wsite + static_cast<int64_t>(o - p.n_classes) * (H + 1) : p.wcls + static_cast<int64_t>(o) * (H + 1);
     const float* f = s_feat + (is_site ? (H + 1) : 0);
+    float wv[17];  // (H+1)/32 rounded up: all weight loads in flight before the first FMA
+#pragma unroll
+    for (int q = 0; q < 17; ++q) wv[q] = (lane + 32 * q) < H + 1 ? __ldg(w + lane + 32 * q) : 0.f;
     float s = 0.f;
-    for (int j = lane; j < H + 1; j += 32) s = fmaf(__ldg(w + j), f[j], s);
+#pragma unroll
+    for (int q = 0; q < 17; ++q) s = fmaf(wv[q], (lane + 32 * q) < H + 1 ? f[lane + 32 * q] : 0.f, s);
     s = warp_sum(s);
     if (lane == 0) s_logit[o] = s + (is_site ? __ldg(p.bsite + o - p.n_classes) : __ldg(p.bcls + o));
   }
