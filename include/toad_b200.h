@@ -58,6 +58,9 @@ enum {
 #define TOAD_FLAG_SAVE_ACTS 4u      /* also store h1,h,a,b (fp32) for toad_bwd */
 #define TOAD_FLAG_DROPOUT 16u        /* training-mode nn.Dropout on h1, h, a, b (model_toad.py:27-29,60-64); needs `saved` */
 #define TOAD_FLAG_TC_SINGLE_CTA 8u  /* debug: every tcgen05 GEMM with cta_group::1 (one CTA per 128-row tile) */
+#define TOAD_FLAG_REUSE_WEIGHT_PLANES 128u /* the bf16 (hi,lo) weight planes left in `workspace` by an earlier call with the
+                                            * same dims (any n_patches), tensor-core path and UNCHANGED parameters are still
+                                            * valid: skip the 3 weight-split launches (eval loops; the caller tracks versions) */
 #define TOAD_FLAG_FC2_WIDE 64u      /* debug: fc2 on 256 x 512 pair tiles like fc1 */
 #define TOAD_FLAG_TC_PAIR_ALL 32u   /* debug: every tcgen05 GEMM as CTA pairs (cta_group::2), including the fp32-fed fc1 */
 

@@ -179,3 +179,27 @@ def test_input_validation():
         model(torch.from_numpy(x).cuda()[:, :512], sd)       # wrong width / non-contiguous
     with pytest.raises(ValueError):
         model(torch.empty((0, 1024), device="cuda"), sd)     # empty bag
+
+
+def test_weight_plane_reuse_tracks_parameter_updates():
+    """Eval loops skip the weight split when nothing changed; an in-place parameter update (optimizer
+    step, load_state_dict) or a workspace regrow must invalidate the cached planes."""
+    g = load_golden("toad_big_n257")
+    params, x, sex = case_inputs(g)
+    model = build_model(params, "big", 18)
+    xd = torch.from_numpy(x).cuda()
+    sd = torch.tensor([sex], device="cuda")
+    with torch.no_grad():
+        o1 = to_np(model(xd, sd)["logits"])
+        o2 = to_np(model(xd, sd)["logits"])                  # second call reuses the planes
+        assert np.array_equal(o1, o2)
+        model.classifier.bias.add_(1.0)                       # head only: trunk planes could be reused, but the key changes
+        o3 = to_np(model(xd, sd)["logits"])
+        np.testing.assert_allclose(o3, o1 + 1.0, rtol=0, atol=1e-6)
+        model.attention_net[0].weight.mul_(0.5)               # trunk weight changed in place
+        o4 = to_np(model(xd, sd)["logits"])
+        assert np.abs(o4 - o3).max() > 1e-3
+        big = torch.randn(5000, 1024, device="cuda")          # forces the workspace to regrow
+        model(big, sd)
+        o5 = to_np(model(xd, sd)["logits"])
+        assert np.array_equal(o4, o5)

@@ -54,15 +54,17 @@ FwdWs carve_fwd(const toad_dims_t* d, int64_t n, uint32_t flags, void* base) {
   FwdWs w{};
   Carver c(base);
   const int64_t Hd = d->hid_dim, D = d->attn_dim, L = d->in_dim;
-  w.ticket = c.take<unsigned int>(64);
-  w.blk_part = c.take<float>(static_cast<size_t>(tail::tail_blocks(n, kSMs)) * tail::PART_STRIDE);
   const bool simt = (flags & TOAD_FLAG_SIMT_FP32) != 0;
-  w.n_parts = simt ? 1 : 2 * static_cast<int>(D / kGateHalf);  // (tile, epilogue warp set) partials
-  w.part = c.take<float>(static_cast<size_t>(w.n_parts) * n * d->n_tasks);
-  if (!simt) {
+  w.ticket = c.take<unsigned int>(64);
+  if (!simt) {  // weight planes first: their offsets do not depend on n (TOAD_FLAG_REUSE_WEIGHT_PLANES)
     w.w1_hi = c.take<bf16>(Hd * L);  w.w1_lo = c.take<bf16>(Hd * L);
     w.w2_hi = c.take<bf16>(Hd * Hd); w.w2_lo = c.take<bf16>(Hd * Hd);
     w.wab_hi = c.take<bf16>(2 * D * Hd); w.wab_lo = c.take<bf16>(2 * D * Hd);
+  }
+  w.blk_part = c.take<float>(static_cast<size_t>(tail::tail_blocks(n, kSMs)) * tail::PART_STRIDE);
+  w.n_parts = simt ? 1 : 2 * static_cast<int>(D / kGateHalf);  // (tile, epilogue warp set) partials
+  w.part = c.take<float>(static_cast<size_t>(w.n_parts) * n * d->n_tasks);
+  if (!simt) {
     w.h1_hi = c.take<bf16>(n * Hd); w.h1_lo = c.take<bf16>(n * Hd);
     w.h_hi = c.take<bf16>(n * Hd);  w.h_lo = c.take<bf16>(n * Hd);
   } else if (!(flags & TOAD_FLAG_SAVE_ACTS)) {
@@ -71,28 +73,6 @@ FwdWs carve_fwd(const toad_dims_t* d, int64_t n, uint32_t flags, void* base) {
   }
   w.bytes = align_up(c.off, 256);
   return w;
-}
-
-struct Prof {
-  cudaEvent_t* ev;  // [max_calls][TOAD_N_STAGES + 1]
-  int max_calls;
-  int n;
-};
-inline int prof_mark(Prof* p, int idx, cudaStream_t st) {
-  if (p == nullptr || p->n >= p->max_calls) return 0;
-  TOAD_CUDA_TRY(cudaEventRecord(p->ev[p->n * (TOAD_N_STAGES + 1) + idx], st));
-  return 0;
-}
-
-DropoutCfg make_drop(const toad_saved_t* sv, uint32_t flags) {
-  DropoutCfg d{};
-  if ((flags & TOAD_FLAG_DROPOUT) && sv != nullptr && sv->dropout_p > 0.f) {
-    d.seed = sv->dropout_seed;
-    const double t = static_cast<double>(sv->dropout_p) * 4294967296.0;
-    d.thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(t);
-    d.scale = 1.0f / (1.0f - sv->dropout_p);
-  }
-  return d;
 }
 
 int check_ws(const void* ws, size_t have, size_t need) {
@@ -209,9 +189,11 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
   const bool cg1 = (flags & TOAD_FLAG_TC_SINGLE_CTA) != 0;
   const bool fc1_pair = (flags & TOAD_FLAG_TC_PAIR_ALL) != 0;
   TOAD_TRY(prof_mark(prof, 0, st));
-  TOAD_TRY(tail::launch_split_planes(P->w1, w.w1_hi, w.w1_lo, static_cast<int64_t>(Hd) * L, st));
-  TOAD_TRY(tail::launch_split_planes(P->w2, w.w2_hi, w.w2_lo, static_cast<int64_t>(Hd) * Hd, st));
-  TOAD_TRY(tail::launch_split_gate_weights(P->wa, P->wb, w.wab_hi, w.wab_lo, D, Hd, kGateHalf, st));
+  if (!(flags & TOAD_FLAG_REUSE_WEIGHT_PLANES)) {
+    TOAD_TRY(tail::launch_split_planes(P->w1, w.w1_hi, w.w1_lo, static_cast<int64_t>(Hd) * L, st));
+    TOAD_TRY(tail::launch_split_planes(P->w2, w.w2_hi, w.w2_lo, static_cast<int64_t>(Hd) * Hd, st));
+    TOAD_TRY(tail::launch_split_gate_weights(P->wa, P->wb, w.wab_hi, w.wab_lo, D, Hd, kGateHalf, st));
+  }
   TOAD_TRY(prof_mark(prof, 1, st));
   {
     tc::GemmTcParams g{};

@@ -170,6 +170,24 @@ class TOAD_fc_mtl_concat(nn.Module):
         self.classifier = self.classifier.to(device)
         self.site_classifier = self.site_classifier.to(device)
 
+    def _weight_plane_flag(self, params, device) -> int:
+        """Inference loops reuse the bf16 weight planes that the previous forward left in the workspace
+        as long as no parameter changed (tensor identity + autograd version counter) and the workspace
+        buffer is still the same allocation (it is grow-only, and the planes sit at n-independent offsets
+        -- but a regrown buffer has lost them)."""
+        if _default_flags() & _lib.FLAG_SIMT_FP32:
+            return 0
+        key = tuple((p.data_ptr(), p._version) for p in params) + (str(device),)
+        buf = self._ws.buf
+        state = (key, None if buf is None else buf.data_ptr(), None if buf is None else buf.numel())
+        reuse = getattr(self, "_plane_state", None) == state and buf is not None
+        self._plane_key_pending = key
+        return _lib.FLAG_REUSE_WEIGHT_PLANES if reuse else 0
+
+    def _note_planes_written(self) -> None:
+        buf = self._ws.buf
+        self._plane_state = (self._plane_key_pending, buf.data_ptr(), buf.numel())
+
     def _dropout_active(self) -> bool:
         return self.dropout and self.training
 
@@ -188,8 +206,9 @@ class TOAD_fc_mtl_concat(nn.Module):
             (logits, site_logits, y_prob, y_hat, site_prob, site_hat, a_raw, features) = _ToadFunction.apply(
                 self, h, sex_f, *params)
         else:
-            out = ops.toad_fwd(self._dims, [p.detach() for p in params], h, sex_f, self._ws, _default_flags(),
-                               prof=self._prof)
+            out = ops.toad_fwd(self._dims, [p.detach() for p in params], h, sex_f, self._ws,
+                               _default_flags() | self._weight_plane_flag(params, h.device), prof=self._prof)
+            self._note_planes_written()
             logits, site_logits, y_prob, y_hat = out["logits"], out["site_logits"], out["y_prob"], out["y_hat"]
             site_prob, site_hat, a_raw, features = out["site_prob"], out["site_hat"], out["a_raw"], out["features"]
         results_dict: Dict[str, torch.Tensor] = {}

@@ -109,7 +109,10 @@ def _saved_struct(saved: Dict[str, torch.Tensor]) -> Saved:
 def toad_fwd(dims: Dims, params: Sequence[torch.Tensor], x: torch.Tensor, sex: torch.Tensor, ws: Workspace,
              flags: int = 0, saved: Optional[Dict[str, torch.Tensor]] = None,
              out: Optional[Dict[str, torch.Tensor]] = None, prof: Optional[int] = None) -> Dict[str, torch.Tensor]:
-    """One TOAD forward (models/model_toad.py:90-116) through the C ABI."""
+    """One TOAD forward (models/model_toad.py:90-116) through the C ABI.
+
+    FLAG_REUSE_WEIGHT_PLANES in `flags` is honoured only if the workspace does not have to grow for this
+    call (a regrown buffer has lost the planes)."""
     lib = _lib.load()
     _check_dev_f32(x, "h")
     if x.dim() != 2 or x.shape[1] != dims.in_dim:
@@ -128,6 +131,9 @@ def toad_fwd(dims: Dims, params: Sequence[torch.Tensor], x: torch.Tensor, sex: t
     p = _params_struct(dims, params)
     nbytes = C.c_size_t()
     _lib.check(lib.toad_fwd_workspace_bytes(C.byref(dims), n, flags, C.byref(nbytes)), "toad_fwd_workspace_bytes")
+    if (flags & _lib.FLAG_REUSE_WEIGHT_PLANES) and (ws.buf is None or ws.buf.numel() < nbytes.value
+                                                    or ws.buf.device != x.device):
+        flags &= ~_lib.FLAG_REUSE_WEIGHT_PLANES
     wptr, wsize = ws.get(nbytes.value, x.device)
     o = _out_struct(out)
     s = _saved_struct(saved) if saved is not None else None
