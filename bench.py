@@ -48,7 +48,9 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index = index
-        self.sm = []
+        self.sm = []      # (perf_counter timestamp, MHz)
+        self.t0 = None    # timed region [t0, t1]; samples outside are dropped in summary()
+        self.t1 = None
         self.max_mhz = None
         self.reason_bits = 0
         self.source = None
@@ -62,12 +64,13 @@ class ClockSampler(threading.Thread):
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
             self.source = "nvml"
             while not self.stop_flag.is_set():
-                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-                try:
-                    self.reason_bits |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
-                except Exception:
-                    self.reason_bits |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-                self.stop_flag.wait(0.005)
+                self.sm.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))))
+                if self.t0 is not None:
+                    try:
+                        self.reason_bits |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                    except Exception:
+                        self.reason_bits |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.stop_flag.wait(0.002)
             return
         except Exception:
             pass
@@ -81,7 +84,7 @@ class ClockSampler(threading.Thread):
                                     "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
                 parts = [x.strip() for x in r.stdout.strip().split(",")]
                 if len(parts) >= 6:
-                    self.sm.append(float(parts[0]))
+                    self.sm.append((time.perf_counter(), float(parts[0])))
                     self.max_mhz = float(parts[1])
                     for i, b in enumerate(bits):
                         if parts[2 + i].lower().startswith("active"):
@@ -91,6 +94,10 @@ class ClockSampler(threading.Thread):
             self.stop_flag.wait(0.05)
 
     def summary(self):
+        inside = [m for (t, m) in self.sm if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e30)]
+        if not inside:
+            inside = [m for (_, m) in self.sm[-3:]]
+        self.sm = inside
         if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"], "samples": 0}
         names = [(self.HW_SLOWDOWN, "hw_slowdown"), (self.HW_THERMAL, "hw_thermal_slowdown"),
@@ -194,21 +201,24 @@ def run_ours(args):
                 model(bags[(i * S + s) % n_bags], sex)
 
     # ---- value: inputs resident in HBM
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()                       # NVML init happens during the warm-up, sampling every 2 ms
     for i in range(args.warmup):
         step(i)
     prof = ops.Profile(args.steps * S)
     model._prof = prof.handle
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
-    if sampler:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler:
+        sampler.t0 = time.perf_counter()
     ev0.record()
     for i in range(args.steps):
         step(i)
     ev1.record()
     barrier()
     if sampler:
+        sampler.t1 = time.perf_counter()
         sampler.stop_flag.set()
     elapsed_ms = ev0.elapsed_time(ev1)
     model._prof = None

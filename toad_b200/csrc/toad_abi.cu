@@ -75,6 +75,28 @@ FwdWs carve_fwd(const toad_dims_t* d, int64_t n, uint32_t flags, void* base) {
   return w;
 }
 
+struct Prof {
+  cudaEvent_t* ev;  // [max_calls][TOAD_N_STAGES + 1]
+  int max_calls;
+  int n;
+};
+inline int prof_mark(Prof* p, int idx, cudaStream_t st) {
+  if (p == nullptr || p->n >= p->max_calls) return 0;
+  TOAD_CUDA_TRY(cudaEventRecord(p->ev[p->n * (TOAD_N_STAGES + 1) + idx], st));
+  return 0;
+}
+
+DropoutCfg make_drop(const toad_saved_t* sv, uint32_t flags) {
+  DropoutCfg d{};
+  if ((flags & TOAD_FLAG_DROPOUT) && sv != nullptr && sv->dropout_p > 0.f) {
+    d.seed = sv->dropout_seed;
+    const double t = static_cast<double>(sv->dropout_p) * 4294967296.0;
+    d.thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(t);
+    d.scale = 1.0f / (1.0f - sv->dropout_p);
+  }
+  return d;
+}
+
 int check_ws(const void* ws, size_t have, size_t need) {
   if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 255) != 0 || have < need) return TOAD_ERR_WORKSPACE;
   return 0;

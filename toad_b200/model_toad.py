@@ -143,6 +143,8 @@ class TOAD_fc_mtl_concat(nn.Module):
         self._ws = ops.Workspace()
         self._ws_bwd = ops.Workspace()
         self._prof = None  # optional ops.Profile handle (bench.py roofline leg)
+        self._plane_state = None        # (parameter versions, workspace identity) the cached weight planes belong to
+        self._plane_key_pending = None
 
     # -- parameters in C-ABI (= state_dict) order
     def _param_list(self) -> List[torch.Tensor]:
@@ -175,18 +177,20 @@ class TOAD_fc_mtl_concat(nn.Module):
         as long as no parameter changed (tensor identity + autograd version counter) and the workspace
         buffer is still the same allocation (it is grow-only, and the planes sit at n-independent offsets
         -- but a regrown buffer has lost them)."""
+        self._plane_key_pending = None
         if _default_flags() & _lib.FLAG_SIMT_FP32:
             return 0
         key = tuple((p.data_ptr(), p._version) for p in params) + (str(device),)
         buf = self._ws.buf
         state = (key, None if buf is None else buf.data_ptr(), None if buf is None else buf.numel())
-        reuse = getattr(self, "_plane_state", None) == state and buf is not None
+        reuse = buf is not None and self._plane_state == state
         self._plane_key_pending = key
         return _lib.FLAG_REUSE_WEIGHT_PLANES if reuse else 0
 
     def _note_planes_written(self) -> None:
         buf = self._ws.buf
-        self._plane_state = (self._plane_key_pending, buf.data_ptr(), buf.numel())
+        self._plane_state = None if self._plane_key_pending is None or buf is None else \
+            (self._plane_key_pending, buf.data_ptr(), buf.numel())
 
     def _dropout_active(self) -> bool:
         return self.dropout and self.training
