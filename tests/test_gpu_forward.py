@@ -203,3 +203,30 @@ def test_weight_plane_reuse_tracks_parameter_updates():
         model(big, sd)
         o5 = to_np(model(xd, sd)["logits"])
         assert np.array_equal(o4, o5)
+
+
+def test_giga_slide_attention_only_and_topk():
+    """Config 5 shape: one N=200,000 bag -- attention_only scores vs the fp32 oracle and the heat-map top-k
+    (values exact w.r.t. our own scores, index sets equal to the oracle's up to its own ulp-level ties)."""
+    from toad_b200 import ops
+    n = 200000
+    params = O.make_params(0, "big", 18)
+    x = O.make_bag(5, n)
+    model = build_model(params, "big", 18)
+    xd = torch.from_numpy(x).cuda()
+    with torch.no_grad():
+        a0 = model(xd, torch.tensor([0.0], device="cuda"), attention_only=True)
+        full = model(xd, torch.tensor([0.0], device="cuda"))
+    torch.cuda.synchronize()
+    assert tuple(a0.shape) == (n,)
+    ref = O.toad_forward(x, 0.0, params, dtype=np.float32)      # numpy fp32 restatement (~2 s on CPU)
+    np.testing.assert_allclose(to_np(a0), ref["A"][0], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(to_np(full["logits"]), ref["logits"], rtol=1e-3, atol=2e-5)
+    for t in range(2):
+        scores = full["A"][t].contiguous()
+        for k in (1, 10, 100, 1000):
+            vals, idx = ops.topk(scores, k)
+            tv, ti = torch.topk(scores, k)
+            assert torch.equal(vals, tv)
+            if k <= 100:
+                assert topk_sets_match(to_np(scores), ref["A"][t].astype(np.float64), k, ulps=256)
