@@ -150,15 +150,17 @@ int toad_fwd_profiled(const toad_dims_t* dims, const toad_params_t* params, cons
                       const float* sex, const toad_fwd_out_t* out, const toad_saved_t* saved, void* workspace,
                       size_t workspace_bytes, uint32_t flags, toad_stream_t stream, void* prof);
 
-int toad_bwd_workspace_bytes(const toad_dims_t* dims, int64_t n_patches, size_t* bytes);
+int toad_bwd_workspace_bytes(const toad_dims_t* dims, int64_t n_patches, uint32_t flags, size_t* bytes);
 
-/* Gradients of sum(dlogits*logits) + sum(dsite_logits*site_logits) w.r.t. the 14
+/* flags: 0 = the five large contractions (2 dgrad, 3 wgrad with split-K) on the tcgen05 split-bf16 GEMM;
+ * TOAD_FLAG_SIMT_FP32 = all of them on fp32 CUDA cores.
+ * Gradients of sum(dlogits*logits) + sum(dsite_logits*site_logits) w.r.t. the 14
  * parameters, written (not accumulated) into grad_flat in toad_param_offsets order.
  * fwd_out / saved are the buffers the forward (with TOAD_FLAG_SAVE_ACTS) filled. */
 int toad_bwd(const toad_dims_t* dims, const toad_params_t* params, const float* x, int64_t n_patches,
              const toad_fwd_out_t* fwd_out, const toad_saved_t* saved, const float* dlogits,
              const float* dsite_logits, float* grad_flat, void* workspace, size_t workspace_bytes,
-             toad_stream_t stream);
+             uint32_t flags, toad_stream_t stream);
 
 /* Standalone gated attention head: A[N, n_tasks] = Wc(tanh(Wa x + ba) * sigmoid(Wb x + bb)) + bc. */
 int toad_attn_gated_workspace_bytes(int32_t L, int32_t D, int32_t n_tasks, int64_t n, uint32_t flags, size_t* bytes);

@@ -70,7 +70,8 @@ def test_workspace_queries_and_argument_errors(lib):
     tc_bytes = n.value
     assert lib.toad_fwd_workspace_bytes(C.byref(d), 50000, 2, C.byref(n)) == 0
     assert 0 < tc_bytes < (1 << 30) and n.value > 0
-    assert lib.toad_bwd_workspace_bytes(C.byref(d), 50000, C.byref(n)) == 0 and n.value > 0
+    assert lib.toad_bwd_workspace_bytes(C.byref(d), 50000, 0, C.byref(n)) == 0 and n.value > 0
+    assert lib.toad_bwd_workspace_bytes(C.byref(d), 50000, 2, C.byref(n)) == 0 and n.value > 0
     assert lib.toad_fwd_workspace_bytes(C.byref(d), 0, 0, C.byref(n)) == -1           # empty bag
     assert lib.toad_fwd_workspace_bytes(None, 10, 0, C.byref(n)) == -1               # null dims
     bad = Dims(1000, 512, 384, 2, 18)                                                # in_dim % 64 != 0

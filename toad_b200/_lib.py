@@ -82,9 +82,9 @@ def load() -> C.CDLL:
     lib.toad_fwd.argtypes = [C.POINTER(Dims), C.POINTER(Params), _f32p, C.c_int64, _f32p, C.POINTER(FwdOut),
                              C.POINTER(Saved), C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
     lib.toad_fwd_profiled.argtypes = lib.toad_fwd.argtypes + [C.c_void_p]
-    lib.toad_bwd_workspace_bytes.argtypes = [C.POINTER(Dims), C.c_int64, C.POINTER(C.c_size_t)]
+    lib.toad_bwd_workspace_bytes.argtypes = [C.POINTER(Dims), C.c_int64, C.c_uint32, C.POINTER(C.c_size_t)]
     lib.toad_bwd.argtypes = [C.POINTER(Dims), C.POINTER(Params), _f32p, C.c_int64, C.POINTER(FwdOut),
-                             C.POINTER(Saved), _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]
+                             C.POINTER(Saved), _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
     lib.toad_attn_gated_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_uint32,
                                                     C.POINTER(C.c_size_t)]
     lib.toad_attn_gated_fwd.argtypes = [C.c_int32, C.c_int32, C.c_int32] + [_f32p] * 7 + [C.c_int64, _f32p,

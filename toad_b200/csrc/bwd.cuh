@@ -140,6 +140,87 @@ __global__ void reduce_strided_kernel(const float* __restrict__ part, float* __r
   out[i] = s;
 }
 
+// ---- transposes feeding the tensor-core wgrad GEMMs (dW = dY^T . X needs both operands K-major in the
+// patch index): out planes [C, ldT] (hi, lo) with out[c][r] = in[r][c]; 32 x 32 tiles through smem.
+__global__ void transpose_split_kernel(const float* __restrict__ in, int64_t R, int C, int64_t ld_in,
+                                       __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+                                       int64_t ldT) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int64_t r = r0 + i;
+    const int c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? in[r * ld_in + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i;
+    const int64_t r = r0 + threadIdx.x;
+    if (c < C && r < R) {
+      const float v = tile[threadIdx.x][i];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      out_hi[static_cast<int64_t>(c) * ldT + r] = h;
+      out_lo[static_cast<int64_t>(c) * ldT + r] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
+inline int launch_transpose_split(const float* in, int64_t R, int C, int64_t ld_in, __nv_bfloat16* out_hi,
+                                  __nv_bfloat16* out_lo, int64_t ldT, cudaStream_t stream) {
+  if (R <= 0 || C <= 0) return 0;
+  dim3 grid(static_cast<unsigned>((R + 31) / 32), static_cast<unsigned>((C + 31) / 32));
+  transpose_split_kernel<<<grid, dim3(32, 8), 0, stream>>>(in, R, C, ld_in, out_hi, out_lo, ldT);
+  TOAD_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// (hi, lo) planes [R, C] -> transposed planes [C, ldT]
+__global__ void transpose_planes_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfloat16* __restrict__ in_lo,
+                                        int64_t R, int C, __nv_bfloat16* __restrict__ out_hi,
+                                        __nv_bfloat16* __restrict__ out_lo, int64_t ldT) {
+  __shared__ __nv_bfloat16 th[32][34], tl[32][34];
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int64_t r = r0 + i;
+    const int c = c0 + threadIdx.x;
+    const bool ok = r < R && c < C;
+    th[i][threadIdx.x] = ok ? in_hi[r * C + c] : __float2bfloat16_rn(0.f);
+    tl[i][threadIdx.x] = ok ? in_lo[r * C + c] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i;
+    const int64_t r = r0 + threadIdx.x;
+    if (c < C && r < R) {
+      out_hi[static_cast<int64_t>(c) * ldT + r] = th[threadIdx.x][i];
+      out_lo[static_cast<int64_t>(c) * ldT + r] = tl[threadIdx.x][i];
+    }
+  }
+}
+
+inline int launch_transpose_planes(const __nv_bfloat16* in_hi, const __nv_bfloat16* in_lo, int64_t R, int C,
+                                   __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int64_t ldT, cudaStream_t stream) {
+  if (R <= 0 || C <= 0) return 0;
+  dim3 grid(static_cast<unsigned>((R + 31) / 32), static_cast<unsigned>((C + 31) / 32));
+  transpose_planes_kernel<<<grid, dim3(32, 8), 0, stream>>>(in_hi, in_lo, R, C, out_hi, out_lo, ldT);
+  TOAD_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// column sums of (hi + lo) planes [N, C]: per-CTA partials [gridDim.x][C] (thread per column)
+__global__ void colsum_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                     float* __restrict__ part, int64_t N, int C, int rows_per_block) {
+  const int c = threadIdx.x;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
+  int64_t r1 = r0 + rows_per_block;
+  if (r1 > N) r1 = N;
+  float s = 0.f;
+  for (int64_t row = r0; row < r1; ++row) s += __bfloat162float(hi[row * C + c]) + __bfloat162float(lo[row * C + c]);
+  part[static_cast<int64_t>(blockIdx.x) * C + c] = s;
+}
+
 inline int launch_reduce_strided(const float* part, float* out, int64_t n, int64_t stride, int splits,
                                  cudaStream_t stream) {
   if (n <= 0) return 0;

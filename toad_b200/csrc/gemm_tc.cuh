@@ -58,9 +58,11 @@ struct Cfg {
 };
 
 struct GemmTcParams {
-  // A operand when A_MODE == A_F32
+  // A operand when A_MODE == A_F32 (lda = row stride in floats); for plane-fed modes lda / ldb are the
+  // row strides of the (hi, lo) planes in elements (0 = K; must be multiples of 8)
   const float* a_f32;
   int64_t lda;
+  int64_t ldb;
   int64_t M;
   int32_t N;
   int32_t K;
@@ -99,6 +101,17 @@ struct GemmTcParams {
   // row*N + col; EPI_GATE uses DROP_A / DROP_B with index row*D + gate column.
   DropoutCfg drop;
   uint32_t drop_layer;
+  // split-K (TMA-fed A only): the K range is cut into k_splits slices of kb_per_split K blocks; slice s
+  // writes its fp32 partial tile to out_f32 + s * M * ld_f32 (bias only in slice 0); a reduction follows.
+  int32_t k_splits;       // 0 or 1 = no split
+  int32_t kb_per_split;
+  // dgrad extras (plane-fed EPI_LINEAR): out = (acc + pool_p[m][0]*pool_v[n] + pool_p[m][1]*pool_v[N+n])
+  //                                              * (mask_f32[m, n] > 0) * out_scale
+  const float* pool_p;    // [M, 2] or nullptr
+  const float* pool_v;    // [2, N]
+  const float* mask_f32;  // [M, ld_mask] or nullptr
+  int64_t ld_mask;
+  float out_scale;        // 0 = 1
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -331,8 +344,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   // work units: (128*CG) x BLOCK_N tiles, n fastest; this CTA owns rows [m0, m0+128) of its unit
   const int m_units = static_cast<int>((p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG));
   const int n_tiles = p.N / BLOCK_N;
-  const int num_tiles = m_units * n_tiles;
-  const int num_kb = p.K / BLOCK_K;
+  const int mn_tiles = m_units * n_tiles;
+  const int k_splits = (A_MODE != A_F32 && p.k_splits > 1) ? p.k_splits : 1;
+  const int num_tiles = mn_tiles * k_splits;  // tile = split * mn_tiles + (m_unit * n_tiles + n_tile)
+  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;  // TMA zero-fills a K tail (A_F32 callers keep K % 64 == 0)
+  const int kb_per = k_splits > 1 ? p.kb_per_split : num_kb;
   const int unit0 = blockIdx.x / CG;
   const int unit_stride = gridDim.x / CG;
 
@@ -377,9 +393,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
-      const int n0 = (tile % n_tiles) * BLOCK_N + static_cast<int>(cta_rank) * C::B_SUB_ROWS;
-      const int m0 = (tile / n_tiles) * (BLOCK_M * CG) + static_cast<int>(cta_rank) * BLOCK_M;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
+      const int kb0 = split * kb_per, kb1 = (kb0 + kb_per) < num_kb ? (kb0 + kb_per) : num_kb;
+      const int n0 = (mn % n_tiles) * BLOCK_N + static_cast<int>(cta_rank) * C::B_SUB_ROWS;
+      const int m0 = (mn / n_tiles) * (BLOCK_M * CG) + static_cast<int>(cta_rank) * BLOCK_M;
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
         if (lane == 0) {
           const uint32_t sa = tiles_base + stage * C::STAGE_BYTES;
@@ -430,7 +448,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         mbar_wait(smem_u32(&bar_tmem_empty[acc]), ((it / C::ACC_STAGES) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem0 = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int split = tile / mn_tiles;
+        const int kb0 = split * kb_per, kb1 = (kb0 + kb_per) < num_kb ? (kb0 + kb_per) : num_kb;
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(&bar_full_b[stage]), phase);
           if (A_MODE == A_F32) mbar_wait(smem_u32(&bar_full_a[stage]), phase);
           tc_fence_after();
@@ -447,7 +467,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 #pragma unroll
               for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                 const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);  // +32 B per K step
-                umma_bf16<CG>(d_tmem, a_hi + koff, b_hi + koff, idesc, (kb | k) != 0);
+                umma_bf16<CG>(d_tmem, a_hi + koff, b_hi + koff, idesc, (kb > kb0) || (k != 0));
               }
 #pragma unroll
               for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
@@ -461,7 +481,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
               }
             }
             umma_commit<CG>(smem_u32(&bar_empty[stage]));  // smem slot free (in both CTAs) once these MMAs retire
-            if (kb == num_kb - 1) umma_commit<CG>(smem_u32(&bar_tmem_full[acc]));  // accumulator ready
+            if (kb == kb1 - 1) umma_commit<CG>(smem_u32(&bar_tmem_full[acc]));  // accumulator ready
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -476,9 +496,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     const int eh = (warp - 4) >> 2;
     int it = 0;
     for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
-      const int n_tile = tile % n_tiles;
+      const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
+      const int n_tile = mn % n_tiles;
       const int n0 = n_tile * BLOCK_N;
-      const int m0 = (tile / n_tiles) * (BLOCK_M * CG) + static_cast<int>(cta_rank) * BLOCK_M;
+      const int m0 = (mn / n_tiles) * (BLOCK_M * CG) + static_cast<int>(cta_rank) * BLOCK_M;
       const int acc = it % C::ACC_STAGES;
       mbar_wait(smem_u32(&bar_tmem_full[acc]), (it / C::ACC_STAGES) & 1);
       tc_fence_after();
@@ -518,11 +539,32 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
               for (int e = 0; e < 8; ++e) {
                 const int i = q * 8 + e;
                 float t = __uint_as_float(r[i]);
-                if (p.bias != nullptr) t += __ldg(p.bias + col0 + i);
+                if (p.bias != nullptr && split == 0) t += __ldg(p.bias + col0 + i);
                 const uint32_t wh = uh[e >> 1], wl = ul[e >> 1];
                 t += (e & 1) ? (bf16hi_to_f32(wh) + bf16hi_to_f32(wl)) : (bf16lo_to_f32(wh) + bf16lo_to_f32(wl));
                 if (p.relu) t = fmaxf(t, 0.0f);
                 r[i] = __float_as_uint(t);
+              }
+            }
+            if (A_MODE != A_F32 && (p.pool_p != nullptr || p.mask_f32 != nullptr || p.out_scale != 0.f)) {
+              // backward dgrad epilogue (uniform branch; never taken by the forward kernels)
+              float p0 = 0.f, p1 = 0.f;
+              if (p.pool_p != nullptr && row_ok) { p0 = __ldg(p.pool_p + row * 2); p1 = __ldg(p.pool_p + row * 2 + 1); }
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (p.mask_f32 != nullptr && row_ok)
+                  mk = *reinterpret_cast<const float4*>(p.mask_f32 + row * p.ld_mask + col0 + q * 4);
+                const float mv[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int i = q * 4 + e;
+                  float t = __uint_as_float(r[i]);
+                  if (p.pool_p != nullptr) t += p0 * __ldg(p.pool_v + col0 + i) + p1 * __ldg(p.pool_v + p.N + col0 + i);
+                  t = mv[e] > 0.f ? t : 0.f;
+                  if (p.out_scale != 0.f) t *= p.out_scale;
+                  r[i] = __float_as_uint(t);
+                }
               }
             }
             if (p.drop.thresh != 0u) {  // training only: one big uniform branch, never predicated into the hot path
@@ -532,7 +574,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 r[i] = __float_as_uint(dropout_apply(p.drop, p.drop_layer, e0 + i, __uint_as_float(r[i])));
             }
             if (row_ok && p.out_f32 != nullptr) {
-              uint4* dst = reinterpret_cast<uint4*>(p.out_f32 + row * p.ld_f32 + col0);
+              uint4* dst = reinterpret_cast<uint4*>(p.out_f32 + (static_cast<int64_t>(split) * p.M + row) * p.ld_f32 + col0);
 #pragma unroll
               for (int i = 0; i < 8; ++i) dst[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
             }
@@ -753,11 +795,13 @@ int launch_gemm_maps(const GemmTcParams& p, const CUtensorMap& ta_hi, const CUte
                      const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, cudaStream_t stream) {
   using C = Cfg<BLOCK_N, CG>;
   if (p.M <= 0) return 0;
-  if (p.K % BLOCK_K != 0 || p.N % BLOCK_N != 0 || p.K <= 0 || p.N <= 0) return TOAD_ERR_UNSUPPORTED;
+  if ((A_MODE == A_F32 && p.K % BLOCK_K != 0) || p.N % BLOCK_N != 0 || p.K <= 0 || p.N <= 0) return TOAD_ERR_UNSUPPORTED;
+  if (p.k_splits > 1 && (A_MODE == A_F32 || EPI != EPI_LINEAR || p.out_hi != nullptr || p.kb_per_split <= 0)) return TOAD_ERR_ARG;
   if (EPI == EPI_GATE && (p.gate_D > 1024 || p.gate_ntasks < 1 || p.gate_ntasks > 4)) return TOAD_ERR_UNSUPPORTED;
   CUtensorMap tb_hi, tb_lo;
-  TOAD_TRY(make_bf16_tmap(&tb_hi, b_hi, p.N, p.K, C::B_SUB_ROWS));
-  TOAD_TRY(make_bf16_tmap(&tb_lo, b_lo, p.N, p.K, C::B_SUB_ROWS));
+  const int64_t ldb = p.ldb > 0 ? p.ldb : p.K;
+  TOAD_TRY(make_bf16_tmap(&tb_hi, b_hi, p.N, p.K, C::B_SUB_ROWS, ldb));
+  TOAD_TRY(make_bf16_tmap(&tb_lo, b_lo, p.N, p.K, C::B_SUB_ROWS, ldb));
   CUtensorMap to_hi = tb_hi, to_lo = tb_lo;
   if (EPI == EPI_LINEAR && p.out_hi != nullptr) {
     if (p.out_lo == nullptr || p.ld_split % 8 != 0) return TOAD_ERR_ARG;
@@ -768,7 +812,7 @@ int launch_gemm_maps(const GemmTcParams& p, const CUtensorMap& ta_hi, const CUte
   auto kern = gemm_bf16x3_kernel<BLOCK_N, A_MODE, EPI, CG>;
   TOAD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
   const int64_t m_units = (p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG);
-  const int64_t units = m_units * (p.N / BLOCK_N);
+  const int64_t units = m_units * (p.N / BLOCK_N) * (p.k_splits > 1 ? p.k_splits : 1);
   const int64_t max_units = sm_count() / CG;
   const int grid = static_cast<int>(units < max_units ? units : max_units) * CG;
   cudaLaunchConfig_t cfg{};
@@ -796,9 +840,10 @@ int launch_gemm(const GemmTcParams& p, const __nv_bfloat16* a_hi, const __nv_bfl
   if (p.M <= 0) return 0;
   CUtensorMap ta_hi, ta_lo;
   if (A_MODE == A_SPLIT) {
-    if (p.K % BLOCK_K != 0 || p.K <= 0) return TOAD_ERR_UNSUPPORTED;
-    TOAD_TRY(make_bf16_tmap(&ta_hi, a_hi, p.M, p.K, BLOCK_M));
-    TOAD_TRY(make_bf16_tmap(&ta_lo, a_lo, p.M, p.K, BLOCK_M));
+    if (p.K <= 0) return TOAD_ERR_UNSUPPORTED;
+    const int64_t lda = p.lda > 0 ? p.lda : p.K;  // plane row stride in elements (multiple of 8)
+    TOAD_TRY(make_bf16_tmap(&ta_hi, a_hi, p.M, p.K, BLOCK_M, lda));
+    TOAD_TRY(make_bf16_tmap(&ta_lo, a_lo, p.M, p.K, BLOCK_M, lda));
   } else {
     TOAD_TRY(make_bf16_tmap(&ta_hi, b_hi, p.N, p.K, 64));  // placeholders, never dereferenced
     ta_lo = ta_hi;

@@ -355,16 +355,165 @@ BwdWs carve_bwd(const toad_dims_t* d, int64_t n, void* base) {
 }
 }  // namespace
 
-extern "C" int toad_bwd_workspace_bytes(const toad_dims_t* d, int64_t n, size_t* bytes) {
+namespace {
+// ---- tensor-core backward workspace
+struct BwdTcWs {
+  float *dM, *sdot, *P, *dA, *dab, *splitk, *gate_part, *col_part;
+  bf16 *dab_hi, *dab_lo, *dabT_hi, *dabT_lo, *hT_hi, *hT_lo, *h1T_hi, *h1T_lo, *xT_hi, *xT_lo;
+  bf16 *dz2_hi, *dz2_lo, *dz2T_hi, *dz2T_lo, *dz1_hi, *dz1_lo, *dz1T_hi, *dz1T_lo;
+  bf16 *w2T_hi, *w2T_lo, *wabT_hi, *wabT_lo;
+  int gate_blocks, col_blocks;
+  int64_t ldT;
+  size_t bytes;
+};
+BwdTcWs carve_bwd_tc(const toad_dims_t* d, int64_t n, void* base) {
+  BwdTcWs w{};
+  Carver c(base);
+  const int64_t Hd = d->hid_dim, D = d->attn_dim, L = d->in_dim;
+  w.ldT = (n + 63) / 64 * 64;
+  w.dM = c.take<float>(2 * Hd);
+  w.sdot = c.take<float>(64);
+  w.P = c.take<float>(n * 2);
+  w.dA = c.take<float>(n * 2);
+  w.dab = c.take<float>(n * 2 * D);
+  w.dab_hi = c.take<bf16>(n * 2 * D);  w.dab_lo = c.take<bf16>(n * 2 * D);
+  w.dabT_hi = c.take<bf16>(2 * D * w.ldT); w.dabT_lo = c.take<bf16>(2 * D * w.ldT);
+  w.hT_hi = c.take<bf16>(Hd * w.ldT);  w.hT_lo = c.take<bf16>(Hd * w.ldT);
+  w.h1T_hi = c.take<bf16>(Hd * w.ldT); w.h1T_lo = c.take<bf16>(Hd * w.ldT);
+  w.xT_hi = c.take<bf16>(L * w.ldT);   w.xT_lo = c.take<bf16>(L * w.ldT);
+  w.dz2_hi = c.take<bf16>(n * Hd);     w.dz2_lo = c.take<bf16>(n * Hd);
+  w.dz2T_hi = c.take<bf16>(Hd * w.ldT); w.dz2T_lo = c.take<bf16>(Hd * w.ldT);
+  w.dz1_hi = c.take<bf16>(n * Hd);     w.dz1_lo = c.take<bf16>(n * Hd);
+  w.dz1T_hi = c.take<bf16>(Hd * w.ldT); w.dz1T_lo = c.take<bf16>(Hd * w.ldT);
+  w.w2T_hi = c.take<bf16>(Hd * Hd);    w.w2T_lo = c.take<bf16>(Hd * Hd);
+  w.wabT_hi = c.take<bf16>(Hd * 2 * D); w.wabT_lo = c.take<bf16>(Hd * 2 * D);
+  int64_t big = Hd * L;
+  if (2 * D * Hd > big) big = 2 * D * Hd;
+  w.splitk = c.take<float>(static_cast<size_t>(kSMs / 2) * 256 * 256);  // <= one 256x256 fp32 tile per CTA pair (+ slack below)
+  (void)big;
+  int64_t gb = (n + 127) / 128;
+  if (gb > 2 * kSMs) gb = 2 * kSMs;
+  w.gate_blocks = static_cast<int>(gb);
+  w.col_blocks = static_cast<int>(gb);
+  w.gate_part = c.take<float>(static_cast<size_t>(gb) * (4 * D + 2));
+  w.col_part = c.take<float>(static_cast<size_t>(gb) * Hd);
+  w.bytes = align_up(c.off, 256);
+  return w;
+}
+
+// dW[M_out, N_in] = A^T-planes [M_out, n] . (B^T-planes [N_in, n])^T with K = n patches, split-K over CTA pairs;
+// the fp32 partial tiles are then summed in fixed order into `dst` (row stride N_in).
+int wgrad_tc(const bf16* aT_hi, const bf16* aT_lo, const bf16* bT_hi, const bf16* bT_lo, int M_out, int N_in, int64_t n,
+             int64_t ldT, float* splitk, float* dst, int64_t dst_rows_first, float* dst2, cudaStream_t st) {
+  tc::GemmTcParams g{};
+  g.M = M_out; g.N = N_in; g.K = static_cast<int32_t>(n); g.lda = ldT; g.ldb = ldT;
+  const int num_kb = static_cast<int>((n + 63) / 64);
+  const int units = ((M_out + 255) / 256) * (N_in / 256);
+  int S = (kSMs / 2) / units;
+  if (S < 1) S = 1;
+  if (S > num_kb) S = num_kb;
+  const int kb_per = (num_kb + S - 1) / S;
+  S = (num_kb + kb_per - 1) / kb_per;  // no empty slices
+  g.k_splits = S; g.kb_per_split = kb_per;
+  g.out_f32 = splitk; g.ld_f32 = N_in;
+  TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, aT_hi, aT_lo, bT_hi, bT_lo, st)));
+  const int64_t stride = static_cast<int64_t>(M_out) * N_in;
+  if (dst2 == nullptr) return bwd::launch_reduce_strided(splitk, dst, stride, stride, S, st);
+  TOAD_TRY(bwd::launch_reduce_strided(splitk, dst, dst_rows_first * N_in, stride, S, st));
+  return bwd::launch_reduce_strided(splitk + dst_rows_first * N_in, dst2, stride - dst_rows_first * N_in, stride, S, st);
+}
+
+int bwd_tc(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t n, const toad_fwd_out_t* fo,
+           const toad_saved_t* sv, const float* dlogits, const float* dsite, float* grad, void* workspace,
+           size_t workspace_bytes, toad_stream_t stream) {
+  BwdTcWs w = carve_bwd_tc(d, n, workspace);
+  TOAD_TRY(check_ws(workspace, workspace_bytes, w.bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Hd = d->hid_dim, D = d->attn_dim, L = d->in_dim;
+  if (sv->dropout_p < 0.f || sv->dropout_p >= 1.f) return TOAD_ERR_ARG;
+  const float keep = 1.0f - sv->dropout_p, inv_keep = 1.0f / keep;
+  int64_t off[15];
+  toad_param_offsets(d, off);
+  float *g_w1 = grad + off[0], *g_b1 = grad + off[1], *g_w2 = grad + off[2], *g_b2 = grad + off[3];
+  float *g_wa = grad + off[4], *g_ba = grad + off[5], *g_wb = grad + off[6], *g_bb = grad + off[7];
+  float *g_wc = grad + off[8], *g_bc = grad + off[9], *g_wcls = grad + off[10], *g_bcls = grad + off[11];
+  float *g_wsite = grad + off[12], *g_bsite = grad + off[13];
+
+  // heads, softmax-pooling and gate backward: small HBM-bound kernels (shared with the fp32 path)
+  bwd::heads_bwd_kernel<<<1, 2 * bwd::H, 0, st>>>(dlogits, dsite, fo->features, P->wcls, P->wsite, d->n_classes, g_wcls,
+                                                   g_bcls, g_wsite, g_bsite, w.dM, w.sdot);
+  TOAD_CUDA_TRY(cudaGetLastError());
+  {
+    int64_t blocks = (n + 7) / 8;
+    if (blocks > 8 * kSMs) blocks = 8 * kSMs;
+    bwd::pool_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(sv->h, fo->a_raw, fo->softmax_stats, w.dM, w.sdot,
+                                                                         w.P, w.dA, n);
+    TOAD_CUDA_TRY(cudaGetLastError());
+  }
+  {
+    const int rpb = static_cast<int>((n + w.gate_blocks - 1) / w.gate_blocks);
+    bwd::gate_bwd_kernel<<<w.gate_blocks, D, 0, st>>>(sv->a, sv->b, w.dA, P->wc, w.dab, w.gate_part, n, D, rpb, keep);
+    TOAD_CUDA_TRY(cudaGetLastError());
+    const int64_t stride = 4 * D + 2;
+    TOAD_TRY(bwd::launch_reduce_strided(w.gate_part, g_wc, 2 * D, stride, w.gate_blocks, st));
+    TOAD_TRY(bwd::launch_reduce_strided(w.gate_part + 2 * D, g_ba, D, stride, w.gate_blocks, st));
+    TOAD_TRY(bwd::launch_reduce_strided(w.gate_part + 3 * D, g_bb, D, stride, w.gate_blocks, st));
+    TOAD_TRY(bwd::launch_reduce_strided(w.gate_part + 4 * D, g_bc, 2, stride, w.gate_blocks, st));
+  }
+  // operand preparation: (hi, lo) planes, K-major in whichever index the GEMM contracts over
+  TOAD_TRY(tail::launch_split_planes(w.dab, w.dab_hi, w.dab_lo, n * 2 * D, st));
+  TOAD_TRY(bwd::launch_transpose_split(w.dab, n, 2 * D, 2 * D, w.dabT_hi, w.dabT_lo, w.ldT, st));
+  TOAD_TRY(bwd::launch_transpose_split(sv->h, n, Hd, Hd, w.hT_hi, w.hT_lo, w.ldT, st));
+  TOAD_TRY(bwd::launch_transpose_split(sv->h1, n, Hd, Hd, w.h1T_hi, w.h1T_lo, w.ldT, st));
+  TOAD_TRY(bwd::launch_transpose_split(x, n, L, L, w.xT_hi, w.xT_lo, w.ldT, st));
+  TOAD_TRY(bwd::launch_transpose_split(P->w2, Hd, Hd, Hd, w.w2T_hi, w.w2T_lo, Hd, st));                  // W2^T   [in, out]
+  TOAD_TRY(bwd::launch_transpose_split(P->wa, D, Hd, Hd, w.wabT_hi, w.wabT_lo, 2 * D, st));              // [Wa;Wb]^T [hid, 2D]
+  TOAD_TRY(bwd::launch_transpose_split(P->wb, D, Hd, Hd, w.wabT_hi + D, w.wabT_lo + D, 2 * D, st));
+
+  // dWa | dWb = dab^T . h
+  TOAD_TRY(wgrad_tc(w.dabT_hi, w.dabT_lo, w.hT_hi, w.hT_lo, 2 * D, Hd, n, w.ldT, w.splitk, g_wa, D, g_wb, st));
+  // dz2 = (dab . [Wa;Wb] + P0 dM0 + P1 dM1) * (h > 0) / keep      -> planes
+  {
+    tc::GemmTcParams g{};
+    g.M = n; g.N = Hd; g.K = 2 * D;
+    g.pool_p = w.P; g.pool_v = w.dM; g.mask_f32 = sv->h; g.ld_mask = Hd; g.out_scale = inv_keep;
+    g.out_hi = w.dz2_hi; g.out_lo = w.dz2_lo; g.ld_split = Hd;
+    TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, w.dab_hi, w.dab_lo, w.wabT_hi, w.wabT_lo, st)));
+  }
+  const int rpb = static_cast<int>((n + w.col_blocks - 1) / w.col_blocks);
+  bwd::colsum_planes_kernel<<<w.col_blocks, Hd, 0, st>>>(w.dz2_hi, w.dz2_lo, w.col_part, n, Hd, rpb);
+  TOAD_CUDA_TRY(cudaGetLastError());
+  TOAD_TRY(bwd::launch_reduce_strided(w.col_part, g_b2, Hd, Hd, w.col_blocks, st));
+  TOAD_TRY(bwd::launch_transpose_planes(w.dz2_hi, w.dz2_lo, n, Hd, w.dz2T_hi, w.dz2T_lo, w.ldT, st));
+  // dW2 = dz2^T . h1
+  TOAD_TRY(wgrad_tc(w.dz2T_hi, w.dz2T_lo, w.h1T_hi, w.h1T_lo, Hd, Hd, n, w.ldT, w.splitk, g_w2, 0, nullptr, st));
+  // dz1 = (dz2 . W2) * (h1 > 0) / keep
+  {
+    tc::GemmTcParams g{};
+    g.M = n; g.N = Hd; g.K = Hd;
+    g.mask_f32 = sv->h1; g.ld_mask = Hd; g.out_scale = inv_keep;
+    g.out_hi = w.dz1_hi; g.out_lo = w.dz1_lo; g.ld_split = Hd;
+    TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, w.dz2_hi, w.dz2_lo, w.w2T_hi, w.w2T_lo, st)));
+  }
+  bwd::colsum_planes_kernel<<<w.col_blocks, Hd, 0, st>>>(w.dz1_hi, w.dz1_lo, w.col_part, n, Hd, rpb);
+  TOAD_CUDA_TRY(cudaGetLastError());
+  TOAD_TRY(bwd::launch_reduce_strided(w.col_part, g_b1, Hd, Hd, w.col_blocks, st));
+  TOAD_TRY(bwd::launch_transpose_planes(w.dz1_hi, w.dz1_lo, n, Hd, w.dz1T_hi, w.dz1T_lo, w.ldT, st));
+  // dW1 = dz1^T . x
+  return wgrad_tc(w.dz1T_hi, w.dz1T_lo, w.xT_hi, w.xT_lo, Hd, L, n, w.ldT, w.splitk, g_w1, 0, nullptr, st);
+}
+}  // namespace
+
+extern "C" int toad_bwd_workspace_bytes(const toad_dims_t* d, int64_t n, uint32_t flags, size_t* bytes) {
   TOAD_TRY(check_dims(d));
   if (bytes == nullptr || n <= 0) return TOAD_ERR_ARG;
-  *bytes = carve_bwd(d, n, nullptr).bytes;
+  *bytes = (flags & TOAD_FLAG_SIMT_FP32) ? carve_bwd(d, n, nullptr).bytes : carve_bwd_tc(d, n, nullptr).bytes;
   return 0;
 }
 
-extern "C" int toad_bwd(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t n, const toad_fwd_out_t* fo,
-             const toad_saved_t* sv, const float* dlogits, const float* dsite, float* grad, void* workspace,
-             size_t workspace_bytes, toad_stream_t stream) {
+static int bwd_simt(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t n, const toad_fwd_out_t* fo,
+                    const toad_saved_t* sv, const float* dlogits, const float* dsite, float* grad, void* workspace,
+                    size_t workspace_bytes, toad_stream_t stream) {
   TOAD_TRY(check_dims(d));
   if (!P || !x || !fo || !sv || !dlogits || !dsite || !grad || n <= 0) return TOAD_ERR_ARG;
   if (!fo->a_raw || !fo->features || !fo->softmax_stats || !sv->h1 || !sv->h || !sv->a || !sv->b) return TOAD_ERR_ARG;
@@ -463,6 +612,16 @@ extern "C" int toad_bwd(const toad_dims_t* d, const toad_params_t* P, const floa
     TOAD_TRY(bwd::launch_reduce_strided(w.splitk, g_w1, static_cast<int64_t>(Hd) * L, static_cast<int64_t>(Hd) * L, w.splits, st));
   }
   return 0;
+}
+
+extern "C" int toad_bwd(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t n, const toad_fwd_out_t* fo,
+                        const toad_saved_t* sv, const float* dlogits, const float* dsite, float* grad, void* workspace,
+                        size_t workspace_bytes, uint32_t flags, toad_stream_t stream) {
+  TOAD_TRY(check_dims(d));
+  if (!P || !x || !fo || !sv || !dlogits || !dsite || !grad || n <= 0) return TOAD_ERR_ARG;
+  if (!fo->a_raw || !fo->features || !fo->softmax_stats || !sv->h1 || !sv->h || !sv->a || !sv->b) return TOAD_ERR_ARG;
+  if (flags & TOAD_FLAG_SIMT_FP32) return bwd_simt(d, P, x, n, fo, sv, dlogits, dsite, grad, workspace, workspace_bytes, stream);
+  return bwd_tc(d, P, x, n, fo, sv, dlogits, dsite, grad, workspace, workspace_bytes, stream);
 }
 
 // ------------------------------------------------------------------------------------------ Attn_Net_Gated

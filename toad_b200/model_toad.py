@@ -106,7 +106,8 @@ class _ToadFunction(torch.autograd.Function):
             dlogits = torch.zeros_like(ctx.out["logits"])
         if dsite_logits is None:
             dsite_logits = torch.zeros_like(ctx.out["site_logits"])
-        flat = ops.toad_bwd(dims, ctx.params, ctx.h, ctx.out, ctx.saved, dlogits, dsite_logits, module._ws_bwd)
+        flat = ops.toad_bwd(dims, ctx.params, ctx.h, ctx.out, ctx.saved, dlogits, dsite_logits, module._ws_bwd,
+                            flags=_default_flags())
         off = ops.param_offsets(dims)
         grads = tuple(flat[off[i]:off[i + 1]].view_as(p) if ctx.needs_input_grad[3 + i] else None
                       for i, p in enumerate(ctx.params))

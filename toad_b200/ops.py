@@ -148,7 +148,7 @@ def toad_fwd(dims: Dims, params: Sequence[torch.Tensor], x: torch.Tensor, sex: t
 
 def toad_bwd(dims: Dims, params: Sequence[torch.Tensor], x: torch.Tensor, out: Dict[str, torch.Tensor],
              saved: Dict[str, torch.Tensor], dlogits: torch.Tensor, dsite_logits: torch.Tensor, ws: Workspace,
-             grad_flat: Optional[torch.Tensor] = None) -> torch.Tensor:
+             grad_flat: Optional[torch.Tensor] = None, flags: int = 0) -> torch.Tensor:
     """Gradients of the 14 parameters as one flat fp32 buffer (toad_param_offsets order)."""
     lib = _lib.load()
     n = x.shape[0]
@@ -162,12 +162,13 @@ def toad_bwd(dims: Dims, params: Sequence[torch.Tensor], x: torch.Tensor, out: D
     _check_dev_f32(ds, "dsite_logits", (2,))
     p = _params_struct(dims, params)
     nbytes = C.c_size_t()
-    _lib.check(lib.toad_bwd_workspace_bytes(C.byref(dims), n, C.byref(nbytes)), "toad_bwd_workspace_bytes")
+    flags &= _lib.FLAG_SIMT_FP32
+    _lib.check(lib.toad_bwd_workspace_bytes(C.byref(dims), n, flags, C.byref(nbytes)), "toad_bwd_workspace_bytes")
     wptr, wsize = ws.get(nbytes.value, x.device)
     o = _out_struct(out)
     s = _saved_struct(saved)
     _lib.check(lib.toad_bwd(C.byref(dims), C.byref(p), x.data_ptr(), n, C.byref(o), C.byref(s), dl.data_ptr(),
-                            ds.data_ptr(), grad_flat.data_ptr(), wptr, wsize, _stream()), "toad_bwd")
+                            ds.data_ptr(), grad_flat.data_ptr(), wptr, wsize, flags, _stream()), "toad_bwd")
     return grad_flat
 
 
