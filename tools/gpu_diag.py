@@ -20,7 +20,7 @@ os.makedirs(OUT, exist_ok=True)
 
 STEPS = ["lin_64_f32", "lin_64_split", "lin_128", "lin_256", "lin_multi", "pair_64_f32", "pair_64_split", "pair_256",
          "pair_multi", "wide_small", "wide_multi", "attn_gated", "simt_fwd", "tc_fwd_small", "tc_fwd_10k", "tc_fwd_10k_cg1", "topk", "bwd_simt",
-         "bwd_tc", "timing", "lin_timing", "resnet_s64", "resnet_s256", "resnet_timing"]
+         "bwd_tc", "timing", "lin_timing", "resnet_s64", "resnet_s256", "resnet_timing", "train_timing"]
 
 
 def log(rec):
@@ -193,6 +193,41 @@ def run_step(step):
         return bwd_case(step, False)
     if step == "timing":
         return timing(step)
+    if step == "train_timing":
+        import torch
+        from models.model_toad import TOAD_fc_mtl_concat
+        rec = {"step": step, "ok": True}
+        for mode in ("tc", "simt"):
+            os.environ["TOAD_B200_SIMT"] = "1" if mode == "simt" else "0"
+            torch.manual_seed(0)
+            model = TOAD_fc_mtl_concat(n_classes=18)
+            model.relocate()
+            model.train()
+            opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-5)
+            x = torch.randn(50000, 1024, device="cuda")
+            sex = torch.ones(1, device="cuda")
+            lab, site = torch.tensor([3], device="cuda"), torch.tensor([1], device="cuda")
+            ce = torch.nn.CrossEntropyLoss()
+
+            def one(with_opt=True):
+                r = model(x, sex)
+                loss = 0.75 * ce(r["logits"], lab) + 0.25 * ce(r["site_logits"], site)
+                loss.backward()
+                if with_opt:
+                    opt.step()
+                    opt.zero_grad()
+            for _ in range(3):
+                one()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                one()
+            e1.record()
+            torch.cuda.synchronize()
+            rec[mode + "_train_step_ms"] = round(e0.elapsed_time(e1) / 10, 3)
+        os.environ["TOAD_B200_SIMT"] = "0"
+        return rec
     if step == "lin_timing":
         import torch
         from toad_b200 import ops
