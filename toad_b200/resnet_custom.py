@@ -29,18 +29,23 @@ model_urls = {  # resnet_custom.py:11-17
 }
 
 
+def _conv_bn(owner: nn.Module, idx: int, cin: int, cout: int, k: int, stride: int) -> None:
+    """Register `conv{idx}` (bias-free) and `bn{idx}` on `owner` -- the torchvision attribute names the
+    reference's checkpoints use (resnet_custom.py:24-31)."""
+    setattr(owner, "conv%d" % idx, nn.Conv2d(cin, cout, kernel_size=k, stride=stride, padding=k // 2, bias=False))
+    setattr(owner, "bn%d" % idx, nn.BatchNorm2d(cout))
+
+
 class Bottleneck_Baseline(nn.Module):
-    """Parameter container with the reference's layout (resnet_custom.py:19-34); never called."""
+    """Parameter container for one bottleneck (1x1 -> 3x3/stride -> 1x1 x4, resnet_custom.py:19-34).
+    It is never called: the whole trunk runs in toad_resnet_fwd."""
     expansion = 4
 
     def __init__(self, inplanes, planes, stride=1, downsample=None):
         super().__init__()
-        self.conv1 = nn.Conv2d(inplanes, planes, kernel_size=1, bias=False)
-        self.bn1 = nn.BatchNorm2d(planes)
-        self.conv2 = nn.Conv2d(planes, planes, kernel_size=3, stride=stride, padding=1, bias=False)
-        self.bn2 = nn.BatchNorm2d(planes)
-        self.conv3 = nn.Conv2d(planes, planes * self.expansion, kernel_size=1, bias=False)
-        self.bn3 = nn.BatchNorm2d(planes * self.expansion)
+        for idx, (cin, cout, k, s) in enumerate(((inplanes, planes, 1, 1), (planes, planes, 3, stride),
+                                                 (planes, planes * self.expansion, 1, 1)), start=1):
+            _conv_bn(self, idx, cin, cout, k, s)
         self.relu = nn.ReLU(inplace=True)
         self.downsample = downsample
         self.stride = stride
@@ -49,41 +54,43 @@ class Bottleneck_Baseline(nn.Module):
 class ResNet_Baseline(nn.Module):
     """resnet_custom.py:57-109.  `layers[3]` is ignored exactly as in the reference (no layer4 / fc)."""
 
+    STAGES = ((64, 1), (128, 2), (256, 2))   # (planes, stride) of layer1..layer3
+
     def __init__(self, block, layers):
-        self.inplanes = 64
         super().__init__()
+        if list(layers[:3]) != [3, 4, 6] or block is not Bottleneck_Baseline:
+            raise NotImplementedError("toad_b200 implements the resnet50_baseline configuration ([3, 4, 6, 3] bottlenecks)")
+        self.inplanes = 64
         self.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
         self.relu = nn.ReLU(inplace=True)
         self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
-        self.layer1 = self._make_layer(block, 64, layers[0])
-        self.layer2 = self._make_layer(block, 128, layers[1], stride=2)
-        self.layer3 = self._make_layer(block, 256, layers[2], stride=2)
+        for i, ((planes, stride), blocks) in enumerate(zip(self.STAGES, layers), start=1):
+            setattr(self, "layer%d" % i, self._make_layer(block, planes, blocks, stride))
         self.avgpool = nn.AdaptiveAvgPool2d(1)
-        for m in self.modules():
-            if isinstance(m, nn.Conv2d):
-                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
-            elif isinstance(m, nn.BatchNorm2d):
-                nn.init.constant_(m.weight, 1)
-                nn.init.constant_(m.bias, 0)
-        if list(layers[:3]) != [3, 4, 6] or block is not Bottleneck_Baseline:
-            raise NotImplementedError("toad_b200 implements the resnet50_baseline configuration ([3, 4, 6, 3] bottlenecks)")
+        self.apply(self._init_module)          # kaiming-normal(fan_out) convs, BN weight 1 / bias 0 (:72-77)
         self._prepared = None
         self._prepared_key = None
         self._ws = ops.Workspace()
 
+    @staticmethod
+    def _init_module(m: nn.Module) -> None:
+        if isinstance(m, nn.Conv2d):
+            nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+        elif isinstance(m, nn.BatchNorm2d):
+            nn.init.ones_(m.weight)
+            nn.init.zeros_(m.bias)
+
     def _make_layer(self, block, planes, blocks, stride=1):
-        downsample = None
-        if stride != 1 or self.inplanes != planes * block.expansion:
-            downsample = nn.Sequential(
-                nn.Conv2d(self.inplanes, planes * block.expansion, kernel_size=1, stride=stride, bias=False),
-                nn.BatchNorm2d(planes * block.expansion),
-            )
-        layers = [block(self.inplanes, planes, stride, downsample)]
-        self.inplanes = planes * block.expansion
-        for _ in range(1, blocks):
-            layers.append(block(self.inplanes, planes))
-        return nn.Sequential(*layers)
+        out_ch = planes * block.expansion
+        shortcut = None
+        if stride != 1 or self.inplanes != out_ch:   # projection shortcut on the first block (:82-87)
+            shortcut = nn.Sequential(nn.Conv2d(self.inplanes, out_ch, kernel_size=1, stride=stride, bias=False),
+                                     nn.BatchNorm2d(out_ch))
+        seq = [block(self.inplanes, planes, stride, shortcut)]
+        self.inplanes = out_ch
+        seq += [block(out_ch, planes) for _ in range(blocks - 1)]
+        return nn.Sequential(*seq)
 
     # -- tensors in state_dict order without num_batches_tracked (the C ABI's `tensors` array)
     def _tensor_list(self):
