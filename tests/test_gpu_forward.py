@@ -231,3 +231,21 @@ def test_giga_slide_attention_only_and_topk():
             if k <= 100:
                 # vs the fp32 oracle the band must cover the split-bf16 score error (~2e-5 abs), not just ulps
                 assert topk_sets_match(to_np(scores), ref["A"][t].astype(np.float64), k, ulps=2048)
+
+
+def test_sex_covariate_enters_linearly():
+    """sex is concatenated to the pooled vector (model_toad.py:99): logits(sex=1) - logits(sex=0) equals the
+    last column of each head's weight, and the attention scores do not depend on it."""
+    g = load_golden("toad_big_n257")
+    params, x, _ = case_inputs(g)
+    model = build_model(params, "big", 18)
+    xd = torch.from_numpy(x).cuda()
+    with torch.no_grad():
+        o0 = model(xd, torch.tensor([0.0], device="cuda"), return_features=True)
+        o1 = model(xd, torch.tensor([1.0], device="cuda"), return_features=True)
+        o1i = model(xd, torch.tensor([1], device="cuda"))          # LongTensor sex, as collate_MIL_mtl_concat builds it
+    assert torch.equal(o0["A"], o1["A"])
+    np.testing.assert_allclose(to_np(o1["logits"] - o0["logits"])[0], params[O.PARAM_KEYS[10]][:, 512], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(to_np(o1["site_logits"] - o0["site_logits"])[0], params[O.PARAM_KEYS[12]][:, 512], rtol=0, atol=2e-6)
+    assert to_np(o0["features"])[0, 512] == 0.0 and to_np(o1["features"])[1, 512] == 1.0
+    assert torch.equal(o1i["logits"], o1["logits"])
