@@ -11,8 +11,9 @@
 //   warp 0      TMA producer: B_hi/B_lo tiles (and A_hi/A_lo when A is already split)
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16)
 //   warp 2      TMEM allocator
-//   warps 4-11  epilogue: tcgen05.ld accumulator -> registers -> bias/activation -> smem staging -> TMA store
-//   warps 12-19 (A_MODE 0 only) A converter: fp32 rows from global -> (hi,lo) bf16 pairs written
+//   warps 4-11  epilogue (4-7 when fp32-fed): tcgen05.ld accumulator -> registers -> bias/activation -> smem
+//               staging -> TMA store
+//   next 8      (A_MODE 0 only) A converter: fp32 rows from global -> (hi,lo) bf16 pairs written
 //               straight into the 128B-swizzled UMMA operand layout, loads one K block ahead
 // Pipelines: smem ring (full/empty mbarriers) between producer/converter and MMA, and a
 // 2-deep TMEM accumulator ring (tmem_full/tmem_empty) between MMA and epilogue, so the
@@ -81,7 +82,8 @@ struct GemmTcParams {
   const float* gate_wc;  // [ntasks, D]
   int32_t gate_D;
   int32_t gate_ntasks;  // 1..4
-  float* gate_part;     // [2 * n_tiles][M][ntasks] partial scores (no bias): one per (tile, epilogue warp set)
+  float* gate_part;     // [sets * n_tiles][M][ntasks] partial scores (no bias): one per (tile, epilogue warp set);
+                        // sets = 2 for plane-fed A, 1 for fp32-fed A
   float* gate_a;        // nullable [M, D]
   float* gate_b;        // nullable [M, D]
   // A_CONV: rows are output pixels (b, oh, ow) raster; K blocks walk (tap, 64-channel chunk); the A tile
@@ -202,7 +204,10 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the 8 epilogue warps
+template <int THREADS>
+__device__ __forceinline__ void epi_barrier() {  // all epilogue warps of the CTA
+  asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+}
 
 template <int CG>
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
@@ -318,13 +323,18 @@ __device__ __forceinline__ float fast_tanh(float z) { return fmaf(2.0f, fast_sig
 constexpr int GATE_SMEM_FLOATS = 4 * 1024;  // ba | bb | wc rows (<= 2 tasks staged) for D <= 1024
 
 template <int BLOCK_N, int A_MODE, int EPI, int CG>
-__global__ void __launch_bounds__(A_MODE == A_F32 ? 640 : 384, 1)
+__global__ void __launch_bounds__(A_MODE == A_F32 ? 512 : 384, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
                    const GemmTcParams p) {
   using C = Cfg<BLOCK_N, CG>;
   static_assert(EPI != EPI_GATE || BLOCK_N <= 256, "the gate epilogue pairs two 128-column halves of a 256-wide tile");
+  // epilogue warp sets: plane-fed kernels run 8 epilogue warps (two per TMEM lane quarter, each taking one
+  // 32-column half of every 64-column chunk); the fp32-fed kernels keep 4 so that, with their 8 converter
+  // warps, the CTA stays at 512 threads / 128 registers.
+  constexpr int EPI_SETS = A_MODE == A_F32 ? 1 : 2;
+  constexpr int CONV_WARP0 = 4 + 4 * EPI_SETS;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full_b[STAGES];
@@ -360,7 +370,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&bar_tmem_full[a]), 1);
-      mbar_init(smem_u32(&bar_tmem_empty[a]), 8 * CG);  // one arrive per epilogue warp (8 per CTA)
+      mbar_init(smem_u32(&bar_tmem_empty[a]), 4 * EPI_SETS * CG);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -488,8 +498,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
       }
     }
-  } else if (warp >= 4 && warp < 12) {
-    // ------------------------------------------------------------------ epilogue (8 warps)
+  } else if (warp >= 4 && warp < CONV_WARP0) {
+    // ------------------------------------------------------------------ epilogue (4 * EPI_SETS warps)
     // warp -> (TMEM lane quarter ew = warp % 4, column half eh): the two warps of a lane quarter split every
     // 64-column chunk into its two 32-column halves.
     const int ew = (warp - 4) & 3;  // == warp % 4: the TMEM lane quarter this warp may access
@@ -518,10 +528,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           if (p.out_hi != nullptr) {
             // staging buffer free again? (the previous TMA store must have finished READING it)
             if (warp == 4 && lane == 0) tma_store_wait_read();
-            epi_barrier();
+            epi_barrier<128 * EPI_SETS>();
           }
-          {
-            const int h = eh;  // this warp's 32-column half of the 64-column chunk
+#pragma unroll 1
+          for (int h = eh; h < 2; h += EPI_SETS) {  // this warp's 32-column half (halves) of the 64-column chunk
             uint32_t r[32];
             tmem_ld32(t_row + cc * 64 + h * 32, r);
             tmem_ld_wait();
@@ -535,11 +545,18 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 vl = *reinterpret_cast<const uint4*>(p.res_lo + row * p.ld_res + col0 + q * 8);
               }
               const uint32_t uh[4] = {vh.x, vh.y, vh.z, vh.w}, ul[4] = {vl.x, vl.y, vl.z, vl.w};
+              // bias for these 8 columns as two 128-bit broadcast loads (32 scalar loads per half-chunk
+              // saturated the LSU queue: stall_lg in the ncu source view of the ResNet 1x1 convolutions)
+              float bv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              if (p.bias != nullptr && split == 0) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + q * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + q * 8 + 4));
+                bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+              }
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 const int i = q * 8 + e;
-                float t = __uint_as_float(r[i]);
-                if (p.bias != nullptr && split == 0) t += __ldg(p.bias + col0 + i);
+                float t = __uint_as_float(r[i]) + bv[e];
                 const uint32_t wh = uh[e >> 1], wl = ul[e >> 1];
                 t += (e & 1) ? (bf16hi_to_f32(wh) + bf16hi_to_f32(wl)) : (bf16lo_to_f32(wh) + bf16lo_to_f32(wl));
                 if (p.relu) t = fmaxf(t, 0.0f);
@@ -556,11 +573,17 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 if (p.mask_f32 != nullptr && row_ok)
                   mk = *reinterpret_cast<const float4*>(p.mask_f32 + row * p.ld_mask + col0 + q * 4);
                 const float mv[4] = {mk.x, mk.y, mk.z, mk.w};
+                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                if (p.pool_p != nullptr) {
+                  v0 = __ldg(reinterpret_cast<const float4*>(p.pool_v + col0 + q * 4));
+                  v1 = __ldg(reinterpret_cast<const float4*>(p.pool_v + p.N + col0 + q * 4));
+                }
+                const float pv0[4] = {v0.x, v0.y, v0.z, v0.w}, pv1[4] = {v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const int i = q * 4 + e;
                   float t = __uint_as_float(r[i]);
-                  if (p.pool_p != nullptr) t += p0 * __ldg(p.pool_v + col0 + i) + p1 * __ldg(p.pool_v + p.N + col0 + i);
+                  if (p.pool_p != nullptr) t += p0 * pv0[e] + p1 * pv1[e];
                   t = mv[e] > 0.f ? t : 0.f;
                   if (p.out_scale != 0.f) t *= p.out_scale;
                   r[i] = __float_as_uint(t);
@@ -595,7 +618,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           }
           if (p.out_hi != nullptr) {
             fence_proxy_async_smem();
-            epi_barrier();
+            epi_barrier<128 * EPI_SETS>();
             if (warp == 4 && lane == 0) {
               tma_store_2d(&tm_o_hi, stage_hi, n0 + cc * 64, m0);
               tma_store_2d(&tm_o_lo, stage_lo, n0 + cc * 64, m0);
@@ -608,7 +631,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         const int j0 = n_tile * HALF;
         float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-        for (int c = eh; c < HALF / 32; c += 2) {  // the two warps of a lane quarter alternate 32-column chunks
+        for (int c = eh; c < HALF / 32; c += EPI_SETS) {  // the warps of a lane quarter alternate 32-column chunks
           uint32_t ra[32], rb[32];
           tmem_ld32(t_row + c * 32, ra);
           tmem_ld32(t_row + HALF + c * 32, rb);
@@ -649,7 +672,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           }
         }
         if (row_ok) {
-          float* dst = p.gate_part + (static_cast<int64_t>(n_tile * 2 + eh) * p.M + row) * p.gate_ntasks;
+          float* dst = p.gate_part + (static_cast<int64_t>(n_tile * EPI_SETS + eh) * p.M + row) * p.gate_ntasks;
 #pragma unroll
           for (int t = 0; t < 4; ++t)
             if (t < p.gate_ntasks) dst[t] = s[t];
@@ -662,11 +685,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         else mbar_arrive_cluster(smem_u32(&bar_tmem_empty[acc]), 0);
       }
     }
-  } else if (A_MODE == A_F32 && warp >= 12) {
+  } else if (A_MODE == A_F32 && warp >= CONV_WARP0) {
     // ------------------------------------------------------------------ A converter (8 warps)
     // Each half-warp streams one 256 B row segment (64 fp32) per load instruction; a thread turns its
     // 4 floats into 4 (hi) + 4 (lo) bf16 = one 8 B store into each swizzled tile.
-    const int cw = warp - 12;  // 0..7: rows cw*16 .. cw*16+15 of the tile
+    const int cw = warp - CONV_WARP0;  // 0..7: rows cw*16 .. cw*16+15 of the tile
     const int hw = lane >> 4, l16 = lane & 15;
     const int my_tiles = unit0 < num_tiles ? (num_tiles - unit0 + unit_stride - 1) / unit_stride : 0;
     const int64_t total = static_cast<int64_t>(my_tiles) * num_kb;
@@ -817,7 +840,7 @@ int launch_gemm_maps(const GemmTcParams& p, const CUtensorMap& ta_hi, const CUte
   const int grid = static_cast<int>(units < max_units ? units : max_units) * CG;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
-  cfg.blockDim = dim3(A_MODE == A_F32 ? 640 : 384);
+  cfg.blockDim = dim3(A_MODE == A_F32 ? 512 : 384);
   cfg.dynamicSmemBytes = kSmem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

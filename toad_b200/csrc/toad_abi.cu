@@ -636,7 +636,7 @@ AgWs carve_ag(int L, int D, int nt, int64_t n, uint32_t flags, void* base) {
   AgWs w{};
   Carver c(base);
   const bool simt = (flags & TOAD_FLAG_SIMT_FP32) != 0;
-  w.n_parts = simt ? 1 : 2 * (D / kGateHalf);
+  w.n_parts = simt ? 1 : D / kGateHalf;  // fp32-fed gate kernel: one epilogue warp set
   w.part = c.take<float>(static_cast<size_t>(w.n_parts) * n * nt);
   if (simt) {
     w.a = c.take<float>(n * D);

@@ -30,6 +30,8 @@ def _check_dev_f32(t: torch.Tensor, name: str, shape: Optional[Sequence[int]] = 
         raise ValueError("%s must be float32, got %s" % (name, t.dtype))
     if not t.is_contiguous():
         raise ValueError("%s must be contiguous" % name)
+    if t.data_ptr() % 16 != 0:
+        raise ValueError("%s must be 16-byte aligned (the kernels use 128-bit loads)" % name)
     if shape is not None and tuple(t.shape) != tuple(shape):
         raise ValueError("%s must have shape %s, got %s" % (name, tuple(shape), tuple(t.shape)))
 
