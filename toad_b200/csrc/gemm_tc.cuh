@@ -511,10 +511,28 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       const int n0 = n_tile * BLOCK_N;
       const int m0 = (mn / n_tiles) * (BLOCK_M * CG) + static_cast<int>(cta_rank) * BLOCK_M;
       const int acc = it % C::ACC_STAGES;
-      mbar_wait(smem_u32(&bar_tmem_full[acc]), (it / C::ACC_STAGES) & 1);
-      tc_fence_after();
       const int64_t row = static_cast<int64_t>(m0) + ew * 32 + lane;
       const bool row_ok = row < p.M;
+      // residual operand (ResNet shortcut): this warp's 32-column half of the NEXT 64-column chunk is fetched
+      // one chunk ahead (and the first one before waiting for the accumulator), hiding the global latency
+      // that otherwise serialises the epilogue of the short-K 1x1 convolutions.
+      const bool has_res = EPI == EPI_LINEAR && A_MODE != A_F32 && p.res_hi != nullptr && row_ok;
+      uint4 res_h[4], res_l[4];
+      auto load_res = [&](int cc_) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          res_h[q] = make_uint4(0u, 0u, 0u, 0u);
+          res_l[q] = make_uint4(0u, 0u, 0u, 0u);
+          if (has_res) {
+            const int64_t o = row * p.ld_res + n0 + cc_ * 64 + eh * 32 + q * 8;
+            res_h[q] = *reinterpret_cast<const uint4*>(p.res_hi + o);
+            res_l[q] = *reinterpret_cast<const uint4*>(p.res_lo + o);
+          }
+        }
+      };
+      if (EPI == EPI_LINEAR && A_MODE != A_F32) load_res(0);
+      mbar_wait(smem_u32(&bar_tmem_full[acc]), (it / C::ACC_STAGES) & 1);
+      tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N;
 
       if (EPI == EPI_LINEAR) {
@@ -534,16 +552,15 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           for (int h = eh; h < 2; h += EPI_SETS) {  // this warp's 32-column half (halves) of the 64-column chunk
             uint32_t r[32];
             tmem_ld32(t_row + cc * 64 + h * 32, r);
+            uint4 cur_h[4], cur_l[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { cur_h[q] = res_h[q]; cur_l[q] = res_l[q]; }
+            if (A_MODE != A_F32 && cc + 1 < BLOCK_N / 64) load_res(cc + 1);  // next chunk's residual, in flight below
             tmem_ld_wait();
             const int col0 = n0 + cc * 64 + h * 32;
-            const bool has_res = A_MODE != A_F32 && p.res_hi != nullptr && row_ok;  // residual only on plane-fed GEMMs
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = make_uint4(0u, 0u, 0u, 0u);
-              if (has_res) {
-                vh = *reinterpret_cast<const uint4*>(p.res_hi + row * p.ld_res + col0 + q * 8);
-                vl = *reinterpret_cast<const uint4*>(p.res_lo + row * p.ld_res + col0 + q * 8);
-              }
+              const uint4 vh = cur_h[q], vl = cur_l[q];
               const uint32_t uh[4] = {vh.x, vh.y, vh.z, vh.w}, ul[4] = {vl.x, vl.y, vl.z, vl.w};
               // bias for these 8 columns as two 128-bit broadcast loads (32 scalar loads per half-chunk
               // saturated the LSU queue: stall_lg in the ncu source view of the ResNet 1x1 convolutions)

@@ -20,7 +20,7 @@ os.makedirs(OUT, exist_ok=True)
 
 STEPS = ["lin_64_f32", "lin_64_split", "lin_128", "lin_256", "lin_multi", "pair_64_f32", "pair_64_split", "pair_256",
          "pair_multi", "wide_small", "wide_multi", "attn_gated", "simt_fwd", "tc_fwd_small", "tc_fwd_10k", "tc_fwd_10k_cg1", "topk", "bwd_simt",
-         "bwd_tc", "timing", "lin_timing", "resnet_s64", "resnet_s256", "resnet_timing", "train_timing"]
+         "bwd_tc", "timing", "lin_timing", "resnet_s64", "resnet_s256", "resnet_timing", "train_timing", "train_breakdown"]
 
 
 def log(rec):
@@ -227,6 +227,36 @@ def run_step(step):
             torch.cuda.synchronize()
             rec[mode + "_train_step_ms"] = round(e0.elapsed_time(e1) / 10, 3)
         os.environ["TOAD_B200_SIMT"] = "0"
+        return rec
+    if step == "train_breakdown":
+        import torch
+        from models.model_toad import TOAD_fc_mtl_concat
+        os.environ["TOAD_B200_SIMT"] = "0"
+        torch.manual_seed(0)
+        model = TOAD_fc_mtl_concat(n_classes=18)
+        model.relocate()
+        model.train()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-5)
+        x = torch.randn(50000, 1024, device="cuda")
+        sex = torch.ones(1, device="cuda")
+        lab, site = torch.tensor([3], device="cuda"), torch.tensor([1], device="cuda")
+        ce = torch.nn.CrossEntropyLoss()
+        rec = {"step": step, "ok": True, "iters": []}
+        for it in range(12):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r = model(x, sex)
+            t1 = time.perf_counter()
+            loss = 0.75 * ce(r["logits"], lab) + 0.25 * ce(r["site_logits"], site)
+            t2 = time.perf_counter()
+            loss.backward()
+            t3 = time.perf_counter()
+            opt.step()
+            opt.zero_grad()
+            t4 = time.perf_counter()
+            torch.cuda.synchronize()
+            t5 = time.perf_counter()
+            rec["iters"].append([round(1e3 * v, 3) for v in (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t5 - t0)])
         return rec
     if step == "lin_timing":
         import torch
