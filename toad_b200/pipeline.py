@@ -53,6 +53,10 @@ class SlideStreamer:
         i = 0
         while staged is not None:
             cur = staged
+            if i >= 1:
+                # the source may recycle the host buffer of item i-1 as soon as item i+1 is requested
+                # (ring-buffer loaders): its H2D copy must have completed, not merely been enqueued
+                self.copied[(cur[0] + self.depth - 1) % self.depth].synchronize()
             nxt = next(it, None)
             staged = stage((cur[0] + 1) % self.depth, nxt) if nxt is not None else None
             cslot, n, sex = cur
