@@ -141,10 +141,10 @@ class TOAD_fc_mtl_concat(nn.Module):
         initialize_weights(self)
         self.dropout = bool(dropout)
         self._dims = ops.make_dims(size[0], size[1], size[2], n_classes)
-        self._ws = ops.Workspace()
+        self._ws_by_stream: Dict[int, ops.Workspace] = {}   # forward scratch, one per CUDA stream (concurrent slides)
         self._ws_bwd = ops.Workspace()
         self._prof = None  # optional ops.Profile handle (bench.py roofline leg)
-        self._plane_state = None        # (parameter versions, workspace identity) the cached weight planes belong to
+        self._plane_state: Dict[int, object] = {}  # per stream: (parameter versions, workspace identity) of the cached planes
         self._plane_key_pending = None
 
     # -- parameters in C-ABI (= state_dict) order
@@ -173,6 +173,16 @@ class TOAD_fc_mtl_concat(nn.Module):
         self.classifier = self.classifier.to(device)
         self.site_classifier = self.site_classifier.to(device)
 
+    @property
+    def _ws(self) -> "ops.Workspace":
+        """Forward workspace of the CURRENT stream: forwards issued on different streams (two slides in
+        flight so that one's partial last wave overlaps the other's kernels) must not share scratch."""
+        sid = torch.cuda.current_stream().cuda_stream if torch.cuda.is_available() else 0
+        ws = self._ws_by_stream.get(sid)
+        if ws is None:
+            ws = self._ws_by_stream[sid] = ops.Workspace()
+        return ws
+
     def _weight_plane_flag(self, params, device) -> int:
         """Inference loops reuse the bf16 weight planes that the previous forward left in the workspace
         as long as no parameter changed (tensor identity + autograd version counter) and the workspace
@@ -182,15 +192,17 @@ class TOAD_fc_mtl_concat(nn.Module):
         if _default_flags() & _lib.FLAG_SIMT_FP32:
             return 0
         key = tuple((p.data_ptr(), p._version) for p in params) + (str(device),)
-        buf = self._ws.buf
+        ws = self._ws
+        buf = ws.buf
         state = (key, None if buf is None else buf.data_ptr(), None if buf is None else buf.numel())
-        reuse = buf is not None and self._plane_state == state
+        reuse = buf is not None and self._plane_state.get(id(ws)) == state
         self._plane_key_pending = key
         return _lib.FLAG_REUSE_WEIGHT_PLANES if reuse else 0
 
     def _note_planes_written(self) -> None:
-        buf = self._ws.buf
-        self._plane_state = None if self._plane_key_pending is None or buf is None else \
+        ws = self._ws
+        buf = ws.buf
+        self._plane_state[id(ws)] = None if self._plane_key_pending is None or buf is None else \
             (self._plane_key_pending, buf.data_ptr(), buf.numel())
 
     def _dropout_active(self) -> bool:
