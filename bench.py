@@ -5,9 +5,11 @@
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
 
 One step = one pass of the hot path over `slides_per_step` synthetic slides (N x 1024 fp32
-each).  `value` = whole-job slides/s with bags resident in HBM (4 distinct 205 MB bags per
-GPU, larger than L2, rotated); `e2e` = the same metric through the public module API with pinned
-host bags copied H2D inside the timed region and results read back.  Prints ONE JSON line.
+each) through `toad_b200.pipeline.ResidentRunner` (two slides in flight on two CUDA streams, so one
+slide's partially filled last waves overlap the other's kernels).  `value` = whole-job slides/s with
+bags resident in HBM (4 distinct 205 MB bags per GPU, larger than L2, rotated); `value_single_stream`
+= the same steps strictly serial; `e2e` = the same metric through the public API with pinned host
+bags copied H2D inside the timed region and results read back.  Prints ONE JSON line.
 """
 import argparse
 import json
@@ -195,7 +197,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(i):
+    from toad_b200.pipeline import ResidentRunner
+    runner = ResidentRunner(model, n_streams=args.streams, device=dev)
+
+    def step(i):   # one step = one batch of S resident slides through the public runner (2 slides in flight)
+        runner.run([bags[(i * S + s) % n_bags] for s in range(S)], [sex] * S)
+
+    def step_serial(i):
         with torch.no_grad():
             for s in range(S):
                 model(bags[(i * S + s) % n_bags], sex)
@@ -231,36 +239,26 @@ def run_ours(args):
     total_slides = args.steps * S * world
     value = total_slides / (elapsed_ms / 1e3)
 
-    # ---- extra: the same loop with two slides in flight on two CUDA streams (a serving loop's natural shape):
-    # one slide's partially filled last waves and its serial tail merge overlap the other slide's kernels
-    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
-    cur = torch.cuda.current_stream(dev)
-
-    def step2(i):
-        with torch.no_grad():
-            for s in range(S):
-                with torch.cuda.stream(streams[s % 2]):
-                    model(bags[(i * S + s) % n_bags], sex)
-    for st_ in streams:
-        st_.wait_stream(cur)
-    for i in range(args.warmup):
-        step2(i)
-    for st_ in streams:
-        cur.wait_stream(st_)
+    # ---- extra: the same K steps strictly serial on one stream: clean per-kernel durations for the roofline
+    # explanation (in the timed region above two slides share the SMs, which stretches every kernel's wall time)
+    prof2 = ops.Profile(args.steps * S)
+    model._prof = prof2.handle
+    for i in range(min(args.warmup, 2)):
+        step_serial(i)
+    prof2.read()
     barrier()
     ev0.record()
-    for st_ in streams:
-        st_.wait_stream(cur)
     for i in range(args.steps):
-        step2(i)
-    for st_ in streams:
-        cur.wait_stream(st_)
+        step_serial(i)
     ev1.record()
     barrier()
+    model._prof = None
+    stages_serial, calls_serial = prof2.read()
+    prof2.close()
     t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    value_two_streams = total_slides / (float(t.item()) / 1e3)
+    value_single_stream = total_slides / (float(t.item()) / 1e3)
 
     # ---- e2e: pinned host bags -> H2D -> forward -> D2H results, through the public API
     host_bags = [torch.randn(n, WIDTH).pin_memory() for _ in range(2)]
@@ -284,26 +282,34 @@ def run_ours(args):
         pk = peaks()
         fc1_ms = stages["fc1_gemm"] / max(calls, 1)
         fc1_tflops = FC1_FLOP_PER_PATCH * n / (fc1_ms * 1e-3) / 1e12 if fc1_ms > 0 else 0.0
-        whole_ms = sum(stages.values()) / max(calls, 1)
+        whole_ms = sum(stages_serial.values()) / max(calls_serial, 1)
+        fc1_serial_ms = stages_serial["fc1_gemm"] / max(calls_serial, 1)
+        fc1_serial_tflops = FC1_FLOP_PER_PATCH * n / (fc1_serial_ms * 1e-3) / 1e12 if fc1_serial_ms > 0 else 0.0
         line = {
             "metric": "slides_per_sec_n50k", "value": value, "unit": "slides/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16x3-split (fp32 accumulate; fp32-class accuracy)", "data": "synthetic",
             "config": {"workload": "TOAD_fc_mtl_concat forward (eval), N=%d x %d fp32, big, n_classes=18" % (n, WIDTH),
-                       "slides_per_step": S, "parallelism": "one slide per GPU, replicas (no collective in eval)",
+                       "slides_per_step": S, "slides_in_flight": args.streams,
+                       "parallelism": "one slide per GPU, replicas (no collective in eval)",
                        "l2_policy": "4 distinct 205 MB bags per GPU rotated (inputs larger than the 126 MB L2)"},
             "clocks": sampler.summary() if sampler else None,
             "e2e": {"value": e2e_value, "unit": "slides/s", "h2d_bytes_per_step": int(streamer.h2d_bytes / max(e2e_steps, 1e-9)),
                     "d2h_bytes_per_step": int(streamer.d2h_bytes / max(e2e_steps, 1e-9)), "slides": e2e_slides,
                     "note": "pinned host bags, double-buffered H2D overlapped with compute (toad_b200.pipeline.SlideStreamer)"},
-            "value_two_streams": value_two_streams,   # same K steps with two slides in flight on two streams
+            "value_single_stream": value_single_stream,   # the same K steps strictly serial on one stream
             "gpu_launches": 4 * S * args.steps + 3,   # per slide: 3 tcgen05 GEMM + 1 pooling tail (+ 3 weight-split launches once)
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16x3_kernel<256,A_F32,EPI_LINEAR> (fc1, 44% of FLOPs)",
                          "achieved": fc1_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                          "frac": fc1_tflops / pk["bf16_tflops"], "peak_source": pk["src"] + " bf16 burst",
                          "executed_tflops": 3 * fc1_tflops, "executed_frac": 3 * fc1_tflops / pk["bf16_tflops"],
-                         "note": "achieved = algorithmic fp32 FLOPs of fc1 / CUDA-event time; the kernel executes 3 bf16 "
-                                 "tensor passes per algorithmic FLOP (split precision), so frac tops out at 1/3",
+                         "note": "achieved = algorithmic fp32 FLOPs of fc1 / CUDA-event time of the kernel in the timed "
+                                 "region (two slides in flight share the SMs there, which stretches each launch); the kernel "
+                                 "executes 3 bf16 tensor passes per algorithmic FLOP (split precision), so frac tops out at 1/3",
+                         "serial": {"achieved": fc1_serial_tflops, "frac": fc1_serial_tflops / pk["bf16_tflops"],
+                                    "executed_frac": 3 * fc1_serial_tflops / pk["bf16_tflops"],
+                                    "stage_ms": {k: v / max(calls_serial, 1) for k, v in stages_serial.items()},
+                                    "note": "same kernel timed alone (single-stream pass of the same K steps)"},
                          "traffic": None,
                          "stage_ms": {k: v / max(calls, 1) for k, v in stages.items()},
                          "forward_hbm_gbs": BYTES_PER_PATCH * n / (whole_ms * 1e-3) / 1e9 if whole_ms > 0 else None,
@@ -389,6 +395,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-patches", type=int, default=N_PATCHES)
     ap.add_argument("--slides-per-step", type=int, default=8)
+    ap.add_argument("--streams", type=int, default=2, help="slides in flight per GPU (toad_b200.pipeline.ResidentRunner)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-resnet", action="store_true")
     args = ap.parse_args()

@@ -73,3 +73,31 @@ class SlideStreamer:
             i += 1
         compute.synchronize()
         return results
+
+
+class ResidentRunner:
+    """Forward over slides that are already resident in device memory, `n_streams` slides in flight.
+
+    The GEMM kernels are persistent (one CTA per SM, static tile lists), so a single slide leaves SMs idle in
+    its partially filled last waves (196 pair tiles on 74 CTA pairs at N = 50k) and during the serial merge of
+    the pooling tail; with a second slide queued on another CUDA stream those SMs pick up the other slide's
+    CTAs.  The module keeps one forward workspace per stream (`TOAD_fc_mtl_concat._ws`).
+    """
+
+    def __init__(self, model, n_streams: int = 2, device: Optional[torch.device] = None):
+        self.model = model
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, n_streams))]
+
+    @torch.no_grad()
+    def run(self, bags: Iterable[torch.Tensor], sexes: Iterable[torch.Tensor]) -> List[dict]:
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            s.wait_stream(cur)            # inputs produced on the caller's stream are visible
+        out: List[dict] = []
+        for i, (bag, sex) in enumerate(zip(bags, sexes)):
+            with torch.cuda.stream(self.streams[i % len(self.streams)]):
+                out.append(self.model(bag, sex))
+        for s in self.streams:
+            cur.wait_stream(s)            # results are ordered before anything the caller enqueues next
+        return out
