@@ -299,19 +299,22 @@ def run_ours(args):
                     "note": "pinned host bags, double-buffered H2D overlapped with compute (toad_b200.pipeline.SlideStreamer)"},
             "value_single_stream": value_single_stream,   # the same K steps strictly serial on one stream
             "gpu_launches": 4 * S * args.steps + 3,   # per slide: 3 tcgen05 GEMM + 1 pooling tail (+ 3 weight-split launches once)
-            "roofline": {"bound": "tensor", "kernel": "gemm_bf16x3_kernel<256,A_F32,EPI_LINEAR> (fc1, 44% of FLOPs)",
-                         "achieved": fc1_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                         "frac": fc1_tflops / pk["bf16_tflops"], "peak_source": pk["src"] + " bf16 burst",
-                         "executed_tflops": 3 * fc1_tflops, "executed_frac": 3 * fc1_tflops / pk["bf16_tflops"],
-                         "note": "achieved = algorithmic fp32 FLOPs of fc1 / CUDA-event time of the kernel in the timed "
-                                 "region (two slides in flight share the SMs there, which stretches each launch); the kernel "
-                                 "executes 3 bf16 tensor passes per algorithmic FLOP (split precision), so frac tops out at 1/3",
-                         "serial": {"achieved": fc1_serial_tflops, "frac": fc1_serial_tflops / pk["bf16_tflops"],
-                                    "executed_frac": 3 * fc1_serial_tflops / pk["bf16_tflops"],
-                                    "stage_ms": {k: v / max(calls_serial, 1) for k, v in stages_serial.items()},
-                                    "note": "same kernel timed alone (single-stream pass of the same K steps)"},
-                         "traffic": None,
-                         "stage_ms": {k: v / max(calls, 1) for k, v in stages.items()},
+            "roofline": {"bound": "tensor", "kernel": "gemm_bf16x3_kernel<512,A_F32,EPI_LINEAR,2> (fc1, 44% of FLOPs)",
+                         "achieved": fc1_serial_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": fc1_serial_tflops / pk["bf16_tflops"], "peak_source": pk["src"] + " bf16 burst",
+                         "executed_tflops": 3 * fc1_serial_tflops, "executed_frac": 3 * fc1_serial_tflops / pk["bf16_tflops"],
+                         "note": "achieved = algorithmic fp32 FLOPs of fc1 / its average CUDA-event duration when the kernel has "
+                                 "the GPU to itself (the single-stream pass behind value_single_stream); the kernel executes 3 "
+                                 "bf16 tensor passes per algorithmic FLOP (split precision), so frac tops out at 1/3",
+                         "traffic": 250.4e6 if n == N_PATCHES else None,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel per launch, ncu --set full "
+                                         "(profiles/r1d_gemm_full.txt: 207.1 MB + 43.3 MB; algorithmic 205 MB x + 102 MB h1 planes, "
+                                         "part of which is still in L2 when the kernel ends)",
+                         "stage_ms": {k: v / max(calls_serial, 1) for k, v in stages_serial.items()},
+                         "in_flight": {"achieved": fc1_tflops, "frac": fc1_tflops / pk["bf16_tflops"],
+                                       "stage_ms": {k: v / max(calls, 1) for k, v in stages.items()},
+                                       "note": "the same launches inside the headline region, where two slides share the "
+                                               "SMs: each launch is stretched, the sum of both streams' work finishes sooner"},
                          "forward_hbm_gbs": BYTES_PER_PATCH * n / (whole_ms * 1e-3) / 1e9 if whole_ms > 0 else None,
                          "hbm_peak_gbs": pk["hbm_gbs"]},
         }
@@ -394,7 +397,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-patches", type=int, default=N_PATCHES)
-    ap.add_argument("--slides-per-step", type=int, default=8)
+    ap.add_argument("--slides-per-step", type=int, default=16)
     ap.add_argument("--streams", type=int, default=2, help="slides in flight per GPU (toad_b200.pipeline.ResidentRunner)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-resnet", action="store_true")
