@@ -36,7 +36,7 @@ enum { A_F32 = 0, A_SPLIT = 1, A_CONV = 2 };  // A_CONV: implicit-GEMM convoluti
 // 256 x BLOCK_N tile: each CTA stages its own 128 rows of A and HALF of the B tile, the leader CTA
 // issues UMMA M=256 reading both CTAs' shared memory, accumulators land in each CTA's own TMEM.
 // Halves the per-SM weight traffic (L2->smem and smem->tensor core) and frees room for a 3rd stage.
-template <int BLOCK_N, int CG = 1>
+template <int BLOCK_N, int CG = 1, int OUT_BUFS = 1>
 struct Cfg {
   static_assert(BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256 || BLOCK_N == 512, "BLOCK_N");
   static_assert(CG == 1 || CG == 2, "CG");
@@ -51,11 +51,16 @@ struct Cfg {
   static constexpr int B_SUB_ROWS = UMMA_N / CG;     // rows of one sub-tile staged by one CTA
   static constexpr int B_TILE_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 6 ? 6 : (192 * 1024) / STAGE_BYTES;
+  // OUT_BUFS staging tiles for the epilogue's TMA store: 1 = the store of chunk c must finish reading smem before
+  // chunk c+1 is staged; 2 = double buffered (one operand stage less), for store-/epilogue-bound shapes (ResNet).
+  static_assert(OUT_BUFS == 1 || OUT_BUFS == 2, "OUT_BUFS");
+  static constexpr int RING_BYTES = 192 * 1024 - (OUT_BUFS - 1) * 32 * 1024;
+  static constexpr int STAGES = RING_BYTES / STAGE_BYTES > 6 ? 6 : RING_BYTES / STAGE_BYTES;
+  static_assert(STAGES >= 2, "need at least a double-buffered operand ring");
   static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // accumulator ring (128/256/512: powers of 2)
   static constexpr int OUT_STAGE_BYTES = 2 * BLOCK_M * 128;  // (hi, lo) 128 x 64 bf16 staging tiles for the TMA store
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + slack for 1024 B alignment
-  static constexpr int SMEM_BYTES_LINEAR = SMEM_BYTES + OUT_STAGE_BYTES;
+  static constexpr int SMEM_BYTES_LINEAR = SMEM_BYTES + OUT_BUFS * OUT_STAGE_BYTES;
 };
 
 struct GemmTcParams {
@@ -202,7 +207,10 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void tma_store_wait_read() {  // all but the PENDING most recent store groups have read smem
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
+}
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 template <int THREADS>
 __device__ __forceinline__ void epi_barrier() {  // all epilogue warps of the CTA
@@ -322,13 +330,13 @@ __device__ __forceinline__ float fast_tanh(float z) { return fmaf(2.0f, fast_sig
 // ---------------------------------------------------------------------------------------------
 constexpr int GATE_SMEM_FLOATS = 4 * 1024;  // ba | bb | wc rows (<= 2 tasks staged) for D <= 1024
 
-template <int BLOCK_N, int A_MODE, int EPI, int CG>
+template <int BLOCK_N, int A_MODE, int EPI, int CG, int OUT_BUFS = 1>
 __global__ void __launch_bounds__(A_MODE == A_F32 ? 512 : 384, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
                    const GemmTcParams p) {
-  using C = Cfg<BLOCK_N, CG>;
+  using C = Cfg<BLOCK_N, CG, OUT_BUFS>;
   static_assert(EPI != EPI_GATE || BLOCK_N <= 256, "the gate epilogue pairs two 128-column halves of a 256-wide tile");
   // epilogue warp sets: plane-fed kernels run 8 epilogue warps (two per TMEM lane quarter, each taking one
   // 32-column half of every 64-column chunk); the fp32-fed kernels keep 4 so that, with their 8 converter
@@ -505,6 +513,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     const int ew = (warp - 4) & 3;  // == warp % 4: the TMEM lane quarter this warp may access
     const int eh = (warp - 4) >> 2;
     int it = 0;
+    uint32_t out_chunk = 0;  // running count of staged chunks (selects the staging buffer)
     for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
       const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
       const int n_tile = mn % n_tiles;
@@ -538,14 +547,16 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       if (EPI == EPI_LINEAR) {
         // 64 columns at a time: TMEM -> registers -> bias/ReLU -> (hi,lo) bf16 -> 128B-swizzled smem
         // staging tile -> one TMA store per plane (full 128 B row segments, rows >= M clipped by TMA).
-        const uint32_t stage_hi = tiles_base + STAGES * C::STAGE_BYTES;
-        const uint32_t stage_lo = stage_hi + BLOCK_M * 128;
+        const uint32_t stage0 = tiles_base + STAGES * C::STAGE_BYTES;
         const int r_local = ew * 32 + lane;
 #pragma unroll 1
         for (int cc = 0; cc < BLOCK_N / 64; ++cc) {
+          const uint32_t stage_hi = stage0 + (out_chunk % OUT_BUFS) * C::OUT_STAGE_BYTES;
+          const uint32_t stage_lo = stage_hi + BLOCK_M * 128;
+          ++out_chunk;
           if (p.out_hi != nullptr) {
-            // staging buffer free again? (the previous TMA store must have finished READING it)
-            if (warp == 4 && lane == 0) tma_store_wait_read();
+            // staging buffer free again? (the TMA store that last used it must have finished READING it)
+            if (warp == 4 && lane == 0) tma_store_wait_read<OUT_BUFS - 1>();
             epi_barrier<128 * EPI_SETS>();
           }
 #pragma unroll 1
@@ -830,10 +841,10 @@ inline int make_nhwc_tmap(CUtensorMap* map, const void* ptr, int64_t B, int64_t 
 }
 
 // Launch with ready-made A tensor maps (unused for A_F32).  B operand: planes b_hi/b_lo [N, K] bf16.
-template <int BLOCK_N, int A_MODE, int EPI, int CG>
+template <int BLOCK_N, int A_MODE, int EPI, int CG, int OUT_BUFS = 1>
 int launch_gemm_maps(const GemmTcParams& p, const CUtensorMap& ta_hi, const CUtensorMap& ta_lo,
                      const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N, CG>;
+  using C = Cfg<BLOCK_N, CG, OUT_BUFS>;
   if (p.M <= 0) return 0;
   if ((A_MODE == A_F32 && p.K % BLOCK_K != 0) || p.N % BLOCK_N != 0 || p.K <= 0 || p.N <= 0) return TOAD_ERR_UNSUPPORTED;
   if (p.k_splits > 1 && (A_MODE == A_F32 || EPI != EPI_LINEAR || p.out_hi != nullptr || p.kb_per_split <= 0)) return TOAD_ERR_ARG;
@@ -849,7 +860,7 @@ int launch_gemm_maps(const GemmTcParams& p, const CUtensorMap& ta_hi, const CUte
     TOAD_TRY(make_bf16_tmap(&to_lo, p.out_lo, p.M, p.N, BLOCK_M, p.ld_split));
   }
   constexpr int kSmem = EPI == EPI_LINEAR ? C::SMEM_BYTES_LINEAR : C::SMEM_BYTES;
-  auto kern = gemm_bf16x3_kernel<BLOCK_N, A_MODE, EPI, CG>;
+  auto kern = gemm_bf16x3_kernel<BLOCK_N, A_MODE, EPI, CG, OUT_BUFS>;
   TOAD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
   const int64_t m_units = (p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG);
   const int64_t units = m_units * (p.N / BLOCK_N) * (p.k_splits > 1 ? p.k_splits : 1);
@@ -873,7 +884,7 @@ int launch_gemm_maps(const GemmTcParams& p, const CUtensorMap& ta_hi, const CUte
 }
 
 // A operand: fp32 (a_f32/lda in p) when A_MODE == A_F32, else the planes a_hi/a_lo [M, K] bf16.
-template <int BLOCK_N, int A_MODE, int EPI, int CG = 1>
+template <int BLOCK_N, int A_MODE, int EPI, int CG = 1, int OUT_BUFS = 1>
 int launch_gemm(const GemmTcParams& p, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,
                 const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, cudaStream_t stream) {
   static_assert(A_MODE != A_CONV, "use launch_conv_gemm");
@@ -888,12 +899,12 @@ int launch_gemm(const GemmTcParams& p, const __nv_bfloat16* a_hi, const __nv_bfl
     TOAD_TRY(make_bf16_tmap(&ta_hi, b_hi, p.N, p.K, 64));  // placeholders, never dereferenced
     ta_lo = ta_hi;
   }
-  return launch_gemm_maps<BLOCK_N, A_MODE, EPI, CG>(p, ta_hi, ta_lo, b_hi, b_lo, stream);
+  return launch_gemm_maps<BLOCK_N, A_MODE, EPI, CG, OUT_BUFS>(p, ta_hi, ta_lo, b_hi, b_lo, stream);
 }
 
 // Convolution as implicit GEMM: input planes NHWC [B, H, W, Cin] (hi, lo), weights [Cout, taps*Cin] with
 // K order (kh, kw, cin), output planes [B*Ho*Wo, Cout].  ksize in {1, 3}; stride in {1, 2}; pad = ksize/2.
-template <int BLOCK_N, int CG>
+template <int BLOCK_N, int CG, int OUT_BUFS = 1>
 int launch_conv_gemm(GemmTcParams p, const __nv_bfloat16* in_hi, const __nv_bfloat16* in_lo, int B, int H, int W,
                      int Cin, int ksize, int stride, const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo,
                      cudaStream_t stream) {
@@ -915,7 +926,7 @@ int launch_conv_gemm(GemmTcParams p, const __nv_bfloat16* in_hi, const __nv_bflo
   CUtensorMap ta_hi, ta_lo;
   TOAD_TRY(make_nhwc_tmap(&ta_hi, in_hi, B, H, W, Cin, wb, hb, bb, stride));
   TOAD_TRY(make_nhwc_tmap(&ta_lo, in_lo, B, H, W, Cin, wb, hb, bb, stride));
-  return launch_gemm_maps<BLOCK_N, A_CONV, EPI_LINEAR, CG>(p, ta_hi, ta_lo, w_hi, w_lo, stream);
+  return launch_gemm_maps<BLOCK_N, A_CONV, EPI_LINEAR, CG, OUT_BUFS>(p, ta_hi, ta_lo, w_hi, w_lo, stream);
 }
 
 }  // namespace tc

@@ -756,6 +756,7 @@ extern "C" int toad_linear_bf16x3(const float* x, const float* wgt, const float*
 namespace {
 
 struct ConvSpec { int cin, cout, k, stride; };
+constexpr int kResOutBufs = 2;
 
 // the 43 convolutions in state_dict order (resnet_custom.py:57-94 with layers [3,4,6])
 int build_specs(ConvSpec* specs) {
@@ -843,16 +844,18 @@ int run_conv(const ConvSpec& cs, const PreparedConv& pc, const bf16* in_hi, cons
   g.relu = relu ? 1 : 0;
   g.out_hi = out_hi; g.out_lo = out_lo; g.ld_split = cs.cout;
   g.res_hi = res_hi; g.res_lo = res_lo; g.ld_res = cs.cout;
+  // OUT_BUFS = 2: the trunk's layers are store-/epilogue-bound (short K, wide outputs), so the TMA-store staging
+  // is double buffered at the price of one operand stage.
   if (cs.k == 1 && cs.stride == 1) {  // plain GEMM over the NHWC plane
     g.M = static_cast<int64_t>(B) * H * W;
     g.K = cs.cin;
-    if (cs.cout % 256 == 0) return tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, in_hi, in_lo, pc.hi, pc.lo, st);
-    if (cs.cout % 128 == 0) return tc::launch_gemm<128, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, in_hi, in_lo, pc.hi, pc.lo, st);
-    return tc::launch_gemm<64, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, in_hi, in_lo, pc.hi, pc.lo, st);
+    if (cs.cout % 256 == 0) return tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 2, kResOutBufs>(g, in_hi, in_lo, pc.hi, pc.lo, st);
+    if (cs.cout % 128 == 0) return tc::launch_gemm<128, tc::A_SPLIT, tc::EPI_LINEAR, 2, kResOutBufs>(g, in_hi, in_lo, pc.hi, pc.lo, st);
+    return tc::launch_gemm<64, tc::A_SPLIT, tc::EPI_LINEAR, 2, kResOutBufs>(g, in_hi, in_lo, pc.hi, pc.lo, st);
   }
-  if (cs.cout % 256 == 0) return tc::launch_conv_gemm<256, 2>(g, in_hi, in_lo, B, H, W, cs.cin, cs.k, cs.stride, pc.hi, pc.lo, st);
-  if (cs.cout % 128 == 0) return tc::launch_conv_gemm<128, 2>(g, in_hi, in_lo, B, H, W, cs.cin, cs.k, cs.stride, pc.hi, pc.lo, st);
-  return tc::launch_conv_gemm<64, 2>(g, in_hi, in_lo, B, H, W, cs.cin, cs.k, cs.stride, pc.hi, pc.lo, st);
+  if (cs.cout % 256 == 0) return tc::launch_conv_gemm<256, 2, kResOutBufs>(g, in_hi, in_lo, B, H, W, cs.cin, cs.k, cs.stride, pc.hi, pc.lo, st);
+  if (cs.cout % 128 == 0) return tc::launch_conv_gemm<128, 2, kResOutBufs>(g, in_hi, in_lo, B, H, W, cs.cin, cs.k, cs.stride, pc.hi, pc.lo, st);
+  return tc::launch_conv_gemm<64, 2, kResOutBufs>(g, in_hi, in_lo, B, H, W, cs.cin, cs.k, cs.stride, pc.hi, pc.lo, st);
 }
 
 }  // namespace
@@ -916,7 +919,7 @@ extern "C" int toad_resnet_fwd(const void* prepared, const float* x, int32_t B, 
     g.out_hi = w.stem_hi + static_cast<int64_t>(b0) * H1 * W1 * 64;
     g.out_lo = w.stem_lo + static_cast<int64_t>(b0) * H1 * W1 * 64;
     g.ld_split = 64;
-    TOAD_TRY((tc::launch_gemm<64, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, w.col_hi, w.col_lo, P.conv[0].hi, P.conv[0].lo, st)));
+    TOAD_TRY((tc::launch_gemm<64, tc::A_SPLIT, tc::EPI_LINEAR, 2, kResOutBufs>(g, w.col_hi, w.col_lo, P.conv[0].hi, P.conv[0].lo, st)));
   }
   // ---- maxpool 3x3/s2 (resnet_custom.py:100)
   int cur = 0;  // buffer holding the block input
