@@ -61,6 +61,8 @@ enum {
 #define TOAD_FLAG_REUSE_WEIGHT_PLANES 128u /* the bf16 (hi,lo) weight planes left in `workspace` by an earlier call with the
                                             * same dims (any n_patches), tensor-core path and UNCHANGED parameters are still
                                             * valid: skip the 3 weight-split launches (eval loops; the caller tracks versions) */
+#define TOAD_FLAG_BWD_TRANSPOSED 256u /* debug (toad_bwd): wgrads on K-major operands from explicitly transposed planes
+                                       * instead of the MN-major operand path */
 #define TOAD_FLAG_FC2_WIDE 64u      /* debug: fc2 on 256 x 512 pair tiles like fc1 */
 #define TOAD_FLAG_TC_PAIR_ALL 32u   /* debug: every tcgen05 GEMM as CTA pairs (cta_group::2), including the fp32-fed fc1 */
 

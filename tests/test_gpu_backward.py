@@ -83,3 +83,31 @@ def test_optimizer_step_runs_like_the_reference_loop():
         opt.step()
         opt.zero_grad()
     assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("name", ["toad_big_n257", "toad_big_n1000_relu", "toad_big_n10000"])
+def test_mn_major_wgrads_equal_the_transposed_operand_path(name):
+    """The wgrads read dY / X planes MN-major in their natural layout; TOAD_FLAG_BWD_TRANSPOSED contracts
+    the same (hi, lo) values K-major from explicitly transposed copies.  Same products, fp32 accumulation in
+    the same k order per split -> equal up to split-K partition rounding."""
+    g = load_golden(name)
+    params, x, sex = case_inputs(g)
+    grads = []
+    for mode in ("0", "1"):
+        os.environ["TOAD_B200_BWD_T"] = mode
+        try:
+            model = build_model(params, str(g["meta_size_arg"]), int(g["meta_n_classes"]))
+            model.train()
+            r = model(torch.from_numpy(x).cuda(), torch.tensor([sex], device="cuda"))
+            loss_fn = torch.nn.CrossEntropyLoss()
+            loss = 0.75 * loss_fn(r["logits"], torch.tensor([int(g["meta_label"])], device="cuda")) + \
+                0.25 * loss_fn(r["site_logits"], torch.tensor([int(g["meta_site"])], device="cuda"))
+            loss.backward()
+            torch.cuda.synchronize()
+            grads.append({k: to_np(p.grad) for k, p in model.named_parameters()})
+        finally:
+            os.environ["TOAD_B200_BWD_T"] = "0"
+    for k in grads[0]:
+        a, b = grads[0][k].astype(np.float64), grads[1][k].astype(np.float64)
+        scale = max(np.abs(b).max(), 1e-12)
+        assert np.abs(a - b).max() <= 2e-5 * scale, (k, np.abs(a - b).max(), scale)

@@ -18,6 +18,7 @@ FLAG_TC_SINGLE_CTA = 8
 FLAG_DROPOUT = 16
 FLAG_TC_PAIR_ALL = 32
 FLAG_REUSE_WEIGHT_PLANES = 128
+FLAG_BWD_TRANSPOSED = 256
 
 EXPORTS = [
     "toad_abi_version", "toad_error_string", "toad_param_offsets", "toad_dropout_hash",

@@ -30,7 +30,9 @@ constexpr int UMMA_K = 16;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
 
 enum { EPI_LINEAR = 0, EPI_GATE = 1 };
-enum { A_F32 = 0, A_SPLIT = 1, A_CONV = 2 };  // A_CONV: implicit-GEMM convolution over NHWC (hi,lo) planes
+enum { A_F32 = 0, A_SPLIT = 1, A_CONV = 2, A_MN = 3 };
+// A_CONV: implicit-GEMM convolution over NHWC (hi,lo) planes.  A_MN: both operands MN-major -- A(m,k) and B(n,k)
+// are read from planes stored [k, m] / [k, n] (the wgrad dW = dY^T . X with k = patch index: no transposes).
 
 // CG = 1: one CTA per tile (UMMA M=128).  CG = 2: a CTA pair (cluster of 2, cta_group::2) shares one
 // 256 x BLOCK_N tile: each CTA stages its own 128 rows of A and HALF of the B tile, the leader CTA
@@ -310,10 +312,21 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                     // SWIZZLE_128B         bits [61,64)
   return d;
 }
-// Instruction descriptor: D=f32, A=B=bf16, both K-major, M = 128*CG, N = BLOCK_N.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
-         (static_cast<uint32_t>(m >> 4) << 24);
+// MN-major operand, SWIZZLE_128B: the tile is a row of [64 k-rows x 64 mn-elements (128 B)] boxes (one TMA box
+// each, 8 KB); inside a box 8-row groups are 1024 B apart (SBO), boxes along MN are 8192 B apart (LBO).
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(8192 >> 4) << 16;  // leading byte offset: next 64-element block along MN
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;  // stride byte offset: next 8 k-rows
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// Instruction descriptor: D=f32, A=B=bf16, M = 128*CG, N = BLOCK_N; mn_major sets both operands MN-major.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, bool mn_major = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (mn_major ? ((1u << 15) | (1u << 16)) : 0u) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 // sigmoid / tanh on the SFU (ex2.approx + rcp.approx): abs error ~2e-7, far below the score tolerance.
@@ -432,6 +445,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           if (A_MODE == A_SPLIT) {
             tma_load_2d<CG>(sa, &tm_a_hi, fb, kb * BLOCK_K, m0);
             tma_load_2d<CG>(sa + A_TILE_BYTES, &tm_a_lo, fb, kb * BLOCK_K, m0);
+          } else if (A_MODE == A_MN) {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j) {  // [64 patches x 64 m] boxes
+              tma_load_2d<CG>(sa + j * 8192, &tm_a_hi, fb, m0 + j * 64, kb * BLOCK_K);
+              tma_load_2d<CG>(sa + A_TILE_BYTES + j * 8192, &tm_a_lo, fb, m0 + j * 64, kb * BLOCK_K);
+            }
           } else if (A_MODE == A_CONV) {
             const int tap = kb / p.conv_cchunks, cc = kb - tap * p.conv_cchunks;
             const int kh = tap / p.conv_kw, kw = tap - kh * p.conv_kw;
@@ -443,11 +462,19 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             tma_load_4d<CG>(sa, &tm_a_hi, fb, cc * BLOCK_K, cw, ch, b0);
             tma_load_4d<CG>(sa + A_TILE_BYTES, &tm_a_lo, fb, cc * BLOCK_K, cw, ch, b0);
           }
+          if (A_MODE == A_MN) {
 #pragma unroll
-          for (int hs = 0; hs < C::N_SUB; ++hs) {  // sub-tile hs = rows [n0 + hs*UMMA_N, +B_SUB_ROWS) of this CTA's share
-            const uint32_t so = hs * (C::B_SUB_ROWS * 128);
-            tma_load_2d<CG>(sa + 2 * A_TILE_BYTES + so, &tm_b_hi, fb, kb * BLOCK_K, n0 + hs * C::UMMA_N);
-            tma_load_2d<CG>(sa + 2 * A_TILE_BYTES + C::B_TILE_BYTES + so, &tm_b_lo, fb, kb * BLOCK_K, n0 + hs * C::UMMA_N);
+            for (int j = 0; j < C::B_SUB_ROWS / 64; ++j) {  // [64 patches x 64 n] boxes of this CTA's share of B
+              tma_load_2d<CG>(sa + 2 * A_TILE_BYTES + j * 8192, &tm_b_hi, fb, n0 + j * 64, kb * BLOCK_K);
+              tma_load_2d<CG>(sa + 2 * A_TILE_BYTES + C::B_TILE_BYTES + j * 8192, &tm_b_lo, fb, n0 + j * 64, kb * BLOCK_K);
+            }
+          } else {
+#pragma unroll
+            for (int hs = 0; hs < C::N_SUB; ++hs) {  // sub-tile hs = rows [n0 + hs*UMMA_N, +B_SUB_ROWS) of this CTA's share
+              const uint32_t so = hs * (C::B_SUB_ROWS * 128);
+              tma_load_2d<CG>(sa + 2 * A_TILE_BYTES + so, &tm_b_hi, fb, kb * BLOCK_K, n0 + hs * C::UMMA_N);
+              tma_load_2d<CG>(sa + 2 * A_TILE_BYTES + C::B_TILE_BYTES + so, &tm_b_lo, fb, kb * BLOCK_K, n0 + hs * C::UMMA_N);
+            }
           }
         }
         __syncwarp();
@@ -457,7 +484,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (is_leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M * CG, C::UMMA_N);
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M * CG, C::UMMA_N, A_MODE == A_MN);
+      // descriptor start-address step per UMMA K (=16): K-major +32 B inside the swizzled row; MN-major +16 k-rows
+      constexpr uint64_t KSTEP = A_MODE == A_MN ? ((16 * 128) >> 4) : ((UMMA_K * 2) >> 4);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -474,27 +503,29 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           tc_fence_after();
           if (lane == 0) {
             const uint32_t sa = tiles_base + stage * C::STAGE_BYTES;
-            const uint64_t a_hi = make_kmajor_sw128_desc(sa);
-            const uint64_t a_lo = make_kmajor_sw128_desc(sa + A_TILE_BYTES);
+            const uint64_t a_hi = A_MODE == A_MN ? make_mnmajor_sw128_desc(sa) : make_kmajor_sw128_desc(sa);
+            const uint64_t a_lo = A_MODE == A_MN ? make_mnmajor_sw128_desc(sa + A_TILE_BYTES) : make_kmajor_sw128_desc(sa + A_TILE_BYTES);
 #pragma unroll
             for (int hs = 0; hs < C::N_SUB; ++hs) {
               const uint32_t so = hs * (C::B_SUB_ROWS * 128);
-              const uint64_t b_hi = make_kmajor_sw128_desc(sa + 2 * A_TILE_BYTES + so);
-              const uint64_t b_lo = make_kmajor_sw128_desc(sa + 2 * A_TILE_BYTES + C::B_TILE_BYTES + so);
+              const uint64_t b_hi = A_MODE == A_MN ? make_mnmajor_sw128_desc(sa + 2 * A_TILE_BYTES + so)
+                                                   : make_kmajor_sw128_desc(sa + 2 * A_TILE_BYTES + so);
+              const uint64_t b_lo = A_MODE == A_MN ? make_mnmajor_sw128_desc(sa + 2 * A_TILE_BYTES + C::B_TILE_BYTES + so)
+                                                   : make_kmajor_sw128_desc(sa + 2 * A_TILE_BYTES + C::B_TILE_BYTES + so);
               const uint32_t d_tmem = d_tmem0 + hs * C::UMMA_N;
 #pragma unroll
               for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);  // +32 B per K step
+                const uint64_t koff = static_cast<uint64_t>(k) * KSTEP;
                 umma_bf16<CG>(d_tmem, a_hi + koff, b_hi + koff, idesc, (kb > kb0) || (k != 0));
               }
 #pragma unroll
               for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);
+                const uint64_t koff = static_cast<uint64_t>(k) * KSTEP;
                 umma_bf16<CG>(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
               }
 #pragma unroll
               for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);
+                const uint64_t koff = static_cast<uint64_t>(k) * KSTEP;
                 umma_bf16<CG>(d_tmem, a_lo + koff, b_hi + koff, idesc, 1);
               }
             }
@@ -841,18 +872,15 @@ inline int make_nhwc_tmap(CUtensorMap* map, const void* ptr, int64_t B, int64_t 
 }
 
 // Launch with ready-made A tensor maps (unused for A_F32).  B operand: planes b_hi/b_lo [N, K] bf16.
+// Launch with ready-made A and B tensor maps.
 template <int BLOCK_N, int A_MODE, int EPI, int CG, int OUT_BUFS = 1>
-int launch_gemm_maps(const GemmTcParams& p, const CUtensorMap& ta_hi, const CUtensorMap& ta_lo,
-                     const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, cudaStream_t stream) {
+int launch_gemm_maps_b(const GemmTcParams& p, const CUtensorMap& ta_hi, const CUtensorMap& ta_lo,
+                       const CUtensorMap& tb_hi, const CUtensorMap& tb_lo, cudaStream_t stream) {
   using C = Cfg<BLOCK_N, CG, OUT_BUFS>;
   if (p.M <= 0) return 0;
   if ((A_MODE == A_F32 && p.K % BLOCK_K != 0) || p.N % BLOCK_N != 0 || p.K <= 0 || p.N <= 0) return TOAD_ERR_UNSUPPORTED;
   if (p.k_splits > 1 && (A_MODE == A_F32 || EPI != EPI_LINEAR || p.out_hi != nullptr || p.kb_per_split <= 0)) return TOAD_ERR_ARG;
   if (EPI == EPI_GATE && (p.gate_D > 1024 || p.gate_ntasks < 1 || p.gate_ntasks > 4)) return TOAD_ERR_UNSUPPORTED;
-  CUtensorMap tb_hi, tb_lo;
-  const int64_t ldb = p.ldb > 0 ? p.ldb : p.K;
-  TOAD_TRY(make_bf16_tmap(&tb_hi, b_hi, p.N, p.K, C::B_SUB_ROWS, ldb));
-  TOAD_TRY(make_bf16_tmap(&tb_lo, b_lo, p.N, p.K, C::B_SUB_ROWS, ldb));
   CUtensorMap to_hi = tb_hi, to_lo = tb_lo;
   if (EPI == EPI_LINEAR && p.out_hi != nullptr) {
     if (p.out_lo == nullptr || p.ld_split % 8 != 0) return TOAD_ERR_ARG;
@@ -883,11 +911,25 @@ int launch_gemm_maps(const GemmTcParams& p, const CUtensorMap& ta_hi, const CUte
   return 0;
 }
 
+// Launch with ready-made A tensor maps (unused for A_F32).  B operand: planes b_hi/b_lo [N, K] bf16.
+template <int BLOCK_N, int A_MODE, int EPI, int CG, int OUT_BUFS = 1>
+int launch_gemm_maps(const GemmTcParams& p, const CUtensorMap& ta_hi, const CUtensorMap& ta_lo,
+                     const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N, CG, OUT_BUFS>;
+  if (p.M <= 0) return 0;
+  if (p.K <= 0 || p.N <= 0) return TOAD_ERR_UNSUPPORTED;
+  CUtensorMap tb_hi, tb_lo;
+  const int64_t ldb = p.ldb > 0 ? p.ldb : p.K;
+  TOAD_TRY(make_bf16_tmap(&tb_hi, b_hi, p.N, p.K, C::B_SUB_ROWS, ldb));
+  TOAD_TRY(make_bf16_tmap(&tb_lo, b_lo, p.N, p.K, C::B_SUB_ROWS, ldb));
+  return launch_gemm_maps_b<BLOCK_N, A_MODE, EPI, CG, OUT_BUFS>(p, ta_hi, ta_lo, tb_hi, tb_lo, stream);
+}
+
 // A operand: fp32 (a_f32/lda in p) when A_MODE == A_F32, else the planes a_hi/a_lo [M, K] bf16.
 template <int BLOCK_N, int A_MODE, int EPI, int CG = 1, int OUT_BUFS = 1>
 int launch_gemm(const GemmTcParams& p, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,
                 const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, cudaStream_t stream) {
-  static_assert(A_MODE != A_CONV, "use launch_conv_gemm");
+  static_assert(A_MODE != A_CONV && A_MODE != A_MN, "use launch_conv_gemm / launch_gemm_mn");
   if (p.M <= 0) return 0;
   CUtensorMap ta_hi, ta_lo;
   if (A_MODE == A_SPLIT) {
@@ -900,6 +942,25 @@ int launch_gemm(const GemmTcParams& p, const __nv_bfloat16* a_hi, const __nv_bfl
     ta_lo = ta_hi;
   }
   return launch_gemm_maps<BLOCK_N, A_MODE, EPI, CG, OUT_BUFS>(p, ta_hi, ta_lo, b_hi, b_lo, stream);
+}
+
+// wgrad-style GEMM with both operands MN-major: C[M, N] = sum_k A(m,k) B(n,k) with A stored as planes [K, M]
+// (row stride lda) and B as planes [K, N] (row stride ldb) -- i.e. dW = dY^T . X straight from the natural
+// [patch, channel] layouts, K = patches.  Split-K / fp32 partial output as configured in p.
+template <int BLOCK_N, int CG>
+int launch_gemm_mn(GemmTcParams p, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const __nv_bfloat16* b_hi,
+                   const __nv_bfloat16* b_lo, cudaStream_t stream) {
+  static_assert(BLOCK_N <= 256, "MN-major path uses one UMMA N tile");
+  if (p.M <= 0 || p.K <= 0) return 0;
+  if (p.M % 64 != 0 || p.N % BLOCK_N != 0) return TOAD_ERR_UNSUPPORTED;
+  const int64_t lda = p.lda > 0 ? p.lda : p.M, ldb = p.ldb > 0 ? p.ldb : p.N;
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  // tensor maps over the [K, channels] planes: box = 64 channels (inner, 128 B) x 64 k-rows
+  TOAD_TRY(make_bf16_tmap(&ta_hi, a_hi, p.K, p.M, 64, lda));
+  TOAD_TRY(make_bf16_tmap(&ta_lo, a_lo, p.K, p.M, 64, lda));
+  TOAD_TRY(make_bf16_tmap(&tb_hi, b_hi, p.K, p.N, 64, ldb));
+  TOAD_TRY(make_bf16_tmap(&tb_lo, b_lo, p.K, p.N, 64, ldb));
+  return launch_gemm_maps_b<BLOCK_N, A_MN, EPI_LINEAR, CG, 1>(p, ta_hi, ta_lo, tb_hi, tb_lo, stream);
 }
 
 // Convolution as implicit GEMM: input planes NHWC [B, H, W, Cin] (hi, lo), weights [Cout, taps*Cin] with

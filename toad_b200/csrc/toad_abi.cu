@@ -362,6 +362,7 @@ struct BwdTcWs {
   bf16 *dab_hi, *dab_lo, *dabT_hi, *dabT_lo, *hT_hi, *hT_lo, *h1T_hi, *h1T_lo, *xT_hi, *xT_lo;
   bf16 *dz2_hi, *dz2_lo, *dz2T_hi, *dz2T_lo, *dz1_hi, *dz1_lo, *dz1T_hi, *dz1T_lo;
   bf16 *w2T_hi, *w2T_lo, *wabT_hi, *wabT_lo;
+  bf16 *hp_hi, *hp_lo, *h1p_hi, *h1p_lo, *xp_hi, *xp_lo;  // natural-layout planes of the saved fp32 activations / x
   int gate_blocks, col_blocks;
   int64_t ldT;
   size_t bytes;
@@ -387,6 +388,8 @@ BwdTcWs carve_bwd_tc(const toad_dims_t* d, int64_t n, void* base) {
   w.dz1T_hi = c.take<bf16>(Hd * w.ldT); w.dz1T_lo = c.take<bf16>(Hd * w.ldT);
   w.w2T_hi = c.take<bf16>(Hd * Hd);    w.w2T_lo = c.take<bf16>(Hd * Hd);
   w.wabT_hi = c.take<bf16>(Hd * 2 * D); w.wabT_lo = c.take<bf16>(Hd * 2 * D);
+  // the MN-major wgrads read natural-layout planes; they alias the (then unused) transposed buffers
+  w.hp_hi = w.hT_hi; w.hp_lo = w.hT_lo; w.h1p_hi = w.h1T_hi; w.h1p_lo = w.h1T_lo; w.xp_hi = w.xT_hi; w.xp_lo = w.xT_lo;
   int64_t big = Hd * L;
   if (2 * D * Hd > big) big = 2 * D * Hd;
   w.splitk = c.take<float>(static_cast<size_t>(kSMs / 2) * 256 * 256);  // <= one 256x256 fp32 tile per CTA pair (+ slack below)
@@ -423,9 +426,34 @@ int wgrad_tc(const bf16* aT_hi, const bf16* aT_lo, const bf16* bT_hi, const bf16
   return bwd::launch_reduce_strided(splitk + dst_rows_first * N_in, dst2, stride - dst_rows_first * N_in, stride, S, st);
 }
 
+// dW[M_out, N_in] = dY^T . X straight from the natural [patch, channel] planes (both operands MN-major), split-K.
+int wgrad_mn(const bf16* dy_hi, const bf16* dy_lo, int64_t ld_dy, const bf16* x_hi, const bf16* x_lo, int64_t ld_x,
+             int M_out, int N_in, int64_t n, float* splitk, float* dst, int64_t dst_rows_first, float* dst2,
+             cudaStream_t st) {
+  tc::GemmTcParams g{};
+  g.M = M_out; g.N = N_in; g.K = static_cast<int32_t>(n); g.lda = ld_dy; g.ldb = ld_x;
+  const int num_kb = static_cast<int>((n + 63) / 64);
+  const int units = ((M_out + 255) / 256) * (N_in / 256);
+  int S = (kSMs / 2) / units;
+  if (S < 1) S = 1;
+  if (S > num_kb) S = num_kb;
+  const int kb_per = (num_kb + S - 1) / S;
+  S = (num_kb + kb_per - 1) / kb_per;
+  g.k_splits = S; g.kb_per_split = kb_per;
+  g.out_f32 = splitk; g.ld_f32 = N_in;
+  TOAD_TRY((tc::launch_gemm_mn<256, 2>(g, dy_hi, dy_lo, x_hi, x_lo, st)));
+  const int64_t stride = static_cast<int64_t>(M_out) * N_in;
+  if (dst2 == nullptr) return bwd::launch_reduce_strided(splitk, dst, stride, stride, S, st);
+  TOAD_TRY(bwd::launch_reduce_strided(splitk, dst, dst_rows_first * N_in, stride, S, st));
+  return bwd::launch_reduce_strided(splitk + dst_rows_first * N_in, dst2, stride - dst_rows_first * N_in, stride, S, st);
+}
+
 int bwd_tc(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t n, const toad_fwd_out_t* fo,
            const toad_saved_t* sv, const float* dlogits, const float* dsite, float* grad, void* workspace,
-           size_t workspace_bytes, toad_stream_t stream) {
+           size_t workspace_bytes, uint32_t flags, toad_stream_t stream) {
+  // wgrads: MN-major operands straight from the natural-layout planes (default) or, with the debug flag, K-major
+  // operands from explicitly transposed planes (the first implementation, kept as a cross-check)
+  const bool mn = (flags & TOAD_FLAG_BWD_TRANSPOSED) == 0;
   BwdTcWs w = carve_bwd_tc(d, n, workspace);
   TOAD_TRY(check_ws(workspace, workspace_bytes, w.bytes));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -460,18 +488,25 @@ int bwd_tc(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t
     TOAD_TRY(bwd::launch_reduce_strided(w.gate_part + 3 * D, g_bb, D, stride, w.gate_blocks, st));
     TOAD_TRY(bwd::launch_reduce_strided(w.gate_part + 4 * D, g_bc, 2, stride, w.gate_blocks, st));
   }
-  // operand preparation: (hi, lo) planes, K-major in whichever index the GEMM contracts over
+  // operand preparation: (hi, lo) planes
   TOAD_TRY(tail::launch_split_planes(w.dab, w.dab_hi, w.dab_lo, n * 2 * D, st));
-  TOAD_TRY(bwd::launch_transpose_split(w.dab, n, 2 * D, 2 * D, w.dabT_hi, w.dabT_lo, w.ldT, st));
-  TOAD_TRY(bwd::launch_transpose_split(sv->h, n, Hd, Hd, w.hT_hi, w.hT_lo, w.ldT, st));
-  TOAD_TRY(bwd::launch_transpose_split(sv->h1, n, Hd, Hd, w.h1T_hi, w.h1T_lo, w.ldT, st));
-  TOAD_TRY(bwd::launch_transpose_split(x, n, L, L, w.xT_hi, w.xT_lo, w.ldT, st));
+  if (mn) {
+    TOAD_TRY(tail::launch_split_planes(sv->h, w.hp_hi, w.hp_lo, n * Hd, st));
+    TOAD_TRY(tail::launch_split_planes(sv->h1, w.h1p_hi, w.h1p_lo, n * Hd, st));
+    TOAD_TRY(tail::launch_split_planes(x, w.xp_hi, w.xp_lo, n * L, st));
+  } else {
+    TOAD_TRY(bwd::launch_transpose_split(w.dab, n, 2 * D, 2 * D, w.dabT_hi, w.dabT_lo, w.ldT, st));
+    TOAD_TRY(bwd::launch_transpose_split(sv->h, n, Hd, Hd, w.hT_hi, w.hT_lo, w.ldT, st));
+    TOAD_TRY(bwd::launch_transpose_split(sv->h1, n, Hd, Hd, w.h1T_hi, w.h1T_lo, w.ldT, st));
+    TOAD_TRY(bwd::launch_transpose_split(x, n, L, L, w.xT_hi, w.xT_lo, w.ldT, st));
+  }
   TOAD_TRY(bwd::launch_transpose_split(P->w2, Hd, Hd, Hd, w.w2T_hi, w.w2T_lo, Hd, st));                  // W2^T   [in, out]
   TOAD_TRY(bwd::launch_transpose_split(P->wa, D, Hd, Hd, w.wabT_hi, w.wabT_lo, 2 * D, st));              // [Wa;Wb]^T [hid, 2D]
   TOAD_TRY(bwd::launch_transpose_split(P->wb, D, Hd, Hd, w.wabT_hi + D, w.wabT_lo + D, 2 * D, st));
 
   // dWa | dWb = dab^T . h
-  TOAD_TRY(wgrad_tc(w.dabT_hi, w.dabT_lo, w.hT_hi, w.hT_lo, 2 * D, Hd, n, w.ldT, w.splitk, g_wa, D, g_wb, st));
+  if (mn) TOAD_TRY(wgrad_mn(w.dab_hi, w.dab_lo, 2 * D, w.hp_hi, w.hp_lo, Hd, 2 * D, Hd, n, w.splitk, g_wa, D, g_wb, st));
+  else TOAD_TRY(wgrad_tc(w.dabT_hi, w.dabT_lo, w.hT_hi, w.hT_lo, 2 * D, Hd, n, w.ldT, w.splitk, g_wa, D, g_wb, st));
   // dz2 = (dab . [Wa;Wb] + P0 dM0 + P1 dM1) * (h > 0) / keep      -> planes
   {
     tc::GemmTcParams g{};
@@ -484,9 +519,13 @@ int bwd_tc(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t
   bwd::colsum_planes_kernel<<<w.col_blocks, Hd, 0, st>>>(w.dz2_hi, w.dz2_lo, w.col_part, n, Hd, rpb);
   TOAD_CUDA_TRY(cudaGetLastError());
   TOAD_TRY(bwd::launch_reduce_strided(w.col_part, g_b2, Hd, Hd, w.col_blocks, st));
-  TOAD_TRY(bwd::launch_transpose_planes(w.dz2_hi, w.dz2_lo, n, Hd, w.dz2T_hi, w.dz2T_lo, w.ldT, st));
   // dW2 = dz2^T . h1
-  TOAD_TRY(wgrad_tc(w.dz2T_hi, w.dz2T_lo, w.h1T_hi, w.h1T_lo, Hd, Hd, n, w.ldT, w.splitk, g_w2, 0, nullptr, st));
+  if (mn) {
+    TOAD_TRY(wgrad_mn(w.dz2_hi, w.dz2_lo, Hd, w.h1p_hi, w.h1p_lo, Hd, Hd, Hd, n, w.splitk, g_w2, 0, nullptr, st));
+  } else {
+    TOAD_TRY(bwd::launch_transpose_planes(w.dz2_hi, w.dz2_lo, n, Hd, w.dz2T_hi, w.dz2T_lo, w.ldT, st));
+    TOAD_TRY(wgrad_tc(w.dz2T_hi, w.dz2T_lo, w.h1T_hi, w.h1T_lo, Hd, Hd, n, w.ldT, w.splitk, g_w2, 0, nullptr, st));
+  }
   // dz1 = (dz2 . W2) * (h1 > 0) / keep
   {
     tc::GemmTcParams g{};
@@ -498,8 +537,9 @@ int bwd_tc(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t
   bwd::colsum_planes_kernel<<<w.col_blocks, Hd, 0, st>>>(w.dz1_hi, w.dz1_lo, w.col_part, n, Hd, rpb);
   TOAD_CUDA_TRY(cudaGetLastError());
   TOAD_TRY(bwd::launch_reduce_strided(w.col_part, g_b1, Hd, Hd, w.col_blocks, st));
-  TOAD_TRY(bwd::launch_transpose_planes(w.dz1_hi, w.dz1_lo, n, Hd, w.dz1T_hi, w.dz1T_lo, w.ldT, st));
   // dW1 = dz1^T . x
+  if (mn) return wgrad_mn(w.dz1_hi, w.dz1_lo, Hd, w.xp_hi, w.xp_lo, L, Hd, L, n, w.splitk, g_w1, 0, nullptr, st);
+  TOAD_TRY(bwd::launch_transpose_planes(w.dz1_hi, w.dz1_lo, n, Hd, w.dz1T_hi, w.dz1T_lo, w.ldT, st));
   return wgrad_tc(w.dz1T_hi, w.dz1T_lo, w.xT_hi, w.xT_lo, Hd, L, n, w.ldT, w.splitk, g_w1, 0, nullptr, st);
 }
 }  // namespace
@@ -621,7 +661,7 @@ extern "C" int toad_bwd(const toad_dims_t* d, const toad_params_t* P, const floa
   if (!P || !x || !fo || !sv || !dlogits || !dsite || !grad || n <= 0) return TOAD_ERR_ARG;
   if (!fo->a_raw || !fo->features || !fo->softmax_stats || !sv->h1 || !sv->h || !sv->a || !sv->b) return TOAD_ERR_ARG;
   if (flags & TOAD_FLAG_SIMT_FP32) return bwd_simt(d, P, x, n, fo, sv, dlogits, dsite, grad, workspace, workspace_bytes, stream);
-  return bwd_tc(d, P, x, n, fo, sv, dlogits, dsite, grad, workspace, workspace_bytes, stream);
+  return bwd_tc(d, P, x, n, fo, sv, dlogits, dsite, grad, workspace, workspace_bytes, flags, stream);
 }
 
 // ------------------------------------------------------------------------------------------ Attn_Net_Gated

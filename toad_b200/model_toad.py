@@ -32,6 +32,8 @@ def _default_flags() -> int:
         flags |= _lib.FLAG_TC_SINGLE_CTA
     if os.environ.get("TOAD_B200_CG2", "0") == "1":   # debug aid: CTA pairs everywhere
         flags |= _lib.FLAG_TC_PAIR_ALL
+    if os.environ.get("TOAD_B200_BWD_T", "0") == "1":  # debug aid: backward wgrads via explicit transposes
+        flags |= _lib.FLAG_BWD_TRANSPOSED
     return flags
 
 

@@ -164,7 +164,7 @@ def toad_bwd(dims: Dims, params: Sequence[torch.Tensor], x: torch.Tensor, out: D
     _check_dev_f32(ds, "dsite_logits", (2,))
     p = _params_struct(dims, params)
     nbytes = C.c_size_t()
-    flags &= _lib.FLAG_SIMT_FP32
+    flags &= (_lib.FLAG_SIMT_FP32 | _lib.FLAG_BWD_TRANSPOSED)
     _lib.check(lib.toad_bwd_workspace_bytes(C.byref(dims), n, flags, C.byref(nbytes)), "toad_bwd_workspace_bytes")
     wptr, wsize = ws.get(nbytes.value, x.device)
     o = _out_struct(out)
