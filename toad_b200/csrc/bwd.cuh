@@ -82,8 +82,11 @@ __global__ void pool_bwd_kernel(const float* __restrict__ h, const float* __rest
 
 // ---- gate backward: dab[n] = [da_pre | db_pre]; per-CTA partials of dWc, dba, dbb, dbc
 // block = D threads (thread j owns gate column j); partial layout per CTA: [dWc0[D] dWc1[D] dba[D] dbb[D] dbc[2]]
+// PLANES: dab goes out as (hi, lo) bf16 planes -- the operand format of the tensor-core dgrad / wgrad -- instead of fp32.
+template <bool PLANES>
 __global__ void gate_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                 const float* __restrict__ dA, const float* __restrict__ wc, float* __restrict__ dab,
+                                __nv_bfloat16* __restrict__ dab_hi, __nv_bfloat16* __restrict__ dab_lo,
                                 float* __restrict__ part, int64_t N, int D, int rows_per_block, float keep) {
   // a, b are the saved POST-dropout activations (a_post = a*mask/keep); keep == 1 without dropout.
   const float inv_keep = 1.f / keep;
@@ -105,8 +108,17 @@ __global__ void gate_bwd_kernel(const float* __restrict__ a, const float* __rest
     const float a_pre = av * keep;  // tanh output where kept (0 where dropped: no gradient there)
     const float dap = (keep < 1.f && av == 0.f) ? 0.f : dg * bv * (1.f - a_pre * a_pre) * inv_keep;
     const float dbp = dg * av * bv * (1.f - bv * keep);
-    dab[row * 2 * D + j] = dap;
-    dab[row * 2 * D + D + j] = dbp;
+    if (PLANES) {
+      __nv_bfloat16 h = __float2bfloat16_rn(dap);
+      dab_hi[row * 2 * D + j] = h;
+      dab_lo[row * 2 * D + j] = __float2bfloat16_rn(dap - __bfloat162float(h));
+      h = __float2bfloat16_rn(dbp);
+      dab_hi[row * 2 * D + D + j] = h;
+      dab_lo[row * 2 * D + D + j] = __float2bfloat16_rn(dbp - __bfloat162float(h));
+    } else {
+      dab[row * 2 * D + j] = dap;
+      dab[row * 2 * D + D + j] = dbp;
+    }
     gba += dap;
     gbb += dbp;
   }
@@ -209,21 +221,96 @@ inline int launch_transpose_planes(const __nv_bfloat16* in_hi, const __nv_bfloat
   return 0;
 }
 
-// column sums of (hi + lo) planes [N, C]: per-CTA partials [gridDim.x][C] (thread per column)
+// column sums of (hi + lo) planes [N, C] (C even): per-CTA partials [gridDim.x][C].  Thread (x, y) owns columns
+// 2x, 2x+1 (one bf16x2 load per plane) of rows r0 + y, r0 + y + blockDim.y, ...; the y lanes are added in order.
 __global__ void colsum_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
                                      float* __restrict__ part, int64_t N, int C, int rows_per_block) {
-  const int c = threadIdx.x;
+  extern __shared__ float2 cs_sm[];  // [blockDim.y][blockDim.x]
+  const int c2 = threadIdx.x, half = C / 2;
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
   int64_t r1 = r0 + rows_per_block;
   if (r1 > N) r1 = N;
+  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(hi);
+  const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(lo);
+  float sx = 0.f, sy = 0.f;
+  for (int64_t row = r0 + threadIdx.y; row < r1; row += blockDim.y) {
+    const float2 a = __bfloat1622float2(h2[row * half + c2]);
+    const float2 b = __bfloat1622float2(l2[row * half + c2]);
+    sx += a.x + b.x;
+    sy += a.y + b.y;
+  }
+  cs_sm[threadIdx.y * blockDim.x + c2] = make_float2(sx, sy);
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    float tx = 0.f, ty = 0.f;
+    for (int y = 0; y < static_cast<int>(blockDim.y); ++y) {
+      const float2 v = cs_sm[y * blockDim.x + c2];
+      tx += v.x;
+      ty += v.y;
+    }
+    float* mine = part + static_cast<int64_t>(blockIdx.x) * C;
+    mine[2 * c2] = tx;
+    mine[2 * c2 + 1] = ty;
+  }
+}
+
+inline int launch_colsum_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* part, int64_t N, int C,
+                                int blocks, cudaStream_t stream) {
+  if (C % 2 != 0 || C / 2 > 1024) return TOAD_ERR_UNSUPPORTED;
+  int ry = 1024 / (C / 2);
+  if (ry > 8) ry = 8;
+  const int rpb = static_cast<int>((N + blocks - 1) / blocks);
+  colsum_planes_kernel<<<blocks, dim3(C / 2, ry), static_cast<size_t>(ry) * (C / 2) * sizeof(float2), stream>>>(
+      hi, lo, part, N, C, rpb);
+  TOAD_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// Same sum for many splits over few columns (per-CTA partials of bias / score-weight gradients): a 32-column x 32-lane
+// CTA, lane y adds splits y, y+32, ... and the 32 lane sums are added in lane order -- fixed order, so deterministic.
+// Up to four column segments [seg_begin[i], seg_begin[i+1]) go to separate destinations in one launch.
+struct ReduceSegs {
+  float* dst[4];
+  int begin[5];
+};
+__global__ void reduce_many_splits_kernel(const float* __restrict__ part, ReduceSegs segs, int n, int64_t stride,
+                                          int splits) {
+  __shared__ float sm[32][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
-  for (int64_t row = r0; row < r1; ++row) s += __bfloat162float(hi[row * C + c]) + __bfloat162float(lo[row * C + c]);
-  part[static_cast<int64_t>(blockIdx.x) * C + c] = s;
+  if (col < n)
+    for (int z = threadIdx.y; z < splits; z += 32) s += part[static_cast<int64_t>(z) * stride + col];
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 32; ++y) t += sm[y][threadIdx.x];
+    int sgi = 0;
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+      if (col >= segs.begin[i]) sgi = i;
+    segs.dst[sgi][col - segs.begin[sgi]] = t;
+  }
+}
+
+inline int launch_reduce_segs(const float* part, const ReduceSegs& segs, int n, int64_t stride, int splits,
+                              cudaStream_t stream) {
+  if (n <= 0) return 0;
+  reduce_many_splits_kernel<<<static_cast<unsigned>((n + 31) / 32), dim3(32, 32), 0, stream>>>(part, segs, n, stride, splits);
+  TOAD_CUDA_TRY(cudaGetLastError());
+  return 0;
 }
 
 inline int launch_reduce_strided(const float* part, float* out, int64_t n, int64_t stride, int splits,
                                  cudaStream_t stream) {
   if (n <= 0) return 0;
+  if (splits > 16 && n <= 4096) {
+    ReduceSegs segs{};
+    const int big = 1 << 30;
+    segs.dst[0] = out; segs.begin[0] = 0; segs.begin[1] = big; segs.begin[2] = big; segs.begin[3] = big; segs.begin[4] = big;
+    return launch_reduce_segs(part, segs, static_cast<int>(n), stride, splits, stream);
+  }
   reduce_strided_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(part, out, n, stride, splits);
   TOAD_CUDA_TRY(cudaGetLastError());
   return 0;

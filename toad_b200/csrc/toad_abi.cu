@@ -358,7 +358,7 @@ BwdWs carve_bwd(const toad_dims_t* d, int64_t n, void* base) {
 namespace {
 // ---- tensor-core backward workspace
 struct BwdTcWs {
-  float *dM, *sdot, *P, *dA, *dab, *splitk, *gate_part, *col_part;
+  float *dM, *sdot, *P, *dA, *splitk, *gate_part, *col_part;
   bf16 *dab_hi, *dab_lo, *dabT_hi, *dabT_lo, *hT_hi, *hT_lo, *h1T_hi, *h1T_lo, *xT_hi, *xT_lo;
   bf16 *dz2_hi, *dz2_lo, *dz2T_hi, *dz2T_lo, *dz1_hi, *dz1_lo, *dz1T_hi, *dz1T_lo;
   bf16 *w2T_hi, *w2T_lo, *wabT_hi, *wabT_lo;
@@ -376,7 +376,6 @@ BwdTcWs carve_bwd_tc(const toad_dims_t* d, int64_t n, void* base) {
   w.sdot = c.take<float>(64);
   w.P = c.take<float>(n * 2);
   w.dA = c.take<float>(n * 2);
-  w.dab = c.take<float>(n * 2 * D);
   w.dab_hi = c.take<bf16>(n * 2 * D);  w.dab_lo = c.take<bf16>(n * 2 * D);
   w.dabT_hi = c.take<bf16>(2 * D * w.ldT); w.dabT_lo = c.take<bf16>(2 * D * w.ldT);
   w.hT_hi = c.take<bf16>(Hd * w.ldT);  w.hT_lo = c.take<bf16>(Hd * w.ldT);
@@ -480,22 +479,21 @@ int bwd_tc(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t
   }
   {
     const int rpb = static_cast<int>((n + w.gate_blocks - 1) / w.gate_blocks);
-    bwd::gate_bwd_kernel<<<w.gate_blocks, D, 0, st>>>(sv->a, sv->b, w.dA, P->wc, w.dab, w.gate_part, n, D, rpb, keep);
+    bwd::gate_bwd_kernel<true><<<w.gate_blocks, D, 0, st>>>(sv->a, sv->b, w.dA, P->wc, nullptr, w.dab_hi, w.dab_lo,
+                                                             w.gate_part, n, D, rpb, keep);
     TOAD_CUDA_TRY(cudaGetLastError());
-    const int64_t stride = 4 * D + 2;
-    TOAD_TRY(bwd::launch_reduce_strided(w.gate_part, g_wc, 2 * D, stride, w.gate_blocks, st));
-    TOAD_TRY(bwd::launch_reduce_strided(w.gate_part + 2 * D, g_ba, D, stride, w.gate_blocks, st));
-    TOAD_TRY(bwd::launch_reduce_strided(w.gate_part + 3 * D, g_bb, D, stride, w.gate_blocks, st));
-    TOAD_TRY(bwd::launch_reduce_strided(w.gate_part + 4 * D, g_bc, 2, stride, w.gate_blocks, st));
+    bwd::ReduceSegs segs{};
+    segs.dst[0] = g_wc; segs.dst[1] = g_ba; segs.dst[2] = g_bb; segs.dst[3] = g_bc;
+    segs.begin[0] = 0; segs.begin[1] = 2 * D; segs.begin[2] = 3 * D; segs.begin[3] = 4 * D; segs.begin[4] = 4 * D + 2;
+    TOAD_TRY(bwd::launch_reduce_segs(w.gate_part, segs, 4 * D + 2, 4 * D + 2, w.gate_blocks, st));
   }
-  // operand preparation: (hi, lo) planes
-  TOAD_TRY(tail::launch_split_planes(w.dab, w.dab_hi, w.dab_lo, n * 2 * D, st));
+  // operand preparation: (hi, lo) planes (dab already left gate_bwd as planes)
   if (mn) {
     TOAD_TRY(tail::launch_split_planes(sv->h, w.hp_hi, w.hp_lo, n * Hd, st));
     TOAD_TRY(tail::launch_split_planes(sv->h1, w.h1p_hi, w.h1p_lo, n * Hd, st));
     TOAD_TRY(tail::launch_split_planes(x, w.xp_hi, w.xp_lo, n * L, st));
   } else {
-    TOAD_TRY(bwd::launch_transpose_split(w.dab, n, 2 * D, 2 * D, w.dabT_hi, w.dabT_lo, w.ldT, st));
+    TOAD_TRY(bwd::launch_transpose_planes(w.dab_hi, w.dab_lo, n, 2 * D, w.dabT_hi, w.dabT_lo, w.ldT, st));
     TOAD_TRY(bwd::launch_transpose_split(sv->h, n, Hd, Hd, w.hT_hi, w.hT_lo, w.ldT, st));
     TOAD_TRY(bwd::launch_transpose_split(sv->h1, n, Hd, Hd, w.h1T_hi, w.h1T_lo, w.ldT, st));
     TOAD_TRY(bwd::launch_transpose_split(x, n, L, L, w.xT_hi, w.xT_lo, w.ldT, st));
@@ -515,9 +513,7 @@ int bwd_tc(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t
     g.out_hi = w.dz2_hi; g.out_lo = w.dz2_lo; g.ld_split = Hd;
     TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, w.dab_hi, w.dab_lo, w.wabT_hi, w.wabT_lo, st)));
   }
-  const int rpb = static_cast<int>((n + w.col_blocks - 1) / w.col_blocks);
-  bwd::colsum_planes_kernel<<<w.col_blocks, Hd, 0, st>>>(w.dz2_hi, w.dz2_lo, w.col_part, n, Hd, rpb);
-  TOAD_CUDA_TRY(cudaGetLastError());
+  TOAD_TRY(bwd::launch_colsum_planes(w.dz2_hi, w.dz2_lo, w.col_part, n, Hd, w.col_blocks, st));
   TOAD_TRY(bwd::launch_reduce_strided(w.col_part, g_b2, Hd, Hd, w.col_blocks, st));
   // dW2 = dz2^T . h1
   if (mn) {
@@ -534,8 +530,7 @@ int bwd_tc(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t
     g.out_hi = w.dz1_hi; g.out_lo = w.dz1_lo; g.ld_split = Hd;
     TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, w.dz2_hi, w.dz2_lo, w.w2T_hi, w.w2T_lo, st)));
   }
-  bwd::colsum_planes_kernel<<<w.col_blocks, Hd, 0, st>>>(w.dz1_hi, w.dz1_lo, w.col_part, n, Hd, rpb);
-  TOAD_CUDA_TRY(cudaGetLastError());
+  TOAD_TRY(bwd::launch_colsum_planes(w.dz1_hi, w.dz1_lo, w.col_part, n, Hd, w.col_blocks, st));
   TOAD_TRY(bwd::launch_reduce_strided(w.col_part, g_b1, Hd, Hd, w.col_blocks, st));
   // dW1 = dz1^T . x
   if (mn) return wgrad_mn(w.dz1_hi, w.dz1_lo, Hd, w.xp_hi, w.xp_lo, L, Hd, L, n, w.splitk, g_w1, 0, nullptr, st);
@@ -585,7 +580,8 @@ static int bwd_simt(const toad_dims_t* d, const toad_params_t* P, const float* x
   // 3. gate backward -> dab, partials of dWc/dba/dbb/dbc
   {
     const int rpb = static_cast<int>((n + w.gate_blocks - 1) / w.gate_blocks);
-    bwd::gate_bwd_kernel<<<w.gate_blocks, D, 0, st>>>(sv->a, sv->b, w.dA, P->wc, w.dab, w.gate_part, n, D, rpb, keep);
+    bwd::gate_bwd_kernel<false><<<w.gate_blocks, D, 0, st>>>(sv->a, sv->b, w.dA, P->wc, w.dab, nullptr, nullptr,
+                                                              w.gate_part, n, D, rpb, keep);
     TOAD_CUDA_TRY(cudaGetLastError());
     const int64_t stride = 4 * D + 2;
     TOAD_TRY(bwd::launch_reduce_strided(w.gate_part, g_wc, 2 * D, stride, w.gate_blocks, st));
