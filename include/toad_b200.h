@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define TOAD_ABI_VERSION 1
+#define TOAD_ABI_VERSION 2
 
 typedef void* toad_stream_t; /* cudaStream_t */
 
@@ -106,11 +106,18 @@ typedef struct {
   float* softmax_stats;/* [n_tasks][2] = (row max, sum of exp) of a_raw; needed by toad_bwd */
 } toad_fwd_out_t;
 
-/* Activations kept for the backward (TOAD_FLAG_SAVE_ACTS), fp32, as the next layer saw them
- * (i.e. after dropout when TOAD_FLAG_DROPOUT is set), plus the dropout configuration: element i of
- * activation L in {1: h1, 2: h, 3: a, 4: b} is kept iff toad_dropout_hash(seed, L, i) >= p * 2^32 and
- * kept values are scaled by 1/(1-p).  The mask is a pure function of (seed, L, i): bitwise parity with
- * torch's Philox stream is impossible, distributional parity is what holds. */
+/* Activations kept for the backward (TOAD_FLAG_SAVE_ACTS) as the next layer saw them (i.e. after dropout
+ * when TOAD_FLAG_DROPOUT is set), plus the dropout configuration: element i of activation L in
+ * {1: h1, 2: h, 3: a, 4: b} is kept iff toad_dropout_hash(seed, L, i) >= p * 2^32 and kept values are
+ * scaled by 1/(1-p).  The mask is a pure function of (seed, L, i): bitwise parity with torch's Philox
+ * stream is impossible, distributional parity is what holds.
+ * Which of h1 / h is needed depends on the path:
+ *   TOAD_FLAG_SIMT_FP32: fp32 h1, h (planes ignored);
+ *   tensor-core path:    the (hi, lo) bf16 planes h1_hi/lo, h_hi/lo -- hi = bf16(v), lo = bf16(v - hi), the operand
+ *                        format of the split-bf16 GEMMs, so the forward keeps exactly what fc2 / the gate consumed and
+ *                        the backward contracts over them again without a conversion pass; fp32 h1 / h are optional
+ *                        extras (written when non-NULL).
+ * a, b are fp32 on both paths. */
 typedef struct {
   float* h1; /* [N, hid] relu(fc1) */
   float* h;  /* [N, hid] relu(fc2) */
@@ -118,6 +125,10 @@ typedef struct {
   float* b;  /* [N, D] sigmoid branch */
   uint64_t dropout_seed;
   float dropout_p; /* 0.25 in the reference; used only with TOAD_FLAG_DROPOUT (forward) / when > 0 (backward) */
+  void* h1_hi; /* [N, hid] bf16 */
+  void* h1_lo;
+  void* h_hi;
+  void* h_lo;
 } toad_saved_t;
 
 /* The mask hash (host-callable, for tests): high 32 bits of splitmix64(seed, layer, index). */

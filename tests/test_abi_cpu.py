@@ -32,7 +32,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_version_and_error_strings(lib):
-    assert lib.toad_abi_version() == 1
+    assert lib.toad_abi_version() == 2
     assert lib.toad_error_string(0) == b"ok"
     assert b"workspace" in lib.toad_error_string(-2)
     assert b"not supported" in lib.toad_error_string(-3)

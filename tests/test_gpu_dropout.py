@@ -65,9 +65,9 @@ def test_dropout_mask_statistics_and_rescale():
     plist = [torch.from_numpy(v).cuda() for v in params.values()]
     sex = torch.tensor([0.0], device="cuda")
     ws = ops.Workspace()
-    base = ops.alloc_saved(dims, n, x.device)
+    base = ops.alloc_saved(dims, n, x.device, _lib.FLAG_SIMT_FP32)
     ops.toad_fwd(dims, plist, x, sex, ws, _lib.FLAG_SIMT_FP32 | _lib.FLAG_SAVE_ACTS, base)
-    drop = ops.alloc_saved(dims, n, x.device)
+    drop = ops.alloc_saved(dims, n, x.device, _lib.FLAG_SIMT_FP32)
     drop["dropout_seed"], drop["dropout_p"] = 99, 0.25
     ops.toad_fwd(dims, plist, x, sex, ws, _lib.FLAG_SIMT_FP32 | _lib.FLAG_SAVE_ACTS | _lib.FLAG_DROPOUT, drop)
     torch.cuda.synchronize()

@@ -19,6 +19,7 @@ FLAG_DROPOUT = 16
 FLAG_TC_PAIR_ALL = 32
 FLAG_REUSE_WEIGHT_PLANES = 128
 FLAG_BWD_TRANSPOSED = 256
+ABI_VERSION = 2
 
 EXPORTS = [
     "toad_abi_version", "toad_error_string", "toad_param_offsets", "toad_dropout_hash",
@@ -49,7 +50,8 @@ class FwdOut(C.Structure):
 
 
 class Saved(C.Structure):
-    _fields_ = [(n, _f32p) for n in ("h1", "h", "a", "b")] + [("dropout_seed", C.c_uint64), ("dropout_p", C.c_float)]
+    _fields_ = [(n, _f32p) for n in ("h1", "h", "a", "b")] + [("dropout_seed", C.c_uint64), ("dropout_p", C.c_float)] + \
+        [(n, C.c_void_p) for n in ("h1_hi", "h1_lo", "h_hi", "h_lo")]
 
 
 class ToadError(RuntimeError):
@@ -108,8 +110,8 @@ def load() -> C.CDLL:
         if name not in ("toad_error_string", "toad_dropout_hash"):
             getattr(lib, name).restype = C.c_int
     lib.toad_dropout_hash.restype = C.c_uint32
-    if lib.toad_abi_version() != 1:
-        raise ToadError("libtoad_b200.so ABI version %d, expected 1" % lib.toad_abi_version())
+    if lib.toad_abi_version() != ABI_VERSION:
+        raise ToadError("libtoad_b200.so ABI version %d, expected %d" % (lib.toad_abi_version(), ABI_VERSION))
     _lib = lib
     return lib
 

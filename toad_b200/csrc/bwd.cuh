@@ -50,7 +50,10 @@ __global__ void heads_bwd_kernel(const float* __restrict__ dlogits, const float*
 }
 
 // ---- softmax-pooling backward per row: P[n,t], dA[n,t] = P (dM_t.h_n - sdot_t)   (warp per row)
-__global__ void pool_bwd_kernel(const float* __restrict__ h, const float* __restrict__ a_raw,
+// PLANES: h is given as its saved (hi, lo) bf16 planes (tensor-core path) instead of fp32.
+template <bool PLANES>
+__global__ void pool_bwd_kernel(const float* __restrict__ h, const __nv_bfloat16* __restrict__ h_hi,
+                                const __nv_bfloat16* __restrict__ h_lo, const float* __restrict__ a_raw,
                                 const float* __restrict__ stats, const float* __restrict__ dM,
                                 const float* __restrict__ sdot, float* __restrict__ P, float* __restrict__ dA,
                                 int64_t N) {
@@ -65,7 +68,15 @@ __global__ void pool_bwd_kernel(const float* __restrict__ h, const float* __rest
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int c = 4 * (lane + 32 * q);
-      const float4 v = ld_stream_f4(h + row * H + c);
+      float4 v;
+      if (PLANES) {
+        const uint2 uh = *reinterpret_cast<const uint2*>(h_hi + row * H + c);
+        const uint2 ul = *reinterpret_cast<const uint2*>(h_lo + row * H + c);
+        v = make_float4(bf16lo_to_f32(uh.x) + bf16lo_to_f32(ul.x), bf16hi_to_f32(uh.x) + bf16hi_to_f32(ul.x),
+                        bf16lo_to_f32(uh.y) + bf16lo_to_f32(ul.y), bf16hi_to_f32(uh.y) + bf16hi_to_f32(ul.y));
+      } else {
+        v = ld_stream_f4(h + row * H + c);
+      }
       d0 += v.x * s_dM[c] + v.y * s_dM[c + 1] + v.z * s_dM[c + 2] + v.w * s_dM[c + 3];
       d1 += v.x * s_dM[H + c] + v.y * s_dM[H + c + 1] + v.z * s_dM[H + c + 2] + v.w * s_dM[H + c + 3];
     }

@@ -119,6 +119,7 @@ struct GemmTcParams {
   const float* pool_p;    // [M, 2] or nullptr
   const float* pool_v;    // [2, N]
   const float* mask_f32;  // [M, ld_mask] or nullptr
+  const __nv_bfloat16* mask_bf16;  // the same mask given as the hi plane of the activation (hi > 0 <=> value > 0), or nullptr
   int64_t ld_mask;
   float out_scale;        // 0 = 1
 };
@@ -622,7 +623,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 r[i] = __float_as_uint(t);
               }
             }
-            if (A_MODE != A_F32 && (p.pool_p != nullptr || p.mask_f32 != nullptr || p.out_scale != 0.f)) {
+            if (A_MODE != A_F32 && (p.pool_p != nullptr || p.mask_f32 != nullptr || p.mask_bf16 != nullptr || p.out_scale != 0.f)) {
               // backward dgrad epilogue (uniform branch; never taken by the forward kernels)
               float p0 = 0.f, p1 = 0.f;
               if (p.pool_p != nullptr && row_ok) { p0 = __ldg(p.pool_p + row * 2); p1 = __ldg(p.pool_p + row * 2 + 1); }
@@ -631,6 +632,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
                 if (p.mask_f32 != nullptr && row_ok)
                   mk = *reinterpret_cast<const float4*>(p.mask_f32 + row * p.ld_mask + col0 + q * 4);
+                if (p.mask_bf16 != nullptr && row_ok) {
+                  const uint2 mb = *reinterpret_cast<const uint2*>(p.mask_bf16 + row * p.ld_mask + col0 + q * 4);
+                  mk = make_float4(bf16lo_to_f32(mb.x), bf16hi_to_f32(mb.x), bf16lo_to_f32(mb.y), bf16hi_to_f32(mb.y));
+                }
                 const float mv[4] = {mk.x, mk.y, mk.z, mk.w};
                 float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
                 if (p.pool_p != nullptr) {

@@ -172,7 +172,10 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
                      out->y_hat == nullptr || out->site_logits == nullptr || out->site_prob == nullptr ||
                      out->site_hat == nullptr || out->softmax_stats == nullptr))
     return TOAD_ERR_ARG;
-  if (save && (saved == nullptr || !saved->h1 || !saved->h || !saved->a || !saved->b)) return TOAD_ERR_ARG;
+  const bool simt = (flags & TOAD_FLAG_SIMT_FP32) != 0;
+  if (save && (saved == nullptr || !saved->a || !saved->b)) return TOAD_ERR_ARG;
+  if (save && simt && (!saved->h1 || !saved->h)) return TOAD_ERR_ARG;
+  if (save && !simt && (!saved->h1_hi || !saved->h1_lo || !saved->h_hi || !saved->h_lo)) return TOAD_ERR_ARG;
   if ((flags & TOAD_FLAG_DROPOUT) && (!save || saved->dropout_p < 0.f || saved->dropout_p >= 1.f)) return TOAD_ERR_ARG;
   const DropoutCfg drop = make_drop(saved, flags);
   FwdWs w = carve_fwd(d, n, flags, workspace);
@@ -210,6 +213,11 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
   // everywhere.
   const bool cg1 = (flags & TOAD_FLAG_TC_SINGLE_CTA) != 0;
   const bool fc1_pair = (flags & TOAD_FLAG_TC_PAIR_ALL) != 0;
+  // activation planes: workspace scratch for inference, the caller's saved buffers when the backward will need them
+  bf16* h1_hi = save ? static_cast<bf16*>(saved->h1_hi) : w.h1_hi;
+  bf16* h1_lo = save ? static_cast<bf16*>(saved->h1_lo) : w.h1_lo;
+  bf16* h_hi = save ? static_cast<bf16*>(saved->h_hi) : w.h_hi;
+  bf16* h_lo = save ? static_cast<bf16*>(saved->h_lo) : w.h_lo;
   TOAD_TRY(prof_mark(prof, 0, st));
   if (!(flags & TOAD_FLAG_REUSE_WEIGHT_PLANES)) {
     TOAD_TRY(tail::launch_split_planes(P->w1, w.w1_hi, w.w1_lo, static_cast<int64_t>(Hd) * L, st));
@@ -222,7 +230,7 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
     g.a_f32 = x; g.lda = L; g.M = n; g.N = Hd; g.K = L; g.bias = P->b1; g.relu = 1;
     g.drop = drop; g.drop_layer = DROP_H1;
     g.out_f32 = save ? saved->h1 : nullptr; g.ld_f32 = Hd;
-    g.out_hi = w.h1_hi; g.out_lo = w.h1_lo; g.ld_split = Hd;
+    g.out_hi = h1_hi; g.out_lo = h1_lo; g.ld_split = Hd;
     if (cg1) TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_LINEAR, 1>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, st)));
     else if (fc1_pair) TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_LINEAR, 2>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, st)));
     else TOAD_TRY((tc::launch_gemm<512, tc::A_F32, tc::EPI_LINEAR, 2>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, st)));
@@ -233,10 +241,10 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
     g.M = n; g.N = Hd; g.K = Hd; g.bias = P->b2; g.relu = 1;
     g.drop = drop; g.drop_layer = DROP_H;
     g.out_f32 = save ? saved->h : nullptr; g.ld_f32 = Hd;
-    g.out_hi = w.h_hi; g.out_lo = w.h_lo; g.ld_split = Hd;
-    if (cg1) TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 1>(g, w.h1_hi, w.h1_lo, w.w2_hi, w.w2_lo, st)));
-    else if (flags & TOAD_FLAG_FC2_WIDE) TOAD_TRY((tc::launch_gemm<512, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, w.h1_hi, w.h1_lo, w.w2_hi, w.w2_lo, st)));
-    else TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, w.h1_hi, w.h1_lo, w.w2_hi, w.w2_lo, st)));
+    g.out_hi = h_hi; g.out_lo = h_lo; g.ld_split = Hd;
+    if (cg1) TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 1>(g, h1_hi, h1_lo, w.w2_hi, w.w2_lo, st)));
+    else if (flags & TOAD_FLAG_FC2_WIDE) TOAD_TRY((tc::launch_gemm<512, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, h1_hi, h1_lo, w.w2_hi, w.w2_lo, st)));
+    else TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, h1_hi, h1_lo, w.w2_hi, w.w2_lo, st)));
   }
   TOAD_TRY(prof_mark(prof, 3, st));
   {
@@ -245,11 +253,11 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
     g.gate_ba = P->ba; g.gate_bb = P->bb; g.gate_wc = P->wc; g.gate_D = D; g.gate_ntasks = d->n_tasks;
     g.gate_part = w.part; g.gate_a = save ? saved->a : nullptr; g.gate_b = save ? saved->b : nullptr;
     g.drop = drop;
-    if (cg1) TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_GATE, 1>(g, w.h_hi, w.h_lo, w.wab_hi, w.wab_lo, st)));
-    else TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_GATE, 2>(g, w.h_hi, w.h_lo, w.wab_hi, w.wab_lo, st)));
+    if (cg1) TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_GATE, 1>(g, h_hi, h_lo, w.wab_hi, w.wab_lo, st)));
+    else TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_GATE, 2>(g, h_hi, h_lo, w.wab_hi, w.wab_lo, st)));
   }
   TOAD_TRY(prof_mark(prof, 4, st));
-  TOAD_TRY(run_tail(d, P, n, sex, out, w, nullptr, w.h_hi, w.h_lo, attn_only, st));
+  TOAD_TRY(run_tail(d, P, n, sex, out, w, nullptr, h_hi, h_lo, attn_only, st));
   TOAD_TRY(prof_mark(prof, 5, st));
   if (prof != nullptr && prof->n < prof->max_calls) prof->n++;
   return 0;
@@ -362,7 +370,7 @@ struct BwdTcWs {
   bf16 *dab_hi, *dab_lo, *dabT_hi, *dabT_lo, *hT_hi, *hT_lo, *h1T_hi, *h1T_lo, *xT_hi, *xT_lo;
   bf16 *dz2_hi, *dz2_lo, *dz2T_hi, *dz2T_lo, *dz1_hi, *dz1_lo, *dz1T_hi, *dz1T_lo;
   bf16 *w2T_hi, *w2T_lo, *wabT_hi, *wabT_lo;
-  bf16 *hp_hi, *hp_lo, *h1p_hi, *h1p_lo, *xp_hi, *xp_lo;  // natural-layout planes of the saved fp32 activations / x
+  bf16 *xp_hi, *xp_lo;  // natural-layout planes of x
   int gate_blocks, col_blocks;
   int64_t ldT;
   size_t bytes;
@@ -388,7 +396,7 @@ BwdTcWs carve_bwd_tc(const toad_dims_t* d, int64_t n, void* base) {
   w.w2T_hi = c.take<bf16>(Hd * Hd);    w.w2T_lo = c.take<bf16>(Hd * Hd);
   w.wabT_hi = c.take<bf16>(Hd * 2 * D); w.wabT_lo = c.take<bf16>(Hd * 2 * D);
   // the MN-major wgrads read natural-layout planes; they alias the (then unused) transposed buffers
-  w.hp_hi = w.hT_hi; w.hp_lo = w.hT_lo; w.h1p_hi = w.h1T_hi; w.h1p_lo = w.h1T_lo; w.xp_hi = w.xT_hi; w.xp_lo = w.xT_lo;
+  w.xp_hi = w.xT_hi; w.xp_lo = w.xT_lo;
   int64_t big = Hd * L;
   if (2 * D * Hd > big) big = 2 * D * Hd;
   w.splitk = c.take<float>(static_cast<size_t>(kSMs / 2) * 256 * 256);  // <= one 256x256 fp32 tile per CTA pair (+ slack below)
@@ -458,6 +466,9 @@ int bwd_tc(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int Hd = d->hid_dim, D = d->attn_dim, L = d->in_dim;
   if (sv->dropout_p < 0.f || sv->dropout_p >= 1.f) return TOAD_ERR_ARG;
+  // the saved activations of the tensor-core path are the (hi, lo) planes the forward GEMMs consumed
+  const bf16 *sh1_hi = static_cast<const bf16*>(sv->h1_hi), *sh1_lo = static_cast<const bf16*>(sv->h1_lo);
+  const bf16 *sh_hi = static_cast<const bf16*>(sv->h_hi), *sh_lo = static_cast<const bf16*>(sv->h_lo);
   const float keep = 1.0f - sv->dropout_p, inv_keep = 1.0f / keep;
   int64_t off[15];
   toad_param_offsets(d, off);
@@ -473,8 +484,8 @@ int bwd_tc(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t
   {
     int64_t blocks = (n + 7) / 8;
     if (blocks > 8 * kSMs) blocks = 8 * kSMs;
-    bwd::pool_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(sv->h, fo->a_raw, fo->softmax_stats, w.dM, w.sdot,
-                                                                         w.P, w.dA, n);
+    bwd::pool_bwd_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, st>>>(nullptr, sh_hi, sh_lo, fo->a_raw, fo->softmax_stats,
+                                                                               w.dM, w.sdot, w.P, w.dA, n);
     TOAD_CUDA_TRY(cudaGetLastError());
   }
   {
@@ -489,13 +500,11 @@ int bwd_tc(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t
   }
   // operand preparation: (hi, lo) planes (dab already left gate_bwd as planes)
   if (mn) {
-    TOAD_TRY(tail::launch_split_planes(sv->h, w.hp_hi, w.hp_lo, n * Hd, st));
-    TOAD_TRY(tail::launch_split_planes(sv->h1, w.h1p_hi, w.h1p_lo, n * Hd, st));
     TOAD_TRY(tail::launch_split_planes(x, w.xp_hi, w.xp_lo, n * L, st));
   } else {
     TOAD_TRY(bwd::launch_transpose_planes(w.dab_hi, w.dab_lo, n, 2 * D, w.dabT_hi, w.dabT_lo, w.ldT, st));
-    TOAD_TRY(bwd::launch_transpose_split(sv->h, n, Hd, Hd, w.hT_hi, w.hT_lo, w.ldT, st));
-    TOAD_TRY(bwd::launch_transpose_split(sv->h1, n, Hd, Hd, w.h1T_hi, w.h1T_lo, w.ldT, st));
+    TOAD_TRY(bwd::launch_transpose_planes(sh_hi, sh_lo, n, Hd, w.hT_hi, w.hT_lo, w.ldT, st));
+    TOAD_TRY(bwd::launch_transpose_planes(sh1_hi, sh1_lo, n, Hd, w.h1T_hi, w.h1T_lo, w.ldT, st));
     TOAD_TRY(bwd::launch_transpose_split(x, n, L, L, w.xT_hi, w.xT_lo, w.ldT, st));
   }
   TOAD_TRY(bwd::launch_transpose_split(P->w2, Hd, Hd, Hd, w.w2T_hi, w.w2T_lo, Hd, st));                  // W2^T   [in, out]
@@ -503,13 +512,13 @@ int bwd_tc(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t
   TOAD_TRY(bwd::launch_transpose_split(P->wb, D, Hd, Hd, w.wabT_hi + D, w.wabT_lo + D, 2 * D, st));
 
   // dWa | dWb = dab^T . h
-  if (mn) TOAD_TRY(wgrad_mn(w.dab_hi, w.dab_lo, 2 * D, w.hp_hi, w.hp_lo, Hd, 2 * D, Hd, n, w.splitk, g_wa, D, g_wb, st));
+  if (mn) TOAD_TRY(wgrad_mn(w.dab_hi, w.dab_lo, 2 * D, sh_hi, sh_lo, Hd, 2 * D, Hd, n, w.splitk, g_wa, D, g_wb, st));
   else TOAD_TRY(wgrad_tc(w.dabT_hi, w.dabT_lo, w.hT_hi, w.hT_lo, 2 * D, Hd, n, w.ldT, w.splitk, g_wa, D, g_wb, st));
   // dz2 = (dab . [Wa;Wb] + P0 dM0 + P1 dM1) * (h > 0) / keep      -> planes
   {
     tc::GemmTcParams g{};
     g.M = n; g.N = Hd; g.K = 2 * D;
-    g.pool_p = w.P; g.pool_v = w.dM; g.mask_f32 = sv->h; g.ld_mask = Hd; g.out_scale = inv_keep;
+    g.pool_p = w.P; g.pool_v = w.dM; g.mask_bf16 = sh_hi; g.ld_mask = Hd; g.out_scale = inv_keep;
     g.out_hi = w.dz2_hi; g.out_lo = w.dz2_lo; g.ld_split = Hd;
     TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, w.dab_hi, w.dab_lo, w.wabT_hi, w.wabT_lo, st)));
   }
@@ -517,7 +526,7 @@ int bwd_tc(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t
   TOAD_TRY(bwd::launch_reduce_strided(w.col_part, g_b2, Hd, Hd, w.col_blocks, st));
   // dW2 = dz2^T . h1
   if (mn) {
-    TOAD_TRY(wgrad_mn(w.dz2_hi, w.dz2_lo, Hd, w.h1p_hi, w.h1p_lo, Hd, Hd, Hd, n, w.splitk, g_w2, 0, nullptr, st));
+    TOAD_TRY(wgrad_mn(w.dz2_hi, w.dz2_lo, Hd, sh1_hi, sh1_lo, Hd, Hd, Hd, n, w.splitk, g_w2, 0, nullptr, st));
   } else {
     TOAD_TRY(bwd::launch_transpose_planes(w.dz2_hi, w.dz2_lo, n, Hd, w.dz2T_hi, w.dz2T_lo, w.ldT, st));
     TOAD_TRY(wgrad_tc(w.dz2T_hi, w.dz2T_lo, w.h1T_hi, w.h1T_lo, Hd, Hd, n, w.ldT, w.splitk, g_w2, 0, nullptr, st));
@@ -526,7 +535,7 @@ int bwd_tc(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t
   {
     tc::GemmTcParams g{};
     g.M = n; g.N = Hd; g.K = Hd;
-    g.mask_f32 = sv->h1; g.ld_mask = Hd; g.out_scale = inv_keep;
+    g.mask_bf16 = sh1_hi; g.ld_mask = Hd; g.out_scale = inv_keep;
     g.out_hi = w.dz1_hi; g.out_lo = w.dz1_lo; g.ld_split = Hd;
     TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, w.dz2_hi, w.dz2_lo, w.w2T_hi, w.w2T_lo, st)));
   }
@@ -573,7 +582,7 @@ static int bwd_simt(const toad_dims_t* d, const toad_params_t* P, const float* x
   {
     int64_t blocks = (n + 7) / 8;
     if (blocks > 8 * kSMs) blocks = 8 * kSMs;
-    bwd::pool_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(sv->h, fo->a_raw, fo->softmax_stats, w.dM, w.sdot,
+    bwd::pool_bwd_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, st>>>(sv->h, nullptr, nullptr, fo->a_raw, fo->softmax_stats, w.dM, w.sdot,
                                                                          w.P, w.dA, n);
     TOAD_CUDA_TRY(cudaGetLastError());
   }
@@ -655,7 +664,12 @@ extern "C" int toad_bwd(const toad_dims_t* d, const toad_params_t* P, const floa
                         size_t workspace_bytes, uint32_t flags, toad_stream_t stream) {
   TOAD_TRY(check_dims(d));
   if (!P || !x || !fo || !sv || !dlogits || !dsite || !grad || n <= 0) return TOAD_ERR_ARG;
-  if (!fo->a_raw || !fo->features || !fo->softmax_stats || !sv->h1 || !sv->h || !sv->a || !sv->b) return TOAD_ERR_ARG;
+  if (!fo->a_raw || !fo->features || !fo->softmax_stats || !sv->a || !sv->b) return TOAD_ERR_ARG;
+  if (flags & TOAD_FLAG_SIMT_FP32) {
+    if (!sv->h1 || !sv->h) return TOAD_ERR_ARG;
+  } else if (!sv->h1_hi || !sv->h1_lo || !sv->h_hi || !sv->h_lo) {
+    return TOAD_ERR_ARG;
+  }
   if (flags & TOAD_FLAG_SIMT_FP32) return bwd_simt(d, P, x, n, fo, sv, dlogits, dsite, grad, workspace, workspace_bytes, stream);
   return bwd_tc(d, P, x, n, fo, sv, dlogits, dsite, grad, workspace, workspace_bytes, flags, stream);
 }

@@ -80,7 +80,7 @@ class _ToadFunction(torch.autograd.Function):
         saved = None
         if need_grad or module._dropout_active():
             flags |= _lib.FLAG_SAVE_ACTS
-            saved = ops.alloc_saved(dims, h.shape[0], h.device)
+            saved = ops.alloc_saved(dims, h.shape[0], h.device, flags)
             if module._dropout_active():
                 # nn.Dropout(0.25) x4 (model_toad.py:27-29,60-64): a fresh mask per forward, drawn from
                 # torch's CPU generator so torch.manual_seed() makes training runs repeatable.

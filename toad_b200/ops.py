@@ -86,10 +86,18 @@ def alloc_fwd_out(dims: Dims, n: int, device: torch.device) -> Dict[str, torch.T
     }
 
 
-def alloc_saved(dims: Dims, n: int, device: torch.device) -> Dict[str, torch.Tensor]:
+def alloc_saved(dims: Dims, n: int, device: torch.device, flags: int = 0) -> Dict[str, torch.Tensor]:
+    """Buffers for the activations the backward needs (toad_saved_t): fp32 a, b always; h1 / h as fp32 on the
+    fp32 CUDA-core path, as the (hi, lo) bf16 planes the forward GEMMs consume on the tensor-core path."""
     f32 = dict(dtype=torch.float32, device=device)
-    return {"h1": torch.empty((n, dims.hid_dim), **f32), "h": torch.empty((n, dims.hid_dim), **f32),
-            "a": torch.empty((n, dims.attn_dim), **f32), "b": torch.empty((n, dims.attn_dim), **f32)}
+    s = {"a": torch.empty((n, dims.attn_dim), **f32), "b": torch.empty((n, dims.attn_dim), **f32)}
+    if flags & _lib.FLAG_SIMT_FP32:
+        s["h1"] = torch.empty((n, dims.hid_dim), **f32)
+        s["h"] = torch.empty((n, dims.hid_dim), **f32)
+    else:
+        for k in ("h1_hi", "h1_lo", "h_hi", "h_lo"):
+            s[k] = torch.empty((n, dims.hid_dim), dtype=torch.bfloat16, device=device)
+    return s
 
 
 def _out_struct(out: Dict[str, torch.Tensor]) -> FwdOut:
@@ -101,8 +109,8 @@ def _out_struct(out: Dict[str, torch.Tensor]) -> FwdOut:
 
 def _saved_struct(saved: Dict[str, torch.Tensor]) -> Saved:
     s = Saved()
-    for k in ("h1", "h", "a", "b"):
-        setattr(s, k, saved[k].data_ptr())
+    for k in ("h1", "h", "a", "b", "h1_hi", "h1_lo", "h_hi", "h_lo"):
+        setattr(s, k, saved[k].data_ptr() if saved.get(k) is not None else None)
     s.dropout_seed = int(saved.get("dropout_seed", 0))
     s.dropout_p = float(saved.get("dropout_p", 0.0))
     return s
