@@ -175,6 +175,23 @@ int toad_bwd(const toad_dims_t* dims, const toad_params_t* params, const float* 
              const float* dsite_logits, float* grad_flat, void* workspace, size_t workspace_bytes,
              uint32_t flags, toad_stream_t stream);
 
+/* The loss of the reference training loop (utils/core_utils_mtl_concat.py:213-215) and its gradient in one launch:
+ * loss3 = {w_cls*CE(logits,label) + w_site*CE(site_logits,site), CE(logits,label), CE(site_logits,site)} and
+ * dlogits[n_classes], dsite_logits[2] = d loss3[0] / d(logits, site_logits), ready for toad_bwd.  label / site are
+ * device int64[1] (the loop's label.to(device)); a target outside its range gives NaN for that head (the
+ * reference trips a device assert).  The reference uses w_cls = 0.75, w_site = 0.25. */
+int toad_ce_loss_grad(const float* logits, const float* site_logits, int32_t n_classes, const int64_t* label,
+                      const int64_t* site, float w_cls, float w_site, float* loss3, float* dlogits,
+                      float* dsite_logits, toad_stream_t stream);
+
+/* torch.optim.Adam as the reference builds it (utils/utils.py:65: lr, weight_decay = L2 term added to the
+ * gradient, betas, eps, amsgrad off) applied to all 14 parameter tensors in place, one launch.
+ * grad_flat / exp_avg / exp_avg_sq: flat fp32 buffers in toad_param_offsets order (the moments start at zero);
+ * step = 1 for the first update; grad_scale multiplies the gradient first (1/world_size after a summing all-reduce). */
+int toad_adam_step(const toad_dims_t* dims, const toad_params_t* params, const float* grad_flat, float* exp_avg,
+                   float* exp_avg_sq, int64_t step, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, float grad_scale, toad_stream_t stream);
+
 /* Standalone gated attention head: A[N, n_tasks] = Wc(tanh(Wa x + ba) * sigmoid(Wb x + bb)) + bc. */
 int toad_attn_gated_workspace_bytes(int32_t L, int32_t D, int32_t n_tasks, int64_t n, uint32_t flags, size_t* bytes);
 int toad_attn_gated_fwd(int32_t L, int32_t D, int32_t n_tasks, const float* wa, const float* ba,

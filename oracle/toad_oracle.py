@@ -20,6 +20,7 @@ Reference lines restated (all in /root/reference):
   * TOAD_fc_mtl_concat.forward        models/model_toad.py:90-116
   * initialize_weights                utils/utils.py:150-154
   * training loss 0.75*CE + 0.25*CE   utils/core_utils_mtl_concat.py:213-215
+  * optimizer (torch.optim.Adam)      utils/utils.py:65, core_utils_mtl_concat.py:231-234
 
 Parameter naming follows the reference ``state_dict`` keys with
 ``dropout=False`` (Sequential indices 0, 2, 4):
@@ -206,6 +207,39 @@ def cross_entropy(logits: np.ndarray, label: int) -> float:
 def toad_loss(out: dict, label: int, site: int) -> float:
     """0.75*CE(logits,label) + 0.25*CE(site_logits,site) (core_utils_mtl_concat.py:215)."""
     return 0.75 * cross_entropy(out["logits"], label) + 0.25 * cross_entropy(out["site_logits"], site)
+
+
+def ce_loss_grad(logits: np.ndarray, site_logits: np.ndarray, label: int, site: int,
+                 w_cls: float = 0.75, w_site: float = 0.25, dtype=np.float64):
+    """(loss3, dlogits, dsite_logits) of the training loss (core_utils_mtl_concat.py:213-215):
+    loss3 = [w_cls*CE_cls + w_site*CE_site, CE_cls, CE_site]; d CE/dz = softmax(z) - onehot."""
+    def one(z, y, w):
+        z = np.asarray(z, dtype=dtype).reshape(-1)
+        zs = z - z.max()
+        lse = np.log(np.exp(zs).sum())
+        g = np.exp(zs - lse)
+        g[y] -= 1.0
+        return lse - zs[y], w * g
+    lc, dl = one(logits, label, w_cls)
+    ls, ds = one(site_logits, site, w_site)
+    return np.array([w_cls * lc + w_site * ls, lc, ls], dtype=dtype), dl, ds
+
+
+def adam_step(params: dict, grads: dict, exp_avg: dict, exp_avg_sq: dict, step: int, lr: float,
+              betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, dtype=np.float64) -> None:
+    """One torch.optim.Adam update in place on dicts of arrays -- the optimizer the reference builds
+    (utils/utils.py:65: optim.Adam(..., lr=args.lr, weight_decay=args.reg); amsgrad off, maximize off).
+    PyTorch is the third-party home of this arithmetic (torch/optim/adam.py, _single_tensor_adam); the
+    oracle is pinned against torch.optim.Adam itself in tests/test_oracle_golden.py."""
+    b1, b2 = betas
+    bc1 = 1.0 - b1 ** step
+    bc2 = 1.0 - b2 ** step
+    for k in params:
+        g = grads[k].astype(dtype) + weight_decay * params[k].astype(dtype)
+        exp_avg[k] = (exp_avg[k] + (g - exp_avg[k]) * (1.0 - b1)).astype(dtype)
+        exp_avg_sq[k] = (exp_avg_sq[k] * b2 + (1.0 - b2) * g * g).astype(dtype)
+        denom = np.sqrt(exp_avg_sq[k]) / np.sqrt(bc2) + eps
+        params[k] = (params[k] - (lr / bc1) * (exp_avg[k] / denom)).astype(params[k].dtype)
 
 
 # ----------------------------------------------------------------------------

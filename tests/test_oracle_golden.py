@@ -125,3 +125,44 @@ def test_torch_port_matches_reference_fp32(name):
         np.testing.assert_allclose(out[k].numpy(), g["f32_" + k], rtol=1e-5, atol=1e-6, err_msg=k)
     np.testing.assert_allclose(out["A"].numpy(), g["f32_A"], rtol=0, atol=5e-6)
     assert np.array_equal(out["Y_hat"].numpy(), g["f32_Y_hat"])
+
+
+def test_ce_loss_grad_matches_torch_cross_entropy():
+    """Pin the loss restatement on nn.CrossEntropyLoss + autograd, the calls the reference makes
+    (utils/core_utils_mtl_concat.py:211-215,231)."""
+    import torch
+    rng = np.random.default_rng(4)
+    for C, y, s in ((18, 3, 1), (2, 0, 0), (7, 6, 1)):
+        z = rng.standard_normal((1, C)).astype(np.float32) * 3
+        zs = rng.standard_normal((1, 2)).astype(np.float32)
+        tz, tzs = torch.tensor(z, dtype=torch.float64, requires_grad=True), torch.tensor(zs, dtype=torch.float64, requires_grad=True)
+        ce = torch.nn.CrossEntropyLoss()
+        lc, ls = ce(tz, torch.tensor([y])), ce(tzs, torch.tensor([s]))
+        loss = lc * 0.75 + ls * 0.25
+        loss.backward()
+        loss3, dl, ds = O.ce_loss_grad(z, zs, y, s)
+        np.testing.assert_allclose(loss3, [loss.item(), lc.item(), ls.item()], rtol=1e-12)
+        np.testing.assert_allclose(dl, tz.grad.numpy()[0], rtol=1e-10, atol=1e-14)
+        np.testing.assert_allclose(ds, tzs.grad.numpy()[0], rtol=1e-10, atol=1e-14)
+
+
+def test_adam_restatement_matches_torch_optim_adam():
+    """Pin the optimizer restatement on torch.optim.Adam built the way the reference builds it
+    (utils/utils.py:65: lr, weight_decay), several steps, fp64."""
+    import torch
+    rng = np.random.default_rng(5)
+    shapes = {"w": (5, 7), "b": (7,), "c": (1, 3)}
+    p0 = {k: rng.standard_normal(s) for k, s in shapes.items()}
+    tp = {k: torch.nn.Parameter(torch.tensor(v.copy(), dtype=torch.float64)) for k, v in p0.items()}
+    opt = torch.optim.Adam(tp.values(), lr=1e-2, weight_decay=1e-3)
+    p = {k: v.copy() for k, v in p0.items()}
+    m = {k: np.zeros_like(v) for k, v in p0.items()}
+    v2 = {k: np.zeros_like(v) for k, v in p0.items()}
+    for step in range(1, 6):
+        g = {k: rng.standard_normal(s) * (0.1 if step % 2 else 10.0) for k, s in shapes.items()}
+        for k in tp:
+            tp[k].grad = torch.tensor(g[k].copy(), dtype=torch.float64)
+        opt.step()
+        O.adam_step(p, g, m, v2, step, 1e-2, (0.9, 0.999), 1e-8, 1e-3)
+        for k in p:
+            np.testing.assert_allclose(p[k], tp[k].detach().numpy(), rtol=1e-12, atol=1e-14, err_msg="%s step %d" % (k, step))

@@ -29,6 +29,7 @@ EXPORTS = [
     "toad_linear_workspace_bytes", "toad_linear_bf16x3",
     "toad_profile_create", "toad_profile_destroy", "toad_profile_read", "toad_fwd_profiled",
     "toad_resnet_prepared_bytes", "toad_resnet_prepare", "toad_resnet_workspace_bytes", "toad_resnet_fwd",
+    "toad_ce_loss_grad", "toad_adam_step",
 ]
 
 _f32p = C.c_void_p  # device pointers travel as integers
@@ -106,6 +107,10 @@ def load() -> C.CDLL:
     lib.toad_resnet_fwd.argtypes = [C.c_void_p, _f32p, C.c_int32, C.c_int32, C.c_int32, _f32p, C.c_void_p, C.c_size_t,
                                     C.c_void_p]
     lib.toad_dropout_hash.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64]
+    lib.toad_ce_loss_grad.argtypes = [_f32p, _f32p, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_float, _f32p, _f32p,
+                                      _f32p, C.c_void_p]
+    lib.toad_adam_step.argtypes = [C.POINTER(Dims), C.POINTER(Params), _f32p, _f32p, _f32p, C.c_int64] + [C.c_float] * 6 + \
+        [C.c_void_p]
     for name in EXPORTS:
         if name not in ("toad_error_string", "toad_dropout_hash"):
             getattr(lib, name).restype = C.c_int

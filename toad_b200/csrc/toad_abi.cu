@@ -6,6 +6,8 @@
 #include "bwd.cuh"
 #include "topk.cuh"
 #include "resnet.cuh"
+#include "train.cuh"
+#include <cmath>
 #include <new>
 
 namespace {
@@ -672,6 +674,49 @@ extern "C" int toad_bwd(const toad_dims_t* d, const toad_params_t* P, const floa
   }
   if (flags & TOAD_FLAG_SIMT_FP32) return bwd_simt(d, P, x, n, fo, sv, dlogits, dsite, grad, workspace, workspace_bytes, stream);
   return bwd_tc(d, P, x, n, fo, sv, dlogits, dsite, grad, workspace, workspace_bytes, flags, stream);
+}
+
+// ------------------------------------------------------------------------------------------ loss + optimizer
+extern "C" int toad_ce_loss_grad(const float* logits, const float* site_logits, int32_t n_classes, const int64_t* label,
+                                 const int64_t* site, float w_cls, float w_site, float* loss3, float* dlogits,
+                                 float* dsite_logits, toad_stream_t stream) {
+  if (!logits || !site_logits || !label || !site || !loss3 || !dlogits || !dsite_logits) return TOAD_ERR_ARG;
+  if (n_classes < 1 || n_classes > 1024) return TOAD_ERR_UNSUPPORTED;
+  train::ce_loss_grad_kernel<<<1, 64, 0, static_cast<cudaStream_t>(stream)>>>(logits, site_logits, n_classes, label, site,
+                                                                              w_cls, w_site, loss3, dlogits, dsite_logits);
+  TOAD_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int toad_adam_step(const toad_dims_t* d, const toad_params_t* P, const float* grad_flat, float* exp_avg,
+                              float* exp_avg_sq, int64_t step, float lr, float beta1, float beta2, float eps,
+                              float weight_decay, float grad_scale, toad_stream_t stream) {
+  TOAD_TRY(check_dims(d));
+  if (!P || !grad_flat || !exp_avg || !exp_avg_sq || step < 1) return TOAD_ERR_ARG;
+  if (!(lr >= 0.f) || !(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f) || !(eps >= 0.f) ||
+      !(weight_decay >= 0.f))
+    return TOAD_ERR_ARG;
+  train::AdamArgs a{};
+  // the one entry point that WRITES the parameters (toad_params_t is const for every other caller)
+  const float* const ptrs[14] = {P->w1, P->b1, P->w2, P->b2, P->wa, P->ba, P->wb, P->bb, P->wc, P->bc, P->wcls, P->bcls, P->wsite, P->bsite};
+  for (int i = 0; i < 14; ++i) {
+    if (ptrs[i] == nullptr) return TOAD_ERR_ARG;
+    a.p[i] = const_cast<float*>(ptrs[i]);
+  }
+  toad_param_offsets(d, a.off);
+  a.g = grad_flat; a.m = exp_avg; a.v = exp_avg_sq;
+  a.grad_scale = grad_scale; a.wd = weight_decay; a.b1 = beta1; a.b2 = beta2; a.eps = eps;
+  // bias corrections in double on the host, like torch's python scalars (torch/optim/adam.py _single_tensor_adam)
+  const double bc1 = 1.0 - std::pow(static_cast<double>(beta1), static_cast<double>(step));
+  const double bc2 = 1.0 - std::pow(static_cast<double>(beta2), static_cast<double>(step));
+  a.step_size = static_cast<float>(static_cast<double>(lr) / bc1);
+  a.bc2_sqrt = static_cast<float>(std::sqrt(bc2));
+  const int64_t total = a.off[14];
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 8 * kSMs) blocks = 8 * kSMs;
+  train::adam_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  TOAD_CUDA_TRY(cudaGetLastError());
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------ Attn_Net_Gated

@@ -182,6 +182,42 @@ def toad_bwd(dims: Dims, params: Sequence[torch.Tensor], x: torch.Tensor, out: D
     return grad_flat
 
 
+def ce_loss_grad(logits: torch.Tensor, site_logits: torch.Tensor, label: torch.Tensor, site: torch.Tensor,
+                 w_cls: float = 0.75, w_site: float = 0.25):
+    """(loss3, dlogits, dsite_logits): the training loss of utils/core_utils_mtl_concat.py:213-215 and its gradient
+    w.r.t. both logit vectors, one launch.  loss3 = [total, cls, site] stays on the device."""
+    lib = _lib.load()
+    _check_dev_f32(logits, "logits")
+    _check_dev_f32(site_logits, "site_logits")
+    n_classes = logits.numel()
+    if site_logits.numel() != 2:
+        raise ValueError("site_logits must have 2 elements")
+    for t, name in ((label, "label"), (site, "site")):
+        if not t.is_cuda or t.dtype != torch.int64 or t.numel() != 1:
+            raise ValueError("%s must be a CUDA int64 tensor with one element" % name)
+    loss3 = torch.empty(3, dtype=torch.float32, device=logits.device)
+    dl = torch.empty(n_classes, dtype=torch.float32, device=logits.device)
+    ds = torch.empty(2, dtype=torch.float32, device=logits.device)
+    _lib.check(lib.toad_ce_loss_grad(logits.data_ptr(), site_logits.data_ptr(), n_classes, label.data_ptr(),
+                                     site.data_ptr(), w_cls, w_site, loss3.data_ptr(), dl.data_ptr(), ds.data_ptr(),
+                                     _stream()), "toad_ce_loss_grad")
+    return loss3, dl, ds
+
+
+def adam_step(dims: Dims, params: Sequence[torch.Tensor], grad_flat: torch.Tensor, exp_avg: torch.Tensor,
+              exp_avg_sq: torch.Tensor, step: int, lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
+              weight_decay: float = 0.0, grad_scale: float = 1.0) -> None:
+    """torch.optim.Adam's update (utils/utils.py:65) on the 14 parameter tensors in place, one launch."""
+    lib = _lib.load()
+    total = param_offsets(dims)[14]
+    for t, name in ((grad_flat, "grad_flat"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _check_dev_f32(t, name, (total,))
+    p = _params_struct(dims, params)
+    _lib.check(lib.toad_adam_step(C.byref(dims), C.byref(p), grad_flat.data_ptr(), exp_avg.data_ptr(),
+                                  exp_avg_sq.data_ptr(), int(step), lr, betas[0], betas[1], eps, weight_decay,
+                                  grad_scale, _stream()), "toad_adam_step")
+
+
 def attn_gated_fwd(x: torch.Tensor, wa, ba, wb, bb, wc, bc, ws: Workspace, flags: int = 0) -> torch.Tensor:
     """Attn_Net_Gated.forward (models/model_toad.py:36-41): A [N, n_tasks]."""
     lib = _lib.load()

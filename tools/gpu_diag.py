@@ -20,7 +20,7 @@ os.makedirs(OUT, exist_ok=True)
 
 STEPS = ["lin_64_f32", "lin_64_split", "lin_128", "lin_256", "lin_multi", "pair_64_f32", "pair_64_split", "pair_256",
          "pair_multi", "wide_small", "wide_multi", "attn_gated", "simt_fwd", "tc_fwd_small", "tc_fwd_10k", "tc_fwd_10k_cg1", "topk", "bwd_simt",
-         "bwd_tc", "timing", "lin_timing", "resnet_s64", "resnet_s256", "resnet_timing", "train_timing", "train_breakdown"]
+         "bwd_tc", "timing", "lin_timing", "resnet_s64", "resnet_s256", "resnet_timing", "train_timing", "train_breakdown", "train_spike", "train_fused"]
 
 
 def log(rec):
@@ -257,6 +257,98 @@ def run_step(step):
             torch.cuda.synchronize()
             t5 = time.perf_counter()
             rec["iters"].append([round(1e3 * v, 3) for v in (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t5 - t0)])
+        return rec
+    if step == "train_fused":
+        # FusedTrainStep vs the eager reference loop on the same module, N = 50k and a small bag
+        import torch
+        from models.model_toad import TOAD_fc_mtl_concat
+        from toad_b200.train import FusedTrainStep
+        rec = {"step": step, "ok": True}
+        for n in (50000, 2000):
+            torch.manual_seed(0)
+            model = TOAD_fc_mtl_concat(n_classes=18)
+            model.relocate()
+            model.train()
+            x = torch.randn(n, 1024, device="cuda")
+            sex = torch.ones(1, device="cuda")
+            lab, site = torch.tensor([3], device="cuda"), torch.tensor([1], device="cuda")
+            ce = torch.nn.CrossEntropyLoss()
+            opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-5)
+            fused = FusedTrainStep(model, lr=1e-4, weight_decay=1e-5)
+
+            def eager_step():
+                r = model(x, sex)
+                loss = 0.75 * ce(r["logits"], lab) + 0.25 * ce(r["site_logits"], site)
+                loss.backward()
+                opt.step()
+                opt.zero_grad()
+
+            def fused_step():
+                fused(x, lab, site, sex)
+
+            for name, fn in (("eager", eager_step), ("fused", fused_step)):
+                for _ in range(5):
+                    fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0 = time.perf_counter()
+                e0.record()
+                for _ in range(30):
+                    fn()
+                e1.record()
+                t_issue = time.perf_counter() - t0
+                torch.cuda.synchronize()
+                rec["%s_n%d_ms" % (name, n)] = round(e0.elapsed_time(e1) / 30, 4)
+                rec["%s_n%d_host_issue_ms" % (name, n)] = round(1e3 * t_issue / 30, 4)
+        return rec
+    if step == "train_spike":
+        # where do the periodic multi-ms host stalls in the training loop come from?  Log Python GC events
+        # (generation, duration) against per-iteration times, then repeat with the collector frozen.
+        import gc
+        import torch
+        from models.model_toad import TOAD_fc_mtl_concat
+        torch.manual_seed(0)
+        model = TOAD_fc_mtl_concat(n_classes=18)
+        model.relocate()
+        model.train()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-5)
+        x = torch.randn(50000, 1024, device="cuda")
+        sex = torch.ones(1, device="cuda")
+        lab, site = torch.tensor([3], device="cuda"), torch.tensor([1], device="cuda")
+        ce = torch.nn.CrossEntropyLoss()
+        events = []
+        t_gc = [0.0]
+
+        def cb(phase, info):
+            if phase == "start":
+                t_gc[0] = time.perf_counter()
+            else:
+                events.append((info["generation"], round(1e3 * (time.perf_counter() - t_gc[0]), 3), info["collected"]))
+        gc.callbacks.append(cb)
+        rec = {"step": step, "ok": True}
+        for mode in ("gc_on", "gc_frozen"):
+            if mode == "gc_frozen":
+                gc.collect()
+                gc.freeze()
+                gc.disable()
+            its = []
+            for it in range(25):
+                torch.cuda.synchronize()
+                n_ev = len(events)
+                t0 = time.perf_counter()
+                r = model(x, sex)
+                loss = 0.75 * ce(r["logits"], lab) + 0.25 * ce(r["site_logits"], site)
+                loss.backward()
+                t1 = time.perf_counter()
+                opt.step()
+                t2 = time.perf_counter()
+                opt.zero_grad()
+                torch.cuda.synchronize()
+                t3 = time.perf_counter()
+                its.append([round(1e3 * (t1 - t0), 2), round(1e3 * (t2 - t1), 2), round(1e3 * (t3 - t0), 2), events[n_ev:]])
+            rec[mode] = its
+        rec["mem_alloc_retries"] = torch.cuda.memory_stats().get("num_alloc_retries", -1)
+        rec["num_device_alloc"] = torch.cuda.memory_stats().get("num_device_alloc", -1)
         return rec
     if step == "lin_timing":
         import torch
