@@ -187,10 +187,11 @@ int toad_ce_loss_grad(const float* logits, const float* site_logits, int32_t n_c
 /* torch.optim.Adam as the reference builds it (utils/utils.py:65: lr, weight_decay = L2 term added to the
  * gradient, betas, eps, amsgrad off) applied to all 14 parameter tensors in place, one launch.
  * grad_flat / exp_avg / exp_avg_sq: flat fp32 buffers in toad_param_offsets order (the moments start at zero);
- * step = 1 for the first update; grad_scale multiplies the gradient first (1/world_size after a summing all-reduce). */
+ * step = 1 for the first update; the hyper-parameters are doubles (python floats on the caller's side: 1 - beta
+ * and the bias corrections are formed in double, as torch does); grad_scale multiplies the gradient first (1/world_size after a summing all-reduce). */
 int toad_adam_step(const toad_dims_t* dims, const toad_params_t* params, const float* grad_flat, float* exp_avg,
-                   float* exp_avg_sq, int64_t step, float lr, float beta1, float beta2, float eps,
-                   float weight_decay, float grad_scale, toad_stream_t stream);
+                   float* exp_avg_sq, int64_t step, double lr, double beta1, double beta2, double eps,
+                   double weight_decay, float grad_scale, toad_stream_t stream);
 
 /* Standalone gated attention head: A[N, n_tasks] = Wc(tanh(Wa x + ba) * sigmoid(Wb x + bb)) + bc. */
 int toad_attn_gated_workspace_bytes(int32_t L, int32_t D, int32_t n_tasks, int64_t n, uint32_t flags, size_t* bytes);

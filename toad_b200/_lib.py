@@ -109,7 +109,7 @@ def load() -> C.CDLL:
     lib.toad_dropout_hash.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64]
     lib.toad_ce_loss_grad.argtypes = [_f32p, _f32p, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_float, _f32p, _f32p,
                                       _f32p, C.c_void_p]
-    lib.toad_adam_step.argtypes = [C.POINTER(Dims), C.POINTER(Params), _f32p, _f32p, _f32p, C.c_int64] + [C.c_float] * 6 + \
+    lib.toad_adam_step.argtypes = [C.POINTER(Dims), C.POINTER(Params), _f32p, _f32p, _f32p, C.c_int64] + [C.c_double] * 5 + [C.c_float] + \
         [C.c_void_p]
     for name in EXPORTS:
         if name not in ("toad_error_string", "toad_dropout_hash"):

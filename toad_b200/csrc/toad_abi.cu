@@ -689,12 +689,12 @@ extern "C" int toad_ce_loss_grad(const float* logits, const float* site_logits, 
 }
 
 extern "C" int toad_adam_step(const toad_dims_t* d, const toad_params_t* P, const float* grad_flat, float* exp_avg,
-                              float* exp_avg_sq, int64_t step, float lr, float beta1, float beta2, float eps,
-                              float weight_decay, float grad_scale, toad_stream_t stream) {
+                              float* exp_avg_sq, int64_t step, double lr, double beta1, double beta2, double eps,
+                              double weight_decay, float grad_scale, toad_stream_t stream) {
   TOAD_TRY(check_dims(d));
   if (!P || !grad_flat || !exp_avg || !exp_avg_sq || step < 1) return TOAD_ERR_ARG;
-  if (!(lr >= 0.f) || !(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f) || !(eps >= 0.f) ||
-      !(weight_decay >= 0.f))
+  if (!(lr >= 0.0) || !(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0) || !(eps >= 0.0) ||
+      !(weight_decay >= 0.0))
     return TOAD_ERR_ARG;
   train::AdamArgs a{};
   // the one entry point that WRITES the parameters (toad_params_t is const for every other caller)
@@ -705,11 +705,16 @@ extern "C" int toad_adam_step(const toad_dims_t* d, const toad_params_t* P, cons
   }
   toad_param_offsets(d, a.off);
   a.g = grad_flat; a.m = exp_avg; a.v = exp_avg_sq;
-  a.grad_scale = grad_scale; a.wd = weight_decay; a.b1 = beta1; a.b2 = beta2; a.eps = eps;
+  // hyper-parameters arrive as doubles (python floats on the reference side); derived constants are formed in
+  // double and rounded to fp32 once, which is what torch does with its python scalars
+  a.grad_scale = grad_scale; a.wd = static_cast<float>(weight_decay);
+  a.b1 = static_cast<float>(beta1); a.b2 = static_cast<float>(beta2); a.eps = static_cast<float>(eps);
+  a.one_m_b1 = static_cast<float>(1.0 - beta1);
+  a.one_m_b2 = static_cast<float>(1.0 - beta2);
   // bias corrections in double on the host, like torch's python scalars (torch/optim/adam.py _single_tensor_adam)
-  const double bc1 = 1.0 - std::pow(static_cast<double>(beta1), static_cast<double>(step));
-  const double bc2 = 1.0 - std::pow(static_cast<double>(beta2), static_cast<double>(step));
-  a.step_size = static_cast<float>(static_cast<double>(lr) / bc1);
+  const double bc1 = 1.0 - std::pow(beta1, static_cast<double>(step));
+  const double bc2 = 1.0 - std::pow(beta2, static_cast<double>(step));
+  a.step_size = static_cast<float>(lr / bc1);
   a.bc2_sqrt = static_cast<float>(std::sqrt(bc2));
   const int64_t total = a.off[14];
   int64_t blocks = (total + 255) / 256;

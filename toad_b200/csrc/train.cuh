@@ -70,6 +70,7 @@ struct AdamArgs {
   float* v;
   float grad_scale;  // applied to g first (1/world_size after a summing all-reduce)
   float wd, b1, b2, eps;
+  float one_m_b1, one_m_b2;  // 1 - beta computed in double on the host (as torch's python scalars are)
   float step_size;     // lr / (1 - b1^t)
   float bc2_sqrt;      // sqrt(1 - b2^t)
 };
@@ -85,8 +86,8 @@ __global__ void adam_kernel(const AdamArgs a) {
     const float p = *pp;
     const float g = fmaf(a.wd, p, a.g[i] * a.grad_scale);
     float m = a.m[i], v = a.v[i];
-    m = m + (g - m) * (1.f - a.b1);                // exp_avg.lerp_(grad, 1 - beta1)
-    v = fmaf(1.f - a.b2, g * g, v * a.b2);         // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    m = m + (g - m) * a.one_m_b1;                  // exp_avg.lerp_(grad, 1 - beta1)
+    v = fmaf(a.one_m_b2, g * g, v * a.b2);         // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
     const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
     a.m[i] = m;
     a.v[i] = v;
