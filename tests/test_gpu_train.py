@@ -124,8 +124,12 @@ def test_fused_train_step_tracks_the_eager_reference_loop(name, dropout):
         losses_f.append(to_np(r["loss"]).tolist())
     np.testing.assert_allclose(np.array(losses_f), np.array(losses_e), rtol=2e-4, atol=1e-6)
     for (k, a), b in zip(eager.named_parameters(), fused_m._param_list()):
-        # 3 steps of size <= lr each; the two paths may differ by rounding in a few places
-        np.testing.assert_allclose(to_np(b), to_np(a), rtol=0, atol=0.05 * lr, err_msg=k)
+        # 3 steps of size <= ~lr each.  Adam normalises the update (m / sqrt(v)), so where a gradient entry is ~0 the
+        # last-bit differences between the two loss kernels decide its sign: a handful of entries may differ by
+        # up to the full 3 * lr, everything else must agree closely.
+        d = np.abs(to_np(b).astype(np.float64) - to_np(a))
+        assert d.max() <= 3.5 * lr, (k, d.max())
+        assert (d <= 0.05 * lr).mean() >= 0.999, (k, (d <= 0.05 * lr).mean())
     # the updated parameters are what a following eval forward sees (weight-plane cache invalidated)
     fused_m.eval()
     eager.eval()
