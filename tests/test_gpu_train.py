@@ -129,6 +129,8 @@ def test_fused_train_step_tracks_the_eager_reference_loop(name, dropout):
         # up to the full 3 * lr, everything else must agree closely.
         d = np.abs(to_np(b).astype(np.float64) - to_np(a))
         assert d.max() <= 3.5 * lr, (k, d.max())
+        if k.endswith("attention_c.bias"):
+            continue   # its true gradient is 0 (softmax is shift invariant): Adam turns pure rounding noise into +-lr steps
         assert (d <= 0.05 * lr).mean() >= 0.999, (k, (d <= 0.05 * lr).mean())
     # the updated parameters are what a following eval forward sees (weight-plane cache invalidated)
     fused_m.eval()
