@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--slides", type=int, default=64)
     ap.add_argument("--min-n", type=int, default=5000)
     ap.add_argument("--max-n", type=int, default=80000)
+    ap.add_argument("--eager", action="store_true",
+                    help="module + nn.CrossEntropyLoss + torch.optim.Adam (the reference loop) instead of FusedTrainStep")
     a = ap.parse_args()
     import numpy as np
     import torch
@@ -45,8 +47,12 @@ def main():
     model = TOAD_fc_mtl_concat(n_classes=18)
     model.relocate()
     model.train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-5)
-    bucket = FlatGradBucket(model)
+    if a.eager:
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-5)
+        bucket = FlatGradBucket(model)
+    else:
+        from toad_b200.train import FusedTrainStep
+        fused = FusedTrainStep(model, lr=1e-4, weight_decay=1e-5)
     gen = torch.Generator(device=dev)
     losses = []
     torch.cuda.synchronize()
@@ -58,14 +64,20 @@ def main():
         i = mine[s]
         gen.manual_seed(1000 + i)
         x = torch.randn(lengths[i], 1024, generator=gen, device=dev)
-        out = train_step(model, opt, bucket, x, torch.tensor([labels[i]], device=dev),
-                         torch.tensor([sites[i]], device=dev), torch.tensor([float(sexes[i])], device=dev))
-        losses.append(out["cls_loss"])
+        lab, sit = torch.tensor([labels[i]], device=dev), torch.tensor([sites[i]], device=dev)
+        sx = torch.tensor([float(sexes[i])], device=dev)
+        if a.eager:
+            out = train_step(model, opt, bucket, x, lab, sit, sx)
+            losses.append(out["cls_loss"])
+        else:
+            losses.append(fused(x, lab, sit, sx)["loss"])      # stays on the device: no host sync per step
         patches += lengths[i]
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     dt = time.perf_counter() - t0
+    if not a.eager:
+        losses = [float(l[1].item()) for l in losses]
     # all ranks hold identical parameters after identical averaged steps
     flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
     if world > 1:
@@ -80,7 +92,7 @@ def main():
     if rank == 0:
         print(json.dumps({"n_gpus": world, "steps": steps, "slides": steps * world, "seconds": dt,
                           "slides_per_s": steps * world / dt, "patches_per_s": patches_all / dt,
-                          "params_identical_across_ranks": same_all, "first_losses": losses[:3], "last_losses": losses[-3:]}))
+                          "loop": "eager" if a.eager else "fused", "params_identical_across_ranks": same_all, "first_losses": losses[:3], "last_losses": losses[-3:]}))
     if world > 1:
         dist.destroy_process_group()
 
