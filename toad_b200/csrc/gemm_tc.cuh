@@ -53,8 +53,10 @@ struct Cfg {
   static constexpr int B_SUB_ROWS = UMMA_N / CG;     // rows of one sub-tile staged by one CTA
   static constexpr int B_TILE_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-  // OUT_BUFS staging tiles for the epilogue's TMA store: 1 = the store of chunk c must finish reading smem before
-  // chunk c+1 is staged; 2 = double buffered (one operand stage less), for store-/epilogue-bound shapes (ResNet).
+  // OUT_BUFS x 32 KB of staging for the epilogue's TMA stores, carved into per-warp private (hi, lo) tiles of
+  // 32 rows x 32 columns (4 KB): 4 epilogue warps get 2 * OUT_BUFS tiles each, 8 warps OUT_BUFS each.  With one
+  // tile a warp's store must finish reading smem before its next chunk is staged; with two it overlaps.
+  // OUT_BUFS = 2 costs one operand stage: for store-/epilogue-bound shapes (ResNet).
   static_assert(OUT_BUFS == 1 || OUT_BUFS == 2, "OUT_BUFS");
   static constexpr int RING_BYTES = 192 * 1024 - (OUT_BUFS - 1) * 32 * 1024;
   static constexpr int STAGES = RING_BYTES / STAGE_BYTES > 6 ? 6 : RING_BYTES / STAGE_BYTES;
@@ -136,12 +138,16 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// arrive on the barrier at the same offset in CTA `rank` of this cluster
+// arrive on the barrier at the same offset in CTA `rank` of this cluster.  Default semantics (.release.cta): the
+// explicit .release.cluster form lowers to MEMBAR.ALL.GPU + ERRBAR, which also waits for the caller's in-flight
+// global prefetch loads (7 % of the fc1 converter warps' samples in profiles/r1m).  What crosses the CTA boundary
+// here is ordered by other means: smem operand writes by fence.proxy.async, TMEM reads by tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar), "r"(rank)
       : "memory");
 }
@@ -554,138 +560,153 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       const int acc = it % C::ACC_STAGES;
       const int64_t row = static_cast<int64_t>(m0) + ew * 32 + lane;
       const bool row_ok = row < p.M;
-      // residual operand (ResNet shortcut): this warp's 32-column half of the NEXT 64-column chunk is fetched
-      // one chunk ahead (and the first one before waiting for the accumulator), hiding the global latency
-      // that otherwise serialises the epilogue of the short-K 1x1 convolutions.
-      const bool has_res = EPI == EPI_LINEAR && A_MODE != A_F32 && p.res_hi != nullptr && row_ok;
+      // residual operand (ResNet shortcut): this warp's NEXT 32-column chunk is fetched one chunk ahead (and the
+      // first one before waiting for the accumulator), hiding the global latency that otherwise serialises the
+      // epilogue of the short-K 1x1 convolutions.
+      const bool has_res = EPI == EPI_LINEAR && A_MODE != A_F32 && p.res_hi != nullptr;
       uint4 res_h[4], res_l[4];
-      auto load_res = [&](int cc_) {
+      auto load_res = [&](int c_) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           res_h[q] = make_uint4(0u, 0u, 0u, 0u);
           res_l[q] = make_uint4(0u, 0u, 0u, 0u);
-          if (has_res) {
-            const int64_t o = row * p.ld_res + n0 + cc_ * 64 + eh * 32 + q * 8;
+          if (has_res && row_ok) {
+            const int64_t o = row * p.ld_res + n0 + c_ * 32 + q * 8;
             res_h[q] = *reinterpret_cast<const uint4*>(p.res_hi + o);
             res_l[q] = *reinterpret_cast<const uint4*>(p.res_lo + o);
           }
         }
       };
-      if (EPI == EPI_LINEAR && A_MODE != A_F32) load_res(0);
+      // bias of a 32-column chunk: lane j holds bias[col0 + j] (one coalesced load, fetched one chunk ahead);
+      // the value of column i is broadcast with a shuffle where it is added.
+      const bool has_bias = EPI == EPI_LINEAR && p.bias != nullptr && split == 0;
+      auto load_bias = [&](int c_) { return has_bias ? __ldg(p.bias + n0 + c_ * 32 + lane) : 0.f; };
+      float bias_nxt = 0.f;
+      if (EPI == EPI_LINEAR) {
+        bias_nxt = load_bias(eh);
+        if (A_MODE != A_F32) load_res(eh);
+      }
       mbar_wait(smem_u32(&bar_tmem_full[acc]), (it / C::ACC_STAGES) & 1);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N;
 
       if (EPI == EPI_LINEAR) {
-        // 64 columns at a time: TMEM -> registers -> bias/ReLU -> (hi,lo) bf16 -> 128B-swizzled smem
-        // staging tile -> one TMA store per plane (full 128 B row segments, rows >= M clipped by TMA).
-        const uint32_t stage0 = tiles_base + STAGES * C::STAGE_BYTES;
-        const int r_local = ew * 32 + lane;
+        // 32 columns at a time, every warp on its own: TMEM -> registers -> bias/residual/ReLU -> (hi,lo) bf16 ->
+        // the warp's PRIVATE 64B-swizzled staging tile (32 rows x 64 B per plane) -> one TMA store per plane
+        // (rows >= M clipped by TMA).  No CTA-wide barrier: the warps drift, so one warp's TMEM / store latency
+        // is covered by the others' arithmetic; with WARP_BUFS = 2 a warp's own store overlaps its next chunk.
+        constexpr int N_CHUNKS = BLOCK_N / 32;
+        constexpr int WARP_BUFS = OUT_BUFS * 2 / EPI_SETS;
+        static_assert(WARP_BUFS >= 1, "staging");
+        const uint32_t my_stage = tiles_base + STAGES * C::STAGE_BYTES + ((eh * 4 + ew) * WARP_BUFS) * 4096;
 #pragma unroll 1
-        for (int cc = 0; cc < BLOCK_N / 64; ++cc) {
-          const uint32_t stage_hi = stage0 + (out_chunk % OUT_BUFS) * C::OUT_STAGE_BYTES;
-          const uint32_t stage_lo = stage_hi + BLOCK_M * 128;
-          ++out_chunk;
-          if (p.out_hi != nullptr) {
-            // staging buffer free again? (the TMA store that last used it must have finished READING it)
-            if (warp == 4 && lane == 0) tma_store_wait_read<OUT_BUFS - 1>();
-            epi_barrier<128 * EPI_SETS>();
-          }
-#pragma unroll 1
-          for (int h = eh; h < 2; h += EPI_SETS) {  // this warp's 32-column half (halves) of the 64-column chunk
-            uint32_t r[32];
-            tmem_ld32(t_row + cc * 64 + h * 32, r);
-            uint4 cur_h[4], cur_l[4];
+        for (int c = eh; c < N_CHUNKS; c += EPI_SETS) {
+          const bool last = c + EPI_SETS >= N_CHUNKS;
+          uint32_t r[32];
+          tmem_ld32(t_row + c * 32, r);
+          const float bias_cur = bias_nxt;
+          uint4 cur_h[4], cur_l[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { cur_h[q] = res_h[q]; cur_l[q] = res_l[q]; }
-            if (A_MODE != A_F32 && cc + 1 < BLOCK_N / 64) load_res(cc + 1);  // next chunk's residual, in flight below
-            tmem_ld_wait();
-            const int col0 = n0 + cc * 64 + h * 32;
+          for (int q = 0; q < 4; ++q) { cur_h[q] = res_h[q]; cur_l[q] = res_l[q]; }
+          if (!last) {  // next chunk's bias / residual, in flight below
+            bias_nxt = load_bias(c + EPI_SETS);
+            if (A_MODE != A_F32) load_res(c + EPI_SETS);
+          }
+          tmem_ld_wait();
+          if (last) {  // this warp has drained its share of the accumulator: hand TMEM back before the arithmetic
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 1) mbar_arrive(smem_u32(&bar_tmem_empty[acc]));
+              else mbar_arrive_cluster(smem_u32(&bar_tmem_empty[acc]), 0);
+            }
+          }
+          const int col0 = n0 + c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            r[i] = __float_as_uint(__uint_as_float(r[i]) + __shfl_sync(0xffffffffu, bias_cur, i));
+          if (has_res) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const uint4 vh = cur_h[q], vl = cur_l[q];
               const uint32_t uh[4] = {vh.x, vh.y, vh.z, vh.w}, ul[4] = {vl.x, vl.y, vl.z, vl.w};
-              // bias for these 8 columns as two 128-bit broadcast loads (32 scalar loads per half-chunk
-              // saturated the LSU queue: stall_lg in the ncu source view of the ResNet 1x1 convolutions)
-              float bv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-              if (p.bias != nullptr && split == 0) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + q * 8));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + q * 8 + 4));
-                bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
-              }
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                const int i = q * 8 + e;
-                float t = __uint_as_float(r[i]) + bv[e];
                 const uint32_t wh = uh[e >> 1], wl = ul[e >> 1];
-                t += (e & 1) ? (bf16hi_to_f32(wh) + bf16hi_to_f32(wl)) : (bf16lo_to_f32(wh) + bf16lo_to_f32(wl));
-                if (p.relu) t = fmaxf(t, 0.0f);
-                r[i] = __float_as_uint(t);
-              }
-            }
-            if (A_MODE != A_F32 && (p.pool_p != nullptr || p.mask_f32 != nullptr || p.mask_bf16 != nullptr || p.out_scale != 0.f)) {
-              // backward dgrad epilogue (uniform branch; never taken by the forward kernels)
-              float p0 = 0.f, p1 = 0.f;
-              if (p.pool_p != nullptr && row_ok) { p0 = __ldg(p.pool_p + row * 2); p1 = __ldg(p.pool_p + row * 2 + 1); }
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (p.mask_f32 != nullptr && row_ok)
-                  mk = *reinterpret_cast<const float4*>(p.mask_f32 + row * p.ld_mask + col0 + q * 4);
-                if (p.mask_bf16 != nullptr && row_ok) {
-                  const uint2 mb = *reinterpret_cast<const uint2*>(p.mask_bf16 + row * p.ld_mask + col0 + q * 4);
-                  mk = make_float4(bf16lo_to_f32(mb.x), bf16hi_to_f32(mb.x), bf16lo_to_f32(mb.y), bf16hi_to_f32(mb.y));
-                }
-                const float mv[4] = {mk.x, mk.y, mk.z, mk.w};
-                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-                if (p.pool_p != nullptr) {
-                  v0 = __ldg(reinterpret_cast<const float4*>(p.pool_v + col0 + q * 4));
-                  v1 = __ldg(reinterpret_cast<const float4*>(p.pool_v + p.N + col0 + q * 4));
-                }
-                const float pv0[4] = {v0.x, v0.y, v0.z, v0.w}, pv1[4] = {v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int i = q * 4 + e;
-                  float t = __uint_as_float(r[i]);
-                  if (p.pool_p != nullptr) t += p0 * pv0[e] + p1 * pv1[e];
-                  t = mv[e] > 0.f ? t : 0.f;
-                  if (p.out_scale != 0.f) t *= p.out_scale;
-                  r[i] = __float_as_uint(t);
-                }
-              }
-            }
-            if (p.drop.thresh != 0u) {  // training only: one big uniform branch, never predicated into the hot path
-              const unsigned long long e0 = static_cast<unsigned long long>(row) * p.N + col0;
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                r[i] = __float_as_uint(dropout_apply(p.drop, p.drop_layer, e0 + i, __uint_as_float(r[i])));
-            }
-            if (row_ok && p.out_f32 != nullptr) {
-              uint4* dst = reinterpret_cast<uint4*>(p.out_f32 + (static_cast<int64_t>(split) * p.M + row) * p.ld_f32 + col0);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) dst[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
-            }
-            if (p.out_hi != nullptr) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {  // 8 columns -> one 16 B chunk per plane
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  split2(__uint_as_float(r[8 * q + 2 * e]), __uint_as_float(r[8 * q + 2 * e + 1]), hi[e], lo[e]);
-                const uint32_t off = r_local * 128 + ((((h * 4 + q)) ^ (r_local & 7)) << 4);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_hi + off), "r"(hi[0]), "r"(hi[1]),
-                             "r"(hi[2]), "r"(hi[3]) : "memory");
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_lo + off), "r"(lo[0]), "r"(lo[1]),
-                             "r"(lo[2]), "r"(lo[3]) : "memory");
+                const float rv = (e & 1) ? (bf16hi_to_f32(wh) + bf16hi_to_f32(wl)) : (bf16lo_to_f32(wh) + bf16lo_to_f32(wl));
+                r[q * 8 + e] = __float_as_uint(__uint_as_float(r[q * 8 + e]) + rv);
               }
             }
           }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(fmaxf(__uint_as_float(r[i]), 0.0f));
+          }
+          if (A_MODE != A_F32 && (p.pool_p != nullptr || p.mask_f32 != nullptr || p.mask_bf16 != nullptr || p.out_scale != 0.f)) {
+            // backward dgrad epilogue (uniform branch; never taken by the forward kernels)
+            float p0 = 0.f, p1 = 0.f;
+            if (p.pool_p != nullptr && row_ok) { p0 = __ldg(p.pool_p + row * 2); p1 = __ldg(p.pool_p + row * 2 + 1); }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
+              if (p.mask_f32 != nullptr && row_ok)
+                mk = *reinterpret_cast<const float4*>(p.mask_f32 + row * p.ld_mask + col0 + q * 4);
+              if (p.mask_bf16 != nullptr && row_ok) {
+                const uint2 mb = *reinterpret_cast<const uint2*>(p.mask_bf16 + row * p.ld_mask + col0 + q * 4);
+                mk = make_float4(bf16lo_to_f32(mb.x), bf16hi_to_f32(mb.x), bf16lo_to_f32(mb.y), bf16hi_to_f32(mb.y));
+              }
+              const float mv[4] = {mk.x, mk.y, mk.z, mk.w};
+              float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+              if (p.pool_p != nullptr) {
+                v0 = __ldg(reinterpret_cast<const float4*>(p.pool_v + col0 + q * 4));
+                v1 = __ldg(reinterpret_cast<const float4*>(p.pool_v + p.N + col0 + q * 4));
+              }
+              const float pv0[4] = {v0.x, v0.y, v0.z, v0.w}, pv1[4] = {v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int i = q * 4 + e;
+                float t = __uint_as_float(r[i]);
+                if (p.pool_p != nullptr) t += p0 * pv0[e] + p1 * pv1[e];
+                t = mv[e] > 0.f ? t : 0.f;
+                if (p.out_scale != 0.f) t *= p.out_scale;
+                r[i] = __float_as_uint(t);
+              }
+            }
+          }
+          if (p.drop.thresh != 0u) {  // training only: one big uniform branch, never predicated into the hot path
+            const unsigned long long e0 = static_cast<unsigned long long>(row) * p.N + col0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              r[i] = __float_as_uint(dropout_apply(p.drop, p.drop_layer, e0 + i, __uint_as_float(r[i])));
+          }
+          if (row_ok && p.out_f32 != nullptr) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out_f32 + (static_cast<int64_t>(split) * p.M + row) * p.ld_f32 + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+          }
           if (p.out_hi != nullptr) {
+            const uint32_t buf_hi = my_stage + (out_chunk % WARP_BUFS) * 4096, buf_lo = buf_hi + 2048;
+            ++out_chunk;
+            // staging buffer free again?  (this warp's store that last used it must have finished READING it)
+            if (lane == 0) tma_store_wait_read<WARP_BUFS - 1>();
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {  // 8 columns -> one 16 B chunk per plane
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                split2(__uint_as_float(r[8 * q + 2 * e]), __uint_as_float(r[8 * q + 2 * e + 1]), hi[e], lo[e]);
+              const uint32_t off = lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4);  // SWIZZLE_64B: chunk ^= row bits [1,2]
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf_hi + off), "r"(hi[0]), "r"(hi[1]),
+                           "r"(hi[2]), "r"(hi[3]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf_lo + off), "r"(lo[0]), "r"(lo[1]),
+                           "r"(lo[2]), "r"(lo[3]) : "memory");
+            }
             fence_proxy_async_smem();
-            epi_barrier<128 * EPI_SETS>();
-            if (warp == 4 && lane == 0) {
-              tma_store_2d(&tm_o_hi, stage_hi, n0 + cc * 64, m0);
-              tma_store_2d(&tm_o_lo, stage_lo, n0 + cc * 64, m0);
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tm_o_hi, buf_hi, col0, m0 + ew * 32);
+              tma_store_2d(&tm_o_lo, buf_lo, col0, m0 + ew * 32);
               tma_store_commit();
             }
           }
@@ -742,13 +763,16 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             if (t < p.gate_ntasks) dst[t] = s[t];
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CG == 1) mbar_arrive(smem_u32(&bar_tmem_empty[acc]));
-        else mbar_arrive_cluster(smem_u32(&bar_tmem_empty[acc]), 0);
+      if (EPI != EPI_LINEAR) {  // (the linear epilogue hands TMEM back right after its last tcgen05.ld)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 1) mbar_arrive(smem_u32(&bar_tmem_empty[acc]));
+          else mbar_arrive_cluster(smem_u32(&bar_tmem_empty[acc]), 0);
+        }
       }
     }
+    if (EPI == EPI_LINEAR && lane == 0) tma_store_wait_all();  // this warp's own bulk stores
   } else if (A_MODE == A_F32 && warp >= CONV_WARP0) {
     // ------------------------------------------------------------------ A converter (8 warps)
     // Each half-warp streams one 256 B row segment (64 fp32) per load instruction; a thread turns its
@@ -803,7 +827,6 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     }
   }
 
-  if (EPI == EPI_LINEAR && warp == 4 && lane == 0) tma_store_wait_all();
   tc_fence_before();
   __syncthreads();
   if (CG == 2) cluster_sync_all();  // the leader's MMAs read the peer's smem; nobody leaves early
@@ -843,6 +866,21 @@ inline int make_bf16_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : TOAD_ERR_DRIVER;
+}
+
+// Tensor map for the epilogue's per-warp TMA stores: box = 32 columns (64 B) x 32 rows, 64B swizzle.
+inline int make_bf16_out_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (enc == nullptr) return TOAD_ERR_DRIVER;
+  if (ld == 0) ld = cols;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : TOAD_ERR_DRIVER;
 }
@@ -889,8 +927,8 @@ int launch_gemm_maps_b(const GemmTcParams& p, const CUtensorMap& ta_hi, const CU
   CUtensorMap to_hi = tb_hi, to_lo = tb_lo;
   if (EPI == EPI_LINEAR && p.out_hi != nullptr) {
     if (p.out_lo == nullptr || p.ld_split % 8 != 0) return TOAD_ERR_ARG;
-    TOAD_TRY(make_bf16_tmap(&to_hi, p.out_hi, p.M, p.N, BLOCK_M, p.ld_split));
-    TOAD_TRY(make_bf16_tmap(&to_lo, p.out_lo, p.M, p.N, BLOCK_M, p.ld_split));
+    TOAD_TRY(make_bf16_out_tmap(&to_hi, p.out_hi, p.M, p.N, p.ld_split));
+    TOAD_TRY(make_bf16_out_tmap(&to_lo, p.out_lo, p.M, p.N, p.ld_split));
   }
   constexpr int kSmem = EPI == EPI_LINEAR ? C::SMEM_BYTES_LINEAR : C::SMEM_BYTES;
   auto kern = gemm_bf16x3_kernel<BLOCK_N, A_MODE, EPI, CG, OUT_BUFS>;
