@@ -249,3 +249,19 @@ def test_sex_covariate_enters_linearly():
     np.testing.assert_allclose(to_np(o1["site_logits"] - o0["site_logits"])[0], params[O.PARAM_KEYS[12]][:, 512], rtol=0, atol=2e-6)
     assert to_np(o0["features"])[0, 512] == 0.0 and to_np(o1["features"])[1, 512] == 1.0
     assert torch.equal(o1i["logits"], o1["logits"])
+
+
+@pytest.mark.parametrize("n", [3, 33, 4768, 4896, 37001])
+def test_forward_ragged_partitions_vs_oracle(n):
+    """Patch counts that leave trailing CTAs of the pooling tail -- or a whole merge group of them -- without
+    rows (148 CTAs x rows_per_block > N): empty partials must carry weight 0 through both merge levels."""
+    params = O.make_params(3, "big", 18, 0.02)
+    x = O.make_bag(900 + n, n)
+    model = build_model(params, "big", 18)
+    with torch.no_grad():
+        out = model(torch.from_numpy(x).cuda(), torch.tensor([1.0], device="cuda"), return_features=True)
+    ref = O.toad_forward(x, 1.0, params, dtype=np.float64)
+    for k in ("logits", "site_logits", "Y_prob", "site_prob"):
+        np.testing.assert_allclose(to_np(out[k]), ref[k], rtol=1e-3, atol=2e-6, err_msg=k)
+    np.testing.assert_allclose(to_np(out["features"]), ref["features"], rtol=1e-3, atol=2e-5)
+    np.testing.assert_allclose(to_np(out["A"]), ref["A"], rtol=0, atol=1e-4)

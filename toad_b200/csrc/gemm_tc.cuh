@@ -350,8 +350,27 @@ __device__ __forceinline__ float fast_tanh(float z) { return fmaf(2.0f, fast_sig
 // ---------------------------------------------------------------------------------------------
 constexpr int GATE_SMEM_FLOATS = 4 * 1024;  // ba | bb | wc rows (<= 2 tasks staged) for D <= 1024
 
+// Epilogue warp sets (x4 warps, one per TMEM lane quarter).  Plane-fed kernels run 2 sets (384 threads).  The
+// fp32-fed kernels also carry 8 converter warps: 1 set = 512 threads / 128 registers each; 2 sets (linear epilogue
+// only) = 640 threads, where setmaxnreg moves registers from the 4 control warps to the converters.
+#ifndef TOAD_F32_LINEAR_EPI_SETS
+#define TOAD_F32_LINEAR_EPI_SETS 2
+#endif
+template <int A_MODE, int EPI>
+__host__ __device__ constexpr int epi_sets() {
+  return A_MODE != A_F32 ? 2 : (EPI == EPI_LINEAR ? TOAD_F32_LINEAR_EPI_SETS : 1);
+}
+template <int A_MODE, int EPI>
+__host__ __device__ constexpr int cta_threads() {
+  return A_MODE == A_F32 ? (4 + 4 * epi_sets<A_MODE, EPI>() + 8) * 32 : 384;
+}
+template <int REGS>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
+
 template <int BLOCK_N, int A_MODE, int EPI, int CG, int OUT_BUFS = 1>
-__global__ void __launch_bounds__(A_MODE == A_F32 ? 512 : 384, 1)
+__global__ void __launch_bounds__(cta_threads<A_MODE, EPI>(), 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
@@ -361,7 +380,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   // epilogue warp sets: plane-fed kernels run 8 epilogue warps (two per TMEM lane quarter, each taking one
   // 32-column half of every 64-column chunk); the fp32-fed kernels keep 4 so that, with their 8 converter
   // warps, the CTA stays at 512 threads / 128 registers.
-  constexpr int EPI_SETS = A_MODE == A_F32 ? 1 : 2;
+  constexpr int EPI_SETS = epi_sets<A_MODE, EPI>();
   constexpr int CONV_WARP0 = 4 + 4 * EPI_SETS;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -426,6 +445,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
+#ifdef TOAD_SETMAXNREG
+  if (A_MODE == A_F32 && EPI_SETS == 2) {  // 640 threads start at 96 registers: 4 control warps -> 40, 8 converter warps -> 120
+    if (warp < 4) setmaxnreg_dec<40>();
+    else if (warp >= CONV_WARP0) setmaxnreg_inc<120>();
+  }
+#endif
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (all lanes loop, lane 0 issues)
     int stage = 0;
@@ -939,7 +964,7 @@ int launch_gemm_maps_b(const GemmTcParams& p, const CUtensorMap& ta_hi, const CU
   const int grid = static_cast<int>(units < max_units ? units : max_units) * CG;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
-  cfg.blockDim = dim3(A_MODE == A_F32 ? 512 : 384);
+  cfg.blockDim = dim3(cta_threads<A_MODE, EPI>());
   cfg.dynamicSmemBytes = kSmem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

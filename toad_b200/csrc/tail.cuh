@@ -16,11 +16,14 @@ namespace tail {
 
 constexpr int H = 512;          // hid_dim (model_toad.py:56, both size_args)
 constexpr int T = 2;            // n_tasks (model_toad.py:66)
-constexpr int THREADS = 1024;   // 32 warps, one CTA per SM
+constexpr int THREADS = 512;    // 16 warps, one CTA per SM, <= 128 registers: 4 rows (8 KB) in flight per warp
 constexpr int WARPS = THREADS / 32;
+constexpr int ROWS_IN_FLIGHT = 4;
+constexpr int MIN_GROUP = 8;    // two-level merge: the last CTA of each group of >= 8 folds the group, the last group folds all
+constexpr int MAX_GROUPS = 32;
+constexpr int MAX_HEADS_SMEM = 64;  // head rows staged in shared memory (64 x 513 floats = 128 KB)
 constexpr int MAX_CHUNK = 2048; // rows per CTA (scores cached in smem)
-constexpr int MAX_BLOCKS = 1024;   // (max,sum) staging of the merge fits s_score: 2*T*MAX_BLOCKS floats
-constexpr int PART_STRIDE = T * (H + 2);  // per-CTA partial: acc[T][H], then (m,l)[T]
+constexpr int PART_STRIDE = T * (H + 2);  // one partial: acc[T][H], then (m,l)[T]
 
 enum { H_F32 = 0, H_SPLIT = 1 };
 
@@ -39,13 +42,18 @@ struct TailParams {
   const float* wsite; const float* bsite;
   float* features; float* logits; float* y_prob; int64_t* y_hat;
   float* site_logits; float* site_prob; int64_t* site_hat; float* stats;
-  float* blk_part;     // [gridDim.x][PART_STRIDE]
-  unsigned int* ticket;
+  float* blk_part;     // [gridDim.x + MAX_GROUPS][PART_STRIDE]: per-CTA partials, then the group partials
+  unsigned int* ticket;  // [1 + MAX_GROUPS] zero-initialised counters (self-resetting): global, then one per group
+  int32_t group;       // CTAs per group
+  int32_t heads_in_smem;  // head weights staged in shared memory (n_classes + 2 <= MAX_HEADS_SMEM)
+#ifdef TOAD_TAIL_DEBUG
+  int32_t dbg_stop;    // profiling builds only (tools/_ab): leave the kernel after phase dbg_stop
+#endif
   int32_t attention_only;
 };
 
 inline int tail_blocks(int64_t n, int sms) {
-  int64_t b = static_cast<int64_t>(sms);  // one 1024-thread CTA per SM: fewer partials for the final merge
+  int64_t b = static_cast<int64_t>(sms);  // one CTA per SM
   const int64_t need = (n + MAX_CHUNK - 1) / MAX_CHUNK;
   if (b < need) b = need;
   const int64_t most = (n + 31) / 32;  // at least 32 rows per CTA
@@ -54,10 +62,82 @@ inline int tail_blocks(int64_t n, int sms) {
   return static_cast<int>(b);
 }
 
+inline int tail_group(int nb) {
+  int g = (nb + MAX_GROUPS - 1) / MAX_GROUPS;
+  return g < MIN_GROUP ? MIN_GROUP : g;
+}
+
+// Fold n partials {acc[T][H], (m, l)[T]} at src (stride PART_STRIDE, read through L2) in fixed order:
+//   m = max_b m_b ;  l = sum_b exp(m_b - m) l_b ;  acc = sum_b exp(m_b - m) acc_b
+// Results: s_m / s_l (valid after the call), and acc: thread c4 < 256 returns float4 column c4 of the flattened
+// [T][H] accumulator (task c4 >> 7).  All THREADS threads of the CTA call it.  s_stage: 3*T*MAX_FOLD floats of
+// scratch, s_half: 256 float4.  Latency-lean: the first accumulator loads are in flight before anything waits;
+// warp t derives task t's maximum, weights and sum with one (m, l) load per lane and warp shuffles (n <= 32: a
+// single L2 round trip); one barrier publishes the weights, one joins the two halves of the sum.
+constexpr int MAX_FOLD = 512;
+__device__ __forceinline__ float4 fold_partials(const float* __restrict__ src, int n, float* s_stage, float4* s_half,
+                                                float* s_m, float* s_l) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c4 = tid & 255, bg = tid >> 8;  // 2 thread groups x 256 float4 columns
+  const int t = c4 >> 7;                    // 128 float4 per task
+  const int bper = (n + 1) / 2;
+  const int b0 = bg * bper, b1 = (b0 + bper) < n ? (b0 + bper) : n;
+  float4 v8[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    if (b0 + u < b1) v8[u] = __ldcg(reinterpret_cast<const float4*>(src + static_cast<int64_t>(b0 + u) * PART_STRIDE) + c4);
+  float* s_wt = s_stage;                                            // [T][n] weights exp(m_b - m)
+  float2* s_ml = reinterpret_cast<float2*>(s_stage + T * MAX_FOLD);  // [T][n] (m_b, l_b)
+  if (warp < T) {
+    const float* ml = src + T * H + 2 * warp;
+    float mloc = -INFINITY;
+    for (int b = lane; b < n; b += 32) {
+      const float2 v = __ldcg(reinterpret_cast<const float2*>(ml + static_cast<int64_t>(b) * PART_STRIDE));
+      s_ml[warp * n + b] = v;
+      mloc = fmaxf(mloc, v.x);
+    }
+    const float m = warp_max(mloc);
+    float lloc = 0.f;
+    for (int b = lane; b < n; b += 32) {
+      const float2 v = s_ml[warp * n + b];  // (written by this same lane)
+      const float w = v.x == -INFINITY ? 0.f : expf(v.x - m);  // empty partial (also when all are empty): weight 0
+      s_wt[warp * n + b] = w;
+      lloc = fmaf(w, v.y, lloc);
+    }
+    const float l = warp_sum(lloc);
+    if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
+  }
+  __syncthreads();
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int b = b0; b < b1; b += 8) {
+    float4 cur[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) cur[u] = v8[u];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)  // next batch in flight while this one is consumed
+      if (b + 8 + u < b1) v8[u] = __ldcg(reinterpret_cast<const float4*>(src + static_cast<int64_t>(b + 8 + u) * PART_STRIDE) + c4);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (b + u < b1) {
+        const float sc = s_wt[t * n + b + u];
+        acc.x = fmaf(sc, cur[u].x, acc.x); acc.y = fmaf(sc, cur[u].y, acc.y);
+        acc.z = fmaf(sc, cur[u].z, acc.z); acc.w = fmaf(sc, cur[u].w, acc.w);
+      }
+    }
+  }
+  if (bg == 1) s_half[c4] = acc;
+  __syncthreads();
+  if (bg == 0) {
+    const float4 o = s_half[c4];
+    acc = make_float4(acc.x + o.x, acc.y + o.y, acc.z + o.z, acc.w + o.w);
+  }
+  return acc;
+}
+
 template <int H_MODE>
-__global__ void __launch_bounds__(THREADS) pool_heads_kernel(const TailParams p) {
+__global__ void __launch_bounds__(THREADS, 1) pool_heads_kernel(const TailParams p) {
   extern __shared__ float dsm[];               // [WARPS][T*H] cross-warp reduction buffer
-  __shared__ float s_score[T][MAX_CHUNK];      // this CTA's scores, then reused by the merge
+  __shared__ float s_score[T][MAX_CHUNK];      // this CTA's scores, then exp(score - max); reused by the merge
   __shared__ float s_red[T][WARPS];
   __shared__ float s_m[T], s_l[T];
   __shared__ unsigned int s_ticket;
@@ -67,21 +147,48 @@ __global__ void __launch_bounds__(THREADS) pool_heads_kernel(const TailParams p)
   if (r1 > p.N) r1 = p.N;
   const int rows = r1 > r0 ? static_cast<int>(r1 - r0) : 0;
 
+  // head weights -> shared memory in the background (used only by the CTA that ends up evaluating the heads)
+  float* s_w = dsm + WARPS * T * H;            // [n_classes + 2][H + 1]
+  if (p.heads_in_smem && !p.attention_only) {
+    const int n_cls = p.n_classes * (H + 1), n_all = n_cls + 2 * (H + 1);
+    for (int i = tid; i < n_all; i += THREADS) {
+      const float* src = i < n_cls ? p.wcls + i : p.wsite + (i - n_cls);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(s_w + i))), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+
   // ---- phase 1: finish the scores (sum split-N partials + bias), write A_raw, local max
   float lmax[T] = {-INFINITY, -INFINITY};
+  const float bc0 = __ldg(p.bc), bc1 = __ldg(p.bc + 1);
   for (int i = tid; i < rows; i += THREADS) {
     const int64_t row = r0 + i;
+    float s0 = 0.f, s1 = 0.f;
+    for (int z0 = 0; z0 < p.n_parts; z0 += 8) {  // 8 independent loads in flight (n_parts = 6 for "big"), summed in order
+      float2 v[8];
 #pragma unroll
-    for (int t = 0; t < T; ++t) {
-      float s = 0.f;
-      for (int z = 0; z < p.n_parts; ++z) s += __ldg(p.part + (static_cast<int64_t>(z) * p.N + row) * T + t);
-      s += __ldg(p.bc + t);
-      p.a_raw[static_cast<int64_t>(t) * p.N + row] = s;
-      s_score[t][i] = s;
-      lmax[t] = fmaxf(lmax[t], s);
+      for (int z = 0; z < 8; ++z)
+        v[z] = z0 + z < p.n_parts ? __ldg(reinterpret_cast<const float2*>(p.part + (static_cast<int64_t>(z0 + z) * p.N + row) * T))
+                                  : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int z = 0; z < 8; ++z) {
+        s0 += v[z].x;
+        s1 += v[z].y;
+      }
     }
+    s0 += bc0;
+    s1 += bc1;
+    p.a_raw[row] = s0;
+    p.a_raw[p.N + row] = s1;
+    s_score[0][i] = s0;
+    s_score[1][i] = s1;
+    lmax[0] = fmaxf(lmax[0], s0);
+    lmax[1] = fmaxf(lmax[1], s1);
   }
   if (p.attention_only) return;
+#ifdef TOAD_TAIL_DEBUG
+  if (p.dbg_stop == 1) return;
+#endif
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const float m = warp_max(lmax[t]);
@@ -95,45 +202,79 @@ __global__ void __launch_bounds__(THREADS) pool_heads_kernel(const TailParams p)
   }
   __syncthreads();
   const float m0 = s_m[0], m1 = s_m[1];
+  // softmax numerators once per row (not once per lane of the streaming warp), and their sums
+  float l0 = 0.f, l1 = 0.f;
+  for (int i = tid; i < rows; i += THREADS) {
+    const float e0 = expf(s_score[0][i] - m0), e1 = expf(s_score[1][i] - m1);
+    s_score[0][i] = e0;
+    s_score[1][i] = e1;
+    l0 += e0;
+    l1 += e1;
+  }
+  l0 = warp_sum(l0);
+  l1 = warp_sum(l1);
+  __syncthreads();  // s_red (maxima) consumed; numerators visible to every warp
+  if (lane == 0) { s_red[0][warp] = l0; s_red[1][warp] = l1; }
 
-  // ---- phase 2: stream h once; warp per row, 16 columns per lane
+  // ---- phase 2: stream h once; warp per row, 16 columns per lane, ROWS_IN_FLIGHT rows (8 KB per warp) in flight
   float acc0[16], acc1[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) { acc0[i] = 0.f; acc1[i] = 0.f; }
-  float l0 = 0.f, l1 = 0.f;
-  for (int i = warp; i < rows; i += WARPS) {
-    const int64_t row = r0 + i;
-    const float p0 = expf(s_score[0][i] - m0);
-    const float p1 = expf(s_score[1][i] - m1);
-    l0 += p0;
-    l1 += p1;
-    float hv[16];
-    if (H_MODE == H_F32) {
-      const float* hr = p.h_f32 + row * H;
+  for (int i = warp; i < rows; i += WARPS * ROWS_IN_FLIGHT) {
+    uint4 raw[ROWS_IN_FLIGHT][4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 v = ld_stream_f4(hr + 4 * (lane + 32 * q));
-        hv[4 * q] = v.x; hv[4 * q + 1] = v.y; hv[4 * q + 2] = v.z; hv[4 * q + 3] = v.w;
-      }
-    } else {
+    for (int u = 0; u < ROWS_IN_FLIGHT; ++u) {
+      const int iu = i + u * WARPS;
+      const int64_t row = r0 + (iu < rows ? iu : i);  // past the chunk: re-read row i (its weight is zeroed below)
+      if (H_MODE == H_F32) {
+        const float* hr = p.h_f32 + row * H;
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const uint4 vh = ld_stream_u4(p.h_hi + row * H + q * 256 + lane * 8);
-        const uint4 vl = ld_stream_u4(p.h_lo + row * H + q * 256 + lane * 8);
-        const uint32_t uh[4] = {vh.x, vh.y, vh.z, vh.w}, ul[4] = {vl.x, vl.y, vl.z, vl.w};
+        for (int q = 0; q < 4; ++q) {
+          const float4 v = ld_stream_f4(hr + 4 * (lane + 32 * q));
+          raw[u][q] = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+        }
+      } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          hv[8 * q + 2 * e] = bf16lo_to_f32(uh[e]) + bf16lo_to_f32(ul[e]);
-          hv[8 * q + 2 * e + 1] = bf16hi_to_f32(uh[e]) + bf16hi_to_f32(ul[e]);
+        for (int q = 0; q < 2; ++q) {
+          raw[u][2 * q] = ld_stream_u4(p.h_hi + row * H + q * 256 + lane * 8);
+          raw[u][2 * q + 1] = ld_stream_u4(p.h_lo + row * H + q * 256 + lane * 8);
         }
       }
     }
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      acc0[e] = fmaf(p0, hv[e], acc0[e]);
-      acc1[e] = fmaf(p1, hv[e], acc1[e]);
+    for (int u = 0; u < ROWS_IN_FLIGHT; ++u) {
+      const int iu = i + u * WARPS;
+      const bool ok = iu < rows;
+      const float p0 = ok ? s_score[0][iu] : 0.f, p1 = ok ? s_score[1][iu] : 0.f;
+      float hv[16];
+      if (H_MODE == H_F32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          hv[4 * q] = __uint_as_float(raw[u][q].x); hv[4 * q + 1] = __uint_as_float(raw[u][q].y);
+          hv[4 * q + 2] = __uint_as_float(raw[u][q].z); hv[4 * q + 3] = __uint_as_float(raw[u][q].w);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const uint4 vh = raw[u][2 * q], vl = raw[u][2 * q + 1];
+          const uint32_t uh[4] = {vh.x, vh.y, vh.z, vh.w}, ul[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            hv[8 * q + 2 * e] = bf16lo_to_f32(uh[e]) + bf16lo_to_f32(ul[e]);
+            hv[8 * q + 2 * e + 1] = bf16hi_to_f32(uh[e]) + bf16hi_to_f32(ul[e]);
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        acc0[e] = fmaf(p0, hv[e], acc0[e]);
+        acc1[e] = fmaf(p1, hv[e], acc1[e]);
+      }
     }
   }
+#ifdef TOAD_TAIL_DEBUG
+  if (p.dbg_stop == 2) { if (acc0[0] + acc1[3] == 123.456f) p.stats[0] = 1.f; return; }
+#endif
   // column owned by accumulator e of this lane
   auto col_of = [&](int e) -> int {
     return H_MODE == H_F32 ? 4 * (lane + 32 * (e >> 2)) + (e & 3) : (e >> 3) * 256 + lane * 8 + (e & 7);
@@ -143,7 +284,6 @@ __global__ void __launch_bounds__(THREADS) pool_heads_kernel(const TailParams p)
     dsm[warp * (T * H) + col_of(e)] = acc0[e];
     dsm[warp * (T * H) + H + col_of(e)] = acc1[e];
   }
-  if (lane == 0) { s_red[0][warp] = l0; s_red[1][warp] = l1; }
   __syncthreads();
   float* mine = p.blk_part + static_cast<int64_t>(blockIdx.x) * PART_STRIDE;
   for (int c = tid; c < T * H; c += THREADS) {
@@ -159,79 +299,53 @@ __global__ void __launch_bounds__(THREADS) pool_heads_kernel(const TailParams p)
     mine[T * H + 2 * tid + 1] = l;
   }
 
-  // ---- phase 3: last CTA merges all partials in fixed order and evaluates the heads
+  // ---- phase 3: two-level merge, fixed order, no float atomics.  The last CTA of each group (atomic ticket)
+  // folds the group's partials; the last group to finish folds the group partials and evaluates the heads.
+  // (One CTA folding all 148 partials -- 600 KB through one SM's L2 port -- was half of this kernel's time.)
+  const int nb = gridDim.x;
+  const int grp = blockIdx.x / p.group, n_groups = (nb + p.group - 1) / p.group;
+  const int g0 = grp * p.group, g_cnt = (g0 + p.group <= nb ? p.group : nb - g0);
+  float* grp_part = p.blk_part + static_cast<int64_t>(nb) * PART_STRIDE;
+  float4* s_half = reinterpret_cast<float4*>(dsm + 4096);  // [2][256] float4 scratch
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_ticket = atomicAdd(p.ticket + 1 + grp, 1u);
+  __syncthreads();
+  if (s_ticket != static_cast<unsigned int>(g_cnt - 1)) return;
+#ifdef TOAD_TAIL_DEBUG
+  if (p.dbg_stop == 3) { if (tid == 0) p.ticket[1 + grp] = 0u; return; }
+#endif
+  __threadfence();
+  {
+    const float4 v = fold_partials(p.blk_part + static_cast<int64_t>(g0) * PART_STRIDE, g_cnt, &s_score[0][0], s_half, s_m, s_l);
+    float* gp = grp_part + static_cast<int64_t>(grp) * PART_STRIDE;
+    if (tid < 256) reinterpret_cast<float4*>(gp)[tid] = v;
+    if (tid < T) {
+      gp[T * H + 2 * tid] = s_m[tid];
+      gp[T * H + 2 * tid + 1] = s_l[tid];
+    }
+    if (tid == 0) p.ticket[1 + grp] = 0u;  // ready for the next launch on this workspace
+  }
   __threadfence();
   __syncthreads();
   if (tid == 0) s_ticket = atomicAdd(p.ticket, 1u);
   __syncthreads();
-  if (s_ticket != gridDim.x - 1) return;
+  if (s_ticket != static_cast<unsigned int>(n_groups - 1)) return;
+#ifdef TOAD_TAIL_DEBUG
+  if (p.dbg_stop == 4) { if (tid == 0) *p.ticket = 0u; return; }
+#endif
   __threadfence();
-  const int nb = gridDim.x;
-  // stage every CTA's (max, sum) pair in smem with parallel L2 loads, then two threads fold them
-  // serially from smem (fixed order, ~3k cycles) instead of chasing ~300 dependent L2 latencies.
-  float* s_scale = &s_score[0][0];  // [nb][T] max -> scale;  [nb][T] sums behind it (nb <= MAX_BLOCKS)
-  float* s_lb = s_scale + nb * T;
-  for (int i = tid; i < nb * T; i += THREADS) {
-    const int b = i / T, t = i % T;
-    s_scale[i] = __ldcg(p.blk_part + static_cast<int64_t>(b) * PART_STRIDE + T * H + 2 * t);
-    s_lb[i] = __ldcg(p.blk_part + static_cast<int64_t>(b) * PART_STRIDE + T * H + 2 * t + 1);
-  }
-  __syncthreads();
+  const float4 pooled = fold_partials(grp_part, n_groups, &s_score[0][0], s_half, s_m, s_l);
   if (tid < T) {
-    float m = -INFINITY;
-    for (int b = 0; b < nb; ++b) m = fmaxf(m, s_scale[b * T + tid]);
-    s_m[tid] = m;
-  }
-  __syncthreads();
-  for (int i = tid; i < nb * T; i += THREADS) s_scale[i] = expf(s_scale[i] - s_m[i % T]);  // exp(-inf) = 0: empty CTA
-  __syncthreads();
-  if (tid < T) {
-    float l = 0.f;
-    for (int b = 0; b < nb; ++b) l = fmaf(s_scale[b * T + tid], s_lb[b * T + tid], l);
-    s_l[tid] = l;
     p.stats[2 * tid] = s_m[tid];
-    p.stats[2 * tid + 1] = l;
+    p.stats[2 * tid + 1] = s_l[tid];
   }
-  __syncthreads();
-  // weighted sum of the per-CTA accumulators: 2 thread groups x 256 float4 columns, 8 independent
-  // 16 B L2 loads in flight per thread, partial sums combined in fixed order through smem.
   float* s_feat = dsm;                 // [T][H+1]
-  float4* s_half = reinterpret_cast<float4*>(dsm + 4096);  // [4][256] float4 scratch (dsm is 128 KB)
   const float sexv = __ldg(p.sex);
-  {
-    const int c4 = tid & 255, bg = tid >> 8;  // 4 partial-groups x 256 float4 columns
-    const int t = c4 >> 7;  // 128 float4 per task
-    const int bper = (nb + 3) / 4;
-    const int b0 = bg * bper, b1 = (b0 + bper) < nb ? (b0 + bper) : nb;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int b = b0;
-    for (; b + 8 <= b1; b += 8) {
-      float4 v8[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        v8[u] = __ldcg(reinterpret_cast<const float4*>(p.blk_part + static_cast<int64_t>(b + u) * PART_STRIDE) + c4);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float sc = s_scale[(b + u) * T + t];
-        acc.x = fmaf(sc, v8[u].x, acc.x); acc.y = fmaf(sc, v8[u].y, acc.y);
-        acc.z = fmaf(sc, v8[u].z, acc.z); acc.w = fmaf(sc, v8[u].w, acc.w);
-      }
-    }
-    for (; b < b1; ++b) {
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(p.blk_part + static_cast<int64_t>(b) * PART_STRIDE) + c4);
-      const float sc = s_scale[b * T + t];
-      acc.x = fmaf(sc, v.x, acc.x); acc.y = fmaf(sc, v.y, acc.y);
-      acc.z = fmaf(sc, v.z, acc.z); acc.w = fmaf(sc, v.w, acc.w);
-    }
-    s_half[bg * 256 + c4] = acc;
-  }
-  __syncthreads();
   if (tid < 256) {
-    const float4 a0 = s_half[tid], a1 = s_half[256 + tid], a2 = s_half[512 + tid], a3 = s_half[768 + tid];
     const int t = tid >> 7, j = (tid & 127) * 4;
     const float inv = 1.0f / s_l[t];
-    const float v[4] = {(((a0.x + a1.x) + a2.x) + a3.x) * inv, (((a0.y + a1.y) + a2.y) + a3.y) * inv,
-                        (((a0.z + a1.z) + a2.z) + a3.z) * inv, (((a0.w + a1.w) + a2.w) + a3.w) * inv};
+    const float v[4] = {pooled.x * inv, pooled.y * inv, pooled.z * inv, pooled.w * inv};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       s_feat[t * (H + 1) + j + e] = v[e];
@@ -243,16 +357,26 @@ __global__ void __launch_bounds__(THREADS) pool_heads_kernel(const TailParams p)
     p.features[tid * (H + 1) + H] = sexv;
   }
   __syncthreads();
-  // heads: task 0 pooled vector -> classifier, task 1 -> site_classifier (model_toad.py:101,105)
+#ifdef TOAD_TAIL_DEBUG
+  if (p.dbg_stop == 5) { if (tid == 0) *p.ticket = 0u; return; }
+#endif
+  // heads: task 0 pooled vector -> classifier, task 1 -> site_classifier (model_toad.py:101,105).  The weight
+  // rows were copied to shared memory by cp.async at kernel start (every CTA: only the last one gets here, and
+  // none knows in advance), so no global latency is left on this serial path.
   float* s_logit = dsm + T * (H + 1);  // [n_classes + 2]
   const int n_out = p.n_classes + 2;
+  if (p.heads_in_smem) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+  }
   for (int o = warp; o < n_out; o += WARPS) {
     const bool is_site = o >= p.n_classes;
-    const float* w = is_site ? p.wsite + static_cast<int64_t>(o - p.n_classes) * (H + 1) : p.wcls + static_cast<int64_t>(o) * (H + 1);
+    const float* wg = is_site ? p.wsite + static_cast<int64_t>(o - p.n_classes) * (H + 1) : p.wcls + static_cast<int64_t>(o) * (H + 1);
+    const float* w = p.heads_in_smem ? s_w + o * (H + 1) : wg;
     const float* f = s_feat + (is_site ? (H + 1) : 0);
     float wv[17];  // (H+1)/32 rounded up: all weight loads in flight before the first FMA
 #pragma unroll
-    for (int q = 0; q < 17; ++q) wv[q] = (lane + 32 * q) < H + 1 ? __ldg(w + lane + 32 * q) : 0.f;
+    for (int q = 0; q < 17; ++q) wv[q] = (lane + 32 * q) < H + 1 ? w[lane + 32 * q] : 0.f;
     float s = 0.f;
 #pragma unroll
     for (int q = 0; q < 17; ++q) s = fmaf(wv[q], (lane + 32 * q) < H + 1 ? f[lane + 32 * q] : 0.f, s);
@@ -260,23 +384,30 @@ __global__ void __launch_bounds__(THREADS) pool_heads_kernel(const TailParams p)
     if (lane == 0) s_logit[o] = s + (is_site ? __ldg(p.bsite + o - p.n_classes) : __ldg(p.bcls + o));
   }
   __syncthreads();
-  if (tid < 2) {
-    const int off = tid == 0 ? 0 : p.n_classes;
-    const int cnt = tid == 0 ? p.n_classes : 2;
-    float* lg = tid == 0 ? p.logits : p.site_logits;
-    float* pr = tid == 0 ? p.y_prob : p.site_prob;
-    int64_t* hat = tid == 0 ? p.y_hat : p.site_hat;
+  if (warp < 2) {  // warp 0: classifier softmax / top-1, warp 1: site (ties -> lowest index, like torch.topk)
+    const int off = warp == 0 ? 0 : p.n_classes;
+    const int cnt = warp == 0 ? p.n_classes : 2;
+    float* lg = warp == 0 ? p.logits : p.site_logits;
+    float* pr = warp == 0 ? p.y_prob : p.site_prob;
+    int64_t* hat = warp == 0 ? p.y_hat : p.site_hat;
     float mx = -INFINITY;
-    int arg = 0;
-    for (int c = 0; c < cnt; ++c) {
+    int arg = 0x7fffffff;
+    for (int c = lane; c < cnt; c += 32) {
       const float v = s_logit[off + c];
       lg[c] = v;
       if (v > mx) { mx = v; arg = c; }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+    }
     float sum = 0.f;
-    for (int c = 0; c < cnt; ++c) sum += expf(s_logit[off + c] - mx);
-    for (int c = 0; c < cnt; ++c) pr[c] = expf(s_logit[off + c] - mx) / sum;
-    hat[0] = arg;
+    for (int c = lane; c < cnt; c += 32) sum += expf(s_logit[off + c] - mx);
+    sum = warp_sum(sum);
+    for (int c = lane; c < cnt; c += 32) pr[c] = expf(s_logit[off + c] - mx) / sum;
+    if (lane == 0) hat[0] = arg == 0x7fffffff ? 0 : arg;
   }
   if (tid == 0) *p.ticket = 0u;  // ready for the next launch on this workspace
 }
@@ -285,11 +416,17 @@ template <int H_MODE>
 int launch_tail(const TailParams& p_in, int sms, cudaStream_t stream) {
   TailParams p = p_in;
   if (p.N <= 0) return TOAD_ERR_ARG;
+  if (p.n_classes + 2 > 1024) return TOAD_ERR_UNSUPPORTED;
   const int nb = tail_blocks(p.N, sms);
-  if (nb > MAX_BLOCKS) return TOAD_ERR_UNSUPPORTED;
+  p.group = tail_group(nb);
+#ifdef TOAD_TAIL_DEBUG
+  { const char* e = getenv("TOAD_TAIL_STOP"); p.dbg_stop = e ? atoi(e) : 0; }
+#endif
+  if (p.group > MAX_FOLD) return TOAD_ERR_UNSUPPORTED;  // > 16k CTAs = 33M patches
   p.rows_per_block = static_cast<int32_t>((p.N + nb - 1) / nb);
   if (p.rows_per_block > MAX_CHUNK) return TOAD_ERR_UNSUPPORTED;
-  const int dyn = WARPS * T * H * static_cast<int>(sizeof(float));
+  p.heads_in_smem = (p.n_classes + 2) <= MAX_HEADS_SMEM ? 1 : 0;
+  const int dyn = (WARPS * T * H + (p.heads_in_smem ? (p.n_classes + 2) * (H + 1) : 0)) * static_cast<int>(sizeof(float));
   auto kern = pool_heads_kernel<H_MODE>;
   TOAD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
   kern<<<nb, THREADS, dyn, stream>>>(p);

@@ -63,7 +63,7 @@ FwdWs carve_fwd(const toad_dims_t* d, int64_t n, uint32_t flags, void* base) {
     w.w2_hi = c.take<bf16>(Hd * Hd); w.w2_lo = c.take<bf16>(Hd * Hd);
     w.wab_hi = c.take<bf16>(2 * D * Hd); w.wab_lo = c.take<bf16>(2 * D * Hd);
   }
-  w.blk_part = c.take<float>(static_cast<size_t>(tail::tail_blocks(n, kSMs)) * tail::PART_STRIDE);
+  w.blk_part = c.take<float>(static_cast<size_t>(tail::tail_blocks(n, kSMs) + tail::MAX_GROUPS) * tail::PART_STRIDE);
   w.n_parts = simt ? 1 : 2 * static_cast<int>(D / kGateHalf);  // (tile, epilogue warp set) partials
   w.part = c.take<float>(static_cast<size_t>(w.n_parts) * n * d->n_tasks);
   if (!simt) {
@@ -184,7 +184,7 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
   TOAD_TRY(check_ws(workspace, workspace_bytes, w.bytes));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int Hd = d->hid_dim, D = d->attn_dim, L = d->in_dim;
-  TOAD_CUDA_TRY(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), st));
+  TOAD_CUDA_TRY(cudaMemsetAsync(w.ticket, 0, 64 * sizeof(unsigned int), st));
 
   if (flags & TOAD_FLAG_SIMT_FP32) {
     float* h1 = save ? saved->h1 : w.h1;

@@ -10,8 +10,10 @@ import sys
 def main():
     rep, kid = sys.argv[1], sys.argv[2]
     top_n = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", ":::%s" % kid],
-                         capture_output=True, text=True).stdout
+    cmd = ["ncu", "-i", rep, "--page", "source", "--csv"]
+    if kid != "all":   # "all": single-kernel report (prints the first kernel)
+        cmd += ["--kernel-id", ":::%s" % kid]
+    out = subprocess.run(cmd, capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     h = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     print(rows[0][:2])
