@@ -74,7 +74,8 @@ def load() -> C.CDLL:
         except Exception as e:  # no silent fallback: say exactly what is missing
             raise ToadError("libtoad_b200.so is missing and could not be built with nvcc (%s). "
                             "Run `python -c 'import __graft_entry__ as g; g.build()'`." % e) from e
-    lib = C.CDLL(LIB_PATH)
+    # TOAD_B200_LIB: A/B aid (tools/): load another build of the same ABI instead of the in-tree library
+    lib = C.CDLL(os.environ.get("TOAD_B200_LIB") or LIB_PATH)
     missing = [s for s in EXPORTS if not hasattr(lib, s)]
     if missing:
         raise ToadError("libtoad_b200.so lacks symbols: %s" % missing)

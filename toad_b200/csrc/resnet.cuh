@@ -38,34 +38,61 @@ __global__ void fold_conv_kernel(const float* __restrict__ w, const float* __res
 // x NCHW fp32 [B,3,H,W] -> planes [B*Ho*Wo, 192], column k = (kh*7 + kw)*3 + c (147 real, rest 0).
 // One thread produces 8 consecutive columns of one row (one 16 B store per plane).
 constexpr int STEM_K = 147, STEM_KPAD = 192;
-__global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
-                                   __nv_bfloat16* __restrict__ lo, int B, int H, int W, int Ho, int Wo) {
-  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int64_t total = static_cast<int64_t>(B) * Ho * Wo * (STEM_KPAD / 8);
-  if (gid >= total) return;
-  const int kg = static_cast<int>(gid % (STEM_KPAD / 8));
-  const int64_t row = gid / (STEM_KPAD / 8);
-  const int ow = static_cast<int>(row % Wo);
-  const int oh = static_cast<int>((row / Wo) % Ho);
-  const int b = static_cast<int>(row / (static_cast<int64_t>(Wo) * Ho));
-  float v[8];
+constexpr int STEM_THREADS = 192;  // 24 column groups x 8 output pixels per pass
+// One CTA per output row (b, oh): the 7 input rows x 3 channels it touches are staged in shared memory with
+// coalesced 128-bit loads (zero padded: 3 columns each side, rows outside the image), then thread (kg, ow) gathers
+// its 8 columns through 8 per-thread constant offsets -- no div/mod and no scattered global loads in the loop.
+__global__ void __launch_bounds__(STEM_THREADS) stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                                                   __nv_bfloat16* __restrict__ lo, int B, int H, int W, int Ho,
+                                                                   int Wo) {
+  extern __shared__ float s_in[];  // [3][7][W + 8]: element (c, kh, iw + 4)
+  const int PW = W + 8;
+  const int b = blockIdx.x / Ho, oh = blockIdx.x % Ho;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 21 * 2; i += STEM_THREADS) {  // the two 4-wide pad strips of every staged row
+    const int r = i >> 1, side = i & 1;
+    *reinterpret_cast<float4*>(s_in + r * PW + (side ? W + 4 : 0)) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int W4 = W / 4;
+  for (int i = tid; i < 21 * W4; i += STEM_THREADS) {
+    const int r = i / W4, q = i - r * W4;  // r = c * 7 + kh
+    const int c = r / 7, kh = r - c * 7;
+    const int ih = oh * 2 + kh - 3;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ih >= 0 && ih < H) v = ld_stream_f4(x + ((static_cast<int64_t>(b) * 3 + c) * H + ih) * W + q * 4);
+    *reinterpret_cast<float4*>(s_in + r * PW + 4 + q * 4) = v;
+  }
+  const int kg = tid % 24, ow0 = tid / 24;
+  int off[8];  // smem offset of column k = kg*8 + e for ow = 0 (-1: zero padding column)
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int k = kg * 8 + e;
-    float t = 0.f;
-    if (k < STEM_K) {
-      const int c = k % 3, tap = k / 3;
-      const int kh = tap / 7, kw = tap % 7;
-      const int ih = oh * 2 + kh - 3, iw = ow * 2 + kw - 3;
-      if (ih >= 0 && ih < H && iw >= 0 && iw < W) t = __ldg(x + ((static_cast<int64_t>(b) * 3 + c) * H + ih) * W + iw);
-    }
-    v[e] = t;
+    const int c = k % 3, tap = k / 3;
+    const int kh = tap / 7, kw = tap % 7;
+    off[e] = k < STEM_K ? (c * 7 + kh) * PW + 4 + kw - 3 : -1;
   }
-  uint32_t h[4], l[4];
+  __syncthreads();
+  const int64_t row0 = (static_cast<int64_t>(b) * Ho + oh) * Wo;
+  for (int ow = ow0; ow < Wo; ow += STEM_THREADS / 24) {
+    float v[8];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) split2(v[2 * e], v[2 * e + 1], h[e], l[e]);
-  *reinterpret_cast<uint4*>(hi + row * STEM_KPAD + kg * 8) = make_uint4(h[0], h[1], h[2], h[3]);
-  *reinterpret_cast<uint4*>(lo + row * STEM_KPAD + kg * 8) = make_uint4(l[0], l[1], l[2], l[3]);
+    for (int e = 0; e < 8; ++e) v[e] = off[e] >= 0 ? s_in[off[e] + 2 * ow] : 0.f;
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split2(v[2 * e], v[2 * e + 1], h[e], l[e]);
+    const int64_t o = (row0 + ow) * STEM_KPAD + kg * 8;
+    *reinterpret_cast<uint4*>(hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+inline int launch_stem_im2col(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int H, int W, int Ho, int Wo,
+                              cudaStream_t stream) {
+  if (W % 4 != 0) return TOAD_ERR_UNSUPPORTED;
+  const int smem = 21 * (W + 8) * static_cast<int>(sizeof(float));
+  if (smem > 48 * 1024) TOAD_CUDA_TRY(cudaFuncSetAttribute(stem_im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  stem_im2col_kernel<<<static_cast<unsigned>(B) * Ho, STEM_THREADS, smem, stream>>>(x, hi, lo, B, H, W, Ho, Wo);
+  TOAD_CUDA_TRY(cudaGetLastError());
+  return 0;
 }
 
 // MaxPool2d(3, stride 2, pad 1) on NHWC planes (resnet_custom.py:64,100).  Thread = (output pixel, 8 channels).

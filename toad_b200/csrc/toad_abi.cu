@@ -857,6 +857,10 @@ namespace {
 
 struct ConvSpec { int cin, cout, k, stride; };
 constexpr int kResOutBufs = 2;
+#ifndef TOAD_RESNET_CHUNK
+#define TOAD_RESNET_CHUNK 64
+#endif
+constexpr int kResChunk = TOAD_RESNET_CHUNK;  // images per stem + layer1 pass (L2 residency of layer1's activations)
 
 // the 43 convolutions in state_dict order (resnet_custom.py:57-94 with layers [3,4,6])
 int build_specs(ConvSpec* specs) {
@@ -901,7 +905,7 @@ Prepared carve_prepared(void* base) {
 }
 
 struct ResWs {
-  bf16 *col_hi, *col_lo, *stem_hi, *stem_lo;
+  bf16 *col_hi, *col_lo, *stem_hi, *stem_lo, *pool_hi, *pool_lo;
   bf16 *buf_hi[5], *buf_lo[5];
   int stem_chunk;
   size_t bytes;
@@ -911,13 +915,15 @@ ResWs carve_resnet(int B, int H, int W, void* base) {
   ResWs w{};
   Carver c(base);
   const int64_t H1 = H / 2, W1 = W / 2, H2 = H / 4, W2 = W / 4;
-  w.stem_chunk = B < 64 ? B : 64;
+  w.stem_chunk = B < kResChunk ? B : kResChunk;
   const size_t col = static_cast<size_t>(w.stem_chunk) * H1 * W1 * resnet::STEM_KPAD;
   w.col_hi = c.take<bf16>(col);
   w.col_lo = c.take<bf16>(col);
-  const size_t stem = static_cast<size_t>(B) * H1 * W1 * 64;
+  const size_t stem = static_cast<size_t>(w.stem_chunk) * H1 * W1 * 64;
   w.stem_hi = c.take<bf16>(stem);
   w.stem_lo = c.take<bf16>(stem);
+  w.pool_hi = c.take<bf16>(stem / 4);
+  w.pool_lo = c.take<bf16>(stem / 4);
   const size_t act = static_cast<size_t>(B) * H2 * W2 * 256;
   for (int i = 0; i < 5; ++i) {
     w.buf_hi[i] = c.take<bf16>(act);
@@ -1006,51 +1012,66 @@ extern "C" int toad_resnet_fwd(const void* prepared, const float* x, int32_t B, 
   build_specs(specs);
   const int H1 = H / 2, W1 = W / 2, H2 = H / 4, W2 = W / 4;
 
-  // ---- stem: conv1 7x7/s2 (im2col + GEMM) + BN + ReLU, in chunks of images (resnet_custom.py:97-99)
-  for (int b0 = 0; b0 < B; b0 += w.stem_chunk) {
-    const int nb = (B - b0) < w.stem_chunk ? (B - b0) : w.stem_chunk;
-    const int64_t rows = static_cast<int64_t>(nb) * H1 * W1;
-    const int64_t threads = rows * (resnet::STEM_KPAD / 8);
-    resnet::stem_im2col_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
-        x + static_cast<int64_t>(b0) * 3 * H * W, w.col_hi, w.col_lo, nb, H, W, H1, W1);
-    TOAD_CUDA_TRY(cudaGetLastError());
-    tc::GemmTcParams g{};
-    g.M = rows; g.N = 64; g.K = resnet::STEM_KPAD; g.bias = P.conv[0].bias; g.relu = 1;
-    g.out_hi = w.stem_hi + static_cast<int64_t>(b0) * H1 * W1 * 64;
-    g.out_lo = w.stem_lo + static_cast<int64_t>(b0) * H1 * W1 * 64;
-    g.ld_split = 64;
-    TOAD_TRY((tc::launch_gemm<64, tc::A_SPLIT, tc::EPI_LINEAR, 2, kResOutBufs>(g, w.col_hi, w.col_lo, P.conv[0].hi, P.conv[0].lo, st)));
-  }
-  // ---- maxpool 3x3/s2 (resnet_custom.py:100)
-  int cur = 0;  // buffer holding the block input
-  {
-    const int64_t threads = static_cast<int64_t>(B) * H2 * W2 * (64 / 8);
-    resnet::maxpool3x3s2_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
-        w.stem_hi, w.stem_lo, w.buf_hi[cur], w.buf_lo[cur], B, H1, W1, 64);
-    TOAD_CUDA_TRY(cudaGetLastError());
-  }
-  // ---- layer1..layer3: bottleneck blocks (resnet_custom.py:35-55)
-  int ci = 1, h = H2, wd = W2;
-  const int blocks[3] = {3, 4, 6};
-  for (int l = 0; l < 3; ++l) {
+  // One layer (a chain of bottleneck blocks, resnet_custom.py:35-55) over `bc` images: block 0 reads `in` and has
+  // the downsample branch; intermediates rotate through the 4 scratch plane pairs; the last block writes `out`.
+  struct Planes { bf16* hi; bf16* lo; };
+  auto run_layer = [&](int l, int ci, int bc, int h, int wd, Planes in, const Planes* s, Planes out) -> int {
+    const int blocks[3] = {3, 4, 6};
+    Planes x = in;
+    int xs = -1;  // scratch slot holding x (-1: external)
     for (int i = 0; i < blocks[l]; ++i) {
       const ConvSpec &c1 = specs[ci], &c2 = specs[ci + 1], &c3 = specs[ci + 2];
-      const bool has_ds = i == 0;
-      const int t1 = (cur + 1) % 5, t2 = (cur + 2) % 5, r = (cur + 3) % 5, y = (cur + 4) % 5;
+      const bool has_ds = i == 0, is_last = i == blocks[l] - 1;
+      int free_slots[4], nf = 0;
+      for (int q = 0; q < 4; ++q)
+        if (q != xs) free_slots[nf++] = q;
+      const Planes t1 = s[free_slots[0]], t2 = s[free_slots[1]];
+      const int ys = free_slots[2];
+      const Planes y = is_last ? out : s[ys];
       const int ho = h / c2.stride, wo = wd / c2.stride;
-      TOAD_TRY(run_conv(c1, P.conv[ci], w.buf_hi[cur], w.buf_lo[cur], B, h, wd, w.buf_hi[t1], w.buf_lo[t1], nullptr, nullptr, true, st));
-      TOAD_TRY(run_conv(c2, P.conv[ci + 1], w.buf_hi[t1], w.buf_lo[t1], B, h, wd, w.buf_hi[t2], w.buf_lo[t2], nullptr, nullptr, true, st));
-      const bf16 *res_hi = w.buf_hi[cur], *res_lo = w.buf_lo[cur];
-      if (has_ds) {
-        TOAD_TRY(run_conv(specs[ci + 3], P.conv[ci + 3], w.buf_hi[cur], w.buf_lo[cur], B, h, wd, w.buf_hi[r], w.buf_lo[r], nullptr, nullptr, false, st));
-        res_hi = w.buf_hi[r]; res_lo = w.buf_lo[r];
+      TOAD_TRY(run_conv(c1, P.conv[ci], x.hi, x.lo, bc, h, wd, t1.hi, t1.lo, nullptr, nullptr, true, st));
+      TOAD_TRY(run_conv(c2, P.conv[ci + 1], t1.hi, t1.lo, bc, h, wd, t2.hi, t2.lo, nullptr, nullptr, true, st));
+      Planes res = x;
+      if (has_ds) {  // (xs == -1 here: all four scratch slots are free, the fourth holds the shortcut)
+        res = s[free_slots[3]];
+        TOAD_TRY(run_conv(specs[ci + 3], P.conv[ci + 3], x.hi, x.lo, bc, h, wd, res.hi, res.lo, nullptr, nullptr, false, st));
       }
-      TOAD_TRY(run_conv(c3, P.conv[ci + 2], w.buf_hi[t2], w.buf_lo[t2], B, ho, wo, w.buf_hi[y], w.buf_lo[y], res_hi, res_lo, true, st));
-      cur = y;
+      TOAD_TRY(run_conv(c3, P.conv[ci + 2], t2.hi, t2.lo, bc, ho, wo, y.hi, y.lo, res.hi, res.lo, true, st));
+      x = y;
+      xs = is_last ? -1 : ys;
       h = ho; wd = wo;
       ci += has_ds ? 4 : 3;
     }
+    return 0;
+  };
+  const Planes bufs[5] = {{w.buf_hi[0], w.buf_lo[0]}, {w.buf_hi[1], w.buf_lo[1]}, {w.buf_hi[2], w.buf_lo[2]},
+                          {w.buf_hi[3], w.buf_lo[3]}, {w.buf_hi[4], w.buf_lo[4]}};
+
+  // ---- stem (conv1 7x7/s2 as im2col + GEMM, BN, ReLU; resnet_custom.py:97-99), maxpool 3x3/s2 (:100) and layer1,
+  // in chunks of images: layer1's activations are the trunk's largest (4 MB per image and tensor), and a chunk's
+  // producer -> consumer traffic is meant to stay in the 126 MB L2 instead of round-tripping HBM.  layer1's output
+  // of every chunk lands in its slice of bufs[4].
+  const int64_t l1_img = static_cast<int64_t>(H2) * W2 * 256;  // elements per image of a layer1-sized plane
+  for (int b0 = 0; b0 < B; b0 += w.stem_chunk) {
+    const int nb = (B - b0) < w.stem_chunk ? (B - b0) : w.stem_chunk;
+    const int64_t rows = static_cast<int64_t>(nb) * H1 * W1;
+    TOAD_TRY(resnet::launch_stem_im2col(x + static_cast<int64_t>(b0) * 3 * H * W, w.col_hi, w.col_lo, nb, H, W, H1, W1, st));
+    tc::GemmTcParams g{};
+    g.M = rows; g.N = 64; g.K = resnet::STEM_KPAD; g.bias = P.conv[0].bias; g.relu = 1;
+    g.out_hi = w.stem_hi; g.out_lo = w.stem_lo; g.ld_split = 64;
+    TOAD_TRY((tc::launch_gemm<64, tc::A_SPLIT, tc::EPI_LINEAR, 2, kResOutBufs>(g, w.col_hi, w.col_lo, P.conv[0].hi, P.conv[0].lo, st)));
+    const int64_t threads = static_cast<int64_t>(nb) * H2 * W2 * (64 / 8);
+    resnet::maxpool3x3s2_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
+        w.stem_hi, w.stem_lo, w.pool_hi, w.pool_lo, nb, H1, W1, 64);
+    TOAD_CUDA_TRY(cudaGetLastError());
+    const Planes l1_out = {bufs[4].hi + b0 * l1_img, bufs[4].lo + b0 * l1_img};
+    TOAD_TRY(run_layer(0, 1, nb, H2, W2, Planes{w.pool_hi, w.pool_lo}, bufs, l1_out));
   }
+  // ---- layer2, layer3 over the whole batch
+  // (a layer may write its output over its input: only block 0 reads `in`, only the last block writes `out`)
+  TOAD_TRY(run_layer(1, 1 + 10, B, H2, W2, bufs[4], bufs, bufs[4]));
+  TOAD_TRY(run_layer(2, 1 + 10 + 13, B, H2 / 2, W2 / 2, bufs[4], bufs, bufs[4]));
+  const int cur = 4, h = H2 / 4, wd = W2 / 4;
   // ---- global average pool + flatten (resnet_custom.py:106-107)
   resnet::avgpool_kernel<<<dim3(B, 1024 / 256), 256, 0, st>>>(w.buf_hi[cur], w.buf_lo[cur], out, h * wd, 1024);
   TOAD_CUDA_TRY(cudaGetLastError());
