@@ -205,6 +205,12 @@ int toad_topk_workspace_bytes(int64_t n, int32_t k, size_t* bytes);
 int toad_topk(const float* scores, int64_t n, int32_t k, float* out_vals, int64_t* out_idx,
               void* workspace, size_t workspace_bytes, toad_stream_t stream);
 
+/* out[i, :] = table[idx[i], :], rows of row_bytes bytes (a multiple of 4): e.g. the `coords` [N, 2] rows of the
+ * top-k patches for a heatmap (the reference's h5 bags keep coords next to features,
+ * datasets/dataset_mtl_concat.py:377-383).  Out-of-range indices give zero rows. */
+int toad_gather_rows(const void* table, int64_t n_rows, int32_t row_bytes, const int64_t* idx, int32_t k, void* out,
+                     toad_stream_t stream);
+
 /* y[M, N] = act(x[M, K] . w[N, K]^T + bias[N]) on the tcgen05 3-pass split-bf16 path.
  * relu != 0 applies ReLU; bias may be NULL.  K % 64 == 0, N % 64 == 0.
  * variant: bit 0 = feed x as pre-split (hi,lo) bf16 planes through TMA instead of converting

@@ -60,3 +60,19 @@ def test_permutation_invariance_of_the_oracle_forward():
     b = O.toad_forward(x[perm], 1.0, params, dtype=np.float64)
     np.testing.assert_allclose(a["logits"], b["logits"], rtol=1e-12)
     np.testing.assert_allclose(a["A"][:, perm], b["A"], rtol=0, atol=1e-14)
+
+
+def test_topk_accuracy_matches_the_reference_formula():
+    """toad_b200.eval.topk_accuracy == accuracy() of utils/eval_utils_mtl_concat.py:49-63 (restated with torch.topk)."""
+    import numpy as np
+    import torch
+    from toad_b200.eval import topk_accuracy
+    g = torch.Generator().manual_seed(0)
+    probs = torch.softmax(torch.randn(200, 18, generator=g), dim=1)
+    labels = torch.randint(0, 18, (200,), generator=g)
+    topk = (1, 3, 5)
+    _, pred = probs.topk(max(topk), 1, True, True)
+    correct = pred.t().eq(labels.view(1, -1).expand_as(pred.t()))
+    ref = [float(correct[:k].reshape(-1).float().sum(0) / 200) for k in topk]
+    ours = topk_accuracy(probs.numpy(), labels.numpy(), topk)
+    np.testing.assert_allclose(ours, ref, rtol=0, atol=1e-6)   # the reference accumulates in fp32

@@ -25,7 +25,7 @@ EXPORTS = [
     "toad_abi_version", "toad_error_string", "toad_param_offsets", "toad_dropout_hash",
     "toad_fwd_workspace_bytes", "toad_fwd", "toad_bwd_workspace_bytes", "toad_bwd",
     "toad_attn_gated_workspace_bytes", "toad_attn_gated_fwd",
-    "toad_topk_workspace_bytes", "toad_topk",
+    "toad_topk_workspace_bytes", "toad_topk", "toad_gather_rows",
     "toad_linear_workspace_bytes", "toad_linear_bf16x3",
     "toad_profile_create", "toad_profile_destroy", "toad_profile_read", "toad_fwd_profiled",
     "toad_resnet_prepared_bytes", "toad_resnet_prepare", "toad_resnet_workspace_bytes", "toad_resnet_fwd",
@@ -96,6 +96,7 @@ def load() -> C.CDLL:
                                         C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
     lib.toad_topk_workspace_bytes.argtypes = [C.c_int64, C.c_int32, C.POINTER(C.c_size_t)]
     lib.toad_topk.argtypes = [_f32p, C.c_int64, C.c_int32, _f32p, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.toad_gather_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.toad_linear_workspace_bytes.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
     lib.toad_linear_bf16x3.argtypes = [_f32p, _f32p, _f32p, _f32p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]

@@ -792,6 +792,12 @@ extern "C" int toad_topk_workspace_bytes(int64_t n, int32_t k, size_t* bytes) {
   return 0;
 }
 
+extern "C" int toad_gather_rows(const void* table, int64_t n_rows, int32_t row_bytes, const int64_t* idx, int32_t k,
+                                void* out, toad_stream_t stream) {
+  if (!table || !idx || !out) return TOAD_ERR_ARG;
+  return topk::launch_gather_rows(table, n_rows, row_bytes, idx, k, out, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int toad_topk(const float* scores, int64_t n, int32_t k, float* out_vals, int64_t* out_idx, void* workspace,
               size_t workspace_bytes, toad_stream_t stream) {
   (void)workspace; (void)workspace_bytes;

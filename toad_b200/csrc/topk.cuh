@@ -122,5 +122,26 @@ inline int launch_topk(const float* scores, int64_t n, int k, float* out_vals, i
   return 0;
 }
 
+// out[i, :] = table[idx[i], :] for rows of `row_bytes` bytes (4-byte words): the coordinates of the top-k patches
+// (the reference's h5 bags carry `coords` [N, 2] next to `features`, datasets/dataset_mtl_concat.py:377-383).
+__global__ void gather_rows_kernel(const uint32_t* __restrict__ table, int64_t n_rows, int row_words,
+                                   const int64_t* __restrict__ idx, int k, uint32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k * row_words) return;
+  const int r = i / row_words, c = i - r * row_words;
+  const int64_t src = idx[r];
+  out[i] = (src >= 0 && src < n_rows) ? table[src * row_words + c] : 0u;
+}
+
+inline int launch_gather_rows(const void* table, int64_t n_rows, int row_bytes, const int64_t* idx, int k, void* out,
+                              cudaStream_t stream) {
+  if (row_bytes <= 0 || row_bytes % 4 != 0 || k <= 0 || n_rows <= 0) return TOAD_ERR_ARG;
+  const int words = row_bytes / 4, total = k * words;
+  gather_rows_kernel<<<(total + 255) / 256, 256, 0, stream>>>(static_cast<const uint32_t*>(table), n_rows, words, idx, k,
+                                                              static_cast<uint32_t*>(out));
+  TOAD_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace topk
 }  // namespace toad

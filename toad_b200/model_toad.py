@@ -207,6 +207,10 @@ class TOAD_fc_mtl_concat(nn.Module):
         self._plane_state[id(ws)] = None if self._plane_key_pending is None or buf is None else \
             (self._plane_key_pending, buf.data_ptr(), buf.numel())
 
+    @staticmethod
+    def _flags() -> int:
+        return _default_flags()
+
     def _dropout_active(self) -> bool:
         return self.dropout and self.training
 

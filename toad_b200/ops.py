@@ -256,6 +256,34 @@ def topk(scores: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
     return vals, idx
 
 
+def gather_rows(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """table[idx] for a 2-D CUDA table with 4- or 8-byte elements (e.g. patch `coords` [N, 2]) and int64 indices."""
+    lib = _lib.load()
+    if not (isinstance(table, torch.Tensor) and table.is_cuda and table.dim() == 2 and table.is_contiguous()):
+        raise ValueError("table must be a contiguous 2-D CUDA tensor")
+    if table.element_size() not in (4, 8):
+        raise ValueError("table elements must be 4 or 8 bytes wide, got %s" % table.dtype)
+    if not (idx.is_cuda and idx.dtype == torch.int64 and idx.dim() == 1 and idx.is_contiguous()):
+        raise ValueError("idx must be a contiguous 1-D CUDA int64 tensor")
+    out = torch.empty((idx.shape[0], table.shape[1]), dtype=table.dtype, device=table.device)
+    if idx.shape[0] == 0:
+        return out
+    _lib.check(lib.toad_gather_rows(table.data_ptr(), table.shape[0], table.shape[1] * table.element_size(),
+                                    idx.data_ptr(), idx.shape[0], out.data_ptr(), _stream()), "toad_gather_rows")
+    return out
+
+
+def topk_patches(scores: torch.Tensor, k: int, coords: Optional[torch.Tensor] = None):
+    """The k highest-attention patches of one task row (results['A'][t]): (values, indices[, coords of those patches])
+    -- what a heatmap / top-patch consumer of the attention scores asks for."""
+    vals, idx = topk(scores, k)
+    if coords is None:
+        return vals, idx
+    if coords.shape[0] != scores.shape[0]:
+        raise ValueError("coords must have one row per patch")
+    return vals, idx, gather_rows(coords, idx)
+
+
 def linear_bf16x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], relu: bool, ws: Workspace,
                   variant: int = 0) -> torch.Tensor:
     """y = act(x w^T + b) on the tcgen05 split-bf16 GEMM (test hook for the building block)."""

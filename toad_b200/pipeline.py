@@ -29,7 +29,10 @@ class SlideStreamer:
 
     @torch.no_grad()
     def run(self, slides: Iterable[Tuple[torch.Tensor, float]],
-            sink: Optional[Callable[[int, dict], None]] = None) -> List[dict]:
+            sink: Optional[Callable[[int, dict], None]] = None,
+            forward: Optional[Callable[[int, torch.Tensor, torch.Tensor], None]] = None) -> List[dict]:
+        """forward(i, device bag view, sex tensor): replaces `model(bag, sex)` + the per-slide result copies (the
+        caller keeps the results on the device, e.g. toad_b200.eval.SlideEvaluator's tables)."""
         compute = torch.cuda.current_stream(self.device)
         results: List[dict] = []
         pending = []
@@ -62,6 +65,11 @@ class SlideStreamer:
             cslot, n, sex = cur
             compute.wait_event(self.copied[cslot])
             sex_t = torch.tensor([float(sex)], device=self.device)
+            if forward is not None:
+                forward(i, self.bufs[cslot][:n], sex_t)
+                self.freed[cslot].record(compute)
+                i += 1
+                continue
             out = self.model(self.bufs[cslot][:n], sex_t)
             self.freed[cslot].record(compute)
             host = {k: out[k].to("cpu", non_blocking=True) for k in ("logits", "Y_prob", "Y_hat", "site_prob", "site_hat")}

@@ -112,7 +112,9 @@ class ResNet_Baseline(nn.Module):
         _lib.check(lib.toad_resnet_prepare(arr, len(tensors), ptr, nbytes.value, ops._stream()), "toad_resnet_prepare")
         self._prepared, self._prepared_key, self._prepared_ptr, self._prepared_bytes = buf, key, ptr, nbytes.value
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+        """[B, 3, H, W] -> [B, 1024] (resnet_custom.py:96-109).  `out` (optional, beyond the reference's signature):
+        a [B, 1024] fp32 CUDA buffer to write into, e.g. a slice of a slide's feature matrix."""
         if self.training:
             raise NotImplementedError("toad_b200: resnet50_baseline runs in eval mode only (BatchNorm running "
                                       "statistics are folded into the convolutions); call .eval() first")
@@ -122,7 +124,10 @@ class ResNet_Baseline(nn.Module):
         lib = _lib.load()
         self._prepare(x.device)
         B, _, H, W = x.shape
-        out = torch.empty((B, 1024), dtype=torch.float32, device=x.device)
+        if out is None:
+            out = torch.empty((B, 1024), dtype=torch.float32, device=x.device)
+        else:
+            ops._check_dev_f32(out, "out", (B, 1024))
         nbytes = C.c_size_t()
         _lib.check(lib.toad_resnet_workspace_bytes(B, H, W, C.byref(nbytes)), "toad_resnet_workspace_bytes")
         wptr, wsize = self._ws.get(nbytes.value, x.device)
