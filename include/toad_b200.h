@@ -200,7 +200,9 @@ int toad_attn_gated_fwd(int32_t L, int32_t D, int32_t n_tasks, const float* wa, 
                         const float* x, int64_t n, float* A_out, void* workspace, size_t workspace_bytes,
                         uint32_t flags, toad_stream_t stream);
 
-/* top-k of one score row: values descending, ties -> lower index first. */
+/* top-k of one score row: values descending, ties -> lower index first (k <= 2048).  One cooperative launch
+ * over all SMs; `workspace` (toad_topk_workspace_bytes, 16-byte aligned) holds the radix histograms and is
+ * zeroed by the call itself. */
 int toad_topk_workspace_bytes(int64_t n, int32_t k, size_t* bytes);
 int toad_topk(const float* scores, int64_t n, int32_t k, float* out_vals, int64_t* out_idx,
               void* workspace, size_t workspace_bytes, toad_stream_t stream);

@@ -107,3 +107,20 @@ def test_heatmap_topk_on_giga_slide_scores():
         ev, ei = O.topk_indices(s, k)
         np.testing.assert_array_equal(to_np(idx), ei)
         np.testing.assert_array_equal(to_np(vals), ev)
+
+
+@pytest.mark.parametrize("n,k,levels", [(300000, 2048, 7), (123457, 1000, 3), (2049, 2048, 2), (1 << 20, 100, 50)])
+def test_topk_heavy_ties_across_ctas(n, k, levels):
+    """Quantised scores: the k-th value is shared by thousands of patches spread over every CTA's chunk, so the
+    index-ordered tie rule (lowest indices win, like torch.topk / a stable sort) is exercised across CTA boundaries."""
+    from toad_b200 import ops
+    rng = np.random.default_rng(n)
+    s = rng.integers(0, levels, n).astype(np.float32) - 1.5
+    sd = torch.from_numpy(s).cuda()
+    vals, idx = ops.topk(sd, k)
+    ev, ei = O.topk_indices(s, k)
+    np.testing.assert_array_equal(to_np(vals), ev)
+    np.testing.assert_array_equal(to_np(idx), ei)
+    # a second call reuses the (self-zeroed) workspace
+    vals2, idx2 = ops.topk(sd, k)
+    assert torch.equal(vals, vals2) and torch.equal(idx, idx2)

@@ -788,7 +788,7 @@ extern "C" int toad_attn_gated_fwd(int32_t L, int32_t D, int32_t nt, const float
 // ------------------------------------------------------------------------------------------ top-k
 extern "C" int toad_topk_workspace_bytes(int64_t n, int32_t k, size_t* bytes) {
   if (bytes == nullptr || n <= 0 || k <= 0) return TOAD_ERR_ARG;
-  *bytes = 256;  // reserved; the current kernel needs no global scratch
+  *bytes = topk::topk_workspace_bytes();  // global histograms, per-CTA tie counts, the k winners (independent of n, k)
   return 0;
 }
 
@@ -800,9 +800,8 @@ extern "C" int toad_gather_rows(const void* table, int64_t n_rows, int32_t row_b
 
 extern "C" int toad_topk(const float* scores, int64_t n, int32_t k, float* out_vals, int64_t* out_idx, void* workspace,
               size_t workspace_bytes, toad_stream_t stream) {
-  (void)workspace; (void)workspace_bytes;
   if (!scores || !out_vals || !out_idx || n <= 0 || k <= 0) return TOAD_ERR_ARG;
-  return topk::launch_topk(scores, n, k, out_vals, out_idx, static_cast<cudaStream_t>(stream));
+  return topk::launch_topk(scores, n, k, out_vals, out_idx, workspace, workspace_bytes, tc::sm_count(), static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------------------------------ linear (test hook)

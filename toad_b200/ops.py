@@ -50,6 +50,9 @@ class Workspace:
         return aligned, self.buf.numel() - (aligned - ptr)
 
 
+_TOPK_WS: Dict[tuple, "Workspace"] = {}
+
+
 def make_dims(in_dim: int, hid_dim: int, attn_dim: int, n_classes: int, n_tasks: int = 2) -> Dims:
     return Dims(in_dim, hid_dim, attn_dim, n_tasks, n_classes)
 
@@ -252,7 +255,15 @@ def topk(scores: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
         raise ValueError("k must be in [1, N]")
     vals = torch.empty(k, dtype=torch.float32, device=scores.device)
     idx = torch.empty(k, dtype=torch.int64, device=scores.device)
-    _lib.check(lib.toad_topk(scores.data_ptr(), n, k, vals.data_ptr(), idx.data_ptr(), None, 0, _stream()), "toad_topk")
+    nbytes = C.c_size_t()
+    _lib.check(lib.toad_topk_workspace_bytes(n, k, C.byref(nbytes)), "toad_topk_workspace_bytes")
+    # scratch per (device, stream): two top-k calls in flight on different streams must not share histograms
+    key = (scores.device, torch.cuda.current_stream(scores.device).cuda_stream)
+    ws = _TOPK_WS.get(key)
+    if ws is None:
+        ws = _TOPK_WS[key] = Workspace()
+    wptr, wsize = ws.get(nbytes.value, scores.device)
+    _lib.check(lib.toad_topk(scores.data_ptr(), n, k, vals.data_ptr(), idx.data_ptr(), wptr, wsize, _stream()), "toad_topk")
     return vals, idx
 
 
