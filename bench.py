@@ -29,6 +29,7 @@ WIDTH = 1024
 FLOP_PER_PATCH = 2362880            # reference forward, "big", 2 tasks
 FC1_FLOP_PER_PATCH = 2 * 1024 * 512  # dominant kernel: fc1 GEMM
 BYTES_PER_PATCH = 4096 + 8
+TAIL_BYTES_PER_PATCH = 2056          # h row as (hi, lo) bf16 planes + 2 scores
 
 
 def peaks():
@@ -318,7 +319,14 @@ def run_ours(args):
                          "forward_hbm_gbs": BYTES_PER_PATCH * n / (whole_ms * 1e-3) / 1e9 if whole_ms > 0 else None,
                          "hbm_peak_gbs": pk["hbm_gbs"]},
         }
-        if world == 1:
+        # the HBM-bound kernel of the path (softmax over N, P.h pooling, heads): 2,056 B/patch algorithmic
+        tail_ms = stages_serial["pool_tail"] / max(calls_serial, 1)
+        tail_gbs = TAIL_BYTES_PER_PATCH * n / (tail_ms * 1e-3) / 1e9 if tail_ms > 0 else 0.0
+        line["roofline_tail"] = {"bound": "hbm", "kernel": "pool_heads_kernel", "achieved": tail_gbs, "peak": pk["hbm_gbs"],
+                                 "unit": "GB/s", "frac": tail_gbs / pk["hbm_gbs"],
+                                 "note": "CUDA-event stage time (includes the launch gap after the gate GEMM); ~10 us of it is "
+                                         "the serial two-level merge + heads after the streaming phase (DESIGN.md section 5)"}
+        if world == 1 and not args.no_eager_baseline:
             line["eager_gpu_baseline"] = eager_gpu_leg(dev, n)
         if world == 1 and not args.no_resnet:
             line["resnet50_baseline"] = resnet_leg(dev)
@@ -401,6 +409,7 @@ def main():
     ap.add_argument("--streams", type=int, default=2, help="slides in flight per GPU (toad_b200.pipeline.ResidentRunner)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-resnet", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the torch-eager GPU leg (ncu launch lists)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -94,52 +94,80 @@ __global__ void pool_bwd_kernel(const float* __restrict__ h, const __nv_bfloat16
 // ---- gate backward: dab[n] = [da_pre | db_pre]; per-CTA partials of dWc, dba, dbb, dbc
 // block = D threads (thread j owns gate column j); partial layout per CTA: [dWc0[D] dWc1[D] dba[D] dbb[D] dbc[2]]
 // PLANES: dab goes out as (hi, lo) bf16 planes -- the operand format of the tensor-core dgrad / wgrad -- instead of fp32.
+// Thread (rg, cq) = (tid / (D/4), tid % (D/4)) owns gate columns 4cq..4cq+3 of rows r0 + rg, r0 + rg + 4, ...: 128-bit
+// loads of a and b, one 8-byte store per plane and branch; the 4 row groups are added in order through shared memory.
 template <bool PLANES>
 __global__ void gate_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                 const float* __restrict__ dA, const float* __restrict__ wc, float* __restrict__ dab,
                                 __nv_bfloat16* __restrict__ dab_hi, __nv_bfloat16* __restrict__ dab_lo,
                                 float* __restrict__ part, int64_t N, int D, int rows_per_block, float keep) {
+  extern __shared__ float gb_sm[];  // [4 row groups][4 * D + 2]
   // a, b are the saved POST-dropout activations (a_post = a*mask/keep); keep == 1 without dropout.
   const float inv_keep = 1.f / keep;
-  const int j = threadIdx.x;
+  const int quads = D / 4;
+  const int rg = threadIdx.x / quads, cq = threadIdx.x - rg * quads, j0 = 4 * cq;
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
   int64_t r1 = r0 + rows_per_block;
   if (r1 > N) r1 = N;
-  const float w0 = __ldg(wc + j), w1 = __ldg(wc + D + j);
-  float gw0 = 0.f, gw1 = 0.f, gba = 0.f, gbb = 0.f, gc0 = 0.f, gc1 = 0.f;
-  for (int64_t row = r0; row < r1; ++row) {
-    const float da0 = __ldg(dA + row * T), da1 = __ldg(dA + row * T + 1);
-    const float av = a[row * D + j], bv = b[row * D + j];
-    const float g = av * bv;
-    gw0 = fmaf(da0, g, gw0);
-    gw1 = fmaf(da1, g, gw1);
-    gc0 += da0;
-    gc1 += da1;
-    const float dg = da0 * w0 + da1 * w1;
-    const float a_pre = av * keep;  // tanh output where kept (0 where dropped: no gradient there)
-    const float dap = (keep < 1.f && av == 0.f) ? 0.f : dg * bv * (1.f - a_pre * a_pre) * inv_keep;
-    const float dbp = dg * av * bv * (1.f - bv * keep);
-    if (PLANES) {
-      __nv_bfloat16 h = __float2bfloat16_rn(dap);
-      dab_hi[row * 2 * D + j] = h;
-      dab_lo[row * 2 * D + j] = __float2bfloat16_rn(dap - __bfloat162float(h));
-      h = __float2bfloat16_rn(dbp);
-      dab_hi[row * 2 * D + D + j] = h;
-      dab_lo[row * 2 * D + D + j] = __float2bfloat16_rn(dbp - __bfloat162float(h));
-    } else {
-      dab[row * 2 * D + j] = dap;
-      dab[row * 2 * D + D + j] = dbp;
+  const float4 w0 = __ldg(reinterpret_cast<const float4*>(wc + j0)), w1 = __ldg(reinterpret_cast<const float4*>(wc + D + j0));
+  const float w0v[4] = {w0.x, w0.y, w0.z, w0.w}, w1v[4] = {w1.x, w1.y, w1.z, w1.w};
+  float gw0[4] = {0.f, 0.f, 0.f, 0.f}, gw1[4] = {0.f, 0.f, 0.f, 0.f}, gba[4] = {0.f, 0.f, 0.f, 0.f}, gbb[4] = {0.f, 0.f, 0.f, 0.f};
+  float gc0 = 0.f, gc1 = 0.f;
+#pragma unroll 2
+  for (int64_t row = r0 + rg; row < r1; row += 4) {
+    const float2 da = __ldg(reinterpret_cast<const float2*>(dA + row * T));
+    const float4 a4 = ld_stream_f4(a + row * D + j0), b4 = ld_stream_f4(b + row * D + j0);
+    const float av4[4] = {a4.x, a4.y, a4.z, a4.w}, bv4[4] = {b4.x, b4.y, b4.z, b4.w};
+    float dap[4], dbp[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float av = av4[e], bv = bv4[e];
+      const float g = av * bv;
+      gw0[e] = fmaf(da.x, g, gw0[e]);
+      gw1[e] = fmaf(da.y, g, gw1[e]);
+      const float dg = da.x * w0v[e] + da.y * w1v[e];
+      const float a_pre = av * keep;  // tanh output where kept (0 where dropped: no gradient there)
+      dap[e] = (keep < 1.f && av == 0.f) ? 0.f : dg * bv * (1.f - a_pre * a_pre) * inv_keep;
+      dbp[e] = dg * av * bv * (1.f - bv * keep);
+      gba[e] += dap[e];
+      gbb[e] += dbp[e];
     }
-    gba += dap;
-    gbb += dbp;
+    gc0 += da.x;
+    gc1 += da.y;
+    if (PLANES) {
+      uint32_t h[2], l[2];
+      split2(dap[0], dap[1], h[0], l[0]);
+      split2(dap[2], dap[3], h[1], l[1]);
+      *reinterpret_cast<uint2*>(dab_hi + row * 2 * D + j0) = make_uint2(h[0], h[1]);
+      *reinterpret_cast<uint2*>(dab_lo + row * 2 * D + j0) = make_uint2(l[0], l[1]);
+      split2(dbp[0], dbp[1], h[0], l[0]);
+      split2(dbp[2], dbp[3], h[1], l[1]);
+      *reinterpret_cast<uint2*>(dab_hi + row * 2 * D + D + j0) = make_uint2(h[0], h[1]);
+      *reinterpret_cast<uint2*>(dab_lo + row * 2 * D + D + j0) = make_uint2(l[0], l[1]);
+    } else {
+      *reinterpret_cast<float4*>(dab + row * 2 * D + j0) = make_float4(dap[0], dap[1], dap[2], dap[3]);
+      *reinterpret_cast<float4*>(dab + row * 2 * D + D + j0) = make_float4(dbp[0], dbp[1], dbp[2], dbp[3]);
+    }
   }
+  float* sm = gb_sm + rg * (4 * D + 2);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    sm[j0 + e] = gw0[e];
+    sm[D + j0 + e] = gw1[e];
+    sm[2 * D + j0 + e] = gba[e];
+    sm[3 * D + j0 + e] = gbb[e];
+  }
+  if (cq == 0) { sm[4 * D] = gc0; sm[4 * D + 1] = gc1; }  // (every thread of a row group sees the same rows)
+  __syncthreads();
   float* mine = part + static_cast<int64_t>(blockIdx.x) * (4 * D + 2);
-  mine[j] = gw0;
-  mine[D + j] = gw1;
-  mine[2 * D + j] = gba;
-  mine[3 * D + j] = gbb;
-  if (j == 0) { mine[4 * D] = gc0; mine[4 * D + 1] = gc1; }
+  for (int i = threadIdx.x; i < 4 * D + 2; i += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) t += gb_sm[q * (4 * D + 2) + i];
+    mine[i] = t;
+  }
 }
+inline size_t gate_bwd_smem(int D) { return static_cast<size_t>(4) * (4 * D + 2) * sizeof(float); }
 
 // ---- column sums of a [N, C] matrix: per-CTA partials [gridDim.x][C] (thread per column)
 __global__ void colsum_kernel(const float* __restrict__ m, float* __restrict__ part, int64_t N, int C,
@@ -232,46 +260,46 @@ inline int launch_transpose_planes(const __nv_bfloat16* in_hi, const __nv_bfloat
   return 0;
 }
 
-// column sums of (hi + lo) planes [N, C] (C even): per-CTA partials [gridDim.x][C].  Thread (x, y) owns columns
-// 2x, 2x+1 (one bf16x2 load per plane) of rows r0 + y, r0 + y + blockDim.y, ...; the y lanes are added in order.
+// column sums of (hi + lo) planes [N, C] (C % 8 == 0): per-CTA partials [gridDim.x][C].  Thread (x, y) owns columns
+// 8x..8x+7 (one 128-bit load per plane) of rows r0 + y, r0 + y + blockDim.y, ...; the y lanes are added in order.
 __global__ void colsum_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
                                      float* __restrict__ part, int64_t N, int C, int rows_per_block) {
-  extern __shared__ float2 cs_sm[];  // [blockDim.y][blockDim.x]
-  const int c2 = threadIdx.x, half = C / 2;
+  extern __shared__ float cs_sm[];  // [blockDim.y][C]
+  const int c8 = threadIdx.x;
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
   int64_t r1 = r0 + rows_per_block;
   if (r1 > N) r1 = N;
-  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(hi);
-  const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(lo);
-  float sx = 0.f, sy = 0.f;
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
   for (int64_t row = r0 + threadIdx.y; row < r1; row += blockDim.y) {
-    const float2 a = __bfloat1622float2(h2[row * half + c2]);
-    const float2 b = __bfloat1622float2(l2[row * half + c2]);
-    sx += a.x + b.x;
-    sy += a.y + b.y;
-  }
-  cs_sm[threadIdx.y * blockDim.x + c2] = make_float2(sx, sy);
-  __syncthreads();
-  if (threadIdx.y == 0) {
-    float tx = 0.f, ty = 0.f;
-    for (int y = 0; y < static_cast<int>(blockDim.y); ++y) {
-      const float2 v = cs_sm[y * blockDim.x + c2];
-      tx += v.x;
-      ty += v.y;
+    const uint4 vh = ld_stream_u4(hi + row * C + c8 * 8), vl = ld_stream_u4(lo + row * C + c8 * 8);
+    const uint32_t uh[4] = {vh.x, vh.y, vh.z, vh.w}, ul[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      s[2 * e] += bf16lo_to_f32(uh[e]) + bf16lo_to_f32(ul[e]);
+      s[2 * e + 1] += bf16hi_to_f32(uh[e]) + bf16hi_to_f32(ul[e]);
     }
-    float* mine = part + static_cast<int64_t>(blockIdx.x) * C;
-    mine[2 * c2] = tx;
-    mine[2 * c2 + 1] = ty;
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) cs_sm[threadIdx.y * C + c8 * 8 + e] = s[e];
+  __syncthreads();
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  float* mine = part + static_cast<int64_t>(blockIdx.x) * C;
+  for (int c = tid; c < C; c += blockDim.x * blockDim.y) {
+    float t = 0.f;
+    for (int y = 0; y < static_cast<int>(blockDim.y); ++y) t += cs_sm[y * C + c];
+    mine[c] = t;
   }
 }
 
 inline int launch_colsum_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* part, int64_t N, int C,
                                 int blocks, cudaStream_t stream) {
-  if (C % 2 != 0 || C / 2 > 1024) return TOAD_ERR_UNSUPPORTED;
-  int ry = 1024 / (C / 2);
-  if (ry > 8) ry = 8;
+  if (C % 8 != 0 || C / 8 > 1024) return TOAD_ERR_UNSUPPORTED;
+  int ry = 512 / (C / 8);
+  if (ry > 16) ry = 16;
+  if (ry < 1) ry = 1;
   const int rpb = static_cast<int>((N + blocks - 1) / blocks);
-  colsum_planes_kernel<<<blocks, dim3(C / 2, ry), static_cast<size_t>(ry) * (C / 2) * sizeof(float2), stream>>>(
+  colsum_planes_kernel<<<blocks, dim3(C / 8, ry), static_cast<size_t>(ry) * C * sizeof(float), stream>>>(
       hi, lo, part, N, C, rpb);
   TOAD_CUDA_TRY(cudaGetLastError());
   return 0;

@@ -492,7 +492,7 @@ int bwd_tc(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t
   }
   {
     const int rpb = static_cast<int>((n + w.gate_blocks - 1) / w.gate_blocks);
-    bwd::gate_bwd_kernel<true><<<w.gate_blocks, D, 0, st>>>(sv->a, sv->b, w.dA, P->wc, nullptr, w.dab_hi, w.dab_lo,
+    bwd::gate_bwd_kernel<true><<<w.gate_blocks, D, bwd::gate_bwd_smem(D), st>>>(sv->a, sv->b, w.dA, P->wc, nullptr, w.dab_hi, w.dab_lo,
                                                              w.gate_part, n, D, rpb, keep);
     TOAD_CUDA_TRY(cudaGetLastError());
     bwd::ReduceSegs segs{};
@@ -591,7 +591,7 @@ static int bwd_simt(const toad_dims_t* d, const toad_params_t* P, const float* x
   // 3. gate backward -> dab, partials of dWc/dba/dbb/dbc
   {
     const int rpb = static_cast<int>((n + w.gate_blocks - 1) / w.gate_blocks);
-    bwd::gate_bwd_kernel<false><<<w.gate_blocks, D, 0, st>>>(sv->a, sv->b, w.dA, P->wc, w.dab, nullptr, nullptr,
+    bwd::gate_bwd_kernel<false><<<w.gate_blocks, D, bwd::gate_bwd_smem(D), st>>>(sv->a, sv->b, w.dA, P->wc, w.dab, nullptr, nullptr,
                                                               w.gate_part, n, D, rpb, keep);
     TOAD_CUDA_TRY(cudaGetLastError());
     const int64_t stride = 4 * D + 2;
