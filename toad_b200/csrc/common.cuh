@@ -75,6 +75,14 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// 256-bit global store (sm_100: STG.256): one full 32 B sector per lane and instruction, for the epilogues whose lanes
+// each own a contiguous run of a row (a register -> global store of v4 words fills only half a sector at a time).
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&r)[32], int i0) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[i0]), "r"(r[i0 + 1]), "r"(r[i0 + 2]),
+               "r"(r[i0 + 3]), "r"(r[i0 + 4]), "r"(r[i0 + 5]), "r"(r[i0 + 6]), "r"(r[i0 + 7])
+               : "memory");
+}
+
 // 128-bit streaming load that does not pollute L1.
 __device__ __forceinline__ float4 ld_stream_f4(const float* p) {
   float4 r;

@@ -602,6 +602,16 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           }
         }
       };
+      // dgrad ReLU mask (the saved activation's bf16 hi plane, 64 B per row and chunk): fetched one chunk ahead too
+      const bool has_mask16 = EPI == EPI_LINEAR && A_MODE != A_F32 && p.mask_bf16 != nullptr;
+      uint4 msk[4];
+      auto load_mask = [&](int c_) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          msk[q] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);  // bf16 1.0 pairs: keep
+          if (has_mask16 && row_ok) msk[q] = *reinterpret_cast<const uint4*>(p.mask_bf16 + row * p.ld_mask + n0 + c_ * 32 + q * 8);
+        }
+      };
       // bias of a 32-column chunk: lane j holds bias[col0 + j] (one coalesced load, fetched one chunk ahead);
       // the value of column i is broadcast with a shuffle where it is added.
       const bool has_bias = EPI == EPI_LINEAR && p.bias != nullptr && split == 0;
@@ -609,7 +619,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       float bias_nxt = 0.f;
       if (EPI == EPI_LINEAR) {
         bias_nxt = load_bias(eh);
-        if (A_MODE != A_F32) load_res(eh);
+        if (A_MODE != A_F32) { load_res(eh); load_mask(eh); }
       }
       mbar_wait(smem_u32(&bar_tmem_full[acc]), (it / C::ACC_STAGES) & 1);
       tc_fence_after();
@@ -630,12 +640,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           uint32_t r[32];
           tmem_ld32(t_row + c * 32, r);
           const float bias_cur = bias_nxt;
-          uint4 cur_h[4], cur_l[4];
+          uint4 cur_h[4], cur_l[4], cur_m[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) { cur_h[q] = res_h[q]; cur_l[q] = res_l[q]; }
-          if (!last) {  // next chunk's bias / residual, in flight below
+          for (int q = 0; q < 4; ++q) { cur_h[q] = res_h[q]; cur_l[q] = res_l[q]; cur_m[q] = msk[q]; }
+          if (!last) {  // next chunk's bias / residual / mask, in flight below
             bias_nxt = load_bias(c + EPI_SETS);
-            if (A_MODE != A_F32) load_res(c + EPI_SETS);
+            if (A_MODE != A_F32) { load_res(c + EPI_SETS); load_mask(c + EPI_SETS); }
           }
           tmem_ld_wait();
           if (last) {  // this warp has drained its share of the accumulator: hand TMEM back before the arithmetic
@@ -676,9 +686,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
               float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
               if (p.mask_f32 != nullptr && row_ok)
                 mk = *reinterpret_cast<const float4*>(p.mask_f32 + row * p.ld_mask + col0 + q * 4);
-              if (p.mask_bf16 != nullptr && row_ok) {
-                const uint2 mb = *reinterpret_cast<const uint2*>(p.mask_bf16 + row * p.ld_mask + col0 + q * 4);
-                mk = make_float4(bf16lo_to_f32(mb.x), bf16hi_to_f32(mb.x), bf16lo_to_f32(mb.y), bf16hi_to_f32(mb.y));
+              if (p.mask_bf16 != nullptr) {  // (prefetched; rows past M carry the keep pattern and are clipped by TMA)
+                const uint4 m4 = cur_m[q >> 1];
+                const uint32_t mx = (q & 1) ? m4.z : m4.x, my = (q & 1) ? m4.w : m4.y;
+                mk = make_float4(bf16lo_to_f32(mx), bf16hi_to_f32(mx), bf16lo_to_f32(my), bf16hi_to_f32(my));
               }
               const float mv[4] = {mk.x, mk.y, mk.z, mk.w};
               float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
@@ -705,9 +716,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
               r[i] = __float_as_uint(dropout_apply(p.drop, p.drop_layer, e0 + i, __uint_as_float(r[i])));
           }
           if (row_ok && p.out_f32 != nullptr) {
-            uint4* dst = reinterpret_cast<uint4*>(p.out_f32 + (static_cast<int64_t>(split) * p.M + row) * p.ld_f32 + col0);
+            float* dst = p.out_f32 + (static_cast<int64_t>(split) * p.M + row) * p.ld_f32 + col0;  // 32 B aligned (ld % 8 == 0)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dst[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+            for (int i = 0; i < 4; ++i) st_global_v8(dst + 8 * i, r, 8 * i);
           }
           if (p.out_hi != nullptr) {
             const uint32_t buf_hi = my_stage + (out_chunk % WARP_BUFS) * 4096, buf_lo = buf_hi + 2048;
@@ -772,12 +783,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             }
           }
           if (save) {
-            uint4* da = reinterpret_cast<uint4*>(p.gate_a + row * p.gate_D + jc);
-            uint4* db = reinterpret_cast<uint4*>(p.gate_b + row * p.gate_D + jc);
+            float* da = p.gate_a + row * p.gate_D + jc;  // 32 B aligned: gate_D % 8 == 0, jc % 32 == 0
+            float* db = p.gate_b + row * p.gate_D + jc;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              da[i] = make_uint4(ra[4 * i], ra[4 * i + 1], ra[4 * i + 2], ra[4 * i + 3]);
-              db[i] = make_uint4(rb[4 * i], rb[4 * i + 1], rb[4 * i + 2], rb[4 * i + 3]);
+            for (int i = 0; i < 4; ++i) {
+              st_global_v8(da + 8 * i, ra, 8 * i);
+              st_global_v8(db + 8 * i, rb, 8 * i);
             }
           }
         }
@@ -949,6 +960,12 @@ int launch_gemm_maps_b(const GemmTcParams& p, const CUtensorMap& ta_hi, const CU
   if ((A_MODE == A_F32 && p.K % BLOCK_K != 0) || p.N % BLOCK_N != 0 || p.K <= 0 || p.N <= 0) return TOAD_ERR_UNSUPPORTED;
   if (p.k_splits > 1 && (A_MODE == A_F32 || EPI != EPI_LINEAR || p.out_hi != nullptr || p.kb_per_split <= 0)) return TOAD_ERR_ARG;
   if (EPI == EPI_GATE && (p.gate_D > 1024 || p.gate_ntasks < 1 || p.gate_ntasks > 4)) return TOAD_ERR_UNSUPPORTED;
+  // the epilogues' register -> global stores are 256-bit: 32-byte aligned rows
+  if (EPI == EPI_LINEAR && p.out_f32 != nullptr && ((reinterpret_cast<uintptr_t>(p.out_f32) & 31) != 0 || p.ld_f32 % 8 != 0))
+    return TOAD_ERR_ARG;
+  if (EPI == EPI_GATE && p.gate_a != nullptr &&
+      (((reinterpret_cast<uintptr_t>(p.gate_a) | reinterpret_cast<uintptr_t>(p.gate_b)) & 31) != 0 || p.gate_D % 8 != 0))
+    return TOAD_ERR_ARG;
   CUtensorMap to_hi = tb_hi, to_lo = tb_lo;
   if (EPI == EPI_LINEAR && p.out_hi != nullptr) {
     if (p.out_lo == nullptr || p.ld_split % 8 != 0) return TOAD_ERR_ARG;
