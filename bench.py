@@ -5,8 +5,8 @@
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
 
 One step = one pass of the hot path over `slides_per_step` synthetic slides (N x 1024 fp32
-each) through `toad_b200.pipeline.ResidentRunner` (two slides in flight on two CUDA streams, so one
-slide's partially filled last waves overlap the other's kernels).  `value` = whole-job slides/s with
+each) through `toad_b200.pipeline.ResidentRunner` (three slides in flight on three CUDA streams, so one
+slide's partially filled last waves overlap the others' kernels).  `value` = whole-job slides/s with
 bags resident in HBM (4 distinct 205 MB bags per GPU, larger than L2, rotated); `value_single_stream`
 = the same steps strictly serial; `e2e` = the same metric through the public API with pinned host
 bags copied H2D inside the timed region and results read back.  Prints ONE JSON line.
@@ -201,7 +201,7 @@ def run_ours(args):
     from toad_b200.pipeline import ResidentRunner
     runner = ResidentRunner(model, n_streams=args.streams, device=dev)
 
-    def step(i):   # one step = one batch of S resident slides through the public runner (2 slides in flight)
+    def step(i):   # one step = one batch of S resident slides through the public runner (--streams slides in flight)
         runner.run([bags[(i * S + s) % n_bags] for s in range(S)], [sex] * S)
 
     def step_serial(i):
@@ -307,14 +307,14 @@ def run_ours(args):
                          "note": "achieved = algorithmic fp32 FLOPs of fc1 / its average CUDA-event duration when the kernel has "
                                  "the GPU to itself (the single-stream pass behind value_single_stream); the kernel executes 3 "
                                  "bf16 tensor passes per algorithmic FLOP (split precision), so frac tops out at 1/3",
-                         "traffic": 250.4e6 if n == N_PATCHES else None,
+                         "traffic": 256.4e6 if n == N_PATCHES else None,
                          "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel per launch, ncu --set full "
-                                         "(profiles/r1d_gemm_full.txt: 207.1 MB + 43.3 MB; algorithmic 205 MB x + 102 MB h1 planes, "
+                                         "(profiles/r1n_fwd_full.txt: 207.0 MB + 49.4 MB; algorithmic 205 MB x + 102 MB h1 planes, "
                                          "part of which is still in L2 when the kernel ends)",
                          "stage_ms": {k: v / max(calls_serial, 1) for k, v in stages_serial.items()},
                          "in_flight": {"achieved": fc1_tflops, "frac": fc1_tflops / pk["bf16_tflops"],
                                        "stage_ms": {k: v / max(calls, 1) for k, v in stages.items()},
-                                       "note": "the same launches inside the headline region, where two slides share the "
+                                       "note": "the same launches inside the headline region, where the slides in flight share the "
                                                "SMs: each launch is stretched, the sum of both streams' work finishes sooner"},
                          "forward_hbm_gbs": BYTES_PER_PATCH * n / (whole_ms * 1e-3) / 1e9 if whole_ms > 0 else None,
                          "hbm_peak_gbs": pk["hbm_gbs"]},
@@ -406,7 +406,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-patches", type=int, default=N_PATCHES)
     ap.add_argument("--slides-per-step", type=int, default=16)
-    ap.add_argument("--streams", type=int, default=2, help="slides in flight per GPU (toad_b200.pipeline.ResidentRunner)")
+    ap.add_argument("--streams", type=int, default=3, help="slides in flight per GPU (toad_b200.pipeline.ResidentRunner)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-resnet", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the torch-eager GPU leg (ncu launch lists)")
