@@ -8,8 +8,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libtoad_b200.so")
 SOURCES = ["toad_abi.cu"]
-HEADERS = ["common.cuh", "gemm_tc.cuh", "sgemm_simt.cuh", "tail.cuh", "bwd.cuh", "topk.cuh",
-           os.path.join("..", "..", "include", "toad_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "toad_b200.h")]
 
 
 def nvcc_path() -> str:
