@@ -29,7 +29,10 @@ constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
 
-enum { EPI_LINEAR = 0, EPI_GATE = 1 };
+enum { EPI_LINEAR = 0, EPI_GATE = 1, EPI_DGRAD = 2 };
+// EPI_DGRAD: the linear epilogue's staging / store path with the backward's extras (pooling term, ReLU mask, scale)
+// instead of the forward's (bias, residual, ReLU, dropout): two instantiations keep each one's live registers low.
+__host__ __device__ constexpr bool epi_is_linear(int epi) { return epi == EPI_LINEAR || epi == EPI_DGRAD; }
 enum { A_F32 = 0, A_SPLIT = 1, A_CONV = 2, A_MN = 3 };
 // A_CONV: implicit-GEMM convolution over NHWC (hi,lo) planes.  A_MN: both operands MN-major -- A(m,k) and B(n,k)
 // are read from planes stored [k, m] / [k, n] (the wgrad dW = dY^T . X with k = patch index: no transposes).
@@ -358,7 +361,7 @@ constexpr int GATE_SMEM_FLOATS = 4 * 1024;  // ba | bb | wc rows (<= 2 tasks sta
 #endif
 template <int A_MODE, int EPI>
 __host__ __device__ constexpr int epi_sets() {
-  return A_MODE != A_F32 ? 2 : (EPI == EPI_LINEAR ? TOAD_F32_LINEAR_EPI_SETS : 1);
+  return A_MODE != A_F32 ? 2 : (epi_is_linear(EPI) ? TOAD_F32_LINEAR_EPI_SETS : 1);
 }
 template <int A_MODE, int EPI>
 __host__ __device__ constexpr int cta_threads() {
@@ -588,7 +591,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       // residual operand (ResNet shortcut): this warp's NEXT 32-column chunk is fetched one chunk ahead (and the
       // first one before waiting for the accumulator), hiding the global latency that otherwise serialises the
       // epilogue of the short-K 1x1 convolutions.
-      const bool has_res = EPI == EPI_LINEAR && A_MODE != A_F32 && p.res_hi != nullptr;
+      const bool has_res = EPI == EPI_LINEAR && A_MODE != A_F32 && p.res_hi != nullptr;  // (compile-time false for EPI_DGRAD)
       uint4 res_h[4], res_l[4];
       auto load_res = [&](int c_) {
 #pragma unroll
@@ -603,7 +606,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
       };
       // dgrad ReLU mask (the saved activation's bf16 hi plane, 64 B per row and chunk): fetched one chunk ahead too
-      const bool has_mask16 = EPI == EPI_LINEAR && A_MODE != A_F32 && p.mask_bf16 != nullptr;
+      const bool has_mask16 = EPI == EPI_DGRAD && A_MODE != A_F32 && p.mask_bf16 != nullptr;
       uint4 msk[4];
       auto load_mask = [&](int c_) {
 #pragma unroll
@@ -612,6 +615,17 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           if (has_mask16 && row_ok) msk[q] = *reinterpret_cast<const uint4*>(p.mask_bf16 + row * p.ld_mask + n0 + c_ * 32 + q * 8);
         }
       };
+      // dgrad pooling term p[m][0] * v[0][n] + p[m][1] * v[1][n]: the row's two weights once per tile, the chunk's two
+      // 32-column slices of v held one value per lane (fetched a chunk ahead, broadcast by shuffles like the bias)
+      const bool has_pool = EPI == EPI_DGRAD && A_MODE != A_F32 && p.pool_p != nullptr;
+      float pool_p0 = 0.f, pool_p1 = 0.f, pv0_nxt = 0.f, pv1_nxt = 0.f;
+      auto load_pool = [&](int c_) {
+        if (has_pool) {
+          pv0_nxt = __ldg(p.pool_v + n0 + c_ * 32 + lane);
+          pv1_nxt = __ldg(p.pool_v + p.N + n0 + c_ * 32 + lane);
+        }
+      };
+      if (has_pool && row_ok) { pool_p0 = __ldg(p.pool_p + row * 2); pool_p1 = __ldg(p.pool_p + row * 2 + 1); }
       // bias of a 32-column chunk: lane j holds bias[col0 + j] (one coalesced load, fetched one chunk ahead);
       // the value of column i is broadcast with a shuffle where it is added.
       const bool has_bias = EPI == EPI_LINEAR && p.bias != nullptr && split == 0;
@@ -619,13 +633,14 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       float bias_nxt = 0.f;
       if (EPI == EPI_LINEAR) {
         bias_nxt = load_bias(eh);
-        if (A_MODE != A_F32) { load_res(eh); load_mask(eh); }
+        if (A_MODE != A_F32) load_res(eh);
       }
+      if (EPI == EPI_DGRAD && A_MODE != A_F32) { load_mask(eh); load_pool(eh); }
       mbar_wait(smem_u32(&bar_tmem_full[acc]), (it / C::ACC_STAGES) & 1);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N;
 
-      if (EPI == EPI_LINEAR) {
+      if (epi_is_linear(EPI)) {
         // 32 columns at a time, every warp on its own: TMEM -> registers -> bias/residual/ReLU -> (hi,lo) bf16 ->
         // the warp's PRIVATE 64B-swizzled staging tile (32 rows x 64 B per plane) -> one TMA store per plane
         // (rows >= M clipped by TMA).  No CTA-wide barrier: the warps drift, so one warp's TMEM / store latency
@@ -643,9 +658,15 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           uint4 cur_h[4], cur_l[4], cur_m[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) { cur_h[q] = res_h[q]; cur_l[q] = res_l[q]; cur_m[q] = msk[q]; }
-          if (!last) {  // next chunk's bias / residual / mask, in flight below
-            bias_nxt = load_bias(c + EPI_SETS);
-            if (A_MODE != A_F32) { load_res(c + EPI_SETS); load_mask(c + EPI_SETS); }
+          const float pv0_cur = pv0_nxt, pv1_cur = pv1_nxt;
+          if (!last) {  // next chunk's bias / residual (forward) or mask / pooling vectors (dgrad), in flight below
+            if (EPI == EPI_LINEAR) {
+              bias_nxt = load_bias(c + EPI_SETS);
+              if (A_MODE != A_F32) load_res(c + EPI_SETS);
+            } else if (A_MODE != A_F32) {
+              load_mask(c + EPI_SETS);
+              load_pool(c + EPI_SETS);
+            }
           }
           tmem_ld_wait();
           if (last) {  // this warp has drained its share of the accumulator: hand TMEM back before the arithmetic
@@ -657,9 +678,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             }
           }
           const int col0 = n0 + c * 32;
+          if (EPI == EPI_LINEAR) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            r[i] = __float_as_uint(__uint_as_float(r[i]) + __shfl_sync(0xffffffffu, bias_cur, i));
+            for (int i = 0; i < 32; ++i)
+              r[i] = __float_as_uint(__uint_as_float(r[i]) + __shfl_sync(0xffffffffu, bias_cur, i));
+          }
           if (has_res) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -673,14 +696,19 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
               }
             }
           }
-          if (p.relu) {
+          if (EPI == EPI_LINEAR && p.relu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(fmaxf(__uint_as_float(r[i]), 0.0f));
           }
-          if (A_MODE != A_F32 && (p.pool_p != nullptr || p.mask_f32 != nullptr || p.mask_bf16 != nullptr || p.out_scale != 0.f)) {
-            // backward dgrad epilogue (uniform branch; never taken by the forward kernels)
-            float p0 = 0.f, p1 = 0.f;
-            if (p.pool_p != nullptr && row_ok) { p0 = __ldg(p.pool_p + row * 2); p1 = __ldg(p.pool_p + row * 2 + 1); }
+          if (EPI == EPI_DGRAD && A_MODE != A_F32) {
+            // backward dgrad epilogue: + pooling term, ReLU mask of the saved activation, 1/keep
+            if (has_pool) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float t = fmaf(pool_p0, __shfl_sync(0xffffffffu, pv0_cur, i), __uint_as_float(r[i]));
+                r[i] = __float_as_uint(fmaf(pool_p1, __shfl_sync(0xffffffffu, pv1_cur, i), t));
+              }
+            }
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -692,24 +720,17 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 mk = make_float4(bf16lo_to_f32(mx), bf16hi_to_f32(mx), bf16lo_to_f32(my), bf16hi_to_f32(my));
               }
               const float mv[4] = {mk.x, mk.y, mk.z, mk.w};
-              float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-              if (p.pool_p != nullptr) {
-                v0 = __ldg(reinterpret_cast<const float4*>(p.pool_v + col0 + q * 4));
-                v1 = __ldg(reinterpret_cast<const float4*>(p.pool_v + p.N + col0 + q * 4));
-              }
-              const float pv0[4] = {v0.x, v0.y, v0.z, v0.w}, pv1[4] = {v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int i = q * 4 + e;
                 float t = __uint_as_float(r[i]);
-                if (p.pool_p != nullptr) t += p0 * pv0[e] + p1 * pv1[e];
                 t = mv[e] > 0.f ? t : 0.f;
                 if (p.out_scale != 0.f) t *= p.out_scale;
                 r[i] = __float_as_uint(t);
               }
             }
           }
-          if (p.drop.thresh != 0u) {  // training only: one big uniform branch, never predicated into the hot path
+          if (EPI == EPI_LINEAR && p.drop.thresh != 0u) {  // training only: one big uniform branch, never predicated into the hot path
             const unsigned long long e0 = static_cast<unsigned long long>(row) * p.N + col0;
 #pragma unroll
             for (int i = 0; i < 32; ++i)
@@ -799,7 +820,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             if (t < p.gate_ntasks) dst[t] = s[t];
         }
       }
-      if (EPI != EPI_LINEAR) {  // (the linear epilogue hands TMEM back right after its last tcgen05.ld)
+      if (!epi_is_linear(EPI)) {  // (the linear epilogue hands TMEM back right after its last tcgen05.ld)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -808,7 +829,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
       }
     }
-    if (EPI == EPI_LINEAR && lane == 0) tma_store_wait_all();  // this warp's own bulk stores
+    if (epi_is_linear(EPI) && lane == 0) tma_store_wait_all();  // this warp's own bulk stores
   } else if (A_MODE == A_F32 && warp >= CONV_WARP0) {
     // ------------------------------------------------------------------ A converter (8 warps)
     // Each half-warp streams one 256 B row segment (64 fp32) per load instruction; a thread turns its
@@ -959,20 +980,22 @@ int launch_gemm_maps_b(const GemmTcParams& p, const CUtensorMap& ta_hi, const CU
   if (p.M <= 0) return 0;
   if ((A_MODE == A_F32 && p.K % BLOCK_K != 0) || p.N % BLOCK_N != 0 || p.K <= 0 || p.N <= 0) return TOAD_ERR_UNSUPPORTED;
   if (p.k_splits > 1 && (A_MODE == A_F32 || EPI != EPI_LINEAR || p.out_hi != nullptr || p.kb_per_split <= 0)) return TOAD_ERR_ARG;
+  if (EPI != EPI_DGRAD && (p.pool_p != nullptr || p.mask_f32 != nullptr || p.mask_bf16 != nullptr || p.out_scale != 0.f)) return TOAD_ERR_ARG;
+  if (EPI == EPI_DGRAD && (p.bias != nullptr || p.res_hi != nullptr || p.relu != 0 || p.drop.thresh != 0u)) return TOAD_ERR_ARG;
   if (EPI == EPI_GATE && (p.gate_D > 1024 || p.gate_ntasks < 1 || p.gate_ntasks > 4)) return TOAD_ERR_UNSUPPORTED;
   // the epilogues' register -> global stores are 256-bit: 32-byte aligned rows
-  if (EPI == EPI_LINEAR && p.out_f32 != nullptr && ((reinterpret_cast<uintptr_t>(p.out_f32) & 31) != 0 || p.ld_f32 % 8 != 0))
+  if (epi_is_linear(EPI) && p.out_f32 != nullptr && ((reinterpret_cast<uintptr_t>(p.out_f32) & 31) != 0 || p.ld_f32 % 8 != 0))
     return TOAD_ERR_ARG;
   if (EPI == EPI_GATE && p.gate_a != nullptr &&
       (((reinterpret_cast<uintptr_t>(p.gate_a) | reinterpret_cast<uintptr_t>(p.gate_b)) & 31) != 0 || p.gate_D % 8 != 0))
     return TOAD_ERR_ARG;
   CUtensorMap to_hi = tb_hi, to_lo = tb_lo;
-  if (EPI == EPI_LINEAR && p.out_hi != nullptr) {
+  if (epi_is_linear(EPI) && p.out_hi != nullptr) {
     if (p.out_lo == nullptr || p.ld_split % 8 != 0) return TOAD_ERR_ARG;
     TOAD_TRY(make_bf16_out_tmap(&to_hi, p.out_hi, p.M, p.N, p.ld_split));
     TOAD_TRY(make_bf16_out_tmap(&to_lo, p.out_lo, p.M, p.N, p.ld_split));
   }
-  constexpr int kSmem = EPI == EPI_LINEAR ? C::SMEM_BYTES_LINEAR : C::SMEM_BYTES;
+  constexpr int kSmem = epi_is_linear(EPI) ? C::SMEM_BYTES_LINEAR : C::SMEM_BYTES;
   auto kern = gemm_bf16x3_kernel<BLOCK_N, A_MODE, EPI, CG, OUT_BUFS>;
   TOAD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
   const int64_t m_units = (p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG);

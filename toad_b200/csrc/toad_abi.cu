@@ -522,7 +522,7 @@ int bwd_tc(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t
     g.M = n; g.N = Hd; g.K = 2 * D;
     g.pool_p = w.P; g.pool_v = w.dM; g.mask_bf16 = sh_hi; g.ld_mask = Hd; g.out_scale = inv_keep;
     g.out_hi = w.dz2_hi; g.out_lo = w.dz2_lo; g.ld_split = Hd;
-    TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, w.dab_hi, w.dab_lo, w.wabT_hi, w.wabT_lo, st)));
+    TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_DGRAD, 2>(g, w.dab_hi, w.dab_lo, w.wabT_hi, w.wabT_lo, st)));
   }
   TOAD_TRY(bwd::launch_colsum_planes(w.dz2_hi, w.dz2_lo, w.col_part, n, Hd, w.col_blocks, st));
   TOAD_TRY(bwd::launch_reduce_strided(w.col_part, g_b2, Hd, Hd, w.col_blocks, st));
@@ -539,7 +539,7 @@ int bwd_tc(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t
     g.M = n; g.N = Hd; g.K = Hd;
     g.mask_bf16 = sh1_hi; g.ld_mask = Hd; g.out_scale = inv_keep;
     g.out_hi = w.dz1_hi; g.out_lo = w.dz1_lo; g.ld_split = Hd;
-    TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, w.dz2_hi, w.dz2_lo, w.w2T_hi, w.w2T_lo, st)));
+    TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_DGRAD, 2>(g, w.dz2_hi, w.dz2_lo, w.w2T_hi, w.w2T_lo, st)));
   }
   TOAD_TRY(bwd::launch_colsum_planes(w.dz1_hi, w.dz1_lo, w.col_part, n, Hd, w.col_blocks, st));
   TOAD_TRY(bwd::launch_reduce_strided(w.col_part, g_b1, Hd, Hd, w.col_blocks, st));
