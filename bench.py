@@ -180,6 +180,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION/INFO in some environments) goes
+        # to stdout too, so keep NCCL at WARN unless the caller insists
+        if os.environ.get("TOAD_BENCH_KEEP_NCCL_DEBUG", "0") != "1":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     S = args.slides_per_step
     n = args.n_patches

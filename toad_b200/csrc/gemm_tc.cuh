@@ -11,8 +11,9 @@
 //   warp 0      TMA producer: B_hi/B_lo tiles (and A_hi/A_lo when A is already split)
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16)
 //   warp 2      TMEM allocator
-//   warps 4-11  epilogue (4-7 when fp32-fed): tcgen05.ld accumulator -> registers -> bias/activation -> smem
-//               staging -> TMA store
+//   warps 4-11  epilogue (4-7 for the fp32-fed gate kernel): tcgen05.ld accumulator -> registers -> bias / residual /
+//               activation (or the dgrad extras) -> the warp's private 64B-swizzled smem staging tile -> the warp's
+//               own TMA stores; no CTA-wide barrier, TMEM handed back right after the warp's last tcgen05.ld
 //   next 8      (A_MODE 0 only) A converter: fp32 rows from global -> (hi,lo) bf16 pairs written
 //               straight into the 128B-swizzled UMMA operand layout, loads one K block ahead
 // Pipelines: smem ring (full/empty mbarriers) between producer/converter and MMA, and a
@@ -224,11 +225,6 @@ __device__ __forceinline__ void tma_store_wait_read() {  // all but the PENDING 
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
 }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-template <int THREADS>
-__device__ __forceinline__ void epi_barrier() {  // all epilogue warps of the CTA
-  asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
-}
-
 template <int CG>
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
