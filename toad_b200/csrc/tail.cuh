@@ -2,9 +2,12 @@
 //   A_raw = scores^T ; P = softmax(A_raw, dim=1) over all N patches, per task ;
 //   M = P . h ; M = cat(M, sex) ; the two linear heads ; top-1 ; softmaxes.
 // One launch: every CTA streams a contiguous chunk of rows of h exactly once (128-bit
-// coalesced loads, warp-per-row, register accumulators), keeps (max, sum-exp, weighted sum)
-// partials, and the last CTA to finish (atomic ticket) merges the partials in fixed order
-// and evaluates the heads -- deterministic, no float atomics.
+// coalesced loads, warp-per-row with 4 rows in flight, register accumulators), keeps (max,
+// sum-exp, weighted sum) partials; atomic tickets elect the last CTA of each group of >= 8 to
+// fold the group's partials and the last group to fold the group partials and evaluate the
+// heads, all in fixed order -- deterministic, no float atomics.
+// (-DTOAD_TAIL_DEBUG + TOAD_TAIL_STOP=k builds a profiling variant that leaves after phase k:
+//  how the per-phase times in DESIGN.md section 7 were taken.)
 //
 // Also here: the small weight-preparation kernels of the tensor-core path and the
 // attention_c contraction of the fp32 path.
@@ -47,7 +50,7 @@ struct TailParams {
   int32_t group;       // CTAs per group
   int32_t heads_in_smem;  // head weights staged in shared memory (n_classes + 2 <= MAX_HEADS_SMEM)
 #ifdef TOAD_TAIL_DEBUG
-  int32_t dbg_stop;    // profiling builds only (tools/_ab): leave the kernel after phase dbg_stop
+  int32_t dbg_stop;    // profiling builds only: leave the kernel after phase dbg_stop
 #endif
   int32_t attention_only;
 };
