@@ -993,7 +993,15 @@ int launch_gemm_maps_b(const GemmTcParams& p, const CUtensorMap& ta_hi, const CU
   }
   constexpr int kSmem = epi_is_linear(EPI) ? C::SMEM_BYTES_LINEAR : C::SMEM_BYTES;
   auto kern = gemm_bf16x3_kernel<BLOCK_N, A_MODE, EPI, CG, OUT_BUFS>;
-  TOAD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+  {  // once per instantiation and device (one process drives one GPU; a repeated call would only cost host time)
+    static int attr_dev = -1;
+    int dev = 0;
+    TOAD_CUDA_TRY(cudaGetDevice(&dev));
+    if (attr_dev != dev) {
+      TOAD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+      attr_dev = dev;
+    }
+  }
   const int64_t m_units = (p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG);
   const int64_t units = m_units * (p.N / BLOCK_N) * (p.k_splits > 1 ? p.k_splits : 1);
   const int64_t max_units = sm_count() / CG;

@@ -151,15 +151,20 @@ class TOAD_fc_mtl_concat(nn.Module):
 
     # -- parameters in C-ABI (= state_dict) order
     def _param_list(self) -> List[torch.Tensor]:
+        cached = self.__dict__.get("_plist")
+        if cached is not None:   # the Parameter objects are fixed at construction (.to() / load_state_dict keep them)
+            return cached
         fc1 = self.attention_net[0]
         fc2 = self.attention_net[3 if self.dropout else 2]
         gate = self.attention_net[-1]
-        return [fc1.weight, fc1.bias, fc2.weight, fc2.bias,
-                gate.attention_a[0].weight, gate.attention_a[0].bias,
-                gate.attention_b[0].weight, gate.attention_b[0].bias,
-                gate.attention_c.weight, gate.attention_c.bias,
-                self.classifier.weight, self.classifier.bias,
-                self.site_classifier.weight, self.site_classifier.bias]
+        plist = [fc1.weight, fc1.bias, fc2.weight, fc2.bias,
+                 gate.attention_a[0].weight, gate.attention_a[0].bias,
+                 gate.attention_b[0].weight, gate.attention_b[0].bias,
+                 gate.attention_c.weight, gate.attention_c.bias,
+                 self.classifier.weight, self.classifier.bias,
+                 self.site_classifier.weight, self.site_classifier.bias]
+        self.__dict__["_plist"] = plist
+        return plist
 
     def relocate(self) -> None:
         """Move to the GPU (reference model_toad.py:77-88).
@@ -185,7 +190,7 @@ class TOAD_fc_mtl_concat(nn.Module):
             ws = self._ws_by_stream[sid] = ops.Workspace()
         return ws
 
-    def _weight_plane_flag(self, params, device) -> int:
+    def _weight_plane_flag(self, params, device, pkey=None) -> int:
         """Inference loops reuse the bf16 weight planes that the previous forward left in the workspace
         as long as no parameter changed (tensor identity + autograd version counter) and the workspace
         buffer is still the same allocation (it is grow-only, and the planes sit at n-independent offsets
@@ -193,7 +198,7 @@ class TOAD_fc_mtl_concat(nn.Module):
         self._plane_key_pending = None
         if _default_flags() & _lib.FLAG_SIMT_FP32:
             return 0
-        key = tuple((p.data_ptr(), p._version) for p in params) + (str(device),)
+        key = (pkey if pkey is not None else tuple((p.data_ptr(), p._version) for p in params)) + (str(device),)
         ws = self._ws
         buf = ws.buf
         state = (key, None if buf is None else buf.data_ptr(), None if buf is None else buf.numel())
@@ -229,8 +234,17 @@ class TOAD_fc_mtl_concat(nn.Module):
             (logits, site_logits, y_prob, y_hat, site_prob, site_hat, a_raw, features) = _ToadFunction.apply(
                 self, h, sex_f, *params)
         else:
-            out = ops.toad_fwd(self._dims, [p.detach() for p in params], h, sex_f, self._ws,
-                               _default_flags() | self._weight_plane_flag(params, h.device), prof=self._prof)
+            # host fast path: the detached views and the validated C parameter block are cached per parameter
+            # version (identity + autograd version counter), so a steady-state forward re-checks nothing
+            pkey = tuple((p.data_ptr(), p._version) for p in params)
+            pc = self.__dict__.get("_pcache")
+            if pc is None or pc[0] != pkey:
+                det = [p.detach() for p in params]
+                pc = (pkey, det, ops._params_struct(self._dims, det))
+                self.__dict__["_pcache"] = pc
+            out = ops.toad_fwd(self._dims, pc[1], h, sex_f, self._ws,
+                               _default_flags() | self._weight_plane_flag(params, h.device, pkey), prof=self._prof,
+                               pstruct=pc[2])
             self._note_planes_written()
             logits, site_logits, y_prob, y_hat = out["logits"], out["site_logits"], out["y_prob"], out["y_hat"]
             site_prob, site_hat, a_raw, features = out["site_prob"], out["site_hat"], out["a_raw"], out["features"]

@@ -75,17 +75,26 @@ def _params_struct(dims: Dims, params: Sequence[torch.Tensor]) -> Params:
 
 
 def alloc_fwd_out(dims: Dims, n: int, device: torch.device) -> Dict[str, torch.Tensor]:
+    """Fresh result tensors of one forward: five allocations instead of nine (the small non-differentiable fp32
+    results and the two int64 predictions are views of shared buffers) -- at N = 10k the host side of a forward costs
+    as much as its kernels."""
+    T, Hd, Cn = dims.n_tasks, dims.hid_dim, dims.n_classes
+    sizes = (T * (Hd + 1), Cn, 2, 2 * T)
+    padded = [(v + 3) // 4 * 4 for v in sizes]          # every view starts 16-byte aligned
+    small = torch.empty(sum(padded), dtype=torch.float32, device=device)
+    feats, y_prob, site_prob, stats = [c[:v] for c, v in zip(torch.split(small, padded), sizes)]
+    hats = torch.empty((2, 1, 1), dtype=torch.int64, device=device)
     f32 = dict(dtype=torch.float32, device=device)
     return {
-        "a_raw": torch.empty((dims.n_tasks, n), **f32),
-        "features": torch.empty((dims.n_tasks, dims.hid_dim + 1), **f32),
-        "logits": torch.empty((1, dims.n_classes), **f32),
-        "y_prob": torch.empty((1, dims.n_classes), **f32),
-        "y_hat": torch.empty((1, 1), dtype=torch.int64, device=device),
+        "a_raw": torch.empty((T, n), **f32),
+        "features": feats.view(T, Hd + 1),
+        "logits": torch.empty((1, Cn), **f32),          # (the two differentiable outputs keep their own storage)
+        "y_prob": y_prob.view(1, Cn),
+        "y_hat": hats[0],
         "site_logits": torch.empty((1, 2), **f32),
-        "site_prob": torch.empty((1, 2), **f32),
-        "site_hat": torch.empty((1, 1), dtype=torch.int64, device=device),
-        "softmax_stats": torch.empty((dims.n_tasks, 2), **f32),
+        "site_prob": site_prob.view(1, 2),
+        "site_hat": hats[1],
+        "softmax_stats": stats.view(T, 2),
     }
 
 
@@ -119,9 +128,13 @@ def _saved_struct(saved: Dict[str, torch.Tensor]) -> Saved:
     return s
 
 
+_FWD_WS_BYTES: Dict[tuple, int] = {}
+
+
 def toad_fwd(dims: Dims, params: Sequence[torch.Tensor], x: torch.Tensor, sex: torch.Tensor, ws: Workspace,
              flags: int = 0, saved: Optional[Dict[str, torch.Tensor]] = None,
-             out: Optional[Dict[str, torch.Tensor]] = None, prof: Optional[int] = None) -> Dict[str, torch.Tensor]:
+             out: Optional[Dict[str, torch.Tensor]] = None, prof: Optional[int] = None,
+             pstruct: Optional[Params] = None) -> Dict[str, torch.Tensor]:
     """One TOAD forward (models/model_toad.py:90-116) through the C ABI.
 
     FLAG_REUSE_WEIGHT_PLANES in `flags` is honoured only if the workspace does not have to grow for this
@@ -141,13 +154,21 @@ def toad_fwd(dims: Dims, params: Sequence[torch.Tensor], x: torch.Tensor, sex: t
     if out is None:
         out = {"a_raw": torch.empty((dims.n_tasks, n), dtype=torch.float32, device=x.device)} if attn_only \
             else alloc_fwd_out(dims, n, x.device)
-    p = _params_struct(dims, params)
-    nbytes = C.c_size_t()
-    _lib.check(lib.toad_fwd_workspace_bytes(C.byref(dims), n, flags, C.byref(nbytes)), "toad_fwd_workspace_bytes")
-    if (flags & _lib.FLAG_REUSE_WEIGHT_PLANES) and (ws.buf is None or ws.buf.numel() < nbytes.value
+    # pstruct: a Params block the caller validated earlier for these very tensors (the module caches it per
+    # parameter version -- 14 shape / dtype / alignment checks per forward are host time the small-N path can't spare)
+    p = pstruct if pstruct is not None else _params_struct(dims, params)
+    wkey = (dims.in_dim, dims.hid_dim, dims.attn_dim, dims.n_tasks, dims.n_classes, n, flags)
+    need = _FWD_WS_BYTES.get(wkey)
+    if need is None:
+        nbytes = C.c_size_t()
+        _lib.check(lib.toad_fwd_workspace_bytes(C.byref(dims), n, flags, C.byref(nbytes)), "toad_fwd_workspace_bytes")
+        if len(_FWD_WS_BYTES) > 4096:
+            _FWD_WS_BYTES.clear()
+        need = _FWD_WS_BYTES[wkey] = nbytes.value
+    if (flags & _lib.FLAG_REUSE_WEIGHT_PLANES) and (ws.buf is None or ws.buf.numel() < need
                                                     or ws.buf.device != x.device):
         flags &= ~_lib.FLAG_REUSE_WEIGHT_PLANES
-    wptr, wsize = ws.get(nbytes.value, x.device)
+    wptr, wsize = ws.get(need, x.device)
     o = _out_struct(out)
     s = _saved_struct(saved) if saved is not None else None
     args = [C.byref(dims), C.byref(p), x.data_ptr(), n, None if attn_only else sex.data_ptr(), C.byref(o),
