@@ -205,7 +205,16 @@ def run_ours(args):
     from toad_b200.pipeline import ResidentRunner
     runner = ResidentRunner(model, n_streams=args.streams, device=dev)
 
+    B = max(1, min(args.batch, 16))
+    if B > 1:   # small bags: B slides back to back per forward_batch call (one set of trunk launches for all of them)
+        cats = [torch.cat([bags[(j + b) % n_bags] for b in range(B)], 0) for j in range(2)]
+        sexes_b = torch.ones(B, device=dev)
+
     def step(i):   # one step = one batch of S resident slides through the public runner (--streams slides in flight)
+        if B > 1:
+            for c in range(S // B):
+                model.forward_batch(cats[(i + c) % 2], [n] * B, sexes_b)
+            return
         runner.run([bags[(i * S + s) % n_bags] for s in range(S)], [sex] * S)
 
     def step_serial(i):
@@ -295,7 +304,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16x3-split (fp32 accumulate; fp32-class accuracy)", "data": "synthetic",
             "config": {"workload": "TOAD_fc_mtl_concat forward (eval), N=%d x %d fp32, big, n_classes=18" % (n, WIDTH),
-                       "slides_per_step": S, "slides_in_flight": args.streams,
+                       "slides_per_step": S, "slides_in_flight": args.streams, "slides_per_call": B,
                        "parallelism": "one slide per GPU, replicas (no collective in eval)",
                        "l2_policy": "4 distinct 205 MB bags per GPU rotated (inputs larger than the 126 MB L2)"},
             "clocks": sampler.summary() if sampler else None,
@@ -411,6 +420,8 @@ def main():
     ap.add_argument("--n-patches", type=int, default=N_PATCHES)
     ap.add_argument("--slides-per-step", type=int, default=16)
     ap.add_argument("--streams", type=int, default=3, help="slides in flight per GPU (toad_b200.pipeline.ResidentRunner)")
+    ap.add_argument("--batch", type=int, default=1,
+                    help="slides per forward_batch call (<= 16, must divide --slides-per-step); 1 = one forward per slide")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-resnet", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the torch-eager GPU leg (ncu launch lists)")

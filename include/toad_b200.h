@@ -150,6 +150,20 @@ int toad_fwd(const toad_dims_t* dims, const toad_params_t* params, const float* 
              const float* sex, const toad_fwd_out_t* out, const toad_saved_t* saved, void* workspace,
              size_t workspace_bytes, uint32_t flags, toad_stream_t stream);
 
+/* Batched eval forward (collate_MIL_mtl_concat, utils/utils.py:30-35, concatenates the bags of a batch the same
+ * way): n_slides <= 16 slides stored back to back in x [offsets[n_slides], in_dim], slide s = rows
+ * [offsets[s], offsets[s+1]) (offsets: HOST array, offsets[0] = 0, no empty slide).  The three trunk GEMMs run once
+ * over all rows -- small bags fill the GPU together and share one set of launches --, the pooling / heads kernel runs
+ * with one grid row per slide.  `out` points at slide-major blocks: a_raw [n_tasks, n_total] (slide s = columns
+ * offsets[s]..), features [S, n_tasks, hid+1], logits / y_prob [S, n_classes], y_hat / site_hat [S] int64,
+ * site_logits / site_prob [S, 2], softmax_stats [S, n_tasks, 2]; sex [S].  Per-row results are bit-identical to
+ * toad_fwd on each slide; pooled results differ only by fp32 summation order. */
+int toad_fwd_batch_workspace_bytes(const toad_dims_t* dims, int64_t n_total, int32_t n_slides, uint32_t flags,
+                                   size_t* bytes);
+int toad_fwd_batch(const toad_dims_t* dims, const toad_params_t* params, const float* x, const int64_t* offsets,
+                   int32_t n_slides, const float* sex, const toad_fwd_out_t* out, void* workspace,
+                   size_t workspace_bytes, uint32_t flags, toad_stream_t stream);
+
 /* Per-stage device timing of toad_fwd (diagnostics; bench.py's roofline leg).  A profile handle
  * owns CUDA events for up to max_calls forwards; toad_fwd_profiled records an event between the
  * stages on `stream` (no synchronisation); toad_profile_read waits for the recorded events,

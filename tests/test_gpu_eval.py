@@ -73,3 +73,33 @@ def test_patch_pipeline_equals_sequential_modules():
     assert torch.equal(feats, f_ref)
     for k in ("logits", "site_logits", "Y_prob", "A", "features"):
         assert torch.equal(out[k], r_ref[k]), k
+
+
+@pytest.mark.parametrize("simt", [False, True])
+def test_forward_batch_equals_per_slide_forward(simt, monkeypatch):
+    """toad_fwd_batch: slides back to back in one matrix, one set of trunk launches.  Raw scores are bit-identical to
+    the per-slide forward (row-wise independent GEMMs, fixed-order partial sums); pooled results agree to fp32
+    summation order; the oracle is the referee for the heads."""
+    monkeypatch.setenv("TOAD_B200_SIMT", "1" if simt else "0")
+    params = O.make_params(11, "big", 18, 0.02)
+    model = build_model(params, "big", 18)
+    ns = [300, 1, 2500, 257, 4097, 33] + [64] * 12          # 18 slides: two C-ABI chunks (16 + 2)
+    bags = [O.make_bag(700 + i, n) for i, n in enumerate(ns)]
+    sexes = torch.tensor([float(i % 2) for i in range(len(ns))], device="cuda")
+    h = torch.from_numpy(np.concatenate(bags, 0)).cuda()
+    res = model.forward_batch(h, ns, sexes, return_features=True)
+    assert len(res) == len(ns)
+    for i, (bag, n) in enumerate(zip(bags, ns)):
+        with torch.no_grad():
+            r = model(torch.from_numpy(bag).cuda(), sexes[i:i + 1], return_features=True)
+        assert res[i]["A"].shape == (2, n) and res[i]["logits"].shape == (1, 18) and res[i]["Y_hat"].shape == (1, 1)
+        assert torch.equal(res[i]["A"], r["A"]), i
+        for k in ("logits", "site_logits", "Y_prob", "site_prob", "features"):
+            np.testing.assert_allclose(to_np(res[i][k]), to_np(r[k]), rtol=2e-5, atol=2e-6, err_msg="%s[%d]" % (k, i))
+        if i < 6:
+            ref = O.toad_forward(bag, float(i % 2), params, dtype=np.float64)
+            np.testing.assert_allclose(to_np(res[i]["logits"]), ref["logits"], rtol=1e-3, atol=2e-5)   # logits that happen to be ~0 get an absolute floor
+            assert int(res[i]["Y_hat"]) == int(np.asarray(ref["Y_hat"]).reshape(-1)[0])
+            assert int(res[i]["site_hat"]) == int(np.asarray(ref["site_hat"]).reshape(-1)[0])
+    with pytest.raises(ValueError):
+        model.forward_batch(h, [h.shape[0] - 1, 0, 1], sexes[:3])

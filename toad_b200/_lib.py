@@ -20,10 +20,12 @@ FLAG_TC_PAIR_ALL = 32
 FLAG_REUSE_WEIGHT_PLANES = 128
 FLAG_BWD_TRANSPOSED = 256
 ABI_VERSION = 2
+MAX_BATCH = 16   # slides per toad_fwd_batch call (tail::MAX_BATCH)
 
 EXPORTS = [
     "toad_abi_version", "toad_error_string", "toad_param_offsets", "toad_dropout_hash",
-    "toad_fwd_workspace_bytes", "toad_fwd", "toad_bwd_workspace_bytes", "toad_bwd",
+    "toad_fwd_workspace_bytes", "toad_fwd", "toad_fwd_batch_workspace_bytes", "toad_fwd_batch",
+    "toad_bwd_workspace_bytes", "toad_bwd",
     "toad_attn_gated_workspace_bytes", "toad_attn_gated_fwd",
     "toad_topk_workspace_bytes", "toad_topk", "toad_gather_rows",
     "toad_linear_workspace_bytes", "toad_linear_bf16x3",
@@ -87,6 +89,9 @@ def load() -> C.CDLL:
     lib.toad_fwd.argtypes = [C.POINTER(Dims), C.POINTER(Params), _f32p, C.c_int64, _f32p, C.POINTER(FwdOut),
                              C.POINTER(Saved), C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
     lib.toad_fwd_profiled.argtypes = lib.toad_fwd.argtypes + [C.c_void_p]
+    lib.toad_fwd_batch_workspace_bytes.argtypes = [C.POINTER(Dims), C.c_int64, C.c_int32, C.c_uint32, C.POINTER(C.c_size_t)]
+    lib.toad_fwd_batch.argtypes = [C.POINTER(Dims), C.POINTER(Params), _f32p, C.POINTER(C.c_int64), C.c_int32, _f32p,
+                                   C.POINTER(FwdOut), C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
     lib.toad_bwd_workspace_bytes.argtypes = [C.POINTER(Dims), C.c_int64, C.c_uint32, C.POINTER(C.c_size_t)]
     lib.toad_bwd.argtypes = [C.POINTER(Dims), C.POINTER(Params), _f32p, C.c_int64, C.POINTER(FwdOut),
                              C.POINTER(Saved), _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]

@@ -30,23 +30,35 @@ constexpr int PART_STRIDE = T * (H + 2);  // one partial: acc[T][H], then (m,l)[
 
 enum { H_F32 = 0, H_SPLIT = 1 };
 
+constexpr int MAX_BATCH = 16;   // slides per launch (grid.y) of the batched forward
+struct TailBatch {              // slide s = rows [off[s], off[s+1]) of the trunk's row space
+  int32_t n_slides;
+  int32_t pad;
+  int64_t off[MAX_BATCH + 1];
+};
+
+// One launch serves grid.y slides whose rows sit back to back in the trunk's arrays (toad_fwd_batch); the plain
+// forward is the n_slides = 1 case.  Per-slide outputs / scratch are slide-major blocks behind the given pointers.
 struct TailParams {
-  const float* part;   // [n_parts][N][T] score partials (no bias)
+  const float* part;   // [n_parts][stride][T] score partials (no bias)
   int32_t n_parts;
   const float* bc;     // [T]
-  float* a_raw;        // [T][N]
+  float* a_raw;        // [T][stride]
+  int64_t stride;      // total rows of the trunk arrays (= N for a single slide)
+  TailBatch batch;
+  int32_t parts_per_slide;  // partial blocks per slide in blk_part (gridDim.x + MAX_GROUPS)
   const float* h_f32;  // [N, H]          (H_F32)
   const __nv_bfloat16* h_hi;  // [N, H]   (H_SPLIT)
   const __nv_bfloat16* h_lo;
-  int64_t N;
+  int64_t N;           // (host side only: rows of the largest slide, sizes the grid)
   int32_t rows_per_block;
-  const float* sex;    // [1]
+  const float* sex;    // [n_slides]
   const float* wcls; const float* bcls; int32_t n_classes;
   const float* wsite; const float* bsite;
   float* features; float* logits; float* y_prob; int64_t* y_hat;
   float* site_logits; float* site_prob; int64_t* site_hat; float* stats;
-  float* blk_part;     // [gridDim.x + MAX_GROUPS][PART_STRIDE]: per-CTA partials, then the group partials
-  unsigned int* ticket;  // [1 + MAX_GROUPS] zero-initialised counters (self-resetting): global, then one per group
+  float* blk_part;     // per slide [gridDim.x + MAX_GROUPS][PART_STRIDE]: per-CTA partials, then the group partials
+  unsigned int* ticket;  // per slide 64 zero-initialised counters (self-resetting): global, then one per group
   int32_t group;       // CTAs per group
   int32_t heads_in_smem;  // head weights staged in shared memory (n_classes + 2 <= MAX_HEADS_SMEM)
 #ifdef TOAD_TAIL_DEBUG
@@ -145,10 +157,15 @@ __global__ void __launch_bounds__(THREADS, 1) pool_heads_kernel(const TailParams
   __shared__ float s_m[T], s_l[T];
   __shared__ unsigned int s_ticket;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * p.rows_per_block;
-  int64_t r1 = r0 + p.rows_per_block;
-  if (r1 > p.N) r1 = p.N;
-  const int rows = r1 > r0 ? static_cast<int>(r1 - r0) : 0;
+  const int slide = blockIdx.y;
+  const int64_t row_base = p.batch.off[slide];               // first row of this slide in the trunk arrays
+  const int64_t n_rows = p.batch.off[slide + 1] - row_base;
+  const int64_t rpb = (n_rows + gridDim.x - 1) / gridDim.x;  // <= MAX_CHUNK (checked by the host for the largest slide)
+  const int64_t l0_ = static_cast<int64_t>(blockIdx.x) * rpb;
+  int64_t l1_ = l0_ + rpb;
+  if (l1_ > n_rows) l1_ = n_rows;
+  const int rows = l1_ > l0_ ? static_cast<int>(l1_ - l0_) : 0;
+  const int64_t r0 = row_base + l0_;                         // global row of this CTA's first row
 
   // head weights -> shared memory in the background (used only by the CTA that ends up evaluating the heads)
   float* s_w = dsm + WARPS * T * H;            // [n_classes + 2][H + 1]
@@ -171,7 +188,7 @@ __global__ void __launch_bounds__(THREADS, 1) pool_heads_kernel(const TailParams
       float2 v[8];
 #pragma unroll
       for (int z = 0; z < 8; ++z)
-        v[z] = z0 + z < p.n_parts ? __ldg(reinterpret_cast<const float2*>(p.part + (static_cast<int64_t>(z0 + z) * p.N + row) * T))
+        v[z] = z0 + z < p.n_parts ? __ldg(reinterpret_cast<const float2*>(p.part + (static_cast<int64_t>(z0 + z) * p.stride + row) * T))
                                   : make_float2(0.f, 0.f);
 #pragma unroll
       for (int z = 0; z < 8; ++z) {
@@ -182,7 +199,7 @@ __global__ void __launch_bounds__(THREADS, 1) pool_heads_kernel(const TailParams
     s0 += bc0;
     s1 += bc1;
     p.a_raw[row] = s0;
-    p.a_raw[p.N + row] = s1;
+    p.a_raw[p.stride + row] = s1;
     s_score[0][i] = s0;
     s_score[1][i] = s1;
     lmax[0] = fmaxf(lmax[0], s0);
@@ -288,7 +305,9 @@ __global__ void __launch_bounds__(THREADS, 1) pool_heads_kernel(const TailParams
     dsm[warp * (T * H) + H + col_of(e)] = acc1[e];
   }
   __syncthreads();
-  float* mine = p.blk_part + static_cast<int64_t>(blockIdx.x) * PART_STRIDE;
+  float* const blk_part = p.blk_part + static_cast<int64_t>(slide) * p.parts_per_slide * PART_STRIDE;
+  unsigned int* const ticket = p.ticket + slide * 64;
+  float* mine = blk_part + static_cast<int64_t>(blockIdx.x) * PART_STRIDE;
   for (int c = tid; c < T * H; c += THREADS) {
     float s = 0.f;
 #pragma unroll
@@ -308,43 +327,50 @@ __global__ void __launch_bounds__(THREADS, 1) pool_heads_kernel(const TailParams
   const int nb = gridDim.x;
   const int grp = blockIdx.x / p.group, n_groups = (nb + p.group - 1) / p.group;
   const int g0 = grp * p.group, g_cnt = (g0 + p.group <= nb ? p.group : nb - g0);
-  float* grp_part = p.blk_part + static_cast<int64_t>(nb) * PART_STRIDE;
+  float* grp_part = blk_part + static_cast<int64_t>(nb) * PART_STRIDE;
   float4* s_half = reinterpret_cast<float4*>(dsm + 4096);  // [2][256] float4 scratch
   __threadfence();
   __syncthreads();
-  if (tid == 0) s_ticket = atomicAdd(p.ticket + 1 + grp, 1u);
+  if (tid == 0) s_ticket = atomicAdd(ticket + 1 + grp, 1u);
   __syncthreads();
   if (s_ticket != static_cast<unsigned int>(g_cnt - 1)) return;
 #ifdef TOAD_TAIL_DEBUG
-  if (p.dbg_stop == 3) { if (tid == 0) p.ticket[1 + grp] = 0u; return; }
+  if (p.dbg_stop == 3) { if (tid == 0) ticket[1 + grp] = 0u; return; }
 #endif
   __threadfence();
   {
-    const float4 v = fold_partials(p.blk_part + static_cast<int64_t>(g0) * PART_STRIDE, g_cnt, &s_score[0][0], s_half, s_m, s_l);
+    const float4 v = fold_partials(blk_part + static_cast<int64_t>(g0) * PART_STRIDE, g_cnt, &s_score[0][0], s_half, s_m, s_l);
     float* gp = grp_part + static_cast<int64_t>(grp) * PART_STRIDE;
     if (tid < 256) reinterpret_cast<float4*>(gp)[tid] = v;
     if (tid < T) {
       gp[T * H + 2 * tid] = s_m[tid];
       gp[T * H + 2 * tid + 1] = s_l[tid];
     }
-    if (tid == 0) p.ticket[1 + grp] = 0u;  // ready for the next launch on this workspace
+    if (tid == 0) ticket[1 + grp] = 0u;  // ready for the next launch on this workspace
   }
   __threadfence();
   __syncthreads();
-  if (tid == 0) s_ticket = atomicAdd(p.ticket, 1u);
+  if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
   __syncthreads();
   if (s_ticket != static_cast<unsigned int>(n_groups - 1)) return;
 #ifdef TOAD_TAIL_DEBUG
-  if (p.dbg_stop == 4) { if (tid == 0) *p.ticket = 0u; return; }
+  if (p.dbg_stop == 4) { if (tid == 0) *ticket = 0u; return; }
 #endif
   __threadfence();
   const float4 pooled = fold_partials(grp_part, n_groups, &s_score[0][0], s_half, s_m, s_l);
+  // this slide's result blocks
+  float* const o_stats = p.stats + slide * 2 * T;
+  float* const o_feat = p.features + static_cast<int64_t>(slide) * T * (H + 1);
+  float* const o_logits = p.logits + static_cast<int64_t>(slide) * p.n_classes;
+  float* const o_prob = p.y_prob + static_cast<int64_t>(slide) * p.n_classes;
+  float* const o_slogits = p.site_logits + slide * 2;
+  float* const o_sprob = p.site_prob + slide * 2;
   if (tid < T) {
-    p.stats[2 * tid] = s_m[tid];
-    p.stats[2 * tid + 1] = s_l[tid];
+    o_stats[2 * tid] = s_m[tid];
+    o_stats[2 * tid + 1] = s_l[tid];
   }
   float* s_feat = dsm;                 // [T][H+1]
-  const float sexv = __ldg(p.sex);
+  const float sexv = __ldg(p.sex + slide);
   if (tid < 256) {
     const int t = tid >> 7, j = (tid & 127) * 4;
     const float inv = 1.0f / s_l[t];
@@ -352,16 +378,16 @@ __global__ void __launch_bounds__(THREADS, 1) pool_heads_kernel(const TailParams
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       s_feat[t * (H + 1) + j + e] = v[e];
-      p.features[t * (H + 1) + j + e] = v[e];
+      o_feat[t * (H + 1) + j + e] = v[e];
     }
   }
   if (tid < T) {
     s_feat[tid * (H + 1) + H] = sexv;
-    p.features[tid * (H + 1) + H] = sexv;
+    o_feat[tid * (H + 1) + H] = sexv;
   }
   __syncthreads();
 #ifdef TOAD_TAIL_DEBUG
-  if (p.dbg_stop == 5) { if (tid == 0) *p.ticket = 0u; return; }
+  if (p.dbg_stop == 5) { if (tid == 0) *ticket = 0u; return; }
 #endif
   // heads: task 0 pooled vector -> classifier, task 1 -> site_classifier (model_toad.py:101,105).  The weight
   // rows were copied to shared memory by cp.async at kernel start (every CTA: only the last one gets here, and
@@ -390,9 +416,9 @@ __global__ void __launch_bounds__(THREADS, 1) pool_heads_kernel(const TailParams
   if (warp < 2) {  // warp 0: classifier softmax / top-1, warp 1: site (ties -> lowest index, like torch.topk)
     const int off = warp == 0 ? 0 : p.n_classes;
     const int cnt = warp == 0 ? p.n_classes : 2;
-    float* lg = warp == 0 ? p.logits : p.site_logits;
-    float* pr = warp == 0 ? p.y_prob : p.site_prob;
-    int64_t* hat = warp == 0 ? p.y_hat : p.site_hat;
+    float* lg = warp == 0 ? o_logits : o_slogits;
+    float* pr = warp == 0 ? o_prob : o_sprob;
+    int64_t* hat = (warp == 0 ? p.y_hat : p.site_hat) + slide;
     float mx = -INFINITY;
     int arg = 0x7fffffff;
     for (int c = lane; c < cnt; c += 32) {
@@ -412,7 +438,7 @@ __global__ void __launch_bounds__(THREADS, 1) pool_heads_kernel(const TailParams
     for (int c = lane; c < cnt; c += 32) pr[c] = expf(s_logit[off + c] - mx) / sum;
     if (lane == 0) hat[0] = arg == 0x7fffffff ? 0 : arg;
   }
-  if (tid == 0) *p.ticket = 0u;  // ready for the next launch on this workspace
+  if (tid == 0) *ticket = 0u;  // ready for the next launch on this workspace
 }
 
 template <int H_MODE>
@@ -420,7 +446,15 @@ int launch_tail(const TailParams& p_in, int sms, cudaStream_t stream) {
   TailParams p = p_in;
   if (p.N <= 0) return TOAD_ERR_ARG;
   if (p.n_classes + 2 > 1024) return TOAD_ERR_UNSUPPORTED;
-  const int nb = tail_blocks(p.N, sms);
+  if (p.batch.n_slides == 0) {  // plain forward: one slide covering all N rows
+    p.batch.n_slides = 1;
+    p.batch.off[0] = 0;
+    p.batch.off[1] = p.N;
+    p.stride = p.N;
+  }
+  if (p.batch.n_slides < 1 || p.batch.n_slides > MAX_BATCH) return TOAD_ERR_ARG;
+  const int nb = tail_blocks(p.N, sms);   // (N = rows of the largest slide)
+  p.parts_per_slide = nb + MAX_GROUPS;
   p.group = tail_group(nb);
 #ifdef TOAD_TAIL_DEBUG
   { const char* e = getenv("TOAD_TAIL_STOP"); p.dbg_stop = e ? atoi(e) : 0; }
@@ -432,7 +466,7 @@ int launch_tail(const TailParams& p_in, int sms, cudaStream_t stream) {
   const int dyn = (WARPS * T * H + (p.heads_in_smem ? (p.n_classes + 2) * (H + 1) : 0)) * static_cast<int>(sizeof(float));
   auto kern = pool_heads_kernel<H_MODE>;
   TOAD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-  kern<<<nb, THREADS, dyn, stream>>>(p);
+  kern<<<dim3(nb, p.batch.n_slides), THREADS, dyn, stream>>>(p);
   TOAD_CUDA_TRY(cudaGetLastError());
   return 0;
 }

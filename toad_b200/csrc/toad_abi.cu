@@ -52,18 +52,18 @@ struct FwdWs {
   size_t bytes;
 };
 
-FwdWs carve_fwd(const toad_dims_t* d, int64_t n, uint32_t flags, void* base) {
+FwdWs carve_fwd(const toad_dims_t* d, int64_t n, uint32_t flags, void* base, int n_slides = 1) {
   FwdWs w{};
   Carver c(base);
   const int64_t Hd = d->hid_dim, D = d->attn_dim, L = d->in_dim;
   const bool simt = (flags & TOAD_FLAG_SIMT_FP32) != 0;
-  w.ticket = c.take<unsigned int>(64);
+  w.ticket = c.take<unsigned int>(64 * tail::MAX_BATCH);  // (fixed size: the weight planes behind it keep their offsets)
   if (!simt) {  // weight planes first: their offsets do not depend on n (TOAD_FLAG_REUSE_WEIGHT_PLANES)
     w.w1_hi = c.take<bf16>(Hd * L);  w.w1_lo = c.take<bf16>(Hd * L);
     w.w2_hi = c.take<bf16>(Hd * Hd); w.w2_lo = c.take<bf16>(Hd * Hd);
     w.wab_hi = c.take<bf16>(2 * D * Hd); w.wab_lo = c.take<bf16>(2 * D * Hd);
   }
-  w.blk_part = c.take<float>(static_cast<size_t>(tail::tail_blocks(n, kSMs) + tail::MAX_GROUPS) * tail::PART_STRIDE);
+  w.blk_part = c.take<float>(static_cast<size_t>(tail::tail_blocks(n, kSMs) + tail::MAX_GROUPS) * tail::PART_STRIDE * n_slides);
   w.n_parts = simt ? 1 : 2 * static_cast<int>(D / kGateHalf);  // (tile, epilogue warp set) partials
   w.part = c.take<float>(static_cast<size_t>(w.n_parts) * n * d->n_tasks);
   if (!simt) {
@@ -106,8 +106,16 @@ int check_ws(const void* ws, size_t have, size_t need) {
 
 int run_tail(const toad_dims_t* d, const toad_params_t* P, int64_t n, const float* sex, const toad_fwd_out_t* out,
              const FwdWs& w, const float* h_f32, const bf16* h_hi, const bf16* h_lo, bool attention_only,
-             cudaStream_t st) {
+             cudaStream_t st, const tail::TailBatch* batch = nullptr) {
   tail::TailParams t{};
+  if (batch != nullptr) {  // several slides back to back in the n rows: grid.y = slide, grid.x sized by the largest
+    t.batch = *batch;
+    t.stride = n;
+    int64_t largest = 0;
+    for (int s = 0; s < batch->n_slides; ++s)
+      if (batch->off[s + 1] - batch->off[s] > largest) largest = batch->off[s + 1] - batch->off[s];
+    n = largest;
+  }
   t.part = w.part; t.n_parts = w.n_parts; t.bc = P->bc; t.a_raw = out->a_raw;
   t.h_f32 = h_f32; t.h_hi = h_hi; t.h_lo = h_lo; t.N = n; t.sex = sex;
   t.wcls = P->wcls; t.bcls = P->bcls; t.n_classes = d->n_classes; t.wsite = P->wsite; t.bsite = P->bsite;
@@ -165,7 +173,7 @@ extern "C" int toad_fwd_workspace_bytes(const toad_dims_t* d, int64_t n, uint32_
 
 static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t n, const float* sex,
                     const toad_fwd_out_t* out, const toad_saved_t* saved, void* workspace, size_t workspace_bytes,
-                    uint32_t flags, toad_stream_t stream, Prof* prof) {
+                    uint32_t flags, toad_stream_t stream, Prof* prof, const tail::TailBatch* batch = nullptr) {
   TOAD_TRY(check_dims(d));
   if (P == nullptr || x == nullptr || out == nullptr || out->a_raw == nullptr || n <= 0) return TOAD_ERR_ARG;
   const bool attn_only = (flags & TOAD_FLAG_ATTENTION_ONLY) != 0;
@@ -180,11 +188,11 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
   if (save && !simt && (!saved->h1_hi || !saved->h1_lo || !saved->h_hi || !saved->h_lo)) return TOAD_ERR_ARG;
   if ((flags & TOAD_FLAG_DROPOUT) && (!save || saved->dropout_p < 0.f || saved->dropout_p >= 1.f)) return TOAD_ERR_ARG;
   const DropoutCfg drop = make_drop(saved, flags);
-  FwdWs w = carve_fwd(d, n, flags, workspace);
+  FwdWs w = carve_fwd(d, n, flags, workspace, batch != nullptr ? batch->n_slides : 1);
   TOAD_TRY(check_ws(workspace, workspace_bytes, w.bytes));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int Hd = d->hid_dim, D = d->attn_dim, L = d->in_dim;
-  TOAD_CUDA_TRY(cudaMemsetAsync(w.ticket, 0, 64 * sizeof(unsigned int), st));
+  TOAD_CUDA_TRY(cudaMemsetAsync(w.ticket, 0, 64 * tail::MAX_BATCH * sizeof(unsigned int), st));
 
   if (flags & TOAD_FLAG_SIMT_FP32) {
     float* h1 = save ? saved->h1 : w.h1;
@@ -202,7 +210,7 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
     TOAD_TRY((simt::launch_sgemm<true, true, simt::EPI_BIAS_SIGMOID>(with_drop(linear_params(h, Hd, P->wb, P->bb, b, n, D, Hd), DROP_B), 1, st)));
     TOAD_TRY(tail::launch_attn_c(a, b, P->wc, w.part, n, D, d->n_tasks, st));
     TOAD_TRY(prof_mark(prof, 4, st));
-    TOAD_TRY(run_tail(d, P, n, sex, out, w, h, nullptr, nullptr, attn_only, st));
+    TOAD_TRY(run_tail(d, P, n, sex, out, w, h, nullptr, nullptr, attn_only, st, batch));
     TOAD_TRY(prof_mark(prof, 5, st));
     if (prof != nullptr && prof->n < prof->max_calls) prof->n++;
     return 0;
@@ -259,7 +267,7 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
     else TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_GATE, 2>(g, h_hi, h_lo, w.wab_hi, w.wab_lo, st)));
   }
   TOAD_TRY(prof_mark(prof, 4, st));
-  TOAD_TRY(run_tail(d, P, n, sex, out, w, nullptr, h_hi, h_lo, attn_only, st));
+  TOAD_TRY(run_tail(d, P, n, sex, out, w, nullptr, h_hi, h_lo, attn_only, st, batch));
   TOAD_TRY(prof_mark(prof, 5, st));
   if (prof != nullptr && prof->n < prof->max_calls) prof->n++;
   return 0;
@@ -269,6 +277,32 @@ extern "C" int toad_fwd(const toad_dims_t* d, const toad_params_t* P, const floa
                         const toad_fwd_out_t* out, const toad_saved_t* saved, void* workspace, size_t workspace_bytes,
                         uint32_t flags, toad_stream_t stream) {
   return fwd_impl(d, P, x, n, sex, out, saved, workspace, workspace_bytes, flags, stream, nullptr);
+}
+
+static int make_batch(const int64_t* offsets, int32_t n_slides, tail::TailBatch* tb) {
+  if (offsets == nullptr || n_slides < 1 || n_slides > tail::MAX_BATCH || offsets[0] != 0) return TOAD_ERR_ARG;
+  tb->n_slides = n_slides;
+  for (int s = 0; s <= n_slides; ++s) tb->off[s] = offsets[s];
+  for (int s = 0; s < n_slides; ++s)
+    if (offsets[s + 1] <= offsets[s]) return TOAD_ERR_ARG;  // empty slide: softmax over zero patches
+  return 0;
+}
+
+extern "C" int toad_fwd_batch_workspace_bytes(const toad_dims_t* d, int64_t n_total, int32_t n_slides, uint32_t flags,
+                                              size_t* bytes) {
+  TOAD_TRY(check_dims(d));
+  if (bytes == nullptr || n_total <= 0 || n_slides < 1 || n_slides > tail::MAX_BATCH) return TOAD_ERR_ARG;
+  *bytes = carve_fwd(d, n_total, flags, nullptr, n_slides).bytes;
+  return 0;
+}
+
+extern "C" int toad_fwd_batch(const toad_dims_t* d, const toad_params_t* P, const float* x, const int64_t* offsets,
+                              int32_t n_slides, const float* sex, const toad_fwd_out_t* out, void* workspace,
+                              size_t workspace_bytes, uint32_t flags, toad_stream_t stream) {
+  tail::TailBatch tb{};
+  TOAD_TRY(make_batch(offsets, n_slides, &tb));
+  if (flags & (TOAD_FLAG_SAVE_ACTS | TOAD_FLAG_DROPOUT | TOAD_FLAG_ATTENTION_ONLY)) return TOAD_ERR_UNSUPPORTED;  // eval only
+  return fwd_impl(d, P, x, offsets[n_slides], sex, out, nullptr, workspace, workspace_bytes, flags, stream, nullptr, &tb);
 }
 
 extern "C" int toad_fwd_profiled(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t n,

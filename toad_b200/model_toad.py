@@ -219,6 +219,47 @@ class TOAD_fc_mtl_concat(nn.Module):
     def _dropout_active(self) -> bool:
         return self.dropout and self.training
 
+    @torch.no_grad()
+    def forward_batch(self, h: torch.Tensor, lengths, sex: torch.Tensor, return_features: bool = False) -> List[Dict[str, torch.Tensor]]:
+        """Eval forward of several slides at once (beyond the reference's surface, which always runs batch_size 1):
+        `h` is the bags concatenated along dim 0 -- what collate_MIL_mtl_concat (utils/utils.py:30-35) builds --,
+        `lengths` their patch counts, `sex` one value per slide.  Returns one results_dict per slide, identical to
+        `forward(h_i, sex_i)` up to fp32 summation order in the pooled quantities (raw scores are bit-identical).
+        Small bags share one set of trunk launches and fill the GPU together; chunks of 16 slides per call."""
+        if self._dropout_active():
+            raise RuntimeError("forward_batch is an inference path: call model.eval() first")
+        params = self._param_list()
+        lengths = [int(n) for n in lengths]
+        sex_f = sex.reshape(-1).to(device=h.device, dtype=torch.float32).contiguous()
+        if sex_f.numel() != len(lengths):
+            raise ValueError("sex must hold one value per slide")
+        pkey = tuple((p.data_ptr(), p._version) for p in params)
+        pc = self.__dict__.get("_pcache")
+        if pc is None or pc[0] != pkey:
+            det = [p.detach() for p in params]
+            pc = (pkey, det, ops._params_struct(self._dims, det))
+            self.__dict__["_pcache"] = pc
+        results: List[Dict[str, torch.Tensor]] = []
+        row = 0
+        for s0 in range(0, len(lengths), _lib.MAX_BATCH):
+            chunk = lengths[s0:s0 + _lib.MAX_BATCH]
+            n_chunk = sum(chunk)
+            out = ops.toad_fwd_batch(self._dims, pc[1], h[row:row + n_chunk], chunk, sex_f[s0:s0 + len(chunk)], self._ws,
+                                     _default_flags() | self._weight_plane_flag(params, h.device, pkey), pstruct=pc[2])
+            self._note_planes_written()
+            off = 0
+            for i, n in enumerate(chunk):
+                r: Dict[str, torch.Tensor] = {}
+                if return_features:
+                    r["features"] = out["features"][i]
+                r.update({"logits": out["logits"][i:i + 1], "Y_prob": out["y_prob"][i:i + 1], "Y_hat": out["y_hat"][i],
+                          "site_logits": out["site_logits"][i:i + 1], "site_prob": out["site_prob"][i:i + 1],
+                          "site_hat": out["site_hat"][i], "A": out["a_raw"][:, off:off + n]})
+                results.append(r)
+                off += n
+            row += n_chunk
+        return results
+
     def forward(self, h: torch.Tensor, sex: torch.Tensor, return_features: bool = False,
                 attention_only: bool = False):
         params = self._param_list()

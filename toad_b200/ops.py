@@ -21,7 +21,7 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def _check_dev_f32(t: torch.Tensor, name: str, shape: Optional[Sequence[int]] = None) -> None:
+def _check_dev_f32(t: torch.Tensor, name: str, shape: Optional[Sequence[int]] = None, align: int = 16) -> None:
     if not isinstance(t, torch.Tensor):
         raise ValueError("%s must be a torch.Tensor" % name)
     if not t.is_cuda:
@@ -30,8 +30,8 @@ def _check_dev_f32(t: torch.Tensor, name: str, shape: Optional[Sequence[int]] = 
         raise ValueError("%s must be float32, got %s" % (name, t.dtype))
     if not t.is_contiguous():
         raise ValueError("%s must be contiguous" % name)
-    if t.data_ptr() % 16 != 0:
-        raise ValueError("%s must be 16-byte aligned (the kernels use 128-bit loads)" % name)
+    if t.data_ptr() % align != 0:
+        raise ValueError("%s must be %d-byte aligned (the kernels use 128-bit loads)" % (name, align))
     if shape is not None and tuple(t.shape) != tuple(shape):
         raise ValueError("%s must have shape %s, got %s" % (name, tuple(shape), tuple(t.shape)))
 
@@ -148,7 +148,7 @@ def toad_fwd(dims: Dims, params: Sequence[torch.Tensor], x: torch.Tensor, sex: t
         raise ValueError("empty bag: softmax over zero patches is undefined")
     attn_only = bool(flags & _lib.FLAG_ATTENTION_ONLY)
     if not attn_only:
-        _check_dev_f32(sex, "sex")
+        _check_dev_f32(sex, "sex", align=4)      # read as scalars: any view of a float tensor will do
         if sex.numel() != 1:
             raise ValueError("sex must hold one value")
     if out is None:
@@ -177,6 +177,50 @@ def toad_fwd(dims: Dims, params: Sequence[torch.Tensor], x: torch.Tensor, sex: t
         _lib.check(lib.toad_fwd(*args), "toad_fwd")
     else:
         _lib.check(lib.toad_fwd_profiled(*(args + [prof])), "toad_fwd_profiled")
+    return out
+
+
+def toad_fwd_batch(dims: Dims, params: Sequence[torch.Tensor], x: torch.Tensor, lengths: Sequence[int], sex: torch.Tensor,
+                   ws: Workspace, flags: int = 0, pstruct: Optional[Params] = None) -> Dict[str, torch.Tensor]:
+    """Eval forward of up to 16 slides stored back to back in x [sum(lengths), in_dim] (toad_fwd_batch): one set of
+    trunk launches for all of them.  Returns slide-major tensors: a_raw [T, n_total], features [S, T, H+1],
+    logits / y_prob [S, C], y_hat / site_hat [S, 1, 1], site_logits / site_prob [S, 2], softmax_stats [S, T, 2]."""
+    lib = _lib.load()
+    _check_dev_f32(x, "h")
+    S = len(lengths)
+    if not (1 <= S <= _lib.MAX_BATCH):
+        raise ValueError("a batch holds 1..%d slides, got %d" % (_lib.MAX_BATCH, S))
+    if any(int(n) < 1 for n in lengths):
+        raise ValueError("empty bag: softmax over zero patches is undefined")
+    n_total = int(sum(int(n) for n in lengths))
+    if x.dim() != 2 or x.shape[1] != dims.in_dim or x.shape[0] != n_total:
+        raise ValueError("h must be [sum(lengths) = %d, %d], got %s" % (n_total, dims.in_dim, tuple(x.shape)))
+    _check_dev_f32(sex, "sex", (S,), align=4)
+    T, Hd, Cn = dims.n_tasks, dims.hid_dim, dims.n_classes
+    f32 = dict(dtype=torch.float32, device=x.device)
+    out = {"a_raw": torch.empty((T, n_total), **f32), "features": torch.empty((S, T, Hd + 1), **f32),
+           "logits": torch.empty((S, Cn), **f32), "y_prob": torch.empty((S, Cn), **f32),
+           "y_hat": torch.empty((S, 1, 1), dtype=torch.int64, device=x.device),
+           "site_logits": torch.empty((S, 2), **f32), "site_prob": torch.empty((S, 2), **f32),
+           "site_hat": torch.empty((S, 1, 1), dtype=torch.int64, device=x.device),
+           "softmax_stats": torch.empty((S, T, 2), **f32)}
+    p = pstruct if pstruct is not None else _params_struct(dims, params)
+    offs = (C.c_int64 * (S + 1))()
+    acc = 0
+    for i, n in enumerate(lengths):
+        offs[i] = acc
+        acc += int(n)
+    offs[S] = acc
+    nbytes = C.c_size_t()
+    _lib.check(lib.toad_fwd_batch_workspace_bytes(C.byref(dims), n_total, S, flags, C.byref(nbytes)),
+               "toad_fwd_batch_workspace_bytes")
+    if (flags & _lib.FLAG_REUSE_WEIGHT_PLANES) and (ws.buf is None or ws.buf.numel() < nbytes.value
+                                                    or ws.buf.device != x.device):
+        flags &= ~_lib.FLAG_REUSE_WEIGHT_PLANES
+    wptr, wsize = ws.get(nbytes.value, x.device)
+    o = _out_struct(out)
+    _lib.check(lib.toad_fwd_batch(C.byref(dims), C.byref(p), x.data_ptr(), offs, S, sex.data_ptr(), C.byref(o), wptr, wsize,
+                                  flags, _stream()), "toad_fwd_batch")
     return out
 
 
