@@ -5,8 +5,9 @@
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
 
 One step = one pass of the hot path over `slides_per_step` synthetic slides (N x 1024 fp32
-each) through `toad_b200.pipeline.ResidentRunner` (three slides in flight on three CUDA streams, so one
-slide's partially filled last waves overlap the others' kernels).  `value` = whole-job slides/s with
+each): by default one `TOAD_fc_mtl_concat.forward_batch` call over the step's 16 slides (bags back to back, one set
+of trunk launches, per-slide pooling); `--batch 1` runs one forward per slide through
+`toad_b200.pipeline.ResidentRunner` (three slides in flight on three CUDA streams).  `value` = whole-job slides/s with
 bags resident in HBM (4 distinct 205 MB bags per GPU, larger than L2, rotated); `value_single_stream`
 = the same steps strictly serial; `e2e` = the same metric through the public API with pinned host
 bags copied H2D inside the timed region and results read back.  Prints ONE JSON line.
@@ -205,7 +206,9 @@ def run_ours(args):
     from toad_b200.pipeline import ResidentRunner
     runner = ResidentRunner(model, n_streams=args.streams, device=dev)
 
-    B = max(1, min(args.batch, 16))
+    B = max(1, min(args.batch, 16, S))
+    while S % B:
+        B -= 1
     if B > 1:   # small bags: B slides back to back per forward_batch call (one set of trunk launches for all of them)
         cats = [torch.cat([bags[(j + b) % n_bags] for b in range(B)], 0) for j in range(2)]
         sexes_b = torch.ones(B, device=dev)
@@ -304,15 +307,17 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16x3-split (fp32 accumulate; fp32-class accuracy)", "data": "synthetic",
             "config": {"workload": "TOAD_fc_mtl_concat forward (eval), N=%d x %d fp32, big, n_classes=18" % (n, WIDTH),
-                       "slides_per_step": S, "slides_in_flight": args.streams, "slides_per_call": B,
+                       "slides_per_step": S, "slides_in_flight": args.streams if B == 1 else 1, "slides_per_call": B,
                        "parallelism": "one slide per GPU, replicas (no collective in eval)",
-                       "l2_policy": "4 distinct 205 MB bags per GPU rotated (inputs larger than the 126 MB L2)"},
+                       "l2_policy": "%d distinct %.0f MB bags per GPU rotated (inputs larger than the 126 MB L2)" % (
+                           n_bags, n * WIDTH * 4 / 1e6)},
             "clocks": sampler.summary() if sampler else None,
             "e2e": {"value": e2e_value, "unit": "slides/s", "h2d_bytes_per_step": int(streamer.h2d_bytes / max(e2e_steps, 1e-9)),
                     "d2h_bytes_per_step": int(streamer.d2h_bytes / max(e2e_steps, 1e-9)), "slides": e2e_slides,
                     "note": "pinned host bags, double-buffered H2D overlapped with compute (toad_b200.pipeline.SlideStreamer)"},
             "value_single_stream": value_single_stream,   # the same K steps strictly serial on one stream
-            "gpu_launches": 4 * S * args.steps + 3,   # per slide: 3 tcgen05 GEMM + 1 pooling tail (+ 3 weight-split launches once)
+            # per forward / forward_batch call: 3 tcgen05 GEMMs + 1 pooling launch (+ 3 weight-split launches once)
+            "gpu_launches": 4 * (S // B if B > 1 else S) * args.steps + 3,
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16x3_kernel<512,A_F32,EPI_LINEAR,2> (fc1, 44% of FLOPs)",
                          "achieved": fc1_serial_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                          "frac": fc1_serial_tflops / pk["bf16_tflops"], "peak_source": pk["src"] + " bf16 burst",
@@ -339,6 +344,8 @@ def run_ours(args):
                                  "unit": "GB/s", "frac": tail_gbs / pk["hbm_gbs"],
                                  "note": "CUDA-event stage time (includes the launch gap after the gate GEMM); ~10 us of it is "
                                          "the serial two-level merge + heads after the streaming phase (DESIGN.md section 5)"}
+        if B > 1:   # forward_batch has no per-stage events: the per-kernel times come from the serial pass only
+            line["roofline"].pop("in_flight", None)
         if world == 1 and not args.no_eager_baseline:
             line["eager_gpu_baseline"] = eager_gpu_leg(dev, n)
         if world == 1 and not args.no_resnet:
@@ -420,7 +427,7 @@ def main():
     ap.add_argument("--n-patches", type=int, default=N_PATCHES)
     ap.add_argument("--slides-per-step", type=int, default=16)
     ap.add_argument("--streams", type=int, default=3, help="slides in flight per GPU (toad_b200.pipeline.ResidentRunner)")
-    ap.add_argument("--batch", type=int, default=1,
+    ap.add_argument("--batch", type=int, default=16,
                     help="slides per forward_batch call (<= 16, must divide --slides-per-step); 1 = one forward per slide")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-resnet", action="store_true")
