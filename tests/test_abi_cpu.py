@@ -83,6 +83,18 @@ def test_workspace_queries_and_argument_errors(lib):
     assert lib.toad_linear_workspace_bytes(128, 64, 64, C.byref(n)) == 0 and n.value > 0
     assert lib.toad_attn_gated_workspace_bytes(1024, 256, 1, 256, 0, C.byref(n)) == 0
     assert lib.toad_attn_gated_workspace_bytes(1000, 256, 1, 256, 0, C.byref(n)) == -3
+    # batched forward: 1..16 slides per call, scratch grows with the slide count, offsets are validated before any launch
+    assert lib.toad_fwd_batch_workspace_bytes(C.byref(d), 50000, 1, 0, C.byref(n)) == 0 and n.value == tc_bytes
+    one = n.value
+    assert lib.toad_fwd_batch_workspace_bytes(C.byref(d), 50000, 16, 0, C.byref(n)) == 0 and n.value > one
+    assert lib.toad_fwd_batch_workspace_bytes(C.byref(d), 50000, 17, 0, C.byref(n)) == -1
+    assert lib.toad_fwd_batch_workspace_bytes(C.byref(d), 50000, 0, 0, C.byref(n)) == -1
+    offs = (C.c_int64 * 3)(0, 10, 10)                                                  # second slide is empty
+    assert lib.toad_fwd_batch(C.byref(d), None, None, offs, 2, None, None, None, 0, 0, None) == -1
+    offs = (C.c_int64 * 3)(5, 10, 20)                                                  # offsets[0] != 0
+    assert lib.toad_fwd_batch(C.byref(d), None, None, offs, 2, None, None, None, 0, 0, None) == -1
+    assert lib.toad_topk_workspace_bytes(200000, 1000, C.byref(n)) == 0 and 0 < n.value < (4 << 20)
+    assert lib.toad_gather_rows(None, 10, 8, None, 1, None, None) == -1
 
 
 def test_module_refuses_cpu_tensors():
