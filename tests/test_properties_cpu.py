@@ -76,3 +76,36 @@ def test_topk_accuracy_matches_the_reference_formula():
     ref = [float(correct[:k].reshape(-1).float().sum(0) / 200) for k in topk]
     ours = topk_accuracy(probs.numpy(), labels.numpy(), topk)
     np.testing.assert_allclose(ours, ref, rtol=0, atol=1e-6)   # the reference accumulates in fp32
+
+
+def test_topk_accuracy_properties():
+    """Monotone in k, 1.0 at k = n_classes, and k = 1 equals plain argmax accuracy."""
+    import numpy as np
+    from toad_b200.eval import topk_accuracy
+    rng = np.random.default_rng(3)
+    probs = rng.random((300, 18))
+    labels = rng.integers(0, 18, 300)
+    acc = topk_accuracy(probs, labels, tuple(range(1, 19)))
+    assert all(a <= b + 1e-15 for a, b in zip(acc, acc[1:])) and acc[-1] == 1.0
+    assert acc[0] == float((probs.argmax(1) == labels).mean())
+
+
+def test_forward_result_buffers_layout():
+    """ops.alloc_fwd_out: reference shapes / dtypes, every tensor contiguous and 16-byte aligned (the C ABI writes them
+    in place), the differentiable outputs in storage of their own."""
+    import torch
+    from toad_b200 import ops
+    d = ops.make_dims(1024, 512, 384, 18)
+    out = ops.alloc_fwd_out(d, 777, torch.device("cpu"))
+    shapes = {"a_raw": (2, 777), "features": (2, 513), "logits": (1, 18), "y_prob": (1, 18), "y_hat": (1, 1),
+              "site_logits": (1, 2), "site_prob": (1, 2), "site_hat": (1, 1), "softmax_stats": (2, 2)}
+    assert set(out) == set(shapes)
+    for k, shp in shapes.items():
+        t = out[k]
+        assert tuple(t.shape) == shp and t.is_contiguous(), k
+        assert t.dtype == (torch.int64 if k.endswith("hat") else torch.float32), k
+        assert t.data_ptr() % (8 if k.endswith("hat") else 16) == 0, k
+    ptr = lambda t: t.untyped_storage().data_ptr()
+    others = [ptr(v) for k, v in out.items() if k not in ("logits", "site_logits")]
+    assert ptr(out["logits"]) not in others and ptr(out["site_logits"]) not in others
+    assert ptr(out["logits"]) != ptr(out["site_logits"])
