@@ -2,7 +2,7 @@
 
 Run in the authoring container only (needs /root/reference, CPU torch):
 
-    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py [case names ...]
 
 The reference module (`/root/reference/models/model_toad.py`) is imported by
 path, loaded with seeded parameters from `oracle.toad_oracle.make_params`
@@ -26,28 +26,13 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 from oracle import toad_oracle as O  # noqa: E402
 
-REF = "/root/reference"
+from tests.golden.ref_import import load_reference_model_toad  # noqa: E402
 
 
 def import_reference():
-    """Import the reference's model module without letting it shadow ours."""
-    saved = list(sys.path)
-    saved_mods = {k: v for k, v in sys.modules.items() if k == "models" or k.startswith("models.")
-                  or k == "utils" or k.startswith("utils.")}
-    for k in saved_mods:
-        del sys.modules[k]
-    sys.path.insert(0, REF)
-    try:
-        import importlib
-        mt = importlib.import_module("models.model_toad")
-        assert mt.__file__.startswith(REF), mt.__file__
-        return mt
-    finally:
-        sys.path[:] = saved
-        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")
-                  or k == "utils" or k.startswith("utils.")]:
-            del sys.modules[k]
-        sys.modules.update(saved_mods)
+    """The reference's model module, loaded by file path (see ref_import.py: the repo's own `models` package
+    shadows the reference's under any sys.path order)."""
+    return load_reference_model_toad()
 
 
 def grad_digest(g: np.ndarray) -> dict:
@@ -58,7 +43,9 @@ def grad_digest(g: np.ndarray) -> dict:
 
 
 def run_case(mt, name, n, size_arg, n_classes, pseed, xseed, sex, bias_std=0.0,
-             kind="randn", grads=False, label=3, site=1, store_A64=True):
+             kind="randn", grads=False, label=3, site=1, store_A64=True, light=False, out_dir=None):
+    """light=True: gradient-parity fixture for a large bag -- drops the per-patch arrays (A, attention_only) so the
+    file stays small; logits / features / loss / gradient digests remain."""
     params = O.make_params(pseed, size_arg, n_classes, bias_std)
     x = O.make_bag(xseed, n, kind=kind)
     torch.manual_seed(0)
@@ -73,8 +60,11 @@ def run_case(mt, name, n, size_arg, n_classes, pseed, xseed, sex, bias_std=0.0,
         r32 = model(torch.from_numpy(x), torch.tensor([float(sex)]), return_features=True)
         a_only = model(torch.from_numpy(x), torch.tensor([float(sex)]), attention_only=True)
     for k, v in r32.items():
+        if light and k == "A":
+            continue
         out["f32_" + k] = v.numpy()
-    out["f32_attention_only"] = a_only.numpy()
+    if not light:
+        out["f32_attention_only"] = a_only.numpy()
     m64 = mt.TOAD_fc_mtl_concat(size_arg=size_arg, n_classes=n_classes)
     m64.load_state_dict(sd, strict=True)
     m64 = m64.double().eval()
@@ -83,7 +73,7 @@ def run_case(mt, name, n, size_arg, n_classes, pseed, xseed, sex, bias_std=0.0,
     with torch.no_grad():
         r64 = m64(x64, s64, return_features=True)
     for k, v in r64.items():
-        if k == "A" and not store_A64:
+        if k == "A" and (light or not store_A64):
             continue
         out["f64_" + k] = v.numpy()
     if grads:
@@ -96,9 +86,10 @@ def run_case(mt, name, n, size_arg, n_classes, pseed, xseed, sex, bias_std=0.0,
         for k, prm in m64.named_parameters():
             for dk, dv in grad_digest(prm.grad.numpy()).items():
                 out["g64_%s__%s" % (k, dk)] = dv
-    path = os.path.join(HERE, name + ".npz")
+    path = os.path.join(out_dir or HERE, name + ".npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+    return path
 
 
 def run_attn_gated(mt, name, n, L, D, n_tasks, seed):
@@ -117,18 +108,34 @@ def run_attn_gated(mt, name, n, L, D, n_tasks, seed):
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
+# name -> keyword arguments of run_case (the committed fixtures; tests/test_oracle_golden.py regenerates one of the
+# small ones from the reference and checks bit-equality with the committed file)
+CASES = {}
+for _n in (1, 2, 255, 256, 257):
+    CASES["toad_big_n%d" % _n] = dict(n=_n, size_arg="big", n_classes=18, pseed=0, xseed=100 + _n, sex=_n % 2,
+                                      bias_std=0.02 if _n in (2, 257) else 0.0, grads=(_n in (1, 257)))
+CASES["toad_small_n300"] = dict(n=300, size_arg="small", n_classes=2, pseed=3, xseed=7, sex=1, bias_std=0.02, grads=True,
+                                label=1, site=0)
+CASES["toad_big_n1000_relu"] = dict(n=1000, size_arg="big", n_classes=18, pseed=0, xseed=9, sex=0, kind="relu", grads=True)
+CASES["toad_big_n10000"] = dict(n=10000, size_arg="big", n_classes=18, pseed=0, xseed=100, sex=0)
+CASES["toad_big_n50000"] = dict(n=50000, size_arg="big", n_classes=18, pseed=0, xseed=150, sex=1)
+# backward parity at config-4 bag sizes (split-K slices, the 74-pair schedule and the segmented reductions behave
+# differently from the N <= 1000 cases): gradient digests only
+CASES["toad_big_n10000_grads"] = dict(n=10000, size_arg="big", n_classes=18, pseed=0, xseed=100, sex=0, bias_std=0.02,
+                                      grads=True, label=7, site=0, light=True)
+CASES["toad_big_n37123_grads"] = dict(n=37123, size_arg="big", n_classes=18, pseed=0, xseed=371, sex=1, bias_std=0.02,
+                                      kind="relu", grads=True, label=11, site=1, light=True)
+
+
 def main():
     mt = import_reference()
     torch.set_num_threads(os.cpu_count())
-    run_attn_gated(mt, "attn_gated_default_n256", 256, 1024, 256, 1, seed=11)
-    for n in (1, 2, 255, 256, 257):
-        run_case(mt, "toad_big_n%d" % n, n, "big", 18, pseed=0, xseed=100 + n, sex=n % 2,
-                 bias_std=0.02 if n in (2, 257) else 0.0, grads=(n in (1, 257)))
-    run_case(mt, "toad_small_n300", 300, "small", 2, pseed=3, xseed=7, sex=1, bias_std=0.02, grads=True,
-             label=1, site=0)
-    run_case(mt, "toad_big_n1000_relu", 1000, "big", 18, pseed=0, xseed=9, sex=0, kind="relu", grads=True)
-    run_case(mt, "toad_big_n10000", 10000, "big", 18, pseed=0, xseed=100, sex=0)
-    run_case(mt, "toad_big_n50000", 50000, "big", 18, pseed=0, xseed=150, sex=1)
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
+    if not only or "attn_gated_default_n256" in only:
+        run_attn_gated(mt, "attn_gated_default_n256", 256, 1024, 256, 1, seed=11)
+    for name, kw in CASES.items():
+        if not only or name in only:
+            run_case(mt, name, **kw)
 
 
 if __name__ == "__main__":

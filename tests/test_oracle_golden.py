@@ -37,6 +37,8 @@ def test_forward_fp64_matches_reference(name):
     params, x, sex = case_inputs(g)
     out = O.toad_forward(x, sex, params, dtype=np.float64)
     for k in ("logits", "Y_prob", "site_logits", "site_prob", "features", "A"):
+        if k == "A" and "f64_A" not in g:
+            continue     # "light" gradient fixtures of large bags carry no per-patch arrays
         np.testing.assert_allclose(out[k], g["f64_" + k], rtol=1e-9, atol=1e-11, err_msg=k)
     assert np.array_equal(out["Y_hat"], g["f64_Y_hat"]) and np.array_equal(out["site_hat"], g["f64_site_hat"])
 
@@ -45,8 +47,8 @@ def test_forward_fp64_matches_reference(name):
 def test_forward_fp32_matches_reference(name):
     """fp32 oracle vs fp32 reference: same math, different BLAS summation order."""
     g = load(name)
-    if int(g["meta_n"]) > 10000:
-        pytest.skip("fp32 numpy pass at 50k is covered by the fp64 test")
+    if int(g["meta_n"]) > 10000 or "f32_A" not in g:
+        pytest.skip("fp32 numpy pass at 50k / of the light gradient fixtures is covered by the fp64 test")
     params, x, sex = case_inputs(g)
     out = O.toad_forward(x, sex, params, dtype=np.float32)
     for k in ("logits", "site_logits", "features"):
@@ -166,3 +168,19 @@ def test_adam_restatement_matches_torch_optim_adam():
         O.adam_step(p, g, m, v2, step, 1e-2, (0.9, 0.999), 1e-8, 1e-3)
         for k in p:
             np.testing.assert_allclose(p[k], tp[k].detach().numpy(), rtol=1e-12, atol=1e-14, err_msg="%s step %d" % (k, step))
+
+
+def test_committed_fixture_regenerates_bit_identically_from_the_reference(tmp_path):
+    """The golden recipe still runs: tests/golden/make_golden.py loads the UNMODIFIED reference by file path and
+    reproduces a committed fixture bit for bit (authoring container only: skipped where /root/reference is absent)."""
+    from tests.golden import make_golden as MG
+    from tests.golden.ref_import import have_reference
+    if not have_reference():
+        pytest.skip("/root/reference is not present on this machine")
+    mt = MG.import_reference()
+    for name in ("toad_big_n257", "toad_small_n300"):
+        path = MG.run_case(mt, name, out_dir=str(tmp_path), **MG.CASES[name])
+        new, old = np.load(path), load(name)
+        assert sorted(new.files) == sorted(old)
+        for k in new.files:
+            assert np.array_equal(new[k], old[k]), (name, k)

@@ -89,10 +89,14 @@ class _ToadFunction(torch.autograd.Function):
                 saved["dropout_p"] = 0.25
         out = ops.toad_fwd(dims, params, h, sex, module._ws, flags, saved)
         ctx.module = module
+        # Nothing this Function RETURNS may be kept on ctx as a plain attribute: output -> grad_fn -> ctx -> output is
+        # a reference cycle Python's GC cannot see through (two differentiable outputs share the grad_fn), and it
+        # would pin the whole N x 1024 bag of every training step.  The backward only reads a_raw / features /
+        # softmax_stats (toad_bwd), which go through save_for_backward (autograd's cycle-free slot for outputs)
+        # together with the bag and the parameters; `saved` holds workspace-like buffers that are not outputs.
         ctx.saved = saved
-        ctx.out = out
-        ctx.h = h
-        ctx.params = params
+        ctx.n_classes = dims.n_classes
+        ctx.save_for_backward(h, out["a_raw"], out["features"], out["softmax_stats"], *params)
         res = (out["logits"], out["site_logits"], out["y_prob"], out["y_hat"], out["site_prob"], out["site_hat"],
                out["a_raw"], out["features"])
         ctx.mark_non_differentiable(*res[2:])
@@ -104,17 +108,24 @@ class _ToadFunction(torch.autograd.Function):
         dims = module._dims
         if ctx.saved is None:
             raise RuntimeError("toad_b200: backward called but the forward ran without saved activations")
+        h, a_raw, features, stats = ctx.saved_tensors[:4]
+        params = ctx.saved_tensors[4:]
         if dlogits is None:
-            dlogits = torch.zeros_like(ctx.out["logits"])
+            dlogits = torch.zeros((1, ctx.n_classes), dtype=torch.float32, device=h.device)
         if dsite_logits is None:
-            dsite_logits = torch.zeros_like(ctx.out["site_logits"])
-        flat = ops.toad_bwd(dims, ctx.params, ctx.h, ctx.out, ctx.saved, dlogits, dsite_logits, module._ws_bwd,
-                            flags=_default_flags())
+            dsite_logits = torch.zeros((1, 2), dtype=torch.float32, device=h.device)
+        fwd_out = {"a_raw": a_raw, "features": features, "softmax_stats": stats}
+        flat = ops.toad_bwd(dims, [p.detach() for p in params], h, fwd_out, ctx.saved, dlogits, dsite_logits,
+                            module._ws_bwd, flags=_default_flags())
         off = ops.param_offsets(dims)
         grads = tuple(flat[off[i]:off[i + 1]].view_as(p) if ctx.needs_input_grad[3 + i] else None
-                      for i, p in enumerate(ctx.params))
+                      for i, p in enumerate(params))
         ctx.saved = None
+        ctx.module = None
         return (None, None, None) + grads
+
+
+_DP_PREFIX = "attention_net.module."     # key form of checkpoints written by the reference on a multi-GPU host
 
 
 class TOAD_fc_mtl_concat(nn.Module):
@@ -148,6 +159,40 @@ class TOAD_fc_mtl_concat(nn.Module):
         self._prof = None  # optional ops.Profile handle (bench.py roofline leg)
         self._plane_state: Dict[int, object] = {}  # per stream: (parameter versions, workspace identity) of the cached planes
         self._plane_key_pending = None
+        self._register_load_state_dict_pre_hook(self._strip_dataparallel_prefix)
+        self.register_load_state_dict_post_hook(self._warn_missing_keys)
+
+    # -- checkpoint compatibility with the reference on multi-GPU hosts.  There `relocate()` wraps attention_net in
+    # nn.DataParallel (model_toad.py:79-82), so its checkpoints name the trunk `attention_net.module.<i>...`; the
+    # callers load with strict=False (eval_utils_mtl_concat.py:28-30), which would silently leave 10 of the 14 tensors at
+    # their random initial values.  Accept both key forms; never load a partial TOAD checkpoint silently.
+    @staticmethod
+    def _strip_dataparallel_prefix(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        dp = prefix + _DP_PREFIX
+        for k in [k for k in state_dict if k.startswith(dp)]:
+            state_dict[prefix + "attention_net." + k[len(dp):]] = state_dict.pop(k)
+
+    @staticmethod
+    def _warn_missing_keys(module, incompatible_keys):
+        if incompatible_keys.missing_keys:
+            import warnings
+            warnings.warn("toad_b200: load_state_dict left %d of this model's tensors untouched (strict=False hides "
+                          "this): %s" % (len(incompatible_keys.missing_keys), incompatible_keys.missing_keys[:4]),
+                          RuntimeWarning, stacklevel=3)
+
+    def state_dict_dataparallel(self) -> Dict[str, torch.Tensor]:
+        """state_dict() with the trunk keys in the `attention_net.module.*` form a multi-GPU reference process expects
+        (its attention_net is an nn.DataParallel, model_toad.py:79-82)."""
+        return {(_DP_PREFIX + k[len("attention_net."):]) if k.startswith("attention_net.") else k: v
+                for k, v in self.state_dict().items()}
+
+    def invalidate_weight_cache(self) -> None:
+        """Forget the cached bf16 weight planes / validated parameter block.  They are keyed on each parameter's
+        (data_ptr, autograd version); writes that bypass the version counter -- `p.data.copy_(...)`, `p.data.mul_()`,
+        raw-pointer writes from another library -- must be followed by this call (optimizers, `load_state_dict`,
+        in-place torch ops on the parameter itself and FusedTrainStep are tracked automatically)."""
+        self._plane_state.clear()
+        self.__dict__.pop("_pcache", None)
 
     # -- parameters in C-ABI (= state_dict) order
     def _param_list(self) -> List[torch.Tensor]:
