@@ -135,6 +135,9 @@ typedef struct {
 uint32_t toad_dropout_hash(uint64_t seed, uint32_t layer, uint64_t index);
 
 int toad_abi_version(void);
+/* Hash of the sources this binary was built from (toad_b200/build.py passes -DTOAD_BUILD_ID): the Python binding
+ * compares it with the sources on disk and rebuilds (or refuses to run) a stale library. */
+const char* toad_build_id(void);
 const char* toad_error_string(int code);
 
 /* Number of fp32 elements of the flat parameter/gradient buffer and the offset of

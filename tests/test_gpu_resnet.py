@@ -42,6 +42,39 @@ def test_resnet_matches_reference(name):
     np.testing.assert_allclose(y, ref, rtol=1e-2, atol=1e-3 * scale)
 
 
+def _oracle_features(params, x):
+    return RO.resnet50_baseline_forward(torch.from_numpy(x), params).numpy()
+
+
+def test_resnet_batch_crossing_the_stem_chunk():
+    """B = 300 at 64x64: the stem + layer1 loop runs two chunks (256 + 44 images, toad_resnet_fwd) whose layer1 outputs
+    land in slices of one buffer; every image is compared with the oracle (the reference's own CPU arithmetic)."""
+    params = RO.make_params(1)
+    x = RO.make_images(21, 300, 64)
+    model = build(params)
+    with torch.no_grad():
+        y = to_np(model(torch.from_numpy(x).cuda()))
+    ref = _oracle_features(params, x)
+    scale = np.abs(ref).max()
+    assert np.abs(y - ref).max() <= 1e-3 * scale, (np.abs(y - ref).max(), scale, int(np.abs(y - ref).max(1).argmax()))
+
+
+def test_resnet_config3_batch_512_at_256():
+    """Config 3's batch (512 patches of 3x256x256): images drawn from both stem chunks and both ends of the batch are
+    checked against the oracle run on just those images (features are batch-independent)."""
+    params = RO.make_params(1)
+    rng = np.random.default_rng(33)
+    x = torch.from_numpy(rng.standard_normal((512, 3, 256, 256), dtype=np.float32))
+    model = build(params)
+    with torch.no_grad():
+        y = to_np(model(x.cuda()))
+    assert y.shape == (512, 1024) and np.isfinite(y).all()
+    pick = [0, 1, 127, 128, 255, 256, 257, 300, 383, 384, 500, 511]
+    ref = _oracle_features(params, x[pick].numpy())
+    scale = np.abs(ref).max()
+    assert np.abs(y[pick] - ref).max() <= 1e-3 * scale, (np.abs(y[pick] - ref).max(), scale)
+
+
 def test_resnet_batch_independence_and_determinism():
     """Each image's features do not depend on its batch neighbours; repeated runs are bit-identical."""
     params = RO.make_params(1)

@@ -23,7 +23,7 @@ ABI_VERSION = 2
 MAX_BATCH = 16   # slides per toad_fwd_batch call (tail::MAX_BATCH)
 
 EXPORTS = [
-    "toad_abi_version", "toad_error_string", "toad_param_offsets", "toad_dropout_hash",
+    "toad_abi_version", "toad_build_id", "toad_error_string", "toad_param_offsets", "toad_dropout_hash",
     "toad_fwd_workspace_bytes", "toad_fwd", "toad_fwd_batch_workspace_bytes", "toad_fwd_batch",
     "toad_bwd_workspace_bytes", "toad_bwd",
     "toad_attn_gated_workspace_bytes", "toad_attn_gated_fwd",
@@ -69,13 +69,17 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        try:
-            from . import build as _build
-            _build.build()
-        except Exception as e:  # no silent fallback: say exactly what is missing
-            raise ToadError("libtoad_b200.so is missing and could not be built with nvcc (%s). "
-                            "Run `python -c 'import __graft_entry__ as g; g.build()'`." % e) from e
+    if not os.environ.get("TOAD_B200_LIB"):
+        # (re)build when the binary is absent or was compiled from other sources than the ones on disk (content
+        # hash, not file times); without nvcc a stale binary is an error, never silently used
+        from . import build as _build
+        if _build.is_stale():
+            try:
+                _build.build()
+            except Exception as e:  # no silent fallback: say exactly what is missing
+                raise ToadError("libtoad_b200.so is %s and could not be built with nvcc (%s). "
+                                "Run `python -c 'import __graft_entry__ as g; g.build()'`."
+                                % ("missing" if not os.path.exists(LIB_PATH) else "stale (csrc/ changed since it was built)", e)) from e
     # TOAD_B200_LIB: A/B aid (tools/): load another build of the same ABI instead of the in-tree library
     lib = C.CDLL(os.environ.get("TOAD_B200_LIB") or LIB_PATH)
     missing = [s for s in EXPORTS if not hasattr(lib, s)]
@@ -119,9 +123,10 @@ def load() -> C.CDLL:
     lib.toad_adam_step.argtypes = [C.POINTER(Dims), C.POINTER(Params), _f32p, _f32p, _f32p, C.c_int64] + [C.c_double] * 5 + [C.c_float] + \
         [C.c_void_p]
     for name in EXPORTS:
-        if name not in ("toad_error_string", "toad_dropout_hash"):
+        if name not in ("toad_error_string", "toad_dropout_hash", "toad_build_id"):
             getattr(lib, name).restype = C.c_int
     lib.toad_dropout_hash.restype = C.c_uint32
+    lib.toad_build_id.restype = C.c_char_p
     if lib.toad_abi_version() != ABI_VERSION:
         raise ToadError("libtoad_b200.so ABI version %d, expected %d" % (lib.toad_abi_version(), ABI_VERSION))
     _lib = lib

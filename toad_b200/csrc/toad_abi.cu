@@ -139,6 +139,11 @@ simt::SgemmParams linear_params(const float* x, int64_t ldx, const float* w, con
 
 extern "C" int toad_abi_version(void) { return TOAD_ABI_VERSION; }
 
+#ifndef TOAD_BUILD_ID
+#define TOAD_BUILD_ID "unknown"
+#endif
+extern "C" const char* toad_build_id(void) { return TOAD_BUILD_ID; }
+
 extern "C" uint32_t toad_dropout_hash(uint64_t seed, uint32_t layer, uint64_t index) {
   return dropout_hash(seed, layer, index);
 }
@@ -435,8 +440,10 @@ BwdTcWs carve_bwd_tc(const toad_dims_t* d, int64_t n, void* base) {
   w.xp_hi = w.xT_hi; w.xp_lo = w.xT_lo;
   int64_t big = Hd * L;
   if (2 * D * Hd > big) big = 2 * D * Hd;
-  w.splitk = c.take<float>(static_cast<size_t>(kSMs / 2) * 256 * 256);  // <= one 256x256 fp32 tile per CTA pair (+ slack below)
-  (void)big;
+  // split-K partials: S slices of one [M_out, N_in] gradient.  S = (74 pairs) / (256x256 tiles) when the gradient has
+  // fewer tiles than pairs -- at most one tile per pair in total --, and S = 1 (the whole matrix once) beyond that.
+  const size_t pair_tiles = static_cast<size_t>(kSMs / 2) * 256 * 256;
+  w.splitk = c.take<float>(pair_tiles > static_cast<size_t>(big) ? pair_tiles : static_cast<size_t>(big));
   int64_t gb = (n + 127) / 128;
   if (gb > 2 * kSMs) gb = 2 * kSMs;
   w.gate_blocks = static_cast<int>(gb);
@@ -584,8 +591,16 @@ int bwd_tc(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t
 }
 }  // namespace
 
+// the tensor-core wgrads tile the [out, in] gradients in 256 x 256 blocks (launch_gemm_mn<256, 2>)
+static int check_bwd_tc_dims(const toad_dims_t* d, uint32_t flags) {
+  if (flags & TOAD_FLAG_SIMT_FP32) return 0;
+  if (d->in_dim % 256 != 0 || d->hid_dim % 256 != 0) return TOAD_ERR_UNSUPPORTED;
+  return 0;
+}
+
 extern "C" int toad_bwd_workspace_bytes(const toad_dims_t* d, int64_t n, uint32_t flags, size_t* bytes) {
   TOAD_TRY(check_dims(d));
+  TOAD_TRY(check_bwd_tc_dims(d, flags));
   if (bytes == nullptr || n <= 0) return TOAD_ERR_ARG;
   *bytes = (flags & TOAD_FLAG_SIMT_FP32) ? carve_bwd(d, n, nullptr).bytes : carve_bwd_tc(d, n, nullptr).bytes;
   return 0;
@@ -699,6 +714,7 @@ extern "C" int toad_bwd(const toad_dims_t* d, const toad_params_t* P, const floa
                         const toad_saved_t* sv, const float* dlogits, const float* dsite, float* grad, void* workspace,
                         size_t workspace_bytes, uint32_t flags, toad_stream_t stream) {
   TOAD_TRY(check_dims(d));
+  TOAD_TRY(check_bwd_tc_dims(d, flags));
   if (!P || !x || !fo || !sv || !dlogits || !dsite || !grad || n <= 0) return TOAD_ERR_ARG;
   if (!fo->a_raw || !fo->features || !fo->softmax_stats || !sv->a || !sv->b) return TOAD_ERR_ARG;
   if (flags & TOAD_FLAG_SIMT_FP32) {

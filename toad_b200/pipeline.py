@@ -108,4 +108,10 @@ class ResidentRunner:
                 out.append(self.model(bag, sex))
         for s in self.streams:
             cur.wait_stream(s)            # results are ordered before anything the caller enqueues next
+        # the result tensors were allocated on the side streams but are consumed on the caller's: tell the caching
+        # allocator, or a later side-stream forward could be handed their blocks while `cur` still reads them
+        for r in out:
+            for t in (r.values() if isinstance(r, dict) else (r,)):
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    t.record_stream(cur)
         return out

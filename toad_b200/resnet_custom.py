@@ -112,6 +112,12 @@ class ResNet_Baseline(nn.Module):
         _lib.check(lib.toad_resnet_prepare(arr, len(tensors), ptr, nbytes.value, ops._stream()), "toad_resnet_prepare")
         self._prepared, self._prepared_key, self._prepared_ptr, self._prepared_bytes = buf, key, ptr, nbytes.value
 
+    def invalidate_weight_cache(self) -> None:
+        """Forget the folded-BN weight planes (keyed on each tensor's (data_ptr, autograd version)): call after writes
+        that bypass the version counter (`p.data.copy_()`, raw-pointer writes); load_state_dict is tracked."""
+        self._prepared = None
+        self._prepared_key = None
+
     def forward(self, x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
         """[B, 3, H, W] -> [B, 1024] (resnet_custom.py:96-109).  `out` (optional, beyond the reference's signature):
         a [B, 1024] fp32 CUDA buffer to write into, e.g. a slice of a slide's feature matrix."""
