@@ -21,6 +21,7 @@
 // epilogue of tile i overlaps the main loop of tile i+1.
 #pragma once
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace toad {
 namespace tc {
@@ -35,6 +36,15 @@ enum { EPI_LINEAR = 0, EPI_GATE = 1, EPI_DGRAD = 2 };
 // instead of the forward's (bias, residual, ReLU, dropout): two instantiations keep each one's live registers low.
 __host__ __device__ constexpr bool epi_is_linear(int epi) { return epi == EPI_LINEAR || epi == EPI_DGRAD; }
 enum { A_F32 = 0, A_SPLIT = 1, A_CONV = 2, A_MN = 3 };
+// Operand precision of one GEMM:
+//   PREC_BF16X3  A ~= A_hi + A_lo, B ~= B_hi + B_lo as bf16 pairs, 3 passes (A_hi.B_hi + A_hi.B_lo + A_lo.B_hi): fp32-class
+//                accuracy (dropped terms O(2^-16)); activations cost 4 B / element in HBM.  The TOAD head and the
+//                "exact" ResNet mode.
+//   PREC_F16X2   A is ONE fp16 plane (2 B / element), B ~= B_hi + B_lo as fp16 pairs, 2 passes (A.B_hi + A.B_lo): the
+//                weights keep ~21 bits, the activations are rounded to fp16 (11 bits, the TF32 input precision cuDNN
+//                uses for the reference's convolutions by default) where a layer stores them.  The ResNet trunk's
+//                default: half the activation traffic, 2/3 of the tensor work.
+enum { PREC_BF16X3 = 0, PREC_F16X2 = 1 };
 // A_CONV: implicit-GEMM convolution over NHWC (hi,lo) planes.  A_MN: both operands MN-major -- A(m,k) and B(n,k)
 // are read from planes stored [k, m] / [k, n] (the wgrad dW = dY^T . X with k = patch index: no transposes).
 
@@ -42,7 +52,7 @@ enum { A_F32 = 0, A_SPLIT = 1, A_CONV = 2, A_MN = 3 };
 // 256 x BLOCK_N tile: each CTA stages its own 128 rows of A and HALF of the B tile, the leader CTA
 // issues UMMA M=256 reading both CTAs' shared memory, accumulators land in each CTA's own TMEM.
 // Halves the per-SM weight traffic (L2->smem and smem->tensor core) and frees room for a 3rd stage.
-template <int BLOCK_N, int CG = 1, int OUT_BUFS = 1>
+template <int BLOCK_N, int CG = 1, int OUT_BUFS = 1, int PREC = PREC_BF16X3>
 struct Cfg {
   static_assert(BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256 || BLOCK_N == 512, "BLOCK_N");
   static_assert(CG == 1 || CG == 2, "CG");
@@ -56,7 +66,9 @@ struct Cfg {
   static constexpr int B_ROWS = BLOCK_N / CG;        // B rows staged by one CTA (N_SUB sub-tiles of B_SUB_ROWS)
   static constexpr int B_SUB_ROWS = UMMA_N / CG;     // rows of one sub-tile staged by one CTA
   static constexpr int B_TILE_BYTES = B_ROWS * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  static constexpr int A_PLANES = PREC == PREC_F16X2 ? 1 : 2;
+  static constexpr int B_OFF = A_PLANES * A_TILE_BYTES;  // stage layout: A plane(s) | B_hi | B_lo
+  static constexpr int STAGE_BYTES = A_PLANES * A_TILE_BYTES + 2 * B_TILE_BYTES;
   // OUT_BUFS x 32 KB of staging for the epilogue's TMA stores, carved into per-warp private (hi, lo) tiles of
   // 32 rows x 32 columns (4 KB): 4 epilogue warps get 2 * OUT_BUFS tiles each, 8 warps OUT_BUFS each.  With one
   // tile a warp's store must finish reading smem before its next chunk is staged; with two it overlaps.
@@ -108,6 +120,16 @@ struct GemmTcParams {
   int32_t conv_pad;      // 0 or 1
   int32_t conv_Wo;
   int32_t conv_Ho;
+  // M tiling of an A_CONV GEMM: every 128-row M sub-tile is one box {64 ch, wb = Wo, hb, bb} of output pixels -- hb
+  // full rows of one image (bb = 1, conv_tpi tiles per image, the last one clipped at Ho) or bb whole images (hb = Ho).
+  // Only the first conv_tile_rows = wb*hb*bb (<= 128) rows of a tile are real; of those rows_valid (a prefix) exist.
+  // Output rows stay the dense raster [B*Ho*Wo, N]: no power-of-two restriction on the image size.
+  int32_t conv_B;
+  int32_t conv_hb;
+  int32_t conv_bb;
+  int32_t conv_tpi;
+  int32_t conv_tile_rows;
+  int32_t conv_mtiles;
   // EPI_LINEAR residual: out = act(acc + bias + (res_hi + res_lo)), planes [M, ld_res]
   const __nv_bfloat16* res_hi;
   const __nv_bfloat16* res_lo;
@@ -334,6 +356,10 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, bool mn_maj
   return (1u << 4) | (1u << 7) | (1u << 10) | (mn_major ? ((1u << 15) | (1u << 16)) : 0u) |
          (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
+// the same with fp16 operands (a_format = b_format = 0), K-major
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
 
 // sigmoid / tanh on the SFU (ex2.approx + rcp.approx): abs error ~2e-7, far below the score tolerance.
 __device__ __forceinline__ float fast_sigmoid(float z) {
@@ -347,6 +373,34 @@ __device__ __forceinline__ float fast_tanh(float z) { return fmaf(2.0f, fast_sig
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
+struct ConvTile { int b0, oh0, rows_valid; int64_t out_row0; };
+__device__ __forceinline__ ConvTile conv_tile(const GemmTcParams& p, int t) {
+  ConvTile c;
+  if (p.conv_tpi == 1) {  // bb whole images per tile
+    c.b0 = t * p.conv_bb; c.oh0 = 0;
+    int nb = p.conv_B - c.b0;
+    nb = nb < 0 ? 0 : (nb > p.conv_bb ? p.conv_bb : nb);
+    c.rows_valid = nb * p.conv_Ho * p.conv_Wo;
+  } else {                // hb rows of one image
+    c.b0 = t / p.conv_tpi; c.oh0 = (t - c.b0 * p.conv_tpi) * p.conv_hb;
+    int nh = p.conv_Ho - c.oh0;
+    nh = nh > p.conv_hb ? p.conv_hb : nh;
+    c.rows_valid = c.b0 < p.conv_B ? nh * p.conv_Wo : 0;
+  }
+  c.out_row0 = (static_cast<int64_t>(c.b0) * p.conv_Ho + c.oh0) * p.conv_Wo;
+  return c;
+}
+__device__ __forceinline__ float2 h2_to_f2(uint32_t w) {
+  const __half2 h = *reinterpret_cast<const __half2*>(&w);
+  return __half22float2(h);
+}
+// two floats -> packed fp16x2 (v0 in the low half), round to nearest, finite saturation (no inf in the activations)
+__device__ __forceinline__ uint32_t pack_f16x2(float v0, float v1) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(v1), "f"(v0));
+  return r;
+}
+
 constexpr int GATE_SMEM_FLOATS = 4 * 1024;  // ba | bb | wc rows (<= 2 tasks staged) for D <= 1024
 
 // Epilogue warp sets (x4 warps, one per TMEM lane quarter).  Plane-fed kernels run 2 sets (384 threads).  The
@@ -368,14 +422,16 @@ __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.
 template <int REGS>
 __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 
-template <int BLOCK_N, int A_MODE, int EPI, int CG, int OUT_BUFS = 1>
+template <int BLOCK_N, int A_MODE, int EPI, int CG, int OUT_BUFS = 1, int PREC = PREC_BF16X3>
 __global__ void __launch_bounds__(cta_threads<A_MODE, EPI>(), 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
                    const GemmTcParams p) {
-  using C = Cfg<BLOCK_N, CG, OUT_BUFS>;
+  using C = Cfg<BLOCK_N, CG, OUT_BUFS, PREC>;
   static_assert(EPI != EPI_GATE || BLOCK_N <= 256, "the gate epilogue pairs two 128-column halves of a 256-wide tile");
+  static_assert(PREC == PREC_BF16X3 || ((A_MODE == A_SPLIT || A_MODE == A_CONV) && EPI == EPI_LINEAR),
+                "the fp16 single-plane mode exists for the plane-fed linear / convolution GEMMs");
   // epilogue warp sets: plane-fed kernels run 8 epilogue warps (two per TMEM lane quarter, each taking one
   // 32-column half of every 64-column chunk); the fp32-fed kernels keep 4 so that, with their 8 converter
   // warps, the CTA stays at 512 threads / 128 registers.
@@ -398,7 +454,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   const uint32_t tiles_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
   // work units: (128*CG) x BLOCK_N tiles, n fastest; this CTA owns rows [m0, m0+128) of its unit
-  const int m_units = static_cast<int>((p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG));
+  const int m_units = A_MODE == A_CONV ? (p.conv_mtiles + CG - 1) / CG
+                                       : static_cast<int>((p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG));
   const int n_tiles = p.N / BLOCK_N;
   const int mn_tiles = m_units * n_tiles;
   const int k_splits = (A_MODE != A_F32 && p.k_splits > 1) ? p.k_splits : 1;
@@ -425,7 +482,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     prefetch_tmap(&tm_b_lo);
     if (A_MODE != A_F32) {
       prefetch_tmap(&tm_a_hi);
-      prefetch_tmap(&tm_a_lo);
+      if (C::A_PLANES == 2) prefetch_tmap(&tm_a_lo);
     }
   }
   if (EPI == EPI_GATE) {  // stage the gate biases and (up to 2) score rows once per CTA
@@ -464,7 +521,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         if (lane == 0) {
           const uint32_t sa = tiles_base + stage * C::STAGE_BYTES;
           const uint32_t fb_local = smem_u32(&bar_full_b[stage]);
-          const uint32_t bytes = 2 * C::B_TILE_BYTES + (A_MODE != A_F32 ? 2 * A_TILE_BYTES : 0);
+          // (a convolution's A box holds conv_tile_rows <= 128 pixels; out-of-image parts are zero-filled AND counted)
+          const uint32_t a_bytes = A_MODE == A_F32 ? 0u : (A_MODE == A_CONV ? static_cast<uint32_t>(p.conv_tile_rows) * 128u
+                                                                            : static_cast<uint32_t>(A_TILE_BYTES));
+          const uint32_t bytes = 2 * C::B_TILE_BYTES + C::A_PLANES * a_bytes;
           uint32_t fb = fb_local;
           if (CG == 1) {
             mbar_expect_tx(fb_local, bytes);
@@ -475,7 +535,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           }
           if (A_MODE == A_SPLIT) {
             tma_load_2d<CG>(sa, &tm_a_hi, fb, kb * BLOCK_K, m0);
-            tma_load_2d<CG>(sa + A_TILE_BYTES, &tm_a_lo, fb, kb * BLOCK_K, m0);
+            if (C::A_PLANES == 2) tma_load_2d<CG>(sa + A_TILE_BYTES, &tm_a_lo, fb, kb * BLOCK_K, m0);
           } else if (A_MODE == A_MN) {
 #pragma unroll
             for (int j = 0; j < BLOCK_M / 64; ++j) {  // [64 patches x 64 m] boxes
@@ -485,26 +545,24 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           } else if (A_MODE == A_CONV) {
             const int tap = kb / p.conv_cchunks, cc = kb - tap * p.conv_cchunks;
             const int kh = tap / p.conv_kw, kw = tap - kh * p.conv_kw;
-            const int hw = p.conv_Ho * p.conv_Wo;
-            const int b0 = m0 / hw, pix = m0 - b0 * hw;
-            const int oh0 = pix / p.conv_Wo, ow0 = pix - oh0 * p.conv_Wo;
-            const int cw = ow0 * p.conv_stride + kw - p.conv_pad;
-            const int ch = oh0 * p.conv_stride + kh - p.conv_pad;
-            tma_load_4d<CG>(sa, &tm_a_hi, fb, cc * BLOCK_K, cw, ch, b0);
-            tma_load_4d<CG>(sa + A_TILE_BYTES, &tm_a_lo, fb, cc * BLOCK_K, cw, ch, b0);
+            const ConvTile ct = conv_tile(p, (mn / n_tiles) * CG + static_cast<int>(cta_rank));
+            const int cw = kw - p.conv_pad;  // (tiles span the full output width)
+            const int ch = ct.oh0 * p.conv_stride + kh - p.conv_pad;
+            tma_load_4d<CG>(sa, &tm_a_hi, fb, cc * BLOCK_K, cw, ch, ct.b0);
+            if (C::A_PLANES == 2) tma_load_4d<CG>(sa + A_TILE_BYTES, &tm_a_lo, fb, cc * BLOCK_K, cw, ch, ct.b0);
           }
           if (A_MODE == A_MN) {
 #pragma unroll
             for (int j = 0; j < C::B_SUB_ROWS / 64; ++j) {  // [64 patches x 64 n] boxes of this CTA's share of B
-              tma_load_2d<CG>(sa + 2 * A_TILE_BYTES + j * 8192, &tm_b_hi, fb, n0 + j * 64, kb * BLOCK_K);
-              tma_load_2d<CG>(sa + 2 * A_TILE_BYTES + C::B_TILE_BYTES + j * 8192, &tm_b_lo, fb, n0 + j * 64, kb * BLOCK_K);
+              tma_load_2d<CG>(sa + C::B_OFF + j * 8192, &tm_b_hi, fb, n0 + j * 64, kb * BLOCK_K);
+              tma_load_2d<CG>(sa + C::B_OFF + C::B_TILE_BYTES + j * 8192, &tm_b_lo, fb, n0 + j * 64, kb * BLOCK_K);
             }
           } else {
 #pragma unroll
             for (int hs = 0; hs < C::N_SUB; ++hs) {  // sub-tile hs = rows [n0 + hs*UMMA_N, +B_SUB_ROWS) of this CTA's share
               const uint32_t so = hs * (C::B_SUB_ROWS * 128);
-              tma_load_2d<CG>(sa + 2 * A_TILE_BYTES + so, &tm_b_hi, fb, kb * BLOCK_K, n0 + hs * C::UMMA_N);
-              tma_load_2d<CG>(sa + 2 * A_TILE_BYTES + C::B_TILE_BYTES + so, &tm_b_lo, fb, kb * BLOCK_K, n0 + hs * C::UMMA_N);
+              tma_load_2d<CG>(sa + C::B_OFF + so, &tm_b_hi, fb, kb * BLOCK_K, n0 + hs * C::UMMA_N);
+              tma_load_2d<CG>(sa + C::B_OFF + C::B_TILE_BYTES + so, &tm_b_lo, fb, kb * BLOCK_K, n0 + hs * C::UMMA_N);
             }
           }
         }
@@ -515,7 +573,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (is_leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M * CG, C::UMMA_N, A_MODE == A_MN);
+      constexpr uint32_t idesc = PREC == PREC_F16X2 ? make_idesc_f16(BLOCK_M * CG, C::UMMA_N)
+                                                    : make_idesc_bf16(BLOCK_M * CG, C::UMMA_N, A_MODE == A_MN);
       // descriptor start-address step per UMMA K (=16): K-major +32 B inside the swizzled row; MN-major +16 k-rows
       constexpr uint64_t KSTEP = A_MODE == A_MN ? ((16 * 128) >> 4) : ((UMMA_K * 2) >> 4);
       int stage = 0;
@@ -539,10 +598,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 #pragma unroll
             for (int hs = 0; hs < C::N_SUB; ++hs) {
               const uint32_t so = hs * (C::B_SUB_ROWS * 128);
-              const uint64_t b_hi = A_MODE == A_MN ? make_mnmajor_sw128_desc(sa + 2 * A_TILE_BYTES + so)
-                                                   : make_kmajor_sw128_desc(sa + 2 * A_TILE_BYTES + so);
-              const uint64_t b_lo = A_MODE == A_MN ? make_mnmajor_sw128_desc(sa + 2 * A_TILE_BYTES + C::B_TILE_BYTES + so)
-                                                   : make_kmajor_sw128_desc(sa + 2 * A_TILE_BYTES + C::B_TILE_BYTES + so);
+              const uint64_t b_hi = A_MODE == A_MN ? make_mnmajor_sw128_desc(sa + C::B_OFF + so)
+                                                   : make_kmajor_sw128_desc(sa + C::B_OFF + so);
+              const uint64_t b_lo = A_MODE == A_MN ? make_mnmajor_sw128_desc(sa + C::B_OFF + C::B_TILE_BYTES + so)
+                                                   : make_kmajor_sw128_desc(sa + C::B_OFF + C::B_TILE_BYTES + so);
               const uint32_t d_tmem = d_tmem0 + hs * C::UMMA_N;
 #pragma unroll
               for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
@@ -554,10 +613,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 const uint64_t koff = static_cast<uint64_t>(k) * KSTEP;
                 umma_bf16<CG>(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
               }
+              if (PREC == PREC_BF16X3) {
 #pragma unroll
-              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                const uint64_t koff = static_cast<uint64_t>(k) * KSTEP;
-                umma_bf16<CG>(d_tmem, a_lo + koff, b_hi + koff, idesc, 1);
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                  const uint64_t koff = static_cast<uint64_t>(k) * KSTEP;
+                  umma_bf16<CG>(d_tmem, a_lo + koff, b_hi + koff, idesc, 1);
+                }
               }
             }
             umma_commit<CG>(smem_u32(&bar_empty[stage]));  // smem slot free (in both CTAs) once these MMAs retire
