@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define TOAD_ABI_VERSION 2
+#define TOAD_ABI_VERSION 3
 
 typedef void* toad_stream_t; /* cudaStream_t */
 
@@ -247,14 +247,23 @@ int toad_linear_bf16x3(const float* x, const float* w, const float* bias, float*
  * tensors: HOST array of TOAD_RESNET_N_TENSORS device pointers (fp32), the module's state_dict in
  * order with the `num_batches_tracked` entries skipped, i.e. for each of the 43 convolutions
  * {conv.weight [Co,Ci,k,k], bn.weight, bn.bias, bn.running_mean, bn.running_var}.
- * x: [B, 3, H, W] fp32 NCHW (H, W multiples of 16, H/4 and W/4 powers of two <= 128);  out: [B, 1024] fp32. */
+ * x: [B, 3, H, W] fp32 NCHW, H and W multiples of 16, W <= 512 (224 x 224, 256 x 256, ...);  out: [B, 1024] fp32.
+ *
+ * flags (the same value for prepare / workspace_bytes / fwd of one prepared block):
+ *   0                       activations stored between layers as ONE fp16 NHWC plane (2 B / element), weights as fp16
+ *                           (hi, lo) pairs, two tensor-core passes per product, fp32 accumulation.  Activation rounding is
+ *                           2^-11 relative, the input precision of the TF32 convolutions cuDNN runs for the reference by
+ *                           default; features land within ~4e-4 of the feature scale of the fp64 reference.
+ *   TOAD_RESNET_FLAG_EXACT  activations as (hi, lo) bf16 plane pairs (4 B / element), three passes: fp32-class accuracy
+ *                           (~7e-5 of the feature scale) at twice the HBM traffic and 1.5x the tensor work. */
 #define TOAD_RESNET_N_TENSORS 215
+#define TOAD_RESNET_FLAG_EXACT 1u
 int toad_resnet_prepared_bytes(size_t* bytes);
 int toad_resnet_prepare(const float* const* tensors, int32_t n_tensors, void* prepared, size_t prepared_bytes,
-                        toad_stream_t stream);
-int toad_resnet_workspace_bytes(int32_t batch, int32_t height, int32_t width, size_t* bytes);
+                        uint32_t flags, toad_stream_t stream);
+int toad_resnet_workspace_bytes(int32_t batch, int32_t height, int32_t width, uint32_t flags, size_t* bytes);
 int toad_resnet_fwd(const void* prepared, const float* x, int32_t batch, int32_t height, int32_t width, float* out,
-                    void* workspace, size_t workspace_bytes, toad_stream_t stream);
+                    void* workspace, size_t workspace_bytes, uint32_t flags, toad_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -31,9 +31,10 @@ def import_reference_resnet():
     return mod
 
 
-def run(mod, name, pseed, xseed, batch, size):
+def run(mod, name, pseed, xseed, batch, size, width=None):
+    """size = image height; width defaults to the height (square patches)."""
     params = RO.make_params(pseed)
-    x = RO.make_images(xseed, batch, size)
+    x = RO.make_images(xseed, batch, size, width)
     model = mod.resnet50_baseline(pretrained=False)
     sd = {k: torch.from_numpy(np.asarray(v).copy()) for k, v in params.items()}
     assert list(model.state_dict().keys()) == list(sd.keys())
@@ -43,16 +44,22 @@ def run(mod, name, pseed, xseed, batch, size):
         y32 = model(torch.from_numpy(x)).numpy()
         y64 = model.double()(torch.from_numpy(x).double()).numpy()
     path = os.path.join(HERE, name + ".npz")
-    np.savez_compressed(path, meta_pseed=pseed, meta_xseed=xseed, meta_batch=batch, meta_size=size, f32_out=y32, f64_out=y64)
+    np.savez_compressed(path, meta_pseed=pseed, meta_xseed=xseed, meta_batch=batch, meta_size=size,
+                        meta_width=width or size, f32_out=y32, f64_out=y64)
     print("wrote", path, y32.shape, os.path.getsize(path) // 1024, "KiB")
 
 
 def main():
     mod = import_reference_resnet()
     torch.set_num_threads(os.cpu_count())
-    run(mod, "resnet_b2_s64", 1, 2, 2, 64)
-    run(mod, "resnet_b3_s128", 1, 3, 3, 128)
-    run(mod, "resnet_b2_s256", 1, 4, 2, 256)
+    only = sys.argv[1:]
+    cases = {"resnet_b2_s64": (1, 2, 2, 64), "resnet_b3_s128": (1, 3, 3, 128), "resnet_b2_s256": (1, 4, 2, 256),
+             # sizes that are not powers of two: the usual 224 x 224 patch, and a non-square one whose late layers
+             # hold several images per M tile (96 x 160 -> 6 x 10 pixels in layer3)
+             "resnet_b2_s224": (1, 5, 2, 224), "resnet_b3_s96x160": (1, 6, 3, 96, 160)}
+    for name, args in cases.items():
+        if not only or name in only:
+            run(mod, name, *args)
 
 
 if __name__ == "__main__":

@@ -32,7 +32,8 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_version_and_error_strings(lib):
-    assert lib.toad_abi_version() == 2
+    from toad_b200 import _lib as L
+    assert lib.toad_abi_version() == L.ABI_VERSION == 3
     assert lib.toad_error_string(0) == b"ok"
     assert b"workspace" in lib.toad_error_string(-2)
     assert b"not supported" in lib.toad_error_string(-3)

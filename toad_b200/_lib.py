@@ -19,7 +19,8 @@ FLAG_DROPOUT = 16
 FLAG_TC_PAIR_ALL = 32
 FLAG_REUSE_WEIGHT_PLANES = 128
 FLAG_BWD_TRANSPOSED = 256
-ABI_VERSION = 2
+ABI_VERSION = 3
+RESNET_FLAG_EXACT = 1   # toad_resnet_*: (hi, lo) bf16 activation planes, 3 passes (fp32-class accuracy)
 MAX_BATCH = 16   # slides per toad_fwd_batch call (tail::MAX_BATCH)
 
 EXPORTS = [
@@ -113,10 +114,10 @@ def load() -> C.CDLL:
     lib.toad_profile_destroy.argtypes = [C.c_void_p]
     lib.toad_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     lib.toad_resnet_prepared_bytes.argtypes = [C.POINTER(C.c_size_t)]
-    lib.toad_resnet_prepare.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]
-    lib.toad_resnet_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
+    lib.toad_resnet_prepare.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
+    lib.toad_resnet_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.POINTER(C.c_size_t)]
     lib.toad_resnet_fwd.argtypes = [C.c_void_p, _f32p, C.c_int32, C.c_int32, C.c_int32, _f32p, C.c_void_p, C.c_size_t,
-                                    C.c_void_p]
+                                    C.c_uint32, C.c_void_p]
     lib.toad_dropout_hash.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64]
     lib.toad_ce_loss_grad.argtypes = [_f32p, _f32p, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_float, _f32p, _f32p,
                                       _f32p, C.c_void_p]

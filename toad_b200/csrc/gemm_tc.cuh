@@ -643,8 +643,21 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       const int n0 = n_tile * BLOCK_N;
       const int m0 = (mn / n_tiles) * (BLOCK_M * CG) + static_cast<int>(cta_rank) * BLOCK_M;
       const int acc = it % C::ACC_STAGES;
-      const int64_t row = static_cast<int64_t>(m0) + ew * 32 + lane;
-      const bool row_ok = row < p.M;
+      // rows of this warp: a plain GEMM tile is 128 dense rows (rows >= M are clipped by the TMA store); a convolution
+      // tile holds rows_valid <= 128 real output pixels starting at raster row out_row0 (see GemmTcParams::conv_*)
+      int64_t tile_row0 = m0;
+      int warp_rows = 32;
+      if (A_MODE == A_CONV) {
+        const ConvTile ct = conv_tile(p, (mn / n_tiles) * CG + static_cast<int>(cta_rank));
+        tile_row0 = ct.out_row0;
+        warp_rows = ct.rows_valid - ew * 32;
+        warp_rows = warp_rows < 0 ? 0 : (warp_rows > 32 ? 32 : warp_rows);
+      }
+      const int64_t row = tile_row0 + ew * 32 + lane;
+      const bool row_ok = A_MODE == A_CONV ? lane < warp_rows : row < p.M;
+      // full warps go through the staged TMA store; a convolution warp cut by the end of its tile stores its valid
+      // rows straight from registers (a TMA box cannot be clipped inside the tensor)
+      const bool use_tma = A_MODE != A_CONV || warp_rows == 32;
       // residual operand (ResNet shortcut): this warp's NEXT 32-column chunk is fetched one chunk ahead (and the
       // first one before waiting for the accumulator), hiding the global latency that otherwise serialises the
       // epilogue of the short-K 1x1 convolutions.
@@ -658,7 +671,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           if (has_res && row_ok) {
             const int64_t o = row * p.ld_res + n0 + c_ * 32 + q * 8;
             res_h[q] = *reinterpret_cast<const uint4*>(p.res_hi + o);
-            res_l[q] = *reinterpret_cast<const uint4*>(p.res_lo + o);
+            if (PREC == PREC_BF16X3) res_l[q] = *reinterpret_cast<const uint4*>(p.res_lo + o);
           }
         }
       };
@@ -703,9 +716,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         // (rows >= M clipped by TMA).  No CTA-wide barrier: the warps drift, so one warp's TMEM / store latency
         // is covered by the others' arithmetic; with WARP_BUFS = 2 a warp's own store overlaps its next chunk.
         constexpr int N_CHUNKS = BLOCK_N / 32;
-        constexpr int WARP_BUFS = OUT_BUFS * 2 / EPI_SETS;
+        // (the fp16 mode stages ONE 2 KB plane per chunk in the same 4 KB slots: twice the buffers)
+        constexpr int WARP_BUFS = (OUT_BUFS * 2 / EPI_SETS) * (PREC == PREC_F16X2 ? 2 : 1);
+        constexpr int WARP_STAGE_BYTES = (OUT_BUFS * 2 / EPI_SETS) * 4096;
         static_assert(WARP_BUFS >= 1, "staging");
-        const uint32_t my_stage = tiles_base + STAGES * C::STAGE_BYTES + ((eh * 4 + ew) * WARP_BUFS) * 4096;
+        const uint32_t my_stage = tiles_base + STAGES * C::STAGE_BYTES + (eh * 4 + ew) * WARP_STAGE_BYTES;
 #pragma unroll 1
         for (int c = eh; c < N_CHUNKS; c += EPI_SETS) {
           const bool last = c + EPI_SETS >= N_CHUNKS;
@@ -740,7 +755,20 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             for (int i = 0; i < 32; ++i)
               r[i] = __float_as_uint(__uint_as_float(r[i]) + __shfl_sync(0xffffffffu, bias_cur, i));
           }
-          if (has_res) {
+          if (has_res && PREC == PREC_F16X2) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 vh = cur_h[q];
+              const uint32_t uh[4] = {vh.x, vh.y, vh.z, vh.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 rv = h2_to_f2(uh[e]);
+                r[q * 8 + 2 * e] = __float_as_uint(__uint_as_float(r[q * 8 + 2 * e]) + rv.x);
+                r[q * 8 + 2 * e + 1] = __float_as_uint(__uint_as_float(r[q * 8 + 2 * e + 1]) + rv.y);
+              }
+            }
+          }
+          if (has_res && PREC == PREC_BF16X3) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const uint4 vh = cur_h[q], vl = cur_l[q];
@@ -798,30 +826,68 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 #pragma unroll
             for (int i = 0; i < 4; ++i) st_global_v8(dst + 8 * i, r, 8 * i);
           }
-          if (p.out_hi != nullptr) {
+          if (p.out_hi != nullptr && PREC == PREC_F16X2) {
+            // one fp16 plane: 32 rows x 64 B per chunk
+            const uint32_t buf = my_stage + (out_chunk % WARP_BUFS) * 2048;
+            ++out_chunk;
+            if (use_tma) {  // staging buffer free again?  (this warp's store that last used it must have finished READING it)
+              if (lane == 0) tma_store_wait_read<WARP_BUFS - 1>();
+              __syncwarp();
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {  // 8 columns -> one 16 B chunk
+              uint32_t h[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h[e] = pack_f16x2(__uint_as_float(r[8 * q + 2 * e]), __uint_as_float(r[8 * q + 2 * e + 1]));
+              if (use_tma) {
+                const uint32_t off = lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4);  // SWIZZLE_64B: chunk ^= row bits [1,2]
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+              } else if (row_ok) {
+                *reinterpret_cast<uint4*>(p.out_hi + row * p.ld_split + col0 + q * 8) = make_uint4(h[0], h[1], h[2], h[3]);
+              }
+            }
+            if (use_tma) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tm_o_hi, buf, col0, static_cast<int>(tile_row0) + ew * 32);
+                tma_store_commit();
+              }
+            }
+          }
+          if (p.out_hi != nullptr && PREC == PREC_BF16X3) {
             const uint32_t buf_hi = my_stage + (out_chunk % WARP_BUFS) * 4096, buf_lo = buf_hi + 2048;
             ++out_chunk;
             // staging buffer free again?  (this warp's store that last used it must have finished READING it)
-            if (lane == 0) tma_store_wait_read<WARP_BUFS - 1>();
-            __syncwarp();
+            if (use_tma) {
+              if (lane == 0) tma_store_wait_read<WARP_BUFS - 1>();
+              __syncwarp();
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {  // 8 columns -> one 16 B chunk per plane
               uint32_t hi[4], lo[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e)
                 split2(__uint_as_float(r[8 * q + 2 * e]), __uint_as_float(r[8 * q + 2 * e + 1]), hi[e], lo[e]);
-              const uint32_t off = lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4);  // SWIZZLE_64B: chunk ^= row bits [1,2]
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf_hi + off), "r"(hi[0]), "r"(hi[1]),
-                           "r"(hi[2]), "r"(hi[3]) : "memory");
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf_lo + off), "r"(lo[0]), "r"(lo[1]),
-                           "r"(lo[2]), "r"(lo[3]) : "memory");
+              if (use_tma) {
+                const uint32_t off = lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4);  // SWIZZLE_64B: chunk ^= row bits [1,2]
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf_hi + off), "r"(hi[0]), "r"(hi[1]),
+                             "r"(hi[2]), "r"(hi[3]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf_lo + off), "r"(lo[0]), "r"(lo[1]),
+                             "r"(lo[2]), "r"(lo[3]) : "memory");
+              } else if (row_ok) {
+                *reinterpret_cast<uint4*>(p.out_hi + row * p.ld_split + col0 + q * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(p.out_lo + row * p.ld_split + col0 + q * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              }
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&tm_o_hi, buf_hi, col0, m0 + ew * 32);
-              tma_store_2d(&tm_o_lo, buf_lo, col0, m0 + ew * 32);
-              tma_store_commit();
+            if (use_tma) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tm_o_hi, buf_hi, col0, static_cast<int>(tile_row0) + ew * 32);
+                tma_store_2d(&tm_o_lo, buf_lo, col0, static_cast<int>(tile_row0) + ew * 32);
+                tma_store_commit();
+              }
             }
           }
         }
@@ -1030,10 +1096,10 @@ inline int make_nhwc_tmap(CUtensorMap* map, const void* ptr, int64_t B, int64_t 
 
 // Launch with ready-made A tensor maps (unused for A_F32).  B operand: planes b_hi/b_lo [N, K] bf16.
 // Launch with ready-made A and B tensor maps.
-template <int BLOCK_N, int A_MODE, int EPI, int CG, int OUT_BUFS = 1>
+template <int BLOCK_N, int A_MODE, int EPI, int CG, int OUT_BUFS = 1, int PREC = PREC_BF16X3>
 int launch_gemm_maps_b(const GemmTcParams& p, const CUtensorMap& ta_hi, const CUtensorMap& ta_lo,
                        const CUtensorMap& tb_hi, const CUtensorMap& tb_lo, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N, CG, OUT_BUFS>;
+  using C = Cfg<BLOCK_N, CG, OUT_BUFS, PREC>;
   if (p.M <= 0) return 0;
   if ((A_MODE == A_F32 && p.K % BLOCK_K != 0) || p.N % BLOCK_N != 0 || p.K <= 0 || p.N <= 0) return TOAD_ERR_UNSUPPORTED;
   if (p.k_splits > 1 && (A_MODE == A_F32 || EPI != EPI_LINEAR || p.out_hi != nullptr || p.kb_per_split <= 0)) return TOAD_ERR_ARG;
@@ -1048,12 +1114,12 @@ int launch_gemm_maps_b(const GemmTcParams& p, const CUtensorMap& ta_hi, const CU
     return TOAD_ERR_ARG;
   CUtensorMap to_hi = tb_hi, to_lo = tb_lo;
   if (epi_is_linear(EPI) && p.out_hi != nullptr) {
-    if (p.out_lo == nullptr || p.ld_split % 8 != 0) return TOAD_ERR_ARG;
+    if ((PREC == PREC_BF16X3 && p.out_lo == nullptr) || p.ld_split % 8 != 0) return TOAD_ERR_ARG;
     TOAD_TRY(make_bf16_out_tmap(&to_hi, p.out_hi, p.M, p.N, p.ld_split));
-    TOAD_TRY(make_bf16_out_tmap(&to_lo, p.out_lo, p.M, p.N, p.ld_split));
+    if (PREC == PREC_BF16X3) TOAD_TRY(make_bf16_out_tmap(&to_lo, p.out_lo, p.M, p.N, p.ld_split));
   }
   constexpr int kSmem = epi_is_linear(EPI) ? C::SMEM_BYTES_LINEAR : C::SMEM_BYTES;
-  auto kern = gemm_bf16x3_kernel<BLOCK_N, A_MODE, EPI, CG, OUT_BUFS>;
+  auto kern = gemm_bf16x3_kernel<BLOCK_N, A_MODE, EPI, CG, OUT_BUFS, PREC>;
   {  // once per instantiation and device (one process drives one GPU; a repeated call would only cost host time)
     static int attr_dev = -1;
     int dev = 0;
@@ -1063,7 +1129,7 @@ int launch_gemm_maps_b(const GemmTcParams& p, const CUtensorMap& ta_hi, const CU
       attr_dev = dev;
     }
   }
-  const int64_t m_units = (p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG);
+  const int64_t m_units = A_MODE == A_CONV ? (p.conv_mtiles + CG - 1) / CG : (p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG);
   const int64_t units = m_units * (p.N / BLOCK_N) * (p.k_splits > 1 ? p.k_splits : 1);
   const int64_t max_units = sm_count() / CG;
   const int grid = static_cast<int>(units < max_units ? units : max_units) * CG;
@@ -1085,21 +1151,21 @@ int launch_gemm_maps_b(const GemmTcParams& p, const CUtensorMap& ta_hi, const CU
 }
 
 // Launch with ready-made A tensor maps (unused for A_F32).  B operand: planes b_hi/b_lo [N, K] bf16.
-template <int BLOCK_N, int A_MODE, int EPI, int CG, int OUT_BUFS = 1>
+template <int BLOCK_N, int A_MODE, int EPI, int CG, int OUT_BUFS = 1, int PREC = PREC_BF16X3>
 int launch_gemm_maps(const GemmTcParams& p, const CUtensorMap& ta_hi, const CUtensorMap& ta_lo,
                      const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N, CG, OUT_BUFS>;
+  using C = Cfg<BLOCK_N, CG, OUT_BUFS, PREC>;
   if (p.M <= 0) return 0;
   if (p.K <= 0 || p.N <= 0) return TOAD_ERR_UNSUPPORTED;
   CUtensorMap tb_hi, tb_lo;
   const int64_t ldb = p.ldb > 0 ? p.ldb : p.K;
   TOAD_TRY(make_bf16_tmap(&tb_hi, b_hi, p.N, p.K, C::B_SUB_ROWS, ldb));
   TOAD_TRY(make_bf16_tmap(&tb_lo, b_lo, p.N, p.K, C::B_SUB_ROWS, ldb));
-  return launch_gemm_maps_b<BLOCK_N, A_MODE, EPI, CG, OUT_BUFS>(p, ta_hi, ta_lo, tb_hi, tb_lo, stream);
+  return launch_gemm_maps_b<BLOCK_N, A_MODE, EPI, CG, OUT_BUFS, PREC>(p, ta_hi, ta_lo, tb_hi, tb_lo, stream);
 }
 
 // A operand: fp32 (a_f32/lda in p) when A_MODE == A_F32, else the planes a_hi/a_lo [M, K] bf16.
-template <int BLOCK_N, int A_MODE, int EPI, int CG = 1, int OUT_BUFS = 1>
+template <int BLOCK_N, int A_MODE, int EPI, int CG = 1, int OUT_BUFS = 1, int PREC = PREC_BF16X3>
 int launch_gemm(const GemmTcParams& p, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,
                 const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, cudaStream_t stream) {
   static_assert(A_MODE != A_CONV && A_MODE != A_MN, "use launch_conv_gemm / launch_gemm_mn");
@@ -1109,12 +1175,13 @@ int launch_gemm(const GemmTcParams& p, const __nv_bfloat16* a_hi, const __nv_bfl
     if (p.K <= 0) return TOAD_ERR_UNSUPPORTED;
     const int64_t lda = p.lda > 0 ? p.lda : p.K;  // plane row stride in elements (multiple of 8)
     TOAD_TRY(make_bf16_tmap(&ta_hi, a_hi, p.M, p.K, BLOCK_M, lda));
-    TOAD_TRY(make_bf16_tmap(&ta_lo, a_lo, p.M, p.K, BLOCK_M, lda));
+    if (PREC == PREC_BF16X3) TOAD_TRY(make_bf16_tmap(&ta_lo, a_lo, p.M, p.K, BLOCK_M, lda));
+    else ta_lo = ta_hi;
   } else {
     TOAD_TRY(make_bf16_tmap(&ta_hi, b_hi, p.N, p.K, 64));  // placeholders, never dereferenced
     ta_lo = ta_hi;
   }
-  return launch_gemm_maps<BLOCK_N, A_MODE, EPI, CG, OUT_BUFS>(p, ta_hi, ta_lo, b_hi, b_lo, stream);
+  return launch_gemm_maps<BLOCK_N, A_MODE, EPI, CG, OUT_BUFS, PREC>(p, ta_hi, ta_lo, b_hi, b_lo, stream);
 }
 
 // wgrad-style GEMM with both operands MN-major: C[M, N] = sum_k A(m,k) B(n,k) with A stored as planes [K, M]
@@ -1136,19 +1203,23 @@ int launch_gemm_mn(GemmTcParams p, const __nv_bfloat16* a_hi, const __nv_bfloat1
   return launch_gemm_maps_b<BLOCK_N, A_MN, EPI_LINEAR, CG, 1>(p, ta_hi, ta_lo, tb_hi, tb_lo, stream);
 }
 
-// Convolution as implicit GEMM: input planes NHWC [B, H, W, Cin] (hi, lo), weights [Cout, taps*Cin] with
-// K order (kh, kw, cin), output planes [B*Ho*Wo, Cout].  ksize in {1, 3}; stride in {1, 2}; pad = ksize/2.
-template <int BLOCK_N, int CG, int OUT_BUFS = 1>
+// Convolution as implicit GEMM: input planes NHWC [B, H, W, Cin] ((hi, lo) bf16, or one fp16 plane for PREC_F16X2),
+// weights [Cout, taps*Cin] with K order (kh, kw, cin), output planes [B*Ho*Wo, Cout].  ksize in {1, 3}; stride in
+// {1, 2}; pad = ksize/2.  Any image size with Wo <= 128 (and even H, W for stride 2): see GemmTcParams::conv_*.
+template <int BLOCK_N, int CG, int OUT_BUFS = 1, int PREC = PREC_BF16X3>
 int launch_conv_gemm(GemmTcParams p, const __nv_bfloat16* in_hi, const __nv_bfloat16* in_lo, int B, int H, int W,
                      int Cin, int ksize, int stride, const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo,
                      cudaStream_t stream) {
-  const int Ho = H / stride, Wo = W / stride;
   if (Cin % BLOCK_K != 0 || (ksize != 1 && ksize != 3) || (stride != 1 && stride != 2)) return TOAD_ERR_UNSUPPORTED;
-  if (Wo > BLOCK_M || (Wo & (Wo - 1)) != 0 || (Ho & (Ho - 1)) != 0) return TOAD_ERR_UNSUPPORTED;
-  // 128 output pixels per tile = wb x hb x bb (full rows first, then rows, then images)
+  if (H % stride != 0 || W % stride != 0) return TOAD_ERR_UNSUPPORTED;
+  const int Ho = H / stride, Wo = W / stride;
+  if (Wo > BLOCK_M || Wo < 1 || Ho < 1) return TOAD_ERR_UNSUPPORTED;
+  // <= 128 output pixels per M tile = wb x hb x bb: full rows first, then whole images
   const int wb = Wo;
-  const int hb = (BLOCK_M / wb) < Ho ? (BLOCK_M / wb) : Ho;
-  const int bb = BLOCK_M / (wb * hb);
+  int hb, bb, tpi;
+  if (Ho * Wo <= BLOCK_M) { hb = Ho; bb = BLOCK_M / (Ho * Wo); tpi = 1; }
+  else { hb = BLOCK_M / Wo; bb = 1; tpi = (Ho + hb - 1) / hb; }
+  if (hb * stride > 256 || wb * stride > 256) return TOAD_ERR_UNSUPPORTED;  // TMA box limits
   p.M = static_cast<int64_t>(B) * Ho * Wo;
   p.K = ksize * ksize * Cin;
   p.conv_kw = ksize;
@@ -1157,10 +1228,17 @@ int launch_conv_gemm(GemmTcParams p, const __nv_bfloat16* in_hi, const __nv_bflo
   p.conv_pad = ksize / 2;
   p.conv_Wo = Wo;
   p.conv_Ho = Ho;
+  p.conv_B = B;
+  p.conv_hb = hb;
+  p.conv_bb = bb;
+  p.conv_tpi = tpi;
+  p.conv_tile_rows = wb * hb * bb;
+  p.conv_mtiles = tpi == 1 ? (B + bb - 1) / bb : B * tpi;
   CUtensorMap ta_hi, ta_lo;
   TOAD_TRY(make_nhwc_tmap(&ta_hi, in_hi, B, H, W, Cin, wb, hb, bb, stride));
-  TOAD_TRY(make_nhwc_tmap(&ta_lo, in_lo, B, H, W, Cin, wb, hb, bb, stride));
-  return launch_gemm_maps<BLOCK_N, A_CONV, EPI_LINEAR, CG, OUT_BUFS>(p, ta_hi, ta_lo, w_hi, w_lo, stream);
+  if (PREC == PREC_BF16X3) TOAD_TRY(make_nhwc_tmap(&ta_lo, in_lo, B, H, W, Cin, wb, hb, bb, stride));
+  else ta_lo = ta_hi;
+  return launch_gemm_maps<BLOCK_N, A_CONV, EPI_LINEAR, CG, OUT_BUFS, PREC>(p, ta_hi, ta_lo, w_hi, w_lo, stream);
 }
 
 }  // namespace tc

@@ -8,6 +8,7 @@
 #include "resnet.cuh"
 #include "train.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <new>
 
 namespace {
@@ -968,37 +969,49 @@ struct ResWs {
   size_t bytes;
 };
 
-ResWs carve_resnet(int B, int H, int W, void* base) {
+// images per stem + layer1 pass (TOAD_RESNET_CHUNK in the environment overrides the default: tuning aid)
+int resnet_chunk() {
+  static int v = []() {
+    const char* e = getenv("TOAD_RESNET_CHUNK");
+    const int c = e != nullptr ? atoi(e) : 0;
+    return c > 0 ? c : kResChunk;
+  }();
+  return v;
+}
+
+// exact = (hi, lo) bf16 plane pairs (4 B / element); default = one fp16 plane (2 B / element, lo pointers stay null)
+ResWs carve_resnet(int B, int H, int W, bool exact, void* base) {
   ResWs w{};
   Carver c(base);
   const int64_t H1 = H / 2, W1 = W / 2, H2 = H / 4, W2 = W / 4;
-  w.stem_chunk = B < kResChunk ? B : kResChunk;
+  w.stem_chunk = B < resnet_chunk() ? B : resnet_chunk();
   const size_t col = static_cast<size_t>(w.stem_chunk) * H1 * W1 * resnet::STEM_KPAD;
   w.col_hi = c.take<bf16>(col);
-  w.col_lo = c.take<bf16>(col);
+  if (exact) w.col_lo = c.take<bf16>(col);
   const size_t stem = static_cast<size_t>(w.stem_chunk) * H1 * W1 * 64;
   w.stem_hi = c.take<bf16>(stem);
-  w.stem_lo = c.take<bf16>(stem);
+  if (exact) w.stem_lo = c.take<bf16>(stem);
   w.pool_hi = c.take<bf16>(stem / 4);
-  w.pool_lo = c.take<bf16>(stem / 4);
+  if (exact) w.pool_lo = c.take<bf16>(stem / 4);
   const size_t act = static_cast<size_t>(B) * H2 * W2 * 256;
   for (int i = 0; i < 5; ++i) {
     w.buf_hi[i] = c.take<bf16>(act);
-    w.buf_lo[i] = c.take<bf16>(act);
+    if (exact) w.buf_lo[i] = c.take<bf16>(act);
   }
   w.bytes = align_up(c.off, 256);
   return w;
 }
 
+// Any H, W that are multiples of 16 up to 512 (the trunk halves the resolution four times; an M tile of the 3x3 /
+// strided convolutions spans full output rows of at most 128 pixels).  224 x 224 and 256 x 256 are the usual patches.
 int check_resnet_shape(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return TOAD_ERR_ARG;
-  if (H % 16 != 0 || W % 16 != 0) return TOAD_ERR_UNSUPPORTED;
-  const int H2 = H / 4, W2 = W / 4;
-  if (W2 > 128 || (W2 & (W2 - 1)) != 0 || (H2 & (H2 - 1)) != 0 || W2 < 4 || H2 < 4) return TOAD_ERR_UNSUPPORTED;
+  if (H % 16 != 0 || W % 16 != 0 || W > 512 || H > 4096) return TOAD_ERR_UNSUPPORTED;
   return 0;
 }
 
 // out planes [M, Cout] = act(conv(in) + bias (+ residual)); in: NHWC planes [B, H, W, Cin]
+template <int PREC>
 int run_conv(const ConvSpec& cs, const PreparedConv& pc, const bf16* in_hi, const bf16* in_lo, int B, int H, int W,
              bf16* out_hi, bf16* out_lo, const bf16* res_hi, const bf16* res_lo, bool relu, cudaStream_t st) {
   tc::GemmTcParams g{};
@@ -1012,59 +1025,18 @@ int run_conv(const ConvSpec& cs, const PreparedConv& pc, const bf16* in_hi, cons
   if (cs.k == 1 && cs.stride == 1) {  // plain GEMM over the NHWC plane
     g.M = static_cast<int64_t>(B) * H * W;
     g.K = cs.cin;
-    if (cs.cout % 256 == 0) return tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 2, kResOutBufs>(g, in_hi, in_lo, pc.hi, pc.lo, st);
-    if (cs.cout % 128 == 0) return tc::launch_gemm<128, tc::A_SPLIT, tc::EPI_LINEAR, 2, kResOutBufs>(g, in_hi, in_lo, pc.hi, pc.lo, st);
-    return tc::launch_gemm<64, tc::A_SPLIT, tc::EPI_LINEAR, 2, kResOutBufs>(g, in_hi, in_lo, pc.hi, pc.lo, st);
+    if (cs.cout % 256 == 0) return tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 2, kResOutBufs, PREC>(g, in_hi, in_lo, pc.hi, pc.lo, st);
+    if (cs.cout % 128 == 0) return tc::launch_gemm<128, tc::A_SPLIT, tc::EPI_LINEAR, 2, kResOutBufs, PREC>(g, in_hi, in_lo, pc.hi, pc.lo, st);
+    return tc::launch_gemm<64, tc::A_SPLIT, tc::EPI_LINEAR, 2, kResOutBufs, PREC>(g, in_hi, in_lo, pc.hi, pc.lo, st);
   }
-  if (cs.cout % 256 == 0) return tc::launch_conv_gemm<256, 2, kResOutBufs>(g, in_hi, in_lo, B, H, W, cs.cin, cs.k, cs.stride, pc.hi, pc.lo, st);
-  if (cs.cout % 128 == 0) return tc::launch_conv_gemm<128, 2, kResOutBufs>(g, in_hi, in_lo, B, H, W, cs.cin, cs.k, cs.stride, pc.hi, pc.lo, st);
-  return tc::launch_conv_gemm<64, 2, kResOutBufs>(g, in_hi, in_lo, B, H, W, cs.cin, cs.k, cs.stride, pc.hi, pc.lo, st);
+  if (cs.cout % 256 == 0) return tc::launch_conv_gemm<256, 2, kResOutBufs, PREC>(g, in_hi, in_lo, B, H, W, cs.cin, cs.k, cs.stride, pc.hi, pc.lo, st);
+  if (cs.cout % 128 == 0) return tc::launch_conv_gemm<128, 2, kResOutBufs, PREC>(g, in_hi, in_lo, B, H, W, cs.cin, cs.k, cs.stride, pc.hi, pc.lo, st);
+  return tc::launch_conv_gemm<64, 2, kResOutBufs, PREC>(g, in_hi, in_lo, B, H, W, cs.cin, cs.k, cs.stride, pc.hi, pc.lo, st);
 }
 
-}  // namespace
-
-extern "C" int toad_resnet_prepared_bytes(size_t* bytes) {
-  if (bytes == nullptr) return TOAD_ERR_ARG;
-  *bytes = carve_prepared(nullptr).bytes;
-  return 0;
-}
-
-extern "C" int toad_resnet_prepare(const float* const* tensors, int32_t n_tensors, void* prepared, size_t prepared_bytes,
-                                   toad_stream_t stream) {
-  if (tensors == nullptr || n_tensors != TOAD_RESNET_N_TENSORS) return TOAD_ERR_ARG;
-  for (int i = 0; i < n_tensors; ++i)
-    if (tensors[i] == nullptr) return TOAD_ERR_ARG;
-  Prepared P = carve_prepared(prepared);
-  TOAD_TRY(check_ws(prepared, prepared_bytes, P.bytes));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  ConvSpec specs[43];
-  build_specs(specs);
-  for (int i = 0; i < 43; ++i) {
-    const float* const* t = tensors + 5 * i;
-    resnet::fold_conv_kernel<<<specs[i].cout, 256, 0, st>>>(t[0], t[1], t[2], t[3], t[4], 1e-5f, P.conv[i].hi, P.conv[i].lo,
-                                                          P.conv[i].bias, specs[i].cout, specs[i].cin, specs[i].k,
-                                                          specs[i].k, kpad_of(specs[i]));
-    TOAD_CUDA_TRY(cudaGetLastError());
-  }
-  return 0;
-}
-
-extern "C" int toad_resnet_workspace_bytes(int32_t B, int32_t H, int32_t W, size_t* bytes) {
-  TOAD_TRY(check_resnet_shape(B, H, W));
-  if (bytes == nullptr) return TOAD_ERR_ARG;
-  *bytes = carve_resnet(B, H, W, nullptr).bytes;
-  return 0;
-}
-
-extern "C" int toad_resnet_fwd(const void* prepared, const float* x, int32_t B, int32_t H, int32_t W, float* out,
-                               void* workspace, size_t workspace_bytes, toad_stream_t stream) {
-  TOAD_TRY(check_resnet_shape(B, H, W));
-  if (prepared == nullptr || x == nullptr || out == nullptr) return TOAD_ERR_ARG;
-  if ((reinterpret_cast<uintptr_t>(prepared) & 255) != 0) return TOAD_ERR_WORKSPACE;
-  Prepared P = carve_prepared(const_cast<void*>(prepared));
-  ResWs w = carve_resnet(B, H, W, workspace);
-  TOAD_TRY(check_ws(workspace, workspace_bytes, w.bytes));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+template <int PREC>
+int resnet_fwd_impl(const Prepared& P, const float* x, int B, int H, int W, float* out, const ResWs& w, cudaStream_t st) {
+  constexpr bool HALF = PREC == tc::PREC_F16X2;
   ConvSpec specs[43];
   build_specs(specs);
   const int H1 = H / 2, W1 = W / 2, H2 = H / 4, W2 = W / 4;
@@ -1086,14 +1058,14 @@ extern "C" int toad_resnet_fwd(const void* prepared, const float* x, int32_t B, 
       const int ys = free_slots[2];
       const Planes y = is_last ? out : s[ys];
       const int ho = h / c2.stride, wo = wd / c2.stride;
-      TOAD_TRY(run_conv(c1, P.conv[ci], x.hi, x.lo, bc, h, wd, t1.hi, t1.lo, nullptr, nullptr, true, st));
-      TOAD_TRY(run_conv(c2, P.conv[ci + 1], t1.hi, t1.lo, bc, h, wd, t2.hi, t2.lo, nullptr, nullptr, true, st));
+      TOAD_TRY(run_conv<PREC>(c1, P.conv[ci], x.hi, x.lo, bc, h, wd, t1.hi, t1.lo, nullptr, nullptr, true, st));
+      TOAD_TRY(run_conv<PREC>(c2, P.conv[ci + 1], t1.hi, t1.lo, bc, h, wd, t2.hi, t2.lo, nullptr, nullptr, true, st));
       Planes res = x;
       if (has_ds) {  // (xs == -1 here: all four scratch slots are free, the fourth holds the shortcut)
         res = s[free_slots[3]];
-        TOAD_TRY(run_conv(specs[ci + 3], P.conv[ci + 3], x.hi, x.lo, bc, h, wd, res.hi, res.lo, nullptr, nullptr, false, st));
+        TOAD_TRY(run_conv<PREC>(specs[ci + 3], P.conv[ci + 3], x.hi, x.lo, bc, h, wd, res.hi, res.lo, nullptr, nullptr, false, st));
       }
-      TOAD_TRY(run_conv(c3, P.conv[ci + 2], t2.hi, t2.lo, bc, ho, wo, y.hi, y.lo, res.hi, res.lo, true, st));
+      TOAD_TRY(run_conv<PREC>(c3, P.conv[ci + 2], t2.hi, t2.lo, bc, ho, wo, y.hi, y.lo, res.hi, res.lo, true, st));
       x = y;
       xs = is_last ? -1 : ys;
       h = ho; wd = wo;
@@ -1105,22 +1077,22 @@ extern "C" int toad_resnet_fwd(const void* prepared, const float* x, int32_t B, 
                           {w.buf_hi[3], w.buf_lo[3]}, {w.buf_hi[4], w.buf_lo[4]}};
 
   // ---- stem (conv1 7x7/s2 as im2col + GEMM, BN, ReLU; resnet_custom.py:97-99), maxpool 3x3/s2 (:100) and layer1,
-  // in chunks of kResChunk images (bounds the im2col scratch: 12.6 MB per image); layer1's output of every chunk
-  // lands in its slice of bufs[4].
+  // in chunks of stem_chunk images (bounds the im2col scratch); layer1's output of every chunk lands in its slice
+  // of bufs[4].
   const int64_t l1_img = static_cast<int64_t>(H2) * W2 * 256;  // elements per image of a layer1-sized plane
   for (int b0 = 0; b0 < B; b0 += w.stem_chunk) {
     const int nb = (B - b0) < w.stem_chunk ? (B - b0) : w.stem_chunk;
     const int64_t rows = static_cast<int64_t>(nb) * H1 * W1;
-    TOAD_TRY(resnet::launch_stem_im2col(x + static_cast<int64_t>(b0) * 3 * H * W, w.col_hi, w.col_lo, nb, H, W, H1, W1, st));
+    TOAD_TRY(resnet::launch_stem_im2col<HALF>(x + static_cast<int64_t>(b0) * 3 * H * W, w.col_hi, w.col_lo, nb, H, W, H1, W1, st));
     tc::GemmTcParams g{};
     g.M = rows; g.N = 64; g.K = resnet::STEM_KPAD; g.bias = P.conv[0].bias; g.relu = 1;
     g.out_hi = w.stem_hi; g.out_lo = w.stem_lo; g.ld_split = 64;
-    TOAD_TRY((tc::launch_gemm<64, tc::A_SPLIT, tc::EPI_LINEAR, 2, kResOutBufs>(g, w.col_hi, w.col_lo, P.conv[0].hi, P.conv[0].lo, st)));
+    TOAD_TRY((tc::launch_gemm<64, tc::A_SPLIT, tc::EPI_LINEAR, 2, kResOutBufs, PREC>(g, w.col_hi, w.col_lo, P.conv[0].hi, P.conv[0].lo, st)));
     const int64_t threads = static_cast<int64_t>(nb) * H2 * W2 * (64 / 8);
-    resnet::maxpool3x3s2_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
+    resnet::maxpool3x3s2_kernel<HALF><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
         w.stem_hi, w.stem_lo, w.pool_hi, w.pool_lo, nb, H1, W1, 64);
     TOAD_CUDA_TRY(cudaGetLastError());
-    const Planes l1_out = {bufs[4].hi + b0 * l1_img, bufs[4].lo + b0 * l1_img};
+    const Planes l1_out = {bufs[4].hi + b0 * l1_img, HALF ? nullptr : bufs[4].lo + b0 * l1_img};
     TOAD_TRY(run_layer(0, 1, nb, H2, W2, Planes{w.pool_hi, w.pool_lo}, bufs, l1_out));
   }
   // ---- layer2, layer3 over the whole batch
@@ -1129,7 +1101,62 @@ extern "C" int toad_resnet_fwd(const void* prepared, const float* x, int32_t B, 
   TOAD_TRY(run_layer(2, 1 + 10 + 13, B, H2 / 2, W2 / 2, bufs[4], bufs, bufs[4]));
   const int cur = 4, h = H2 / 4, wd = W2 / 4;
   // ---- global average pool + flatten (resnet_custom.py:106-107)
-  resnet::avgpool_kernel<<<dim3(B, 1024 / 256), 256, 0, st>>>(w.buf_hi[cur], w.buf_lo[cur], out, h * wd, 1024);
+  resnet::avgpool_kernel<HALF><<<dim3(B, 1024 / 256), 256, 0, st>>>(w.buf_hi[cur], w.buf_lo[cur], out, h * wd, 1024);
   TOAD_CUDA_TRY(cudaGetLastError());
   return 0;
+}
+
+}  // namespace
+
+extern "C" int toad_resnet_prepared_bytes(size_t* bytes) {
+  if (bytes == nullptr) return TOAD_ERR_ARG;
+  *bytes = carve_prepared(nullptr).bytes;
+  return 0;
+}
+
+extern "C" int toad_resnet_prepare(const float* const* tensors, int32_t n_tensors, void* prepared, size_t prepared_bytes,
+                                   uint32_t flags, toad_stream_t stream) {
+  if (tensors == nullptr || n_tensors != TOAD_RESNET_N_TENSORS) return TOAD_ERR_ARG;
+  for (int i = 0; i < n_tensors; ++i)
+    if (tensors[i] == nullptr) return TOAD_ERR_ARG;
+  Prepared P = carve_prepared(prepared);
+  TOAD_TRY(check_ws(prepared, prepared_bytes, P.bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ConvSpec specs[43];
+  build_specs(specs);
+  const bool exact = (flags & TOAD_RESNET_FLAG_EXACT) != 0;
+  for (int i = 0; i < 43; ++i) {
+    const float* const* t = tensors + 5 * i;
+    if (exact)
+      resnet::fold_conv_kernel<false><<<specs[i].cout, 256, 0, st>>>(t[0], t[1], t[2], t[3], t[4], 1e-5f, P.conv[i].hi, P.conv[i].lo,
+                                                                   P.conv[i].bias, specs[i].cout, specs[i].cin, specs[i].k,
+                                                                   specs[i].k, kpad_of(specs[i]));
+    else
+      resnet::fold_conv_kernel<true><<<specs[i].cout, 256, 0, st>>>(t[0], t[1], t[2], t[3], t[4], 1e-5f, P.conv[i].hi, P.conv[i].lo,
+                                                                  P.conv[i].bias, specs[i].cout, specs[i].cin, specs[i].k,
+                                                                  specs[i].k, kpad_of(specs[i]));
+    TOAD_CUDA_TRY(cudaGetLastError());
+  }
+  return 0;
+}
+
+extern "C" int toad_resnet_workspace_bytes(int32_t B, int32_t H, int32_t W, uint32_t flags, size_t* bytes) {
+  TOAD_TRY(check_resnet_shape(B, H, W));
+  if (bytes == nullptr) return TOAD_ERR_ARG;
+  *bytes = carve_resnet(B, H, W, (flags & TOAD_RESNET_FLAG_EXACT) != 0, nullptr).bytes;
+  return 0;
+}
+
+extern "C" int toad_resnet_fwd(const void* prepared, const float* x, int32_t B, int32_t H, int32_t W, float* out,
+                               void* workspace, size_t workspace_bytes, uint32_t flags, toad_stream_t stream) {
+  TOAD_TRY(check_resnet_shape(B, H, W));
+  if (prepared == nullptr || x == nullptr || out == nullptr) return TOAD_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(prepared) & 255) != 0) return TOAD_ERR_WORKSPACE;
+  const bool exact = (flags & TOAD_RESNET_FLAG_EXACT) != 0;
+  Prepared P = carve_prepared(const_cast<void*>(prepared));
+  ResWs w = carve_resnet(B, H, W, exact, workspace);
+  TOAD_TRY(check_ws(workspace, workspace_bytes, w.bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return exact ? resnet_fwd_impl<tc::PREC_BF16X3>(P, x, B, H, W, out, w, st)
+               : resnet_fwd_impl<tc::PREC_F16X2>(P, x, B, H, W, out, w, st);
 }

@@ -4,13 +4,19 @@
 (``ResNet_Baseline(Bottleneck_Baseline, [3, 4, 6, 3])``, truncated after layer3, so the
 ``state_dict`` keys are torchvision's resnet50 names) but ``forward`` runs the whole trunk in
 hand-written sm_100a kernels behind the C ABI (``toad_resnet_fwd``): BatchNorm folded into the
-weights, NHWC (hi, lo) bf16 activations, every convolution a tcgen05 split-bf16 (implicit) GEMM
-with bias / residual / ReLU fused in the epilogue.  Only eval mode (running statistics) is
-implemented -- the reference's use is offline feature extraction.
+weights, NHWC activations, every convolution a tcgen05 (implicit) GEMM with bias / residual / ReLU
+fused in the epilogue.  Only eval mode (running statistics) is implemented -- the reference's use is
+offline feature extraction.
+
+Two arithmetic modes (``model.precision``; env ``TOAD_B200_RESNET_EXACT=1`` selects the second as default):
+``"f16x2"`` (default) keeps activations as one fp16 plane between layers and the weights as fp16 (hi, lo)
+pairs -- activation rounding 2^-11, the input precision of the TF32 convolutions cuDNN runs for the
+reference on a GPU; ``"bf16x3"`` keeps (hi, lo) bf16 plane pairs and three tensor passes (fp32-class).
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -72,6 +78,12 @@ class ResNet_Baseline(nn.Module):
         self._prepared = None
         self._prepared_key = None
         self._ws = ops.Workspace()
+        self.precision = "bf16x3" if os.environ.get("TOAD_B200_RESNET_EXACT", "0") == "1" else "f16x2"
+
+    def _flags(self) -> int:
+        if self.precision not in ("f16x2", "bf16x3"):
+            raise ValueError("precision must be 'f16x2' or 'bf16x3', got %r" % (self.precision,))
+        return _lib.RESNET_FLAG_EXACT if self.precision == "bf16x3" else 0
 
     @staticmethod
     def _init_module(m: nn.Module) -> None:
@@ -99,7 +111,8 @@ class ResNet_Baseline(nn.Module):
     def _prepare(self, device):
         lib = _lib.load()
         tensors = self._tensor_list()
-        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        flags = self._flags()
+        key = tuple((t.data_ptr(), t._version) for t in tensors) + (flags,)
         if self._prepared is not None and key == self._prepared_key and self._prepared.device == device:
             return
         for t in tensors:
@@ -109,7 +122,7 @@ class ResNet_Baseline(nn.Module):
         buf = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=device)
         arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
         ptr = (buf.data_ptr() + 255) // 256 * 256
-        _lib.check(lib.toad_resnet_prepare(arr, len(tensors), ptr, nbytes.value, ops._stream()), "toad_resnet_prepare")
+        _lib.check(lib.toad_resnet_prepare(arr, len(tensors), ptr, nbytes.value, flags, ops._stream()), "toad_resnet_prepare")
         self._prepared, self._prepared_key, self._prepared_ptr, self._prepared_bytes = buf, key, ptr, nbytes.value
 
     def invalidate_weight_cache(self) -> None:
@@ -135,10 +148,11 @@ class ResNet_Baseline(nn.Module):
         else:
             ops._check_dev_f32(out, "out", (B, 1024))
         nbytes = C.c_size_t()
-        _lib.check(lib.toad_resnet_workspace_bytes(B, H, W, C.byref(nbytes)), "toad_resnet_workspace_bytes")
+        flags = self._flags()
+        _lib.check(lib.toad_resnet_workspace_bytes(B, H, W, flags, C.byref(nbytes)), "toad_resnet_workspace_bytes")
         wptr, wsize = self._ws.get(nbytes.value, x.device)
         _lib.check(lib.toad_resnet_fwd(self._prepared_ptr, x.data_ptr(), B, H, W, out.data_ptr(), wptr, wsize,
-                                       ops._stream()), "toad_resnet_fwd")
+                                       flags, ops._stream()), "toad_resnet_fwd")
         return out
 
 
