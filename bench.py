@@ -4,13 +4,13 @@
     python bench.py --gpus 1 --steps K --warmup W            # our arm (1 process per GPU under torchrun)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
 
-One step = one pass of the hot path over `slides_per_step` synthetic slides (N x 1024 fp32
-each): by default one `TOAD_fc_mtl_concat.forward_batch` call over the step's 16 slides (bags back to back, one set
-of trunk launches, per-slide pooling); `--batch 1` runs one forward per slide through
-`toad_b200.pipeline.ResidentRunner` (three slides in flight on three CUDA streams).  `value` = whole-job slides/s with
-bags resident in HBM (4 distinct 205 MB bags per GPU, larger than L2, rotated); `value_single_stream`
-= the same steps strictly serial; `e2e` = the same metric through the public API with pinned host
-bags copied H2D inside the timed region and results read back.  Prints ONE JSON line.
+One step = one pass of the hot path over `slides_per_step` synthetic slides (N x 1024 fp32 each), one
+`model(data, sex)` call per slide on one stream -- the call the reference's train_loop / summary make.  `value` =
+whole-job slides/s with bags resident in HBM (4 distinct 205 MB bags per GPU, larger than L2, rotated);
+`value_in_flight` / `value_forward_batch` = the same work with several slides in flight / per call (APIs beyond the
+reference's); `e2e` = the same metric through the public API with pinned host bags copied H2D inside the timed
+region and results read back (+ the H2D-only ceiling); `train` = config 4, the fused training step with the NCCL
+gradient all-reduce on N GPUs; `resnet50_baseline` = config 3 next to eager cuDNN.  Prints ONE JSON line.
 """
 import argparse
 import json
@@ -168,11 +168,29 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _max_over_ranks(ms, dev, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _sum_over_ranks(v, dev, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([v], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from toad_b200 import ops
-    from toad_b200.pipeline import SlideStreamer
+    from toad_b200.pipeline import ResidentRunner, SlideStreamer
     from models.model_toad import TOAD_fc_mtl_concat
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -181,10 +199,11 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION/INFO in some environments) goes
-        # to stdout too, so keep NCCL at WARN unless the caller insists
-        if os.environ.get("TOAD_BENCH_KEEP_NCCL_DEBUG", "0") != "1":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries exactly one JSON line; NCCL's own log (communicator / rank / transport lines, the evidence that
+        # N ranks really formed one communicator) goes to stderr instead of being muted
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     S = args.slides_per_step
     n = args.n_patches
@@ -203,79 +222,77 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    from toad_b200.pipeline import ResidentRunner
-    runner = ResidentRunner(model, n_streams=args.streams, device=dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    B = max(1, min(args.batch, 16, S))
-    while S % B:
-        B -= 1
-    if B > 1:   # small bags: B slides back to back per forward_batch call (one set of trunk launches for all of them)
-        cats = [torch.cat([bags[(j + b) % n_bags] for b in range(B)], 0) for j in range(2)]
-        sexes_b = torch.ones(B, device=dev)
+    def timed(step_fn, steps, warmup):
+        """W warm-up steps, then exactly `steps` steps between barrier + synchronize, device-timed, max over ranks."""
+        for i in range(warmup):
+            step_fn(i)
+        barrier()
+        ev0.record()
+        for i in range(steps):
+            step_fn(i)
+        ev1.record()
+        barrier()
+        return _max_over_ranks(ev0.elapsed_time(ev1), dev, world)
 
-    def step(i):   # one step = one batch of S resident slides through the public runner (--streams slides in flight)
-        if B > 1:
-            for c in range(S // B):
-                model.forward_batch(cats[(i + c) % 2], [n] * B, sexes_b)
-            return
-        runner.run([bags[(i * S + s) % n_bags] for s in range(S)], [sex] * S)
-
-    def step_serial(i):
+    # ---- value: the reference's own surface -- one `model(data, sex)` call per slide (core_utils_mtl_concat.py:206,
+    # eval_utils_mtl_concat.py:91), strictly serial on the current stream, bags resident in HBM
+    def step_forward(i):
         with torch.no_grad():
             for s in range(S):
                 model(bags[(i * S + s) % n_bags], sex)
 
-    # ---- value: inputs resident in HBM
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()                       # NVML init happens during the warm-up, sampling every 2 ms
     for i in range(args.warmup):
-        step(i)
-    prof = ops.Profile(args.steps * S)
-    model._prof = prof.handle
+        step_forward(i)
     barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if sampler:
         sampler.t0 = time.perf_counter()
     ev0.record()
     for i in range(args.steps):
-        step(i)
+        step_forward(i)
     ev1.record()
     barrier()
     if sampler:
         sampler.t1 = time.perf_counter()
         sampler.stop_flag.set()
-    elapsed_ms = ev0.elapsed_time(ev1)
-    model._prof = None
-    stages, calls = prof.read()
-    prof.close()
-    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
+    elapsed_ms = _max_over_ranks(ev0.elapsed_time(ev1), dev, world)
     total_slides = args.steps * S * world
     value = total_slides / (elapsed_ms / 1e3)
 
-    # ---- extra: the same K steps strictly serial on one stream: clean per-kernel durations for the roofline
-    # explanation (in the timed region above two slides share the SMs, which stretches every kernel's wall time)
-    prof2 = ops.Profile(args.steps * S)
-    model._prof = prof2.handle
-    for i in range(min(args.warmup, 2)):
-        step_serial(i)
-    prof2.read()
-    barrier()
-    ev0.record()
-    for i in range(args.steps):
-        step_serial(i)
-    ev1.record()
-    barrier()
+    # ---- per-kernel CUDA-event stage times of the same forwards (a separate, shorter pass: the stage events sit
+    # between the kernels, so they are kept out of the headline region)
+    prof_calls = min(args.steps * S, 256)
+    prof = ops.Profile(prof_calls)
+    model._prof = prof.handle
+    with torch.no_grad():
+        for c in range(prof_calls):
+            model(bags[c % n_bags], sex)
+    torch.cuda.synchronize()
     model._prof = None
-    stages_serial, calls_serial = prof2.read()
-    prof2.close()
-    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    value_single_stream = total_slides / (float(t.item()) / 1e3)
+    stages_serial, calls_serial = prof.read()
+    prof.close()
+
+    # ---- extras beyond the reference's surface: slides in flight on several streams, and several bags per call
+    extra_steps = max(1, args.steps // 4)
+    runner = ResidentRunner(model, n_streams=args.streams, device=dev)
+    ms = timed(lambda i: runner.run([bags[(i * S + s) % n_bags] for s in range(S)], [sex] * S), extra_steps, 1)
+    value_in_flight = extra_steps * S * world / (ms / 1e3)
+    B = max(1, min(args.batch, 16, S))
+    while S % B:
+        B -= 1
+    cats = [torch.cat([bags[(j + b) % n_bags] for b in range(B)], 0) for j in range(2)]
+    sexes_b = torch.ones(B, device=dev)
+
+    def step_batch(i):
+        for c in range(S // B):
+            model.forward_batch(cats[(i + c) % 2], [n] * B, sexes_b)
+    ms = timed(step_batch, extra_steps, 1)
+    value_forward_batch = extra_steps * S * world / (ms / 1e3)
+    del cats
 
     # ---- e2e: pinned host bags -> H2D -> forward -> D2H results, through the public API
     host_bags = [torch.randn(n, WIDTH).pin_memory() for _ in range(2)]
@@ -288,52 +305,69 @@ def run_ours(args):
     streamer.run([(host_bags[i % 2], float(i % 2)) for i in range(e2e_slides)])
     ev1.record()
     barrier()
-    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
+    e2e_ms = _max_over_ranks(ev0.elapsed_time(ev1), dev, world)
     e2e_value = e2e_slides * world / (e2e_ms / 1e3)
     e2e_steps = e2e_slides / S
+    h2d_per_step, d2h_per_step = int(streamer.h2d_bytes / max(e2e_steps, 1e-9)), int(streamer.d2h_bytes / max(e2e_steps, 1e-9))
+    # the ceiling of that number: the same pinned -> device copies alone, every rank at once
+    copy_reps = 8
+    dst = bags[0]
+    for _ in range(2):
+        dst.copy_(host_bags[0], non_blocking=True)
+    barrier()
+    ev0.record()
+    for i in range(copy_reps):
+        dst.copy_(host_bags[i % 2], non_blocking=True)
+    ev1.record()
+    barrier()
+    h2d_ms = _max_over_ranks(ev0.elapsed_time(ev1), dev, world)
+    h2d_gbs = copy_reps * world * n * WIDTH * 4 / (h2d_ms / 1e3) / 1e9
+    del host_bags, streamer
+
+    train = None if args.no_train else train_leg(args, model, dev, world, rank, barrier)
 
     if rank == 0:
         pk = peaks()
-        fc1_ms = stages["fc1_gemm"] / max(calls, 1)
-        fc1_tflops = FC1_FLOP_PER_PATCH * n / (fc1_ms * 1e-3) / 1e12 if fc1_ms > 0 else 0.0
         whole_ms = sum(stages_serial.values()) / max(calls_serial, 1)
         fc1_serial_ms = stages_serial["fc1_gemm"] / max(calls_serial, 1)
         fc1_serial_tflops = FC1_FLOP_PER_PATCH * n / (fc1_serial_ms * 1e-3) / 1e12 if fc1_serial_ms > 0 else 0.0
+        traffic = None if (args.no_traffic or world > 1) else measure_fc1_traffic(n)
         line = {
             "metric": "slides_per_sec_n50k", "value": value, "unit": "slides/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16x3-split (fp32 accumulate; fp32-class accuracy)", "data": "synthetic",
             "config": {"workload": "TOAD_fc_mtl_concat forward (eval), N=%d x %d fp32, big, n_classes=18" % (n, WIDTH),
-                       "slides_per_step": S, "slides_in_flight": args.streams if B == 1 else 1, "slides_per_call": B,
+                       "slides_per_step": S, "slides_per_call": 1, "slides_in_flight": 1,
+                       "api": "model(data, sex) per slide on one stream -- the call the reference's train_loop / summary make",
                        "parallelism": "one slide per GPU, replicas (no collective in eval)",
                        "l2_policy": "%d distinct %.0f MB bags per GPU rotated (inputs larger than the 126 MB L2)" % (
                            n_bags, n * WIDTH * 4 / 1e6)},
             "clocks": sampler.summary() if sampler else None,
-            "e2e": {"value": e2e_value, "unit": "slides/s", "h2d_bytes_per_step": int(streamer.h2d_bytes / max(e2e_steps, 1e-9)),
-                    "d2h_bytes_per_step": int(streamer.d2h_bytes / max(e2e_steps, 1e-9)), "slides": e2e_slides,
+            "e2e": {"value": e2e_value, "unit": "slides/s", "h2d_bytes_per_step": h2d_per_step,
+                    "d2h_bytes_per_step": d2h_per_step, "slides": e2e_slides,
+                    "h2d_only": {"gb_per_s": h2d_gbs, "slides_per_s_ceiling": h2d_gbs * 1e9 / (n * WIDTH * 4),
+                                 "note": "the same pinned-host -> device copies with no compute, all %d rank(s) at once: "
+                                         "the host-link ceiling of the e2e number" % world},
                     "note": "pinned host bags, double-buffered H2D overlapped with compute (toad_b200.pipeline.SlideStreamer)"},
-            "value_single_stream": value_single_stream,   # the same K steps strictly serial on one stream
-            # per forward / forward_batch call: 3 tcgen05 GEMMs + 1 pooling launch (+ 3 weight-split launches once)
-            "gpu_launches": 4 * (S // B if B > 1 else S) * args.steps + 3,
+            # extras beyond the reference's API (not the headline): several slides in flight / per call
+            "value_in_flight": value_in_flight, "value_forward_batch": value_forward_batch,
+            "extras_note": "value_in_flight = the same per-slide forwards with %d slides in flight on %d CUDA streams "
+                           "(ResidentRunner); value_forward_batch = %d bags per forward_batch call" % (args.streams, args.streams, B),
+            # per forward: 3 tcgen05 GEMMs + 1 pooling launch (+ 3 weight-split launches once)
+            "gpu_launches": 4 * S * args.steps + 3,
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16x3_kernel<512,A_F32,EPI_LINEAR,2> (fc1, 44% of FLOPs)",
                          "achieved": fc1_serial_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                          "frac": fc1_serial_tflops / pk["bf16_tflops"], "peak_source": pk["src"] + " bf16 burst",
                          "executed_tflops": 3 * fc1_serial_tflops, "executed_frac": 3 * fc1_serial_tflops / pk["bf16_tflops"],
-                         "note": "achieved = algorithmic fp32 FLOPs of fc1 / its average CUDA-event duration when the kernel has "
-                                 "the GPU to itself (the single-stream pass behind value_single_stream); the kernel executes 3 "
-                                 "bf16 tensor passes per algorithmic FLOP (split precision), so frac tops out at 1/3",
-                         "traffic": 256.4e6 if n == N_PATCHES else None,
-                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel per launch, ncu --set full "
-                                         "(profiles/r1n_fwd_full.txt: 207.0 MB + 49.4 MB; algorithmic 205 MB x + 102 MB h1 planes, "
-                                         "part of which is still in L2 when the kernel ends)",
+                         "note": "achieved = algorithmic fp32 FLOPs of fc1 / its average CUDA-event duration over %d serial "
+                                 "forwards; the kernel executes 3 bf16 tensor passes per algorithmic FLOP (split precision), "
+                                 "so frac tops out at 1/3" % calls_serial,
+                         "traffic": traffic["bytes"] if traffic else None,
+                         "traffic_note": (traffic["note"] if traffic else
+                                          "not measured in this run (ncu unavailable or --no-traffic); see profiles/ for the "
+                                          "committed capture") + "; algorithmic: %.1f MB of x + %.1f MB of h1 planes" % (
+                                              n * 4096 / 1e6, n * 2048 / 1e6),
                          "stage_ms": {k: v / max(calls_serial, 1) for k, v in stages_serial.items()},
-                         "in_flight": {"achieved": fc1_tflops, "frac": fc1_tflops / pk["bf16_tflops"],
-                                       "stage_ms": {k: v / max(calls, 1) for k, v in stages.items()},
-                                       "note": "the same launches inside the headline region, where the slides in flight share the "
-                                               "SMs: each launch is stretched, the sum of both streams' work finishes sooner"},
                          "forward_hbm_gbs": BYTES_PER_PATCH * n / (whole_ms * 1e-3) / 1e9 if whole_ms > 0 else None,
                          "hbm_peak_gbs": pk["hbm_gbs"]},
         }
@@ -342,14 +376,13 @@ def run_ours(args):
         tail_gbs = TAIL_BYTES_PER_PATCH * n / (tail_ms * 1e-3) / 1e9 if tail_ms > 0 else 0.0
         line["roofline_tail"] = {"bound": "hbm", "kernel": "pool_heads_kernel", "achieved": tail_gbs, "peak": pk["hbm_gbs"],
                                  "unit": "GB/s", "frac": tail_gbs / pk["hbm_gbs"],
-                                 "note": "CUDA-event stage time (includes the launch gap after the gate GEMM); ~10 us of it is "
-                                         "the serial two-level merge + heads after the streaming phase (DESIGN.md section 5)"}
-        if B > 1:   # forward_batch has no per-stage events: the per-kernel times come from the serial pass only
-            line["roofline"].pop("in_flight", None)
+                                 "note": "CUDA-event stage time (includes the launch gap after the gate GEMM)"}
+        if train is not None:
+            line["train"] = train
         if world == 1 and not args.no_eager_baseline:
             line["eager_gpu_baseline"] = eager_gpu_leg(dev, n)
         if world == 1 and not args.no_resnet:
-            line["resnet50_baseline"] = resnet_leg(dev)
+            line["resnet50_baseline"] = resnet_leg(dev, args)
         if world == 1 and not args.no_cpu_baseline:
             rate, done, cores, total = cpu_reference_rate(n, 40, 1, budget_s=15.0)
             line["cpu_baseline"] = {"value": rate, "unit": "slides/s", "cores": cores, "kind": "port",
@@ -359,6 +392,139 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def train_leg(args, model, dev, world, rank, barrier):
+    """Config 4: the reference's training step (core_utils_mtl_concat.py:198-234: forward, 0.75 CE +
+    0.25 CE, backward, Adam) on synthetic slides of N ~ U[5k, 80k] patches, one slide per GPU per step, the flat fp32
+    gradient (4.77 MB) all-reduced over NCCL before the (identical) Adam step on every rank.  64 slides per GPU (weak
+    scaling: 512 slides at 8 GPUs = the config), length-bucketed rounds (toad_b200.distributed.aligned_rounds)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from toad_b200.distributed import aligned_rounds
+    from toad_b200.train import FusedTrainStep
+    per_gpu = args.train_slides
+    rng = np.random.default_rng(7)
+    total = per_gpu * world
+    lengths = rng.integers(5000, 80001, size=total).tolist()
+    labels = rng.integers(0, 18, size=total).tolist()
+    sites = rng.integers(0, 2, size=total).tolist()
+    sexes = rng.integers(0, 2, size=total).tolist()
+    rounds = aligned_rounds(lengths, world, seed=0)
+    max_n = max(lengths)
+    gen = torch.Generator(device=dev).manual_seed(500 + rank)
+    pool = [torch.randn(max_n, WIDTH, generator=gen, device=dev) for _ in range(3)]   # 3 x 328 MB > L2; slides = row prefixes
+    lab_t = [torch.tensor([c], device=dev) for c in range(18)]
+    bin_t = [torch.tensor([c], device=dev) for c in range(2)]
+    sex_t = [torch.tensor([float(c)], device=dev) for c in range(2)]
+    torch.manual_seed(0)
+    for p in model.parameters():            # identical start on every rank (the eval legs never changed them, but be explicit)
+        if world > 1:
+            dist.broadcast(p.data, 0)
+    model.train()
+    fused = FusedTrainStep(model, lr=1e-4, weight_decay=1e-5, max_patches=max_n)
+
+    def run_round(s, r):
+        i = r[rank]
+        real = sum(1 for j in r if j >= 0)
+        if i < 0:
+            fused.step_idle(real)
+            return 0
+        x = pool[s % 3][:lengths[i]]
+        fused.step(x, lab_t[labels[i]], bin_t[sites[i]], sex_t[sexes[i]], n_slides_in_round=real)
+        return lengths[i]
+
+    # warm-up: >= 5 steps, the first on the largest slide (sizes every workspace; first NCCL collective)
+    big = max(range(total), key=lambda j: lengths[j])
+    fused.step(pool[0][:lengths[big]], lab_t[0], bin_t[0], sex_t[0])
+    for s in range(5):
+        run_round(s, rounds[s % len(rounds)])
+    barrier()
+    nst = len(rounds)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(nst)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    patches = 0
+    e0.record()
+    for s, r in enumerate(rounds):
+        fused.timing_events = evs[s]
+        patches += run_round(s, r)
+    e1.record()
+    barrier()
+    fused.timing_events = None
+    ms = _max_over_ranks(e0.elapsed_time(e1), dev, world)
+    comp = sum(e[0].elapsed_time(e[1]) for e in evs) / nst
+    allr = sum(e[1].elapsed_time(e[2]) for e in evs) / nst
+    adam = sum(e[2].elapsed_time(e[3]) for e in evs) / nst
+    comp_max = _max_over_ranks(comp, dev, world)
+    allr_min = -_max_over_ranks(-allr, dev, world)      # the rank that waits least ~ the collective itself
+    patches_all = _sum_over_ranks(float(patches), dev, world)
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    same = 1.0
+    if world > 1:
+        ref = flat.clone()
+        dist.broadcast(ref, 0)
+        same = float(torch.equal(ref, flat))
+    same_all = _sum_over_ranks(same, dev, world) == world
+    # the same slides of THIS rank with no collective: what N independent GPUs would do (efficiency denominator)
+    fused.allreduce = False
+    for s in range(3):
+        run_round(s, rounds[s])
+    torch.cuda.synchronize()
+    e0.record()
+    mine = 0
+    for s, r in enumerate(rounds):
+        if r[rank] >= 0:
+            mine += 1
+            run_round(s, r)
+    e1.record()
+    torch.cuda.synchronize()
+    solo_rate = mine / (e0.elapsed_time(e1) / 1e3)
+    fused.allreduce = True
+    ideal = _sum_over_ranks(solo_rate, dev, world)
+    model.eval()
+    value = total / (ms / 1e3)
+    return {"metric": "train_slides_per_sec_config4", "value": value, "unit": "slides/s", "patches_per_s": patches_all / (ms / 1e3),
+            "steps": nst, "slides": total, "ms_per_step": ms / nst,
+            "split_ms": {"fwd_loss_bwd_max_rank": comp_max, "allreduce_min_rank": allr_min, "allreduce_mean_this_rank": allr,
+                         "adam": adam},
+            "independent_gpus_slides_per_s": ideal, "efficiency_vs_independent_gpus": value / ideal if ideal > 0 else None,
+            "params_identical_across_ranks": bool(same_all),
+            "config": {"workload": "config 4: FusedTrainStep (fwd + 0.75/0.25 CE + bwd + Adam lr 1e-4 wd 1e-5), %d slides per GPU, "
+                                   "N ~ U[5000, 80000] seed 7, mean %.0f patches" % (per_gpu, sum(lengths) / total),
+                       "collective": "1 NCCL all-reduce of the flat fp32 gradient (4,769,960 B) per step" if world > 1 else "none (1 GPU)",
+                       "schedule": "length-bucketed synchronous rounds (aligned_rounds), warm-up 6 steps, device-timed, max over ranks"}}
+
+
+def measure_fc1_traffic(n):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the fc1 kernel, per launch, measured NOW on this box: one short
+    forward-only workload (tools/profile_fwd.py) re-run under `ncu --metrics` (2 counters, 1 replay pass)."""
+    import csv
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k",
+           "regex:gemm_bf16x3", "--csv", sys.executable, os.path.join(ROOT, "tools", "profile_fwd.py"), "--n", str(n),
+           "--iters", "3"]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0")))
+        rows = list(csv.reader(l for l in r.stdout.splitlines() if l.startswith('"')))
+        hdr = rows[0]
+        ki, mi, vi, ii = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
+        per = {}
+        for row in rows[1:]:
+            if "<512, 0, 0, 2" in row[ki].replace("(int)", ""):
+                per.setdefault(row[ii], {})[row[mi]] = float(row[vi].replace(",", ""))
+        vals = [d for d in per.values() if len(d) == 2]
+        if not vals:
+            return None
+        last = vals[-1]                       # the last launch: warm instruction cache, cold data (the bag exceeds L2)
+        rd, wr = last["dram__bytes_read.sum"], last["dram__bytes_write.sum"]
+        return {"bytes": rd + wr, "note": "measured in this run: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum on the fc1 "
+                                          "launch of tools/profile_fwd.py --n %d (read %.1f MB + written %.1f MB)" % (n, rd / 1e6, wr / 1e6)}
+    except Exception:
+        return None
 
 
 def eager_gpu_leg(dev, n):
@@ -389,33 +555,70 @@ def eager_gpu_leg(dev, n):
     return out
 
 
-def resnet_leg(dev):
-    """Secondary number (config 3): resnet50_baseline feature extraction, synthetic 3x256x256 patches."""
+def resnet_leg(dev, args):
+    """Config 3: resnet50_baseline feature extraction, synthetic 3x256x256 patches, batch 512, both arithmetic modes,
+    next to the same network in torch eager on this GPU (cuDNN fp32 and cuDNN + TF32, torch's default for
+    convolutions = what the unmodified reference runs on a GPU)."""
+    import numpy as np
     import torch
     from models.resnet_custom import resnet50_baseline
-    torch.manual_seed(1)
-    model = resnet50_baseline(pretrained=False).to(dev).eval()
-    B = 256
+    from oracle import resnet_oracle as RO
+    params = RO.make_params(1)
+    sd = {k: torch.from_numpy(np.asarray(v).copy()) for k, v in params.items()}
+    B = args.resnet_batch
     x = torch.randn(B, 3, 256, 256, device=dev)
-    with torch.no_grad():
+    pk = peaks()
+    out = {"batch": B, "flop_per_patch": 8562671616, "weights": "kaiming-normal convs, randomised BatchNorm statistics (oracle.make_params(1)), eval mode"}
+    feats = {}
+
+    def timed(fn, reps):
         for _ in range(2):
-            model(x)
+            fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        reps = 4
         for _ in range(reps):
-            model(x)
+            fn()
         e1.record()
         torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    pps = B / ms * 1e3
-    tf = 8.562671616e9 * pps / 1e12
-    pk = peaks()
-    return {"patches_per_s": pps, "batch": B, "ms_per_batch": ms, "algorithmic_tflops": tf,
-            "executed_tflops": 3 * tf, "executed_frac_of_bf16_peak": 3 * tf / pk["bf16_tflops"],
-            "note": "BN-folded implicit-GEMM convs on the split-bf16 tcgen05 kernel (3 tensor passes per FLOP), "
-                    "8.563 GFLOP/patch (SURVEY.md R3); kaiming-init weights, eval mode"}
+        return e0.elapsed_time(e1) / reps
+
+    with torch.no_grad():
+        for prec, passes in (("f16x2", 2), ("bf16x3", 3)):
+            model = resnet50_baseline(pretrained=False)
+            model.load_state_dict(sd, strict=True)
+            model = model.to(dev).eval()
+            model.precision = prec
+            ms = timed(lambda: model(x), 6)
+            pps = B / ms * 1e3
+            tf = 8.562671616e9 * pps / 1e12
+            out[prec] = {"patches_per_s": pps, "ms_per_batch": ms, "algorithmic_tflops": tf, "tensor_passes": passes,
+                         "executed_tflops": passes * tf,
+                         "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                                      "frac": tf / pk["bf16_tflops_sustained"],
+                                      "executed_frac": passes * tf / pk["bf16_tflops_sustained"],
+                                      "peak_source": pk["src"] + " bf16 sustained (a whole-network step)"}}
+            feats[prec] = model(x[:8].contiguous())
+            del model
+        if not args.no_eager_baseline:
+            dp = {k: (v.to(dev) if v.dim() else v) for k, v in sd.items()}
+            nb = min(B, 128)
+            for name, tf32 in (("cudnn_fp32", False), ("cudnn_tf32", True)):
+                torch.backends.cudnn.allow_tf32 = tf32
+                torch.backends.cudnn.benchmark = True
+                ms = timed(lambda: RO.resnet50_baseline_forward(x[:nb], dp), 3)
+                out["eager_" + name] = {"patches_per_s": nb / ms * 1e3, "batch": nb}
+                feats[name] = RO.resnet50_baseline_forward(x[:8].contiguous(), dp)
+            torch.backends.cudnn.allow_tf32 = True
+            out["eager_note"] = ("the reference network (oracle = its own torch calls) in eager mode on this GPU; cudnn_tf32 is "
+                                 "torch's default for convolutions, i.e. what the unmodified reference computes on a GPU")
+        ref = RO.resnet50_baseline_forward(x[:8].cpu().double(), params)         # fp64 reference arithmetic, 8 patches
+        scale = float(ref.abs().max())
+        out["max_err_over_feature_scale_vs_fp64"] = {k: float((v.cpu().double() - ref).abs().max()) / scale for k, v in feats.items()}
+    out["patches_per_s"] = out["f16x2"]["patches_per_s"]
+    out["note"] = ("default mode f16x2: fp16 activation planes between layers, fp16 (hi, lo) weights, 2 tensor passes, fp32 "
+                   "accumulation; bf16x3: (hi, lo) bf16 planes, 3 passes.  DRAM bytes per patch: profiles/ ncu launch lists")
+    return out
 
 
 def main():
@@ -425,7 +628,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-patches", type=int, default=N_PATCHES)
-    ap.add_argument("--slides-per-step", type=int, default=16)
+    ap.add_argument("--slides-per-step", type=int, default=256,
+                    help="slides per step (20 steps x 256 slides = a timed region well above 1 s)")
+    ap.add_argument("--train-slides", type=int, default=64, help="config-4 training leg: slides per GPU")
+    ap.add_argument("--resnet-batch", type=int, default=512)
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the ncu sub-run that measures fc1's DRAM bytes")
     ap.add_argument("--streams", type=int, default=3, help="slides in flight per GPU (toad_b200.pipeline.ResidentRunner)")
     ap.add_argument("--batch", type=int, default=16,
                     help="slides per forward_batch call (<= 16, must divide --slides-per-step); 1 = one forward per slide")

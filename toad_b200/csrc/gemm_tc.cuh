@@ -62,7 +62,9 @@ struct Cfg {
   // (512 columns): a single accumulator buffer, the epilogue no longer overlaps the next main loop.
   static constexpr int N_SUB = BLOCK_N == 512 ? 2 : 1;
   static constexpr int UMMA_N = BLOCK_N / N_SUB;
-  static constexpr int ACC_STAGES = BLOCK_N == 512 ? 1 : 2;
+  // accumulator ring: all 512 TMEM columns (one CTA per SM owns them anyway).  Narrow tiles with a short K loop
+  // (the 1x1 convolutions: one K block per tile) are otherwise paced by the MMA -> epilogue -> MMA round trip.
+  static constexpr int ACC_STAGES = 512 / BLOCK_N > 8 ? 8 : 512 / BLOCK_N;
   static constexpr int B_ROWS = BLOCK_N / CG;        // B rows staged by one CTA (N_SUB sub-tiles of B_SUB_ROWS)
   static constexpr int B_SUB_ROWS = UMMA_N / CG;     // rows of one sub-tile staged by one CTA
   static constexpr int B_TILE_BYTES = B_ROWS * BLOCK_K * 2;
@@ -263,6 +265,32 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
   }
 }
 
+// `bytes` (multiple of 16) starting at the 16-byte aligned global address p -> L2, no destination
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// packed fp32x2 add (Blackwell FADD2): (a0, a1) += (b0, b1)
+__device__ __forceinline__ void add_f32x2(uint32_t& a0, uint32_t& a1, float b0, float b1) {
+  unsigned long long x, y;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "r"(a0), "r"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(y));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(a0), "=r"(a1) : "l"(x));
+}
+// mixed-precision adds (FHADD): a0 += fp16(low half of w), a1 += fp16(high half of w), exact fp32 results
+__device__ __forceinline__ void add_f16x2_to_f32(uint32_t& a0, uint32_t& a1, uint32_t w) {
+  asm("{\n\t.reg .b16 l, h;\n\t.reg .f32 x, y;\n\t"
+      "mov.b32 {l, h}, %2;\n\tmov.b32 x, %0;\n\tmov.b32 y, %1;\n\t"
+      "add.rn.f32.f16 x, l, x;\n\tadd.rn.f32.f16 y, h, y;\n\t"
+      "mov.b32 %0, x;\n\tmov.b32 %1, y;\n\t}"
+      : "+r"(a0), "+r"(a1) : "r"(w));
+}
+// two fp32 bit patterns -> packed fp16x2 (v0 in the low half) with ReLU and finite saturation in the conversion
+__device__ __forceinline__ uint32_t pack_relu_f16x2(uint32_t v0, uint32_t v1) {
+  uint32_t r;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(v1)), "f"(__uint_as_float(v0)));
+  return r;
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -442,8 +470,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   __shared__ __align__(8) uint64_t bar_full_b[STAGES];
   __shared__ __align__(8) uint64_t bar_full_a[STAGES];
   __shared__ __align__(8) uint64_t bar_empty[STAGES];
-  __shared__ __align__(8) uint64_t bar_tmem_full[2];
-  __shared__ __align__(8) uint64_t bar_tmem_empty[2];
+  __shared__ __align__(8) uint64_t bar_tmem_full[C::ACC_STAGES];
+  __shared__ __align__(8) uint64_t bar_tmem_empty[C::ACC_STAGES];
+  // fp16 mode: the whole bias vector staged once per CTA (the epilogue reads it with broadcast 128-bit loads)
+  constexpr int BIAS_SMEM = PREC == PREC_F16X2 ? 1024 : 1;
+  __shared__ __align__(16) float s_bias[BIAS_SMEM];
   __shared__ uint32_t tmem_slot;
   __shared__ float s_gate[EPI == EPI_GATE ? GATE_SMEM_FLOATS : 1];
 
@@ -471,7 +502,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       mbar_init(smem_u32(&bar_full_a[s]), 8 * CG);  // one arrive per converter warp (8 per CTA)
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < C::ACC_STAGES; ++a) {
       mbar_init(smem_u32(&bar_tmem_full[a]), 1);
       mbar_init(smem_u32(&bar_tmem_empty[a]), 4 * EPI_SETS * CG);  // one arrive per epilogue warp
     }
@@ -484,6 +515,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       prefetch_tmap(&tm_a_hi);
       if (C::A_PLANES == 2) prefetch_tmap(&tm_a_lo);
     }
+  }
+  if (PREC == PREC_F16X2) {
+    for (int i = threadIdx.x; i < p.N && i < BIAS_SMEM; i += blockDim.x) s_bias[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.f;
   }
   if (EPI == EPI_GATE) {  // stage the gate biases and (up to 2) score rows once per CTA
     const int D = p.gate_D;
@@ -516,6 +550,28 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       const int kb0 = split * kb_per, kb1 = (kb0 + kb_per) < num_kb ? (kb0 + kb_per) : num_kb;
       const int n0 = (mn % n_tiles) * BLOCK_N + static_cast<int>(cta_rank) * C::B_SUB_ROWS;
       const int m0 = (mn / n_tiles) * (BLOCK_M * CG) + static_cast<int>(cta_rank) * BLOCK_M;
+      // per-tile geometry once (the K loop below is paced by this one warp: no divisions inside it)
+      ConvTile ct{};
+      int tap_kh = 0, tap_kw = 0, tap_cc = 0;
+      if (A_MODE == A_CONV) {
+        ct = conv_tile(p, (mn / n_tiles) * CG + static_cast<int>(cta_rank));
+        const int tap = kb0 / p.conv_cchunks;
+        tap_cc = kb0 - tap * p.conv_cchunks;
+        tap_kh = tap / p.conv_kw;
+        tap_kw = tap - tap_kh * p.conv_kw;
+      }
+      if (EPI == EPI_LINEAR && A_MODE != A_F32 && p.res_hi != nullptr) {
+        // residual operand of this tile -> L2 now (the producer runs a few tiles ahead of the epilogue, whose
+        // one-chunk-ahead register prefetch then meets L2 latency instead of DRAM latency)
+        const int64_t r0 = A_MODE == A_CONV ? ct.out_row0 : static_cast<int64_t>(m0);
+        int nr = A_MODE == A_CONV ? ct.rows_valid : static_cast<int>((p.M - m0) < BLOCK_M ? (p.M - m0) : BLOCK_M);
+        const int c0 = (mn % n_tiles) * BLOCK_N;
+        for (int r = lane; r < nr; r += 32) {
+          const int64_t o = (r0 + r) * p.ld_res + c0;
+          prefetch_l2_bulk(p.res_hi + o, BLOCK_N * 2);
+          if (PREC == PREC_BF16X3) prefetch_l2_bulk(p.res_lo + o, BLOCK_N * 2);
+        }
+      }
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
         if (lane == 0) {
@@ -543,13 +599,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
               tma_load_2d<CG>(sa + A_TILE_BYTES + j * 8192, &tm_a_lo, fb, m0 + j * 64, kb * BLOCK_K);
             }
           } else if (A_MODE == A_CONV) {
-            const int tap = kb / p.conv_cchunks, cc = kb - tap * p.conv_cchunks;
-            const int kh = tap / p.conv_kw, kw = tap - kh * p.conv_kw;
-            const ConvTile ct = conv_tile(p, (mn / n_tiles) * CG + static_cast<int>(cta_rank));
-            const int cw = kw - p.conv_pad;  // (tiles span the full output width)
-            const int ch = ct.oh0 * p.conv_stride + kh - p.conv_pad;
-            tma_load_4d<CG>(sa, &tm_a_hi, fb, cc * BLOCK_K, cw, ch, ct.b0);
-            if (C::A_PLANES == 2) tma_load_4d<CG>(sa + A_TILE_BYTES, &tm_a_lo, fb, cc * BLOCK_K, cw, ch, ct.b0);
+            const int cw = tap_kw - p.conv_pad;  // (tiles span the full output width)
+            const int ch = ct.oh0 * p.conv_stride + tap_kh - p.conv_pad;
+            tma_load_4d<CG>(sa, &tm_a_hi, fb, tap_cc * BLOCK_K, cw, ch, ct.b0);
+            if (C::A_PLANES == 2) tma_load_4d<CG>(sa + A_TILE_BYTES, &tm_a_lo, fb, tap_cc * BLOCK_K, cw, ch, ct.b0);
           }
           if (A_MODE == A_MN) {
 #pragma unroll
@@ -568,6 +621,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (A_MODE == A_CONV) {  // next K block = next (tap, channel chunk), all lanes in step
+          if (++tap_cc == p.conv_cchunks) {
+            tap_cc = 0;
+            if (++tap_kw == p.conv_kw) { tap_kw = 0; ++tap_kh; }
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -698,7 +757,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       if (has_pool && row_ok) { pool_p0 = __ldg(p.pool_p + row * 2); pool_p1 = __ldg(p.pool_p + row * 2 + 1); }
       // bias of a 32-column chunk: lane j holds bias[col0 + j] (one coalesced load, fetched one chunk ahead);
       // the value of column i is broadcast with a shuffle where it is added.
-      const bool has_bias = EPI == EPI_LINEAR && p.bias != nullptr && split == 0;
+      const bool has_bias = EPI == EPI_LINEAR && PREC == PREC_BF16X3 && p.bias != nullptr && split == 0;  // (fp16 mode: s_bias)
       auto load_bias = [&](int c_) { return has_bias ? __ldg(p.bias + n0 + c_ * 32 + lane) : 0.f; };
       float bias_nxt = 0.f;
       if (EPI == EPI_LINEAR) {
@@ -721,7 +780,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         constexpr int WARP_STAGE_BYTES = (OUT_BUFS * 2 / EPI_SETS) * 4096;
         static_assert(WARP_BUFS >= 1, "staging");
         const uint32_t my_stage = tiles_base + STAGES * C::STAGE_BYTES + (eh * 4 + ew) * WARP_STAGE_BYTES;
-#pragma unroll 1
+        // (fp16 mode: the <= 4 chunks of a warp fully unrolled, so the one-chunk-ahead residual prefetch rotates through
+        // renamed registers instead of 16 moves per chunk)
+        constexpr int CHUNK_UNROLL = PREC == PREC_F16X2 ? 4 : 1;
+#pragma unroll CHUNK_UNROLL
         for (int c = eh; c < N_CHUNKS; c += EPI_SETS) {
           const bool last = c + EPI_SETS >= N_CHUNKS;
           uint32_t r[32];
@@ -750,21 +812,29 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             }
           }
           const int col0 = n0 + c * 32;
-          if (EPI == EPI_LINEAR) {
+          if (EPI == EPI_LINEAR && PREC == PREC_BF16X3) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               r[i] = __float_as_uint(__uint_as_float(r[i]) + __shfl_sync(0xffffffffu, bias_cur, i));
           }
-          if (has_res && PREC == PREC_F16X2) {
+          if (PREC == PREC_F16X2) {
+            // lean fp16-mode arithmetic: bias from shared memory (8 broadcast 128-bit loads) with packed fp32x2 adds,
+            // the residual's fp16 halves added straight into the fp32 values (FHADD); ReLU rides on the final conversion
+            const float4* sb = reinterpret_cast<const float4*>(s_bias + col0);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 vh = cur_h[q];
-              const uint32_t uh[4] = {vh.x, vh.y, vh.z, vh.w};
+            for (int q = 0; q < 8; ++q) {
+              const float4 b4 = sb[q];
+              add_f32x2(r[4 * q], r[4 * q + 1], b4.x, b4.y);
+              add_f32x2(r[4 * q + 2], r[4 * q + 3], b4.z, b4.w);
+            }
+            if (has_res) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 rv = h2_to_f2(uh[e]);
-                r[q * 8 + 2 * e] = __float_as_uint(__uint_as_float(r[q * 8 + 2 * e]) + rv.x);
-                r[q * 8 + 2 * e + 1] = __float_as_uint(__uint_as_float(r[q * 8 + 2 * e + 1]) + rv.y);
+              for (int q = 0; q < 4; ++q) {
+                const uint4 vh = cur_h[q];
+                add_f16x2_to_f32(r[q * 8], r[q * 8 + 1], vh.x);
+                add_f16x2_to_f32(r[q * 8 + 2], r[q * 8 + 3], vh.y);
+                add_f16x2_to_f32(r[q * 8 + 4], r[q * 8 + 5], vh.z);
+                add_f16x2_to_f32(r[q * 8 + 6], r[q * 8 + 7], vh.w);
               }
             }
           }
@@ -781,7 +851,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
               }
             }
           }
-          if (EPI == EPI_LINEAR && p.relu) {
+          if (EPI == EPI_LINEAR && PREC == PREC_BF16X3 && p.relu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(fmaxf(__uint_as_float(r[i]), 0.0f));
           }
@@ -815,13 +885,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
               }
             }
           }
-          if (EPI == EPI_LINEAR && p.drop.thresh != 0u) {  // training only: one big uniform branch, never predicated into the hot path
+          if (EPI == EPI_LINEAR && PREC == PREC_BF16X3 && p.drop.thresh != 0u) {  // training only: one big uniform branch, never predicated into the hot path
             const unsigned long long e0 = static_cast<unsigned long long>(row) * p.N + col0;
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               r[i] = __float_as_uint(dropout_apply(p.drop, p.drop_layer, e0 + i, __uint_as_float(r[i])));
           }
-          if (row_ok && p.out_f32 != nullptr) {
+          if (PREC == PREC_BF16X3 && row_ok && p.out_f32 != nullptr) {
             float* dst = p.out_f32 + (static_cast<int64_t>(split) * p.M + row) * p.ld_f32 + col0;  // 32 B aligned (ld % 8 == 0)
 #pragma unroll
             for (int i = 0; i < 4; ++i) st_global_v8(dst + 8 * i, r, 8 * i);
@@ -837,8 +907,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 #pragma unroll
             for (int q = 0; q < 4; ++q) {  // 8 columns -> one 16 B chunk
               uint32_t h[4];
+              if (p.relu) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) h[e] = pack_f16x2(__uint_as_float(r[8 * q + 2 * e]), __uint_as_float(r[8 * q + 2 * e + 1]));
+                for (int e = 0; e < 4; ++e) h[e] = pack_relu_f16x2(r[8 * q + 2 * e], r[8 * q + 2 * e + 1]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h[e] = pack_f16x2(__uint_as_float(r[8 * q + 2 * e]), __uint_as_float(r[8 * q + 2 * e + 1]));
+              }
               if (use_tma) {
                 const uint32_t off = lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4);  // SWIZZLE_64B: chunk ^= row bits [1,2]
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
@@ -1106,6 +1181,7 @@ int launch_gemm_maps_b(const GemmTcParams& p, const CUtensorMap& ta_hi, const CU
   if (EPI != EPI_DGRAD && (p.pool_p != nullptr || p.mask_f32 != nullptr || p.mask_bf16 != nullptr || p.out_scale != 0.f)) return TOAD_ERR_ARG;
   if (EPI == EPI_DGRAD && (p.bias != nullptr || p.res_hi != nullptr || p.relu != 0 || p.drop.thresh != 0u)) return TOAD_ERR_ARG;
   if (EPI == EPI_GATE && (p.gate_D > 1024 || p.gate_ntasks < 1 || p.gate_ntasks > 4)) return TOAD_ERR_UNSUPPORTED;
+  if (PREC == PREC_F16X2 && (p.N > 1024 || p.out_f32 != nullptr || p.k_splits > 1 || p.drop.thresh != 0u)) return TOAD_ERR_UNSUPPORTED;
   // the epilogues' register -> global stores are 256-bit: 32-byte aligned rows
   if (epi_is_linear(EPI) && p.out_f32 != nullptr && ((reinterpret_cast<uintptr_t>(p.out_f32) & 31) != 0 || p.ld_f32 % 8 != 0))
     return TOAD_ERR_ARG;
