@@ -76,13 +76,15 @@ struct Cfg {
   // tile a warp's store must finish reading smem before its next chunk is staged; with two it overlaps.
   // OUT_BUFS = 2 costs one operand stage: for store-/epilogue-bound shapes (ResNet).
   static_assert(OUT_BUFS == 1 || OUT_BUFS == 2, "OUT_BUFS");
-  static constexpr int RING_BYTES = 192 * 1024 - (OUT_BUFS - 1) * 32 * 1024;
+  // (fp16 mode keeps the bias vector in 4 KB of static shared memory: leave room for it under the 227 KB limit)
+  static constexpr int RING_BYTES = 192 * 1024 - (OUT_BUFS - 1) * 32 * 1024 - (PREC == PREC_F16X2 ? 8 * 1024 : 0);
   static constexpr int STAGES = RING_BYTES / STAGE_BYTES > 6 ? 6 : RING_BYTES / STAGE_BYTES;
   static_assert(STAGES >= 2, "need at least a double-buffered operand ring");
   static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // accumulator ring (128/256/512: powers of 2)
   static constexpr int OUT_STAGE_BYTES = 2 * BLOCK_M * 128;  // (hi, lo) 128 x 64 bf16 staging tiles for the TMA store
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + slack for 1024 B alignment
   static constexpr int SMEM_BYTES_LINEAR = SMEM_BYTES + OUT_BUFS * OUT_STAGE_BYTES;
+  static_assert(SMEM_BYTES_LINEAR + (PREC == PREC_F16X2 ? 4096 : 0) + 1024 <= 227 * 1024, "dynamic + static shared memory");
 };
 
 struct GemmTcParams {
