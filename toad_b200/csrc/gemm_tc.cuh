@@ -113,6 +113,7 @@ struct GemmTcParams {
   int32_t gate_ntasks;  // 1..4
   float* gate_part;     // [sets * n_tiles][M][ntasks] partial scores (no bias): one per (tile, epilogue warp set);
                         // sets = 2 for plane-fed A, 1 for fp32-fed A
+  int64_t gate_part_rows;  // rows of one partial plane (0 = M): a row slice of a larger bag writes into the bag's planes
   float* gate_a;        // nullable [M, D]
   float* gate_b;        // nullable [M, D]
   // A_CONV: rows are output pixels (b, oh, ow) raster; K blocks walk (tap, 64-channel chunk); the A tile
@@ -142,6 +143,7 @@ struct GemmTcParams {
   // row*N + col; EPI_GATE uses DROP_A / DROP_B with index row*D + gate column.
   DropoutCfg drop;
   uint32_t drop_layer;
+  int64_t drop_row0;      // global index of row 0 (a row slice of a bag keeps the bag-wide dropout mask)
   // split-K (TMA-fed A only): the K range is cut into k_splits slices of kb_per_split K blocks; slice s
   // writes its fp32 partial tile to out_f32 + s * M * ld_f32 (bias only in slice 0); a reduction follows.
   int32_t k_splits;       // 0 or 1 = no split
@@ -888,7 +890,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             }
           }
           if (EPI == EPI_LINEAR && PREC == PREC_BF16X3 && p.drop.thresh != 0u) {  // training only: one big uniform branch, never predicated into the hot path
-            const unsigned long long e0 = static_cast<unsigned long long>(row) * p.N + col0;
+            const unsigned long long e0 = static_cast<unsigned long long>(row + p.drop_row0) * p.N + col0;
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               r[i] = __float_as_uint(dropout_apply(p.drop, p.drop_layer, e0 + i, __uint_as_float(r[i])));
@@ -986,7 +988,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             rb[i] = __float_as_uint(fast_sigmoid(__uint_as_float(rb[i]) + s_gate[1024 + jc + i]));
           }
           if (p.drop.thresh != 0u) {  // training only: one big uniform branch (see EPI_LINEAR)
-            const unsigned long long e0 = static_cast<unsigned long long>(row) * p.gate_D + jc;
+            const unsigned long long e0 = static_cast<unsigned long long>(row + p.drop_row0) * p.gate_D + jc;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               ra[i] = __float_as_uint(dropout_apply(p.drop, DROP_A, e0 + i, __uint_as_float(ra[i])));
@@ -1014,7 +1016,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           }
         }
         if (row_ok) {
-          float* dst = p.gate_part + (static_cast<int64_t>(n_tile * EPI_SETS + eh) * p.M + row) * p.gate_ntasks;
+          const int64_t plane_rows = p.gate_part_rows > 0 ? p.gate_part_rows : p.M;
+          float* dst = p.gate_part + (static_cast<int64_t>(n_tile * EPI_SETS + eh) * plane_rows + row) * p.gate_ntasks;
 #pragma unroll
           for (int t = 0; t < 4; ++t)
             if (t < p.gate_ntasks) dst[t] = s[t];
