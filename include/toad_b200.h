@@ -167,22 +167,6 @@ int toad_fwd_batch(const toad_dims_t* dims, const toad_params_t* params, const f
                    int32_t n_slides, const float* sex, const toad_fwd_out_t* out, void* workspace,
                    size_t workspace_bytes, uint32_t flags, toad_stream_t stream);
 
-/* The same forward with the trunk's row range cut in two halves that run on two streams (`stream` and
- * aux->stream, both the caller's): the GEMMs are persistent kernels with static tile lists, so one bag leaves
- * SMs idle in its partially filled last waves; the other half's kernels use them.  The library records `ev_fork` on
- * `stream`, makes aux->stream wait for it, issues rows [mid, n) there and rows [0, mid) on `stream`, records `ev_join`
- * on aux->stream and makes `stream` wait for it before the pooling tail: on return all work is ordered on `stream`
- * exactly as after toad_fwd.  Results are identical to toad_fwd (same kernels, same per-row arithmetic, same tail).
- * The two events are plain cudaEvent_t handles the caller created (timing may be disabled).  Tensor-core path only. */
-typedef struct {
-  toad_stream_t stream; /* second stream, != `stream` */
-  void* ev_fork;        /* cudaEvent_t */
-  void* ev_join;        /* cudaEvent_t */
-} toad_aux_stream_t;
-int toad_fwd_2s(const toad_dims_t* dims, const toad_params_t* params, const float* x, int64_t n, const float* sex,
-                const toad_fwd_out_t* out, const toad_saved_t* saved, void* workspace, size_t workspace_bytes,
-                uint32_t flags, toad_stream_t stream, const toad_aux_stream_t* aux);
-
 /* Per-stage device timing of toad_fwd (diagnostics; bench.py's roofline leg).  A profile handle
  * owns CUDA events for up to max_calls forwards; toad_fwd_profiled records an event between the
  * stages on `stream` (no synchronisation); toad_profile_read waits for the recorded events,

@@ -25,7 +25,7 @@ MAX_BATCH = 16   # slides per toad_fwd_batch call (tail::MAX_BATCH)
 
 EXPORTS = [
     "toad_abi_version", "toad_build_id", "toad_error_string", "toad_param_offsets", "toad_dropout_hash",
-    "toad_fwd_workspace_bytes", "toad_fwd", "toad_fwd_2s", "toad_fwd_batch_workspace_bytes", "toad_fwd_batch",
+    "toad_fwd_workspace_bytes", "toad_fwd", "toad_fwd_batch_workspace_bytes", "toad_fwd_batch",
     "toad_bwd_workspace_bytes", "toad_bwd",
     "toad_attn_gated_workspace_bytes", "toad_attn_gated_fwd",
     "toad_topk_workspace_bytes", "toad_topk", "toad_gather_rows",
@@ -56,10 +56,6 @@ class FwdOut(C.Structure):
 class Saved(C.Structure):
     _fields_ = [(n, _f32p) for n in ("h1", "h", "a", "b")] + [("dropout_seed", C.c_uint64), ("dropout_p", C.c_float)] + \
         [(n, C.c_void_p) for n in ("h1_hi", "h1_lo", "h_hi", "h_lo")]
-
-
-class AuxStream(C.Structure):
-    _fields_ = [("stream", C.c_void_p), ("ev_fork", C.c_void_p), ("ev_join", C.c_void_p)]
 
 
 class ToadError(RuntimeError):
@@ -98,7 +94,6 @@ def load() -> C.CDLL:
     lib.toad_fwd.argtypes = [C.POINTER(Dims), C.POINTER(Params), _f32p, C.c_int64, _f32p, C.POINTER(FwdOut),
                              C.POINTER(Saved), C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
     lib.toad_fwd_profiled.argtypes = lib.toad_fwd.argtypes + [C.c_void_p]
-    lib.toad_fwd_2s.argtypes = lib.toad_fwd.argtypes + [C.POINTER(AuxStream)]
     lib.toad_fwd_batch_workspace_bytes.argtypes = [C.POINTER(Dims), C.c_int64, C.c_int32, C.c_uint32, C.POINTER(C.c_size_t)]
     lib.toad_fwd_batch.argtypes = [C.POINTER(Dims), C.POINTER(Params), _f32p, C.POINTER(C.c_int64), C.c_int32, _f32p,
                                    C.POINTER(FwdOut), C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]

@@ -22,6 +22,7 @@
 #pragma once
 #include "common.cuh"
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 namespace toad {
 namespace tc {
@@ -295,6 +296,15 @@ __device__ __forceinline__ uint32_t pack_relu_f16x2(uint32_t v0, uint32_t v1) {
   asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(v1)), "f"(__uint_as_float(v0)));
   return r;
 }
+// Programmatic dependent launch (PDL).  Every kernel of a chain runs `wait` (all memory operations of the preceding
+// grid are complete and visible) BEFORE `launch_dependents`, and touches no kernel-written global memory before the
+// wait: its successor can then start its prologue (barrier init, TMEM allocation, descriptor prefetch) on SMs the
+// last wave of this grid has left, but -- by induction -- never runs ahead of a grid it depends on transitively.
+// Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait_then_release() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -520,6 +530,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       if (C::A_PLANES == 2) prefetch_tmap(&tm_a_lo);
     }
   }
+  pdl_wait_then_release();
   if (PREC == PREC_F16X2) {
     for (int i = threadIdx.x; i < p.N && i < BIAS_SMEM; i += blockDim.x) s_bias[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.f;
   }
@@ -1145,6 +1156,15 @@ inline int make_bf16_out_tmap(CUtensorMap* map, const void* ptr, int64_t rows, i
   return r == CUDA_SUCCESS ? 0 : TOAD_ERR_DRIVER;
 }
 
+// TOAD_B200_PDL=0 in the environment launches every kernel fully serialised (A/B and debugging aid)
+inline bool pdl_enabled() {
+  static bool v = []() {
+    const char* e = getenv("TOAD_B200_PDL");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return v;
+}
+
 inline int sm_count() {
   static int n = []() {
     int dev = 0, v = 0;
@@ -1219,13 +1239,22 @@ int launch_gemm_maps_b(const GemmTcParams& p, const CUtensorMap& ta_hi, const CU
   cfg.blockDim = dim3(cta_threads<A_MODE, EPI>());
   cfg.dynamicSmemBytes = kSmem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CG > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CG;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = CG > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   TOAD_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, p));
   TOAD_CUDA_TRY(cudaGetLastError());
   return 0;

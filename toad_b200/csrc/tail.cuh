@@ -167,6 +167,10 @@ __global__ void __launch_bounds__(THREADS, 1) pool_heads_kernel(const TailParams
   const int rows = l1_ > l0_ ? static_cast<int>(l1_ - l0_) : 0;
   const int64_t r0 = row_base + l0_;                         // global row of this CTA's first row
 
+  // programmatic dependent launch: this grid may have been started while the gate GEMM's last wave was still
+  // running; nothing above touches global memory (see gemm_tc.cuh: pdl_wait_then_release)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // head weights -> shared memory in the background (used only by the CTA that ends up evaluating the heads)
   float* s_w = dsm + WARPS * T * H;            // [n_classes + 2][H + 1]
   if (p.heads_in_smem && !p.attention_only) {
@@ -442,7 +446,7 @@ __global__ void __launch_bounds__(THREADS, 1) pool_heads_kernel(const TailParams
 }
 
 template <int H_MODE>
-int launch_tail(const TailParams& p_in, int sms, cudaStream_t stream) {
+int launch_tail(const TailParams& p_in, int sms, cudaStream_t stream, bool pdl = false) {
   TailParams p = p_in;
   if (p.N <= 0) return TOAD_ERR_ARG;
   if (p.n_classes + 2 > 1024) return TOAD_ERR_UNSUPPORTED;
@@ -466,7 +470,17 @@ int launch_tail(const TailParams& p_in, int sms, cudaStream_t stream) {
   const int dyn = (WARPS * T * H + (p.heads_in_smem ? (p.n_classes + 2) * (H + 1) : 0)) * static_cast<int>(sizeof(float));
   auto kern = pool_heads_kernel<H_MODE>;
   TOAD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-  kern<<<dim3(nb, p.batch.n_slides), THREADS, dyn, stream>>>(p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(nb, p.batch.n_slides);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = dyn;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see pool_heads_kernel: griddepcontrol.wait
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  TOAD_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
   TOAD_CUDA_TRY(cudaGetLastError());
   return 0;
 }

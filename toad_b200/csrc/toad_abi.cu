@@ -124,7 +124,8 @@ int run_tail(const toad_dims_t* d, const toad_params_t* P, int64_t n, const floa
   t.site_logits = out->site_logits; t.site_prob = out->site_prob; t.site_hat = out->site_hat;
   t.stats = out->softmax_stats; t.blk_part = w.blk_part; t.ticket = w.ticket;
   t.attention_only = attention_only ? 1 : 0;
-  return h_f32 ? tail::launch_tail<tail::H_F32>(t, kSMs, st) : tail::launch_tail<tail::H_SPLIT>(t, kSMs, st);
+  // (tensor-core path: launched programmatically dependent on the gate GEMM)
+  return h_f32 ? tail::launch_tail<tail::H_F32>(t, kSMs, st) : tail::launch_tail<tail::H_SPLIT>(t, kSMs, st, tc::pdl_enabled());
 }
 
 simt::SgemmParams linear_params(const float* x, int64_t ldx, const float* w, const float* bias, float* y, int64_t m,
@@ -179,8 +180,7 @@ extern "C" int toad_fwd_workspace_bytes(const toad_dims_t* d, int64_t n, uint32_
 
 static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t n, const float* sex,
                     const toad_fwd_out_t* out, const toad_saved_t* saved, void* workspace, size_t workspace_bytes,
-                    uint32_t flags, toad_stream_t stream, Prof* prof, const tail::TailBatch* batch = nullptr,
-                    const toad_aux_stream_t* aux = nullptr) {
+                    uint32_t flags, toad_stream_t stream, Prof* prof, const tail::TailBatch* batch = nullptr) {
   TOAD_TRY(check_dims(d));
   if (P == nullptr || x == nullptr || out == nullptr || out->a_raw == nullptr || n <= 0) return TOAD_ERR_ARG;
   const bool attn_only = (flags & TOAD_FLAG_ATTENTION_ONLY) != 0;
@@ -242,60 +242,36 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
     TOAD_TRY(tail::launch_split_gate_weights(P->wa, P->wb, w.wab_hi, w.wab_lo, D, Hd, kGateHalf, st));
   }
   TOAD_TRY(prof_mark(prof, 1, st));
-  // The three trunk GEMMs over the rows [r0, r1) of the bag (every row is independent until the pooling tail).
-  auto trunk_rows = [&](int64_t r0, int64_t r1, cudaStream_t ts, bool mark) -> int {
-    const int64_t m = r1 - r0;
-    {
-      tc::GemmTcParams g{};
-      g.a_f32 = x + r0 * L; g.lda = L; g.M = m; g.N = Hd; g.K = L; g.bias = P->b1; g.relu = 1;
-      g.drop = drop; g.drop_layer = DROP_H1; g.drop_row0 = r0;
-      g.out_f32 = save ? saved->h1 + r0 * Hd : nullptr; g.ld_f32 = Hd;
-      g.out_hi = h1_hi + r0 * Hd; g.out_lo = h1_lo + r0 * Hd; g.ld_split = Hd;
-      if (cg1) TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_LINEAR, 1>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, ts)));
-      else if (fc1_pair) TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_LINEAR, 2>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, ts)));
-      else TOAD_TRY((tc::launch_gemm<512, tc::A_F32, tc::EPI_LINEAR, 2>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, ts)));
-    }
-    if (mark) TOAD_TRY(prof_mark(prof, 2, ts));
-    {
-      tc::GemmTcParams g{};
-      g.M = m; g.N = Hd; g.K = Hd; g.bias = P->b2; g.relu = 1;
-      g.drop = drop; g.drop_layer = DROP_H; g.drop_row0 = r0;
-      g.out_f32 = save ? saved->h + r0 * Hd : nullptr; g.ld_f32 = Hd;
-      g.out_hi = h_hi + r0 * Hd; g.out_lo = h_lo + r0 * Hd; g.ld_split = Hd;
-      if (cg1) TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 1>(g, h1_hi + r0 * Hd, h1_lo + r0 * Hd, w.w2_hi, w.w2_lo, ts)));
-      else if (flags & TOAD_FLAG_FC2_WIDE) TOAD_TRY((tc::launch_gemm<512, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, h1_hi + r0 * Hd, h1_lo + r0 * Hd, w.w2_hi, w.w2_lo, ts)));
-      else TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, h1_hi + r0 * Hd, h1_lo + r0 * Hd, w.w2_hi, w.w2_lo, ts)));
-    }
-    if (mark) TOAD_TRY(prof_mark(prof, 3, ts));
-    {
-      tc::GemmTcParams g{};
-      g.M = m; g.N = 2 * D; g.K = Hd;
-      g.gate_ba = P->ba; g.gate_bb = P->bb; g.gate_wc = P->wc; g.gate_D = D; g.gate_ntasks = d->n_tasks;
-      g.gate_part = w.part + r0 * d->n_tasks; g.gate_part_rows = n;
-      g.gate_a = save ? saved->a + r0 * D : nullptr; g.gate_b = save ? saved->b + r0 * D : nullptr;
-      g.drop = drop; g.drop_row0 = r0;
-      if (cg1) TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_GATE, 1>(g, h_hi + r0 * Hd, h_lo + r0 * Hd, w.wab_hi, w.wab_lo, ts)));
-      else TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_GATE, 2>(g, h_hi + r0 * Hd, h_lo + r0 * Hd, w.wab_hi, w.wab_lo, ts)));
-    }
-    return 0;
-  };
-  // Two row halves on two streams (aux given): each GEMM is a persistent kernel with a static tile list, so a single
-  // bag leaves SMs idle in its partially filled last waves (196 pair tiles on 74 CTA pairs at N = 50k); the other
-  // half's kernels pick those SMs up.  The halves write disjoint rows of every buffer; the tail joins them.
-  const int64_t units = (n + 255) / 256;
-  if (aux != nullptr && aux->stream != nullptr && prof == nullptr && units >= 2) {
-    cudaStream_t s2 = static_cast<cudaStream_t>(aux->stream);
-    cudaEvent_t ev_fork = static_cast<cudaEvent_t>(aux->ev_fork), ev_join = static_cast<cudaEvent_t>(aux->ev_join);
-    if (ev_fork == nullptr || ev_join == nullptr) return TOAD_ERR_ARG;
-    const int64_t mid = (units / 2) * 256;
-    TOAD_CUDA_TRY(cudaEventRecord(ev_fork, st));          // weight planes / ticket reset / the caller's inputs are ready
-    TOAD_CUDA_TRY(cudaStreamWaitEvent(s2, ev_fork, 0));
-    TOAD_TRY(trunk_rows(mid, n, s2, false));
-    TOAD_TRY(trunk_rows(0, mid, st, false));
-    TOAD_CUDA_TRY(cudaEventRecord(ev_join, s2));
-    TOAD_CUDA_TRY(cudaStreamWaitEvent(st, ev_join, 0));
-  } else {
-    TOAD_TRY(trunk_rows(0, n, st, true));
+  {
+    tc::GemmTcParams g{};
+    g.a_f32 = x; g.lda = L; g.M = n; g.N = Hd; g.K = L; g.bias = P->b1; g.relu = 1;
+    g.drop = drop; g.drop_layer = DROP_H1;
+    g.out_f32 = save ? saved->h1 : nullptr; g.ld_f32 = Hd;
+    g.out_hi = h1_hi; g.out_lo = h1_lo; g.ld_split = Hd;
+    if (cg1) TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_LINEAR, 1>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, st)));
+    else if (fc1_pair) TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_LINEAR, 2>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, st)));
+    else TOAD_TRY((tc::launch_gemm<512, tc::A_F32, tc::EPI_LINEAR, 2>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, st)));
+  }
+  TOAD_TRY(prof_mark(prof, 2, st));
+  {
+    tc::GemmTcParams g{};
+    g.M = n; g.N = Hd; g.K = Hd; g.bias = P->b2; g.relu = 1;
+    g.drop = drop; g.drop_layer = DROP_H;
+    g.out_f32 = save ? saved->h : nullptr; g.ld_f32 = Hd;
+    g.out_hi = h_hi; g.out_lo = h_lo; g.ld_split = Hd;
+    if (cg1) TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 1>(g, h1_hi, h1_lo, w.w2_hi, w.w2_lo, st)));
+    else if (flags & TOAD_FLAG_FC2_WIDE) TOAD_TRY((tc::launch_gemm<512, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, h1_hi, h1_lo, w.w2_hi, w.w2_lo, st)));
+    else TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, h1_hi, h1_lo, w.w2_hi, w.w2_lo, st)));
+  }
+  TOAD_TRY(prof_mark(prof, 3, st));
+  {
+    tc::GemmTcParams g{};
+    g.M = n; g.N = 2 * D; g.K = Hd;
+    g.gate_ba = P->ba; g.gate_bb = P->bb; g.gate_wc = P->wc; g.gate_D = D; g.gate_ntasks = d->n_tasks;
+    g.gate_part = w.part; g.gate_a = save ? saved->a : nullptr; g.gate_b = save ? saved->b : nullptr;
+    g.drop = drop;
+    if (cg1) TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_GATE, 1>(g, h_hi, h_lo, w.wab_hi, w.wab_lo, st)));
+    else TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_GATE, 2>(g, h_hi, h_lo, w.wab_hi, w.wab_lo, st)));
   }
   TOAD_TRY(prof_mark(prof, 4, st));
   TOAD_TRY(run_tail(d, P, n, sex, out, w, nullptr, h_hi, h_lo, attn_only, st, batch));
@@ -308,14 +284,6 @@ extern "C" int toad_fwd(const toad_dims_t* d, const toad_params_t* P, const floa
                         const toad_fwd_out_t* out, const toad_saved_t* saved, void* workspace, size_t workspace_bytes,
                         uint32_t flags, toad_stream_t stream) {
   return fwd_impl(d, P, x, n, sex, out, saved, workspace, workspace_bytes, flags, stream, nullptr);
-}
-
-extern "C" int toad_fwd_2s(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t n, const float* sex,
-                           const toad_fwd_out_t* out, const toad_saved_t* saved, void* workspace, size_t workspace_bytes,
-                           uint32_t flags, toad_stream_t stream, const toad_aux_stream_t* aux) {
-  if (aux == nullptr || aux->stream == nullptr || aux->stream == stream) return TOAD_ERR_ARG;
-  if (flags & TOAD_FLAG_SIMT_FP32) return TOAD_ERR_UNSUPPORTED;
-  return fwd_impl(d, P, x, n, sex, out, saved, workspace, workspace_bytes, flags, stream, nullptr, nullptr, aux);
 }
 
 static int make_batch(const int64_t* offsets, int32_t n_slides, tail::TailBatch* tb) {
@@ -999,21 +967,8 @@ struct ResWs {
   bf16 *col_hi, *col_lo, *stem_hi, *stem_lo, *pool_hi, *pool_lo;
   bf16 *buf_hi[5], *buf_lo[5];
   int stem_chunk;
-  int stem_sub;
   size_t bytes;
 };
-
-// images per im2col -> stem GEMM -> max-pool pass.  Small on purpose: the im2col plane of these few images (6.3 MB each
-// in fp16) is written, read once by the GEMM and overwritten by the next pass while it is still in the 126 MB L2, so
-// most of it never travels to HBM (TOAD_RESNET_STEM_SUB in the environment overrides: tuning aid).
-int resnet_stem_sub(bool exact) {
-  static int v = []() {
-    const char* e = getenv("TOAD_RESNET_STEM_SUB");
-    const int c = e != nullptr ? atoi(e) : 0;
-    return c > 0 ? c : 0;
-  }();
-  return v > 0 ? v : (exact ? 4 : 8);   // (hi, lo) bf16 planes are twice the bytes per image
-}
 
 // images per stem + layer1 pass (TOAD_RESNET_CHUNK in the environment overrides the default: tuning aid)
 int resnet_chunk() {
@@ -1031,16 +986,14 @@ ResWs carve_resnet(int B, int H, int W, bool exact, void* base) {
   Carver c(base);
   const int64_t H1 = H / 2, W1 = W / 2, H2 = H / 4, W2 = W / 4;
   w.stem_chunk = B < resnet_chunk() ? B : resnet_chunk();
-  w.stem_sub = w.stem_chunk < resnet_stem_sub(exact) ? w.stem_chunk : resnet_stem_sub(exact);
-  const size_t col = static_cast<size_t>(w.stem_sub) * H1 * W1 * resnet::STEM_KPAD;
+  const size_t col = static_cast<size_t>(w.stem_chunk) * H1 * W1 * resnet::STEM_KPAD;
   w.col_hi = c.take<bf16>(col);
   if (exact) w.col_lo = c.take<bf16>(col);
-  const size_t stem = static_cast<size_t>(w.stem_sub) * H1 * W1 * 64;
+  const size_t stem = static_cast<size_t>(w.stem_chunk) * H1 * W1 * 64;
   w.stem_hi = c.take<bf16>(stem);
   if (exact) w.stem_lo = c.take<bf16>(stem);
-  const size_t pool = static_cast<size_t>(w.stem_chunk) * H2 * W2 * 64;
-  w.pool_hi = c.take<bf16>(pool);
-  if (exact) w.pool_lo = c.take<bf16>(pool);
+  w.pool_hi = c.take<bf16>(stem / 4);
+  if (exact) w.pool_lo = c.take<bf16>(stem / 4);
   const size_t act = static_cast<size_t>(B) * H2 * W2 * 256;
   for (int i = 0; i < 5; ++i) {
     w.buf_hi[i] = c.take<bf16>(act);
@@ -1130,20 +1083,16 @@ int resnet_fwd_impl(const Prepared& P, const float* x, int B, int H, int W, floa
   const int64_t l1_img = static_cast<int64_t>(H2) * W2 * 256;  // elements per image of a layer1-sized plane
   for (int b0 = 0; b0 < B; b0 += w.stem_chunk) {
     const int nb = (B - b0) < w.stem_chunk ? (B - b0) : w.stem_chunk;
-    const int64_t pool_img = static_cast<int64_t>(H2) * W2 * 64;
-    for (int s0 = 0; s0 < nb; s0 += w.stem_sub) {
-      const int ns = (nb - s0) < w.stem_sub ? (nb - s0) : w.stem_sub;
-      const int64_t rows = static_cast<int64_t>(ns) * H1 * W1;
-      TOAD_TRY(resnet::launch_stem_im2col<HALF>(x + static_cast<int64_t>(b0 + s0) * 3 * H * W, w.col_hi, w.col_lo, ns, H, W, H1, W1, st));
-      tc::GemmTcParams g{};
-      g.M = rows; g.N = 64; g.K = resnet::STEM_KPAD; g.bias = P.conv[0].bias; g.relu = 1;
-      g.out_hi = w.stem_hi; g.out_lo = w.stem_lo; g.ld_split = 64;
-      TOAD_TRY((tc::launch_gemm<64, tc::A_SPLIT, tc::EPI_LINEAR, 2, kResOutBufs, PREC>(g, w.col_hi, w.col_lo, P.conv[0].hi, P.conv[0].lo, st)));
-      const int64_t threads = static_cast<int64_t>(ns) * H2 * W2 * (64 / 8);
-      resnet::maxpool3x3s2_kernel<HALF><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
-          w.stem_hi, w.stem_lo, w.pool_hi + s0 * pool_img, HALF ? nullptr : w.pool_lo + s0 * pool_img, ns, H1, W1, 64);
-      TOAD_CUDA_TRY(cudaGetLastError());
-    }
+    const int64_t rows = static_cast<int64_t>(nb) * H1 * W1;
+    TOAD_TRY(resnet::launch_stem_im2col<HALF>(x + static_cast<int64_t>(b0) * 3 * H * W, w.col_hi, w.col_lo, nb, H, W, H1, W1, st));
+    tc::GemmTcParams g{};
+    g.M = rows; g.N = 64; g.K = resnet::STEM_KPAD; g.bias = P.conv[0].bias; g.relu = 1;
+    g.out_hi = w.stem_hi; g.out_lo = w.stem_lo; g.ld_split = 64;
+    TOAD_TRY((tc::launch_gemm<64, tc::A_SPLIT, tc::EPI_LINEAR, 2, kResOutBufs, PREC>(g, w.col_hi, w.col_lo, P.conv[0].hi, P.conv[0].lo, st)));
+    const int64_t threads = static_cast<int64_t>(nb) * H2 * W2 * (64 / 8);
+    resnet::maxpool3x3s2_kernel<HALF><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
+        w.stem_hi, w.stem_lo, w.pool_hi, w.pool_lo, nb, H1, W1, 64);
+    TOAD_CUDA_TRY(cudaGetLastError());
     const Planes l1_out = {bufs[4].hi + b0 * l1_img, HALF ? nullptr : bufs[4].lo + b0 * l1_img};
     TOAD_TRY(run_layer(0, 1, nb, H2, W2, Planes{w.pool_hi, w.pool_lo}, bufs, l1_out));
   }

@@ -25,18 +25,6 @@ def initialize_weights(module: nn.Module) -> None:
             m.bias.data.zero_()
 
 
-# Bags of at least this many patches run their trunk as two row halves on two CUDA streams (toad_fwd_2s): the
-# persistent GEMMs of one half fill the partially filled last waves of the other.  Below it a bag does not fill one
-# wave (74 CTA pairs x 256 rows) and the split only adds launches.  TOAD_B200_2S=0 disables it.
-TWO_STREAM_MIN_PATCHES = int(os.environ.get("TOAD_B200_2S_MIN", "24576"))
-
-
-def _aux_for(h: torch.Tensor):
-    if os.environ.get("TOAD_B200_2S", "1") == "0" or h.shape[0] < TWO_STREAM_MIN_PATCHES:
-        return None
-    return ops.AuxStreams.for_current_stream(h.device)
-
-
 def _default_flags() -> int:
     # TOAD_B200_SIMT=1 selects the fp32 CUDA-core GEMMs (debug aid); default is the tcgen05 CTA-pair path.
     flags = _lib.FLAG_SIMT_FP32 if os.environ.get("TOAD_B200_SIMT", "0") == "1" else 0
@@ -99,7 +87,7 @@ class _ToadFunction(torch.autograd.Function):
                 flags |= _lib.FLAG_DROPOUT
                 saved["dropout_seed"] = int(torch.randint(0, 2 ** 62, (1,)).item())
                 saved["dropout_p"] = 0.25
-        out = ops.toad_fwd(dims, params, h, sex, module._ws, flags, saved, aux=_aux_for(h))
+        out = ops.toad_fwd(dims, params, h, sex, module._ws, flags, saved)
         ctx.module = module
         # Nothing this Function RETURNS may be kept on ctx as a plain attribute: output -> grad_fn -> ctx -> output is
         # a reference cycle Python's GC cannot see through (two differentiable outputs share the grad_fn), and it
@@ -342,7 +330,7 @@ class TOAD_fc_mtl_concat(nn.Module):
                 self.__dict__["_pcache"] = pc
             out = ops.toad_fwd(self._dims, pc[1], h, sex_f, self._ws,
                                _default_flags() | self._weight_plane_flag(params, h.device, pkey), prof=self._prof,
-                               pstruct=pc[2], aux=_aux_for(h) if self._prof is None else None)
+                               pstruct=pc[2])
             self._note_planes_written()
             logits, site_logits, y_prob, y_hat = out["logits"], out["site_logits"], out["y_prob"], out["y_hat"]
             site_prob, site_hat, a_raw, features = out["site_prob"], out["site_hat"], out["a_raw"], out["features"]

@@ -50,33 +50,6 @@ class Workspace:
         return aligned, self.buf.numel() - (aligned - ptr)
 
 
-class AuxStreams:
-    """The second stream and the fork / join events toad_fwd_2s needs (caller-owned, include/toad_b200.h), one set per
-    (device, main stream) of a module."""
-    _by_stream: Dict[tuple, "AuxStreams"] = {}
-
-    def __init__(self, device: torch.device) -> None:
-        self.stream = torch.cuda.Stream(device=device)
-        self.ev_fork = torch.cuda.Event()
-        self.ev_join = torch.cuda.Event()
-        cur = torch.cuda.current_stream(device)
-        self.ev_fork.record(cur)          # torch creates the cudaEvent_t lazily: force it, so .cuda_event is a real handle
-        self.ev_join.record(cur)
-        self._struct = _lib.AuxStream(self.stream.cuda_stream, self.ev_fork.cuda_event, self.ev_join.cuda_event)
-
-    def struct(self) -> "_lib.AuxStream":
-        return self._struct
-
-    @classmethod
-    def for_current_stream(cls, device: torch.device) -> "AuxStreams":
-        key = (device.index if device.index is not None else torch.cuda.current_device(),
-               torch.cuda.current_stream(device).cuda_stream)
-        a = cls._by_stream.get(key)
-        if a is None:
-            a = cls._by_stream[key] = cls(device)
-        return a
-
-
 _TOPK_WS: Dict[tuple, "Workspace"] = {}
 
 
@@ -161,7 +134,7 @@ _FWD_WS_BYTES: Dict[tuple, int] = {}
 def toad_fwd(dims: Dims, params: Sequence[torch.Tensor], x: torch.Tensor, sex: torch.Tensor, ws: Workspace,
              flags: int = 0, saved: Optional[Dict[str, torch.Tensor]] = None,
              out: Optional[Dict[str, torch.Tensor]] = None, prof: Optional[int] = None,
-             pstruct: Optional[Params] = None, aux: Optional["AuxStreams"] = None) -> Dict[str, torch.Tensor]:
+             pstruct: Optional[Params] = None) -> Dict[str, torch.Tensor]:
     """One TOAD forward (models/model_toad.py:90-116) through the C ABI.
 
     FLAG_REUSE_WEIGHT_PLANES in `flags` is honoured only if the workspace does not have to grow for this
@@ -200,9 +173,7 @@ def toad_fwd(dims: Dims, params: Sequence[torch.Tensor], x: torch.Tensor, sex: t
     s = _saved_struct(saved) if saved is not None else None
     args = [C.byref(dims), C.byref(p), x.data_ptr(), n, None if attn_only else sex.data_ptr(), C.byref(o),
             C.byref(s) if s is not None else None, wptr, wsize, flags, _stream()]
-    if prof is None and aux is not None and not (flags & _lib.FLAG_SIMT_FP32):
-        _lib.check(lib.toad_fwd_2s(*(args + [C.byref(aux.struct())])), "toad_fwd_2s")
-    elif prof is None:
+    if prof is None:
         _lib.check(lib.toad_fwd(*args), "toad_fwd")
     else:
         _lib.check(lib.toad_fwd_profiled(*(args + [prof])), "toad_fwd_profiled")

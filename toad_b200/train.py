@@ -23,7 +23,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib, ops
-from .model_toad import TOAD_fc_mtl_concat, _aux_for, _default_flags
+from .model_toad import TOAD_fc_mtl_concat, _default_flags
 
 
 class FusedTrainStep:
@@ -124,7 +124,7 @@ class FusedTrainStep:
             saved["dropout_seed"] = int(torch.randint(0, 2 ** 62, (1,)).item())
             saved["dropout_p"] = 0.25
         sex_f = sex.reshape(-1).to(device=data.device, dtype=torch.float32)
-        out = ops.toad_fwd(dims, params, data, sex_f, m._ws, flags, saved, aux=_aux_for(data))
+        out = ops.toad_fwd(dims, params, data, sex_f, m._ws, flags, saved)
         lab = label.reshape(-1).to(device=data.device, dtype=torch.int64)
         sit = site.reshape(-1).to(device=data.device, dtype=torch.int64)
         loss3, dl, ds = ops.ce_loss_grad(out["logits"].reshape(-1), out["site_logits"].reshape(-1), lab, sit,
