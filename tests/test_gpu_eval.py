@@ -73,6 +73,16 @@ def test_patch_pipeline_equals_sequential_modules():
     assert torch.equal(feats, f_ref)
     for k in ("logits", "site_logits", "Y_prob", "A", "features"):
         assert torch.equal(out[k], r_ref[k]), k
+    # the referee: the reference's arithmetic end to end (oracle trunk -> oracle TOAD head), fp64
+    from oracle import resnet_oracle as RO
+    sd = {k: v.detach().cpu().numpy() for k, v in ext.state_dict().items()}
+    f64 = RO.resnet50_baseline_forward(x.cpu().double(), sd).numpy()
+    fscale = np.abs(f64).max()
+    assert np.abs(to_np(feats) - f64).max() <= 1e-3 * fscale
+    oref = O.toad_forward(f64, 1.0, O.make_params(7, "big", 18, 0.02), dtype=np.float64)
+    lscale = np.abs(oref["logits"]).max()
+    assert np.abs(to_np(out["logits"]) - oref["logits"]).max() <= 2e-3 * lscale
+    np.testing.assert_allclose(to_np(out["Y_prob"]), oref["Y_prob"], rtol=1e-2, atol=1e-4)
 
 
 @pytest.mark.parametrize("simt", [False, True])
