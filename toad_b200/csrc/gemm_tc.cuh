@@ -1156,11 +1156,15 @@ inline int make_bf16_out_tmap(CUtensorMap* map, const void* ptr, int64_t rows, i
   return r == CUDA_SUCCESS ? 0 : TOAD_ERR_DRIVER;
 }
 
-// TOAD_B200_PDL=0 in the environment launches every kernel fully serialised (A/B and debugging aid)
+// Programmatic dependent launch is OPT-IN (TOAD_B200_PDL=1 in the environment).  Measured on B200 (profiles/
+// r2h, r2i): on ONE stream it hides the launch gap + prologue of the next kernel (+3 % slides/s at N = 10k, +-0 at
+// 50k); with slides in flight on SEVERAL streams the early-launched CTAs sit on SMs (214 KB of shared memory each)
+// waiting for their predecessor while another stream's runnable kernel needs those SMs: 3-stream throughput fell from
+// ~3500 to 2100 slides/s.  The library cannot know how many streams its caller uses, so the default is off.
 inline bool pdl_enabled() {
   static bool v = []() {
     const char* e = getenv("TOAD_B200_PDL");
-    return !(e != nullptr && e[0] == '0');
+    return e != nullptr && e[0] == '1';
   }();
   return v;
 }
