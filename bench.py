@@ -198,12 +198,16 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    nccl_log = None
     if world > 1:
-        # stdout carries exactly one JSON line; NCCL's own log (communicator / rank / transport lines, the evidence that
-        # N ranks really formed one communicator) goes to stderr instead of being muted
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # stdout carries exactly one JSON line.  NCCL's own log (communicator / rank / transport lines: the evidence that
+        # N ranks really formed one communicator) is NOT muted: every rank logs at INFO into its own file, and replays the
+        # file on stderr when it is done (NCCL's default sink is stdout, where it would break the one-line contract).
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
+        nccl_log = "/tmp/toad_bench_nccl_rank%d_%d.log" % (rank, os.getpid())
+        os.environ["NCCL_DEBUG_FILE"] = nccl_log
         dist.init_process_group("nccl", device_id=dev)
     S = args.slides_per_step
     n = args.n_patches
@@ -392,6 +396,13 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+        try:
+            with open(nccl_log) as f:
+                sys.stderr.write(f.read())
+            sys.stderr.flush()
+            os.remove(nccl_log)
+        except OSError:
+            pass
 
 
 def train_leg(args, model, dev, world, rank, barrier):

@@ -62,6 +62,45 @@ def test_f16_mode_matches_its_cpu_restatement():
     assert np.abs(y - ref).max() <= 2e-4 * scale, np.abs(y - ref).max() / scale
 
 
+def test_widest_supported_patch_two_stem_tiles_per_row():
+    """W = 512: the stem's output rows are 256 pixels = two 128-pixel tiles of the fused implicit-GEMM stem, and
+    layer1's 3x3 tiles span full 128-pixel rows; both modes against the oracle."""
+    params = RO.make_params(1)
+    x = RO.make_images(31, 2, 32, 512)
+    ref = RO.resnet50_baseline_forward(torch.from_numpy(x).double(), params).numpy()
+    scale = np.abs(ref).max()
+    for precision in ("f16x2", "bf16x3"):
+        model = build(params, precision)
+        with torch.no_grad():
+            y = to_np(model(torch.from_numpy(x).cuda()))
+        assert np.abs(y - ref).max() <= TOL[precision] * scale, (precision, np.abs(y - ref).max() / scale)
+
+
+def test_fused_stem_equals_the_im2col_stem(monkeypatch):
+    """The implicit-GEMM stem (stem.cuh) and the explicit im2col + GEMM stem contract the same fp16 operands with the
+    same fp32 accumulation order per K block: features agree far below the fp16 rounding of the activations."""
+    import subprocess
+    import sys
+    code = ("import sys, numpy as np, torch; sys.path.insert(0, %r); from oracle import resnet_oracle as RO; "
+            "from models.resnet_custom import resnet50_baseline; m = resnet50_baseline(); "
+            "m.load_state_dict({k: torch.from_numpy(np.asarray(v).copy()) for k, v in RO.make_params(1).items()}); m = m.cuda().eval(); "
+            "y = m(torch.from_numpy(RO.make_images(8, 3, 96, 160)).cuda()); np.save(sys.argv[1], y.cpu().numpy())")
+    import os
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for forced in ("0", "1"):      # the switch is read once per process: one child per setting
+        with tempfile.NamedTemporaryFile(suffix=".npy", delete=False) as f:
+            path = f.name
+        env = dict(os.environ, TOAD_RESNET_STEM_IM2COL=forced)
+        r = subprocess.run([sys.executable, "-c", code % root, path], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(np.load(path))
+        os.remove(path)
+    scale = np.abs(outs[1]).max()
+    assert np.abs(outs[0] - outs[1]).max() <= 2e-5 * scale, np.abs(outs[0] - outs[1]).max() / scale
+
+
 def test_resnet_shape_contract():
     """Any H, W multiple of 16 up to W = 512 (the reference's AdaptiveAvgPool2d takes any size, resnet_custom.py:106);
     other sizes raise instead of computing something else."""

@@ -1,0 +1,254 @@
+// Fused stem of resnet50_baseline (reference models/resnet_custom.py:61-63, 97-99): conv1 7x7 / stride 2 / pad 3
+// (3 -> 64 channels) + folded BatchNorm + ReLU as an IMPLICIT GEMM on tcgen05 -- the im2col operand is built in shared
+// memory, tile by tile, straight from the NCHW fp32 image and never exists in HBM (the explicit im2col plane is
+// 6.3 MB per 256 x 256 patch in fp16: written once, read once, ~12 % of the trunk's time and ~20 % of its DRAM bytes).
+//
+// One persistent CTA per SM (cta_group::1).  A tile = 128 consecutive output pixels of one output row (b, oh):
+//   A [128 pixels x 192]   k = (kh*7 + kw)*3 + c  (147 real columns, zero padded: three 64-wide K blocks)
+//   B [64 channels x 192]  the folded weights as fp16 (hi, lo) planes (toad_resnet_prepare), loaded ONCE by TMA
+//   D = A.B_hi + A.B_lo    fp32 in TMEM (two 64-column accumulators), fp16 single-plane mode of gemm_tc.cuh
+// Warps: 0 = loads B, 1 = MMA issuer, 2 = TMEM allocator, 4-7 = epilogue (bias + ReLU in the fp16 conversion, 128 B
+// per pixel stored by its own lane), 8-15 = A builders: they stage the 21 input rows (3 channels x 7 taps) the tile
+// touches with coalesced 128-bit loads (zero padded), then gather the swizzled K-major UMMA tile from shared memory
+// through 8 per-thread constant offsets (no div / mod in the loop).  A is double buffered, so building tile i+1
+// overlaps the MMAs of tile i, whose epilogue overlaps the MMAs of tile i+1.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace toad {
+namespace stem {
+
+constexpr int K_REAL = 147, K_PAD = 192, KBLOCKS = 3;
+constexpr int COUT = 64;
+constexpr int TILE_PIX = 128;
+constexpr int BUILD_WARPS = 8, BUILD_THREADS = BUILD_WARPS * 32;
+constexpr int THREADS = (8 + BUILD_WARPS) * 32;         // 512
+constexpr int STG_W = 2 * TILE_PIX + 8;                 // 264 staged input columns per row
+constexpr int STG_ROWS = 21;                            // (channel, kh)
+constexpr int A_KB_BYTES = TILE_PIX * 128;              // 16 KB: one K block of the A tile
+constexpr int A_BUF_BYTES = KBLOCKS * A_KB_BYTES;       // 48 KB
+constexpr int B_KB_BYTES = COUT * 128;                  // 8 KB per plane and K block
+constexpr int B_BYTES = KBLOCKS * 2 * B_KB_BYTES;       // 48 KB
+constexpr int STG_BYTES = STG_ROWS * STG_W * 4;         // 22 KB
+constexpr int SMEM_BYTES = B_BYTES + 2 * A_BUF_BYTES + STG_BYTES + 1024;
+
+struct StemParams {
+  const float* x;        // [B, 3, H, W] fp32 NCHW
+  const float* bias;     // [64] folded BatchNorm bias
+  __nv_bfloat16* out;    // [B*Ho*Wo, 64] fp16 bits, NHWC
+  int32_t B, H, W, Ho, Wo;
+  int32_t tiles_per_row; // ceil(Wo / 128)
+  int32_t n_tiles;       // B * Ho * tiles_per_row
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+stem_conv_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const StemParams p) {
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_b, bar_a_full[2], bar_a_empty[2], bar_acc_full[2], bar_acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_bias[COUT];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sB = base, sA = base + B_BYTES, sStg = sA + 2 * A_BUF_BYTES;
+  float* const stg = reinterpret_cast<float*>(smem_raw + (sStg - smem_u32(smem_raw)));
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar_b), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bar_a_full[i]), BUILD_WARPS);
+      mbar_init(smem_u32(&bar_a_empty[i]), 1);
+      mbar_init(smem_u32(&bar_acc_full[i]), 1);
+      mbar_init(smem_u32(&bar_acc_empty[i]), 4);
+    }
+    fence_barrier_init();
+  }
+  if (threadIdx.x < COUT) s_bias[threadIdx.x] = __ldg(p.bias + threadIdx.x);
+  if (warp == 2) tmem_alloc<1>(smem_u32(&tmem_slot), 2 * COUT);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- the weights, once
+    if (lane == 0) {
+      prefetch_tmap(&tm_b_hi);
+      prefetch_tmap(&tm_b_lo);
+      mbar_expect_tx(smem_u32(&bar_b), B_BYTES);
+      for (int kb = 0; kb < KBLOCKS; ++kb) {
+        tma_load_2d<1>(sB + kb * 2 * B_KB_BYTES, &tm_b_hi, smem_u32(&bar_b), kb * 64, 0);
+        tma_load_2d<1>(sB + kb * 2 * B_KB_BYTES + B_KB_BYTES, &tm_b_lo, smem_u32(&bar_b), kb * 64, 0);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc = make_idesc_f16(TILE_PIX, COUT);
+    mbar_wait(smem_u32(&bar_b), 0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t par = (it >> 1) & 1;
+      mbar_wait(smem_u32(&bar_acc_empty[buf]), par ^ 1);
+      mbar_wait(smem_u32(&bar_a_full[buf]), par);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t d_tmem = tmem_base + buf * COUT;
+#pragma unroll
+        for (int kb = 0; kb < KBLOCKS; ++kb) {
+          const uint64_t a = make_kmajor_sw128_desc(sA + buf * A_BUF_BYTES + kb * A_KB_BYTES);
+          const uint64_t b_hi = make_kmajor_sw128_desc(sB + kb * 2 * B_KB_BYTES);
+          const uint64_t b_lo = make_kmajor_sw128_desc(sB + kb * 2 * B_KB_BYTES + B_KB_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t koff = static_cast<uint64_t>(k) * ((UMMA_K * 2) >> 4);
+            umma_bf16<1>(d_tmem, a + koff, b_hi + koff, idesc, (kb > 0) || (k != 0));
+          }
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t koff = static_cast<uint64_t>(k) * ((UMMA_K * 2) >> 4);
+            umma_bf16<1>(d_tmem, a + koff, b_lo + koff, idesc, 1);
+          }
+        }
+        umma_commit<1>(smem_u32(&bar_a_empty[buf]));   // the A buffer may be rebuilt once these MMAs retire
+        umma_commit<1>(smem_u32(&bar_acc_full[buf]));  // accumulator ready
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ---------------------------------------------------------------- epilogue: lane = output pixel
+    const int ew = warp - 4;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int row_tile = tile / p.tiles_per_row, ow0 = (tile - row_tile * p.tiles_per_row) * TILE_PIX;
+      const int r = ew * 32 + lane;
+      const bool ok = ow0 + r < p.Wo;
+      __nv_bfloat16* dst = p.out + (static_cast<int64_t>(row_tile) * p.Wo + ow0 + r) * COUT;
+      mbar_wait(smem_u32(&bar_acc_full[buf]), (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * COUT;
+#pragma unroll
+      for (int c = 0; c < COUT / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t_row + c * 32, v);
+        tmem_ld_wait();
+        if (c == COUT / 32 - 1) {  // accumulator drained by this warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[buf]));
+        }
+        const float4* sb = reinterpret_cast<const float4*>(s_bias + c * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 b4 = sb[q];
+          add_f32x2(v[4 * q], v[4 * q + 1], b4.x, b4.y);
+          add_f32x2(v[4 * q + 2], v[4 * q + 3], b4.z, b4.w);
+        }
+        if (ok) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint32_t h[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = pack_relu_f16x2(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
+            *reinterpret_cast<uint4*>(dst + c * 32 + q * 8) = make_uint4(h[0], h[1], h[2], h[3]);
+          }
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ---------------------------------------------------------------- A builders (256 threads)
+    const int u = threadIdx.x - 8 * 32;
+    // gather role: 24 (K block, 8-column group) combinations x 10 pixel groups; threads 240..255 only help staging
+    const int combo = u % 24, g = u / 24;
+    const int kb_mine = combo >> 3, jc = combo & 7;
+    int off[8];  // staging offset of column k = kb*64 + jc*8 + e for pixel 0 (-1: zero padding column)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kb_mine * 64 + jc * 8 + e;
+      const int c = k % 3, tap = k / 3;
+      const int kh = tap / 7, kw = tap - kh * 7;
+      off[e] = k < K_REAL ? (c * 7 + kh) * STG_W + kw + 1 : -1;
+    }
+    const int W4 = p.W >> 2;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int row_tile = tile / p.tiles_per_row, ow0 = (tile - row_tile * p.tiles_per_row) * TILE_PIX;
+      const int b = row_tile / p.Ho, oh = row_tile - b * p.Ho;
+      // everybody has finished gathering the previous tile from the staging rows
+      asm volatile("bar.sync 1, %0;" ::"n"(BUILD_THREADS) : "memory");
+      // stage: staging column s of row (c, kh) holds input pixel iw = 2*ow0 - 4 + s of input row ih = 2*oh + kh - 3
+      const int q0 = (2 * ow0 - 4) >> 2;  // first float4 index along W (may be -1)
+      for (int i = u; i < STG_ROWS * (STG_W / 4); i += BUILD_THREADS) {
+        const int rr = i / (STG_W / 4), q = i - rr * (STG_W / 4);
+        const int c = rr / 7, kh = rr - c * 7;
+        const int ih = 2 * oh + kh - 3, q4 = q0 + q;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ih >= 0 && ih < p.H && q4 >= 0 && q4 < W4)
+          v = ld_stream_f4(p.x + ((static_cast<int64_t>(b) * 3 + c) * p.H + ih) * p.W + q4 * 4);
+        *reinterpret_cast<float4*>(stg + rr * STG_W + q * 4) = v;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(BUILD_THREADS) : "memory");
+      // the MMAs that read this A buffer two tiles ago have retired
+      mbar_wait(smem_u32(&bar_a_empty[buf]), ((it >> 1) & 1) ^ 1);
+      if (u < 240) {
+        const uint32_t a_kb = sA + buf * A_BUF_BYTES + kb_mine * A_KB_BYTES;
+        for (int r = g; r < TILE_PIX; r += 10) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = off[e] >= 0 ? stg[off[e] + 2 * r] : 0.f;
+          uint32_t h[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h[e] = pack_f16x2(v[2 * e], v[2 * e + 1]);
+          const uint32_t o = r * 128 + ((jc ^ (r & 7)) << 4);  // SWIZZLE_128B: 16-byte chunk index ^= row & 7
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_kb + o), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+        }
+      }
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_a_full[buf]));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 2 * COUT);
+  }
+}
+
+// x [B, 3, H, W] fp32 -> out [B*(H/2)*(W/2), 64] fp16 NHWC = relu(conv7x7s2(x) * bn_scale + bn_bias).
+// w_hi / w_lo: [64, 192] fp16 planes (K order (kh, kw, c), zero padded), bias [64].  H, W even, W % 4 == 0.
+inline int launch_stem_fused(const float* x, const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const float* bias,
+                             __nv_bfloat16* out, int B, int H, int W, cudaStream_t stream) {
+  if (B <= 0) return 0;
+  if ((H & 1) || (W & 3) || H < 2 || W < 4) return TOAD_ERR_UNSUPPORTED;
+  StemParams p{};
+  p.x = x; p.bias = bias; p.out = out; p.B = B; p.H = H; p.W = W; p.Ho = H / 2; p.Wo = W / 2;
+  p.tiles_per_row = (p.Wo + TILE_PIX - 1) / TILE_PIX;
+  const int64_t tiles = static_cast<int64_t>(B) * p.Ho * p.tiles_per_row;
+  if (tiles > 0x7fffffff) return TOAD_ERR_UNSUPPORTED;
+  p.n_tiles = static_cast<int32_t>(tiles);
+  CUtensorMap tb_hi, tb_lo;
+  TOAD_TRY(tc::make_bf16_tmap(&tb_hi, w_hi, COUT, K_PAD, COUT, K_PAD));
+  TOAD_TRY(tc::make_bf16_tmap(&tb_lo, w_lo, COUT, K_PAD, COUT, K_PAD));
+  {
+    static int attr_dev = -1;
+    int dev = 0;
+    TOAD_CUDA_TRY(cudaGetDevice(&dev));
+    if (attr_dev != dev) {
+      TOAD_CUDA_TRY(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      attr_dev = dev;
+    }
+  }
+  const int sms = tc::sm_count();
+  const int grid = static_cast<int>(tiles < sms ? tiles : sms);
+  stem_conv_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tb_hi, tb_lo, p);
+  TOAD_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace stem
+}  // namespace toad

@@ -6,6 +6,7 @@
 #include "bwd.cuh"
 #include "topk.cuh"
 #include "resnet.cuh"
+#include "stem.cuh"
 #include "train.cuh"
 #include <cmath>
 #include <cstdlib>
@@ -980,15 +981,26 @@ int resnet_chunk() {
   return v;
 }
 
+// TOAD_RESNET_STEM_IM2COL=1: the fp16 mode's stem through the explicit im2col plane + GEMM too (cross-check / A-B aid)
+bool stem_im2col_forced() {
+  static bool v = []() {
+    const char* e = getenv("TOAD_RESNET_STEM_IM2COL");
+    return e != nullptr && e[0] == '1';
+  }();
+  return v;
+}
+
 // exact = (hi, lo) bf16 plane pairs (4 B / element); default = one fp16 plane (2 B / element, lo pointers stay null)
 ResWs carve_resnet(int B, int H, int W, bool exact, void* base) {
   ResWs w{};
   Carver c(base);
   const int64_t H1 = H / 2, W1 = W / 2, H2 = H / 4, W2 = W / 4;
   w.stem_chunk = B < resnet_chunk() ? B : resnet_chunk();
-  const size_t col = static_cast<size_t>(w.stem_chunk) * H1 * W1 * resnet::STEM_KPAD;
-  w.col_hi = c.take<bf16>(col);
-  if (exact) w.col_lo = c.take<bf16>(col);
+  if (exact || stem_im2col_forced()) {  // (the fp16 mode's stem is an implicit GEMM: no im2col plane)
+    const size_t col = static_cast<size_t>(w.stem_chunk) * H1 * W1 * resnet::STEM_KPAD;
+    w.col_hi = c.take<bf16>(col);
+    if (exact) w.col_lo = c.take<bf16>(col);
+  }
   const size_t stem = static_cast<size_t>(w.stem_chunk) * H1 * W1 * 64;
   w.stem_hi = c.take<bf16>(stem);
   if (exact) w.stem_lo = c.take<bf16>(stem);
@@ -1083,12 +1095,18 @@ int resnet_fwd_impl(const Prepared& P, const float* x, int B, int H, int W, floa
   const int64_t l1_img = static_cast<int64_t>(H2) * W2 * 256;  // elements per image of a layer1-sized plane
   for (int b0 = 0; b0 < B; b0 += w.stem_chunk) {
     const int nb = (B - b0) < w.stem_chunk ? (B - b0) : w.stem_chunk;
-    const int64_t rows = static_cast<int64_t>(nb) * H1 * W1;
-    TOAD_TRY(resnet::launch_stem_im2col<HALF>(x + static_cast<int64_t>(b0) * 3 * H * W, w.col_hi, w.col_lo, nb, H, W, H1, W1, st));
-    tc::GemmTcParams g{};
-    g.M = rows; g.N = 64; g.K = resnet::STEM_KPAD; g.bias = P.conv[0].bias; g.relu = 1;
-    g.out_hi = w.stem_hi; g.out_lo = w.stem_lo; g.ld_split = 64;
-    TOAD_TRY((tc::launch_gemm<64, tc::A_SPLIT, tc::EPI_LINEAR, 2, kResOutBufs, PREC>(g, w.col_hi, w.col_lo, P.conv[0].hi, P.conv[0].lo, st)));
+    const float* xb = x + static_cast<int64_t>(b0) * 3 * H * W;
+    if (HALF && !stem_im2col_forced()) {
+      // conv1 + bn1 + relu as one implicit-GEMM kernel (stem.cuh)
+      TOAD_TRY(stem::launch_stem_fused(xb, P.conv[0].hi, P.conv[0].lo, P.conv[0].bias, w.stem_hi, nb, H, W, st));
+    } else {
+      const int64_t rows = static_cast<int64_t>(nb) * H1 * W1;
+      TOAD_TRY(resnet::launch_stem_im2col<HALF>(xb, w.col_hi, w.col_lo, nb, H, W, H1, W1, st));
+      tc::GemmTcParams g{};
+      g.M = rows; g.N = 64; g.K = resnet::STEM_KPAD; g.bias = P.conv[0].bias; g.relu = 1;
+      g.out_hi = w.stem_hi; g.out_lo = w.stem_lo; g.ld_split = 64;
+      TOAD_TRY((tc::launch_gemm<64, tc::A_SPLIT, tc::EPI_LINEAR, 2, kResOutBufs, PREC>(g, w.col_hi, w.col_lo, P.conv[0].hi, P.conv[0].lo, st)));
+    }
     const int64_t threads = static_cast<int64_t>(nb) * H2 * W2 * (64 / 8);
     resnet::maxpool3x3s2_kernel<HALF><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
         w.stem_hi, w.stem_lo, w.pool_hi, w.pool_lo, nb, H1, W1, 64);
