@@ -8,10 +8,14 @@
 //   B [64 channels x 192]  the folded weights as fp16 (hi, lo) planes (toad_resnet_prepare), loaded ONCE by TMA
 //   D = A.B_hi + A.B_lo    fp32 in TMEM (two 64-column accumulators), fp16 single-plane mode of gemm_tc.cuh
 // Warps: 0 = loads B, 1 = MMA issuer, 2 = TMEM allocator, 4-7 = epilogue (bias + ReLU in the fp16 conversion, 128 B
-// per pixel stored by its own lane), 8-15 = A builders: they stage the 21 input rows (3 channels x 7 taps) the tile
-// touches with coalesced 128-bit loads (zero padded), then gather the swizzled K-major UMMA tile from shared memory
-// through 8 per-thread constant offsets (no div / mod in the loop).  A is double buffered, so building tile i+1
-// overlaps the MMAs of tile i, whose epilogue overlaps the MMAs of tile i+1.
+// per pixel stored by its own lane), 8-15 = A builders.  They stage the 21 input rows (3 channels x 7 taps) the tile
+// touches with coalesced 128-bit loads (zero padded; issued one tile ahead into registers, so their latency hides
+// behind the gather of the current tile), EVEN and ODD input columns in separate arrays: output pixel r needs input
+// column 2r + kw - 3, so for a fixed tap a warp's 32 consecutive pixels read 32 consecutive words -- conflict-free.
+// The gather then writes the swizzled K-major UMMA tile: one work item = (8-column group, 32 pixels), the 8 source
+// offsets of a column group come from a 192-entry table built once per CTA (no div / mod in the loop); the 45 padding
+// columns are zeroed once.  A is double buffered: building tile i+1 overlaps the MMAs of tile i, whose epilogue
+// overlaps the MMAs of tile i+1.
 #pragma once
 #include "gemm_tc.cuh"
 
@@ -23,13 +27,17 @@ constexpr int COUT = 64;
 constexpr int TILE_PIX = 128;
 constexpr int BUILD_WARPS = 8, BUILD_THREADS = BUILD_WARPS * 32;
 constexpr int THREADS = (8 + BUILD_WARPS) * 32;         // 512
-constexpr int STG_W = 2 * TILE_PIX + 8;                 // 264 staged input columns per row
+constexpr int STG_W = 2 * TILE_PIX + 8;                 // 264 staged input columns per row ...
+constexpr int STG_HALF_W = STG_W / 2 + 4;               // ... as 132 even + 132 odd ones (pitch 136 floats)
 constexpr int STG_ROWS = 21;                            // (channel, kh)
+constexpr int STG_PARITY = STG_ROWS * STG_HALF_W;       // floats of one parity array
+constexpr int STG_LOADS = (STG_ROWS * (STG_W / 4) + BUILD_THREADS - 1) / BUILD_THREADS;  // float4 loads per thread and tile
+constexpr int REAL_GROUPS = (K_REAL + 7) / 8;           // 19 8-column groups hold real columns
 constexpr int A_KB_BYTES = TILE_PIX * 128;              // 16 KB: one K block of the A tile
 constexpr int A_BUF_BYTES = KBLOCKS * A_KB_BYTES;       // 48 KB
 constexpr int B_KB_BYTES = COUT * 128;                  // 8 KB per plane and K block
 constexpr int B_BYTES = KBLOCKS * 2 * B_KB_BYTES;       // 48 KB
-constexpr int STG_BYTES = STG_ROWS * STG_W * 4;         // 22 KB
+constexpr int STG_BYTES = 2 * STG_PARITY * 4;           // 22 KB
 constexpr int SMEM_BYTES = B_BYTES + 2 * A_BUF_BYTES + STG_BYTES + 1024;
 
 struct StemParams {
@@ -48,6 +56,7 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_const
   __shared__ __align__(8) uint64_t bar_b, bar_a_full[2], bar_a_empty[2], bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_bias[COUT];
+  __shared__ __align__(16) int s_off[K_PAD];   // staging offset of column k for pixel 0 (-1: zero padding column)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sB = base, sA = base + B_BYTES, sStg = sA + 2 * A_BUF_BYTES;
@@ -64,6 +73,14 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_const
     fence_barrier_init();
   }
   if (threadIdx.x < COUT) s_bias[threadIdx.x] = __ldg(p.bias + threadIdx.x);
+  if (threadIdx.x < K_PAD) {
+    // column k = (kh*7 + kw)*3 + c of pixel r reads staged column s = 2r + kw + 1 of row (c, kh):
+    // s even (kw odd) -> even array, index r + (kw + 1)/2;  s odd (kw even) -> odd array, index r + kw/2
+    const int k = threadIdx.x;
+    const int c = k % 3, tap = k / 3;
+    const int kh = tap / 7, kw = tap - kh * 7;
+    s_off[k] = k < K_REAL ? ((kw & 1) ? 0 : STG_PARITY) + (c * 7 + kh) * STG_HALF_W + ((kw + 1) >> 1) : -1;
+  }
   if (warp == 2) tmem_alloc<1>(smem_u32(&tmem_slot), 2 * COUT);
   tc_fence_before();
   __syncthreads();
@@ -158,52 +175,64 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_const
     }
   } else if (warp >= 8) {
     // ---------------------------------------------------------------- A builders (256 threads)
-    const int u = threadIdx.x - 8 * 32;
-    // gather role: 24 (K block, 8-column group) combinations x 10 pixel groups; threads 240..255 only help staging
-    const int combo = u % 24, g = u / 24;
-    const int kb_mine = combo >> 3, jc = combo & 7;
-    int off[8];  // staging offset of column k = kb*64 + jc*8 + e for pixel 0 (-1: zero padding column)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int k = kb_mine * 64 + jc * 8 + e;
-      const int c = k % 3, tap = k / 3;
-      const int kh = tap / 7, kw = tap - kh * 7;
-      off[e] = k < K_REAL ? (c * 7 + kh) * STG_W + kw + 1 : -1;
-    }
+    const int u = threadIdx.x - 8 * 32, bw = warp - 8;
     const int W4 = p.W >> 2;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
+    // the padding columns (k >= 152) of both A buffers: zero once, never written again
+    for (int i = u; i < 2 * TILE_PIX * (8 - (REAL_GROUPS - 16)); i += BUILD_THREADS) {
+      const int buf = i / (TILE_PIX * 5), rem = i - buf * (TILE_PIX * 5);
+      const int r = rem / 5, jc = REAL_GROUPS - 16 + (rem - r * 5);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sA + buf * A_BUF_BYTES + 2 * A_KB_BYTES + r * 128 + ((jc ^ (r & 7)) << 4)), "r"(0u) : "memory");
+    }
+    float4 pre[STG_LOADS];
+    // float4 i of the tile's staging = input columns 4*(q0 + q) .. +3 of row ih = 2*oh + kh - 3 of channel c
+    auto issue_loads = [&](int tile) {
       const int row_tile = tile / p.tiles_per_row, ow0 = (tile - row_tile * p.tiles_per_row) * TILE_PIX;
       const int b = row_tile / p.Ho, oh = row_tile - b * p.Ho;
-      // everybody has finished gathering the previous tile from the staging rows
-      asm volatile("bar.sync 1, %0;" ::"n"(BUILD_THREADS) : "memory");
-      // stage: staging column s of row (c, kh) holds input pixel iw = 2*ow0 - 4 + s of input row ih = 2*oh + kh - 3
-      const int q0 = (2 * ow0 - 4) >> 2;  // first float4 index along W (may be -1)
-      for (int i = u; i < STG_ROWS * (STG_W / 4); i += BUILD_THREADS) {
+      const int q0 = (2 * ow0 - 4) >> 2;  // (may be -1)
+#pragma unroll
+      for (int j = 0; j < STG_LOADS; ++j) {
+        const int i = u + j * BUILD_THREADS;
         const int rr = i / (STG_W / 4), q = i - rr * (STG_W / 4);
         const int c = rr / 7, kh = rr - c * 7;
         const int ih = 2 * oh + kh - 3, q4 = q0 + q;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ih >= 0 && ih < p.H && q4 >= 0 && q4 < W4)
-          v = ld_stream_f4(p.x + ((static_cast<int64_t>(b) * 3 + c) * p.H + ih) * p.W + q4 * 4);
-        *reinterpret_cast<float4*>(stg + rr * STG_W + q * 4) = v;
+        pre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rr < STG_ROWS && tile < p.n_tiles && ih >= 0 && ih < p.H && q4 >= 0 && q4 < W4)
+          pre[j] = ld_stream_f4(p.x + ((static_cast<int64_t>(b) * 3 + c) * p.H + ih) * p.W + q4 * 4);
+      }
+    };
+    issue_loads(blockIdx.x);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      // everybody has finished gathering the previous tile from the staging rows
+      asm volatile("bar.sync 1, %0;" ::"n"(BUILD_THREADS) : "memory");
+#pragma unroll
+      for (int j = 0; j < STG_LOADS; ++j) {   // float4 (s = 4q .. 4q+3) -> even[2q, 2q+1] = (x, z), odd[2q, 2q+1] = (y, w)
+        const int i = u + j * BUILD_THREADS;
+        const int rr = i / (STG_W / 4), q = i - rr * (STG_W / 4);
+        if (rr < STG_ROWS) {
+          *reinterpret_cast<float2*>(stg + rr * STG_HALF_W + 2 * q) = make_float2(pre[j].x, pre[j].z);
+          *reinterpret_cast<float2*>(stg + STG_PARITY + rr * STG_HALF_W + 2 * q) = make_float2(pre[j].y, pre[j].w);
+        }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(BUILD_THREADS) : "memory");
+      issue_loads(tile + gridDim.x);   // next tile's rows: in flight during this tile's gather
       // the MMAs that read this A buffer two tiles ago have retired
       mbar_wait(smem_u32(&bar_a_empty[buf]), ((it >> 1) & 1) ^ 1);
-      if (u < 240) {
-        const uint32_t a_kb = sA + buf * A_BUF_BYTES + kb_mine * A_KB_BYTES;
-        for (int r = g; r < TILE_PIX; r += 10) {
-          float v[8];
+      // work item = (8-column group cg of the 19 real ones, 32-pixel group pg): lane = pixel
+      for (int item = bw; item < REAL_GROUPS * 4; item += BUILD_WARPS) {
+        const int cg = item >> 2, pg = item & 3;
+        const int r = pg * 32 + lane;
+        const int4 o0 = *reinterpret_cast<const int4*>(s_off + cg * 8), o1 = *reinterpret_cast<const int4*>(s_off + cg * 8 + 4);
+        const int off[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+        float v[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = off[e] >= 0 ? stg[off[e] + 2 * r] : 0.f;
-          uint32_t h[4];
+        for (int e = 0; e < 8; ++e) v[e] = off[e] >= 0 ? stg[off[e] + r] : 0.f;
+        uint32_t h[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) h[e] = pack_f16x2(v[2 * e], v[2 * e + 1]);
-          const uint32_t o = r * 128 + ((jc ^ (r & 7)) << 4);  // SWIZZLE_128B: 16-byte chunk index ^= row & 7
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_kb + o), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
-        }
+        for (int e = 0; e < 4; ++e) h[e] = pack_f16x2(v[2 * e], v[2 * e + 1]);
+        const uint32_t dst = sA + buf * A_BUF_BYTES + (cg >> 3) * A_KB_BYTES + r * 128 + (((cg & 7) ^ (r & 7)) << 4);  // SWIZZLE_128B
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
       }
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core
       __syncwarp();
