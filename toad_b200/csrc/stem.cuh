@@ -9,9 +9,10 @@
 //   D = A.B_hi + A.B_lo    fp32 in TMEM (two 64-column accumulators), fp16 single-plane mode of gemm_tc.cuh
 // Warps: 0 = loads B, 1 = MMA issuer, 2 = TMEM allocator, 4-7 = epilogue (bias + ReLU in the fp16 conversion, 128 B
 // per pixel stored by its own lane), 8-15 = A builders.  They stage the 21 input rows (3 channels x 7 taps) the tile
-// touches with coalesced 128-bit loads (zero padded; issued one tile ahead into registers, so their latency hides
-// behind the gather of the current tile), EVEN and ODD input columns in separate arrays: output pixel r needs input
-// column 2r + kw - 3, so for a fixed tap a warp's 32 consecutive pixels read 32 consecutive words -- conflict-free.
+// touches with coalesced cp.async copies (zero filled outside the image) into a 3-deep ring -- two tiles ahead of the
+// gather, and the rows of a tile five rounds ahead are pulled into L2 by bulk prefetches, so neither DRAM nor L2
+// latency sits on the loop --, EVEN and ODD input columns in separate arrays: output pixel r needs input column
+// 2r + kw - 3, so for a fixed tap a warp's 32 consecutive pixels read 32 consecutive words -- conflict-free.
 // The gather then writes the swizzled K-major UMMA tile: one work item = (8-column group, 32 pixels), the 8 source
 // offsets of a column group come from a 192-entry table built once per CTA (no div / mod in the loop); the 45 padding
 // columns are zeroed once.  A is double buffered: building tile i+1 overlaps the MMAs of tile i, whose epilogue
@@ -31,14 +32,15 @@ constexpr int STG_W = 2 * TILE_PIX + 8;                 // 264 staged input colu
 constexpr int STG_HALF_W = STG_W / 2 + 4;               // ... as 132 even + 132 odd ones (pitch 136 floats)
 constexpr int STG_ROWS = 21;                            // (channel, kh)
 constexpr int STG_PARITY = STG_ROWS * STG_HALF_W;       // floats of one parity array
-constexpr int STG_LOADS = (STG_ROWS * (STG_W / 4) + BUILD_THREADS - 1) / BUILD_THREADS;  // float4 loads per thread and tile
+constexpr int STG_BUFS = 3;                             // staging ring: tiles i, i+1, i+2
 constexpr int REAL_GROUPS = (K_REAL + 7) / 8;           // 19 8-column groups hold real columns
 constexpr int A_KB_BYTES = TILE_PIX * 128;              // 16 KB: one K block of the A tile
 constexpr int A_BUF_BYTES = KBLOCKS * A_KB_BYTES;       // 48 KB
 constexpr int B_KB_BYTES = COUT * 128;                  // 8 KB per plane and K block
 constexpr int B_BYTES = KBLOCKS * 2 * B_KB_BYTES;       // 48 KB
 constexpr int STG_BYTES = 2 * STG_PARITY * 4;           // 22 KB
-constexpr int SMEM_BYTES = B_BYTES + 2 * A_BUF_BYTES + STG_BYTES + 1024;
+constexpr int SMEM_BYTES = B_BYTES + 2 * A_BUF_BYTES + STG_BUFS * STG_BYTES + 1024;
+static_assert(SMEM_BYTES + 2048 <= 227 * 1024, "shared memory");
 
 struct StemParams {
   const float* x;        // [B, 3, H, W] fp32 NCHW
@@ -176,47 +178,58 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_const
   } else if (warp >= 8) {
     // ---------------------------------------------------------------- A builders (256 threads)
     const int u = threadIdx.x - 8 * 32, bw = warp - 8;
-    const int W4 = p.W >> 2;
     // the padding columns (k >= 152) of both A buffers: zero once, never written again
     for (int i = u; i < 2 * TILE_PIX * (8 - (REAL_GROUPS - 16)); i += BUILD_THREADS) {
       const int buf = i / (TILE_PIX * 5), rem = i - buf * (TILE_PIX * 5);
       const int r = rem / 5, jc = REAL_GROUPS - 16 + (rem - r * 5);
       asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sA + buf * A_BUF_BYTES + 2 * A_KB_BYTES + r * 128 + ((jc ^ (r & 7)) << 4)), "r"(0u) : "memory");
     }
-    float4 pre[STG_LOADS];
-    // float4 i of the tile's staging = input columns 4*(q0 + q) .. +3 of row ih = 2*oh + kh - 3 of channel c
-    auto issue_loads = [&](int tile) {
-      const int row_tile = tile / p.tiles_per_row, ow0 = (tile - row_tile * p.tiles_per_row) * TILE_PIX;
-      const int b = row_tile / p.Ho, oh = row_tile - b * p.Ho;
-      const int q0 = (2 * ow0 - 4) >> 2;  // (may be -1)
-#pragma unroll
-      for (int j = 0; j < STG_LOADS; ++j) {
-        const int i = u + j * BUILD_THREADS;
-        const int rr = i / (STG_W / 4), q = i - rr * (STG_W / 4);
-        const int c = rr / 7, kh = rr - c * 7;
-        const int ih = 2 * oh + kh - 3, q4 = q0 + q;
-        pre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rr < STG_ROWS && tile < p.n_tiles && ih >= 0 && ih < p.H && q4 >= 0 && q4 < W4)
-          pre[j] = ld_stream_f4(p.x + ((static_cast<int64_t>(b) * 3 + c) * p.H + ih) * p.W + q4 * 4);
-      }
-    };
-    issue_loads(blockIdx.x);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
-      // everybody has finished gathering the previous tile from the staging rows
-      asm volatile("bar.sync 1, %0;" ::"n"(BUILD_THREADS) : "memory");
-#pragma unroll
-      for (int j = 0; j < STG_LOADS; ++j) {   // float4 (s = 4q .. 4q+3) -> even[2q, 2q+1] = (x, z), odd[2q, 2q+1] = (y, w)
-        const int i = u + j * BUILD_THREADS;
-        const int rr = i / (STG_W / 4), q = i - rr * (STG_W / 4);
-        if (rr < STG_ROWS) {
-          *reinterpret_cast<float2*>(stg + rr * STG_HALF_W + 2 * q) = make_float2(pre[j].x, pre[j].z);
-          *reinterpret_cast<float2*>(stg + STG_PARITY + rr * STG_HALF_W + 2 * q) = make_float2(pre[j].y, pre[j].w);
+    // cp.async the 21 x 264 staged words of `tile` into ring slot `slot` (words outside the image: zero fill), one group
+    auto issue_tile = [&](int tile, int slot) {
+      if (tile < p.n_tiles) {
+        const int row_tile = tile / p.tiles_per_row, ow0 = (tile - row_tile * p.tiles_per_row) * TILE_PIX;
+        const int b = row_tile / p.Ho, oh = row_tile - b * p.Ho;
+        const uint32_t dst0 = sStg + slot * STG_BYTES;
+        const float* img = p.x + static_cast<int64_t>(b) * 3 * p.H * p.W;
+        for (int i = u; i < STG_ROWS * STG_W; i += BUILD_THREADS) {
+          const int rr = i / STG_W, sc = i - rr * STG_W;     // staged column sc <-> input column iw = 2*ow0 - 4 + sc
+          const int c = rr / 7, kh = rr - c * 7;
+          const int ih = 2 * oh + kh - 3, iw = 2 * ow0 - 4 + sc;
+          const bool ok = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+          const float* src = ok ? img + (static_cast<int64_t>(c) * p.H + ih) * p.W + iw : p.x;
+          const uint32_t dst = dst0 + (((sc & 1) ? STG_PARITY : 0) + rr * STG_HALF_W + (sc >> 1)) * 4;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(ok ? 4 : 0) : "memory");
         }
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");   // (an empty group past the last tile keeps the counting uniform)
+    };
+    // rows of a tile several rounds ahead -> L2 (one 1 KB bulk prefetch per staged row, warp 8 only)
+    auto prefetch_tile_l2 = [&](int tile) {
+      if (bw != 0 || lane >= STG_ROWS || tile >= p.n_tiles) return;
+      const int row_tile = tile / p.tiles_per_row, ow0 = (tile - row_tile * p.tiles_per_row) * TILE_PIX;
+      const int b = row_tile / p.Ho, oh = row_tile - b * p.Ho;
+      const int c = lane / 7, kh = lane - c * 7;
+      const int ih = 2 * oh + kh - 3;
+      int w0 = 2 * ow0 - 4, w1 = w0 + STG_W;
+      w0 = w0 < 0 ? 0 : w0;
+      w1 = w1 > p.W ? p.W : w1;
+      if (ih >= 0 && ih < p.H && w1 > w0)
+        prefetch_l2_bulk(p.x + ((static_cast<int64_t>(b) * 3 + c) * p.H + ih) * p.W + w0, static_cast<uint32_t>(w1 - w0) * 4u);
+    };
+    const int G = gridDim.x;
+    issue_tile(blockIdx.x, 0);
+    issue_tile(blockIdx.x + G, 1);
+    for (int a = 2; a < 5; ++a) prefetch_tile_l2(blockIdx.x + a * G);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += G, ++it) {
+      const int buf = it & 1;
+      const float* const cur = stg + (it % STG_BUFS) * (STG_BYTES / 4);
+      // everybody has finished gathering the previous tile: its ring slot is the one refilled now
       asm volatile("bar.sync 1, %0;" ::"n"(BUILD_THREADS) : "memory");
-      issue_loads(tile + gridDim.x);   // next tile's rows: in flight during this tile's gather
+      issue_tile(tile + 2 * G, (it + 2) % STG_BUFS);
+      prefetch_tile_l2(tile + 5 * G);
+      asm volatile("cp.async.wait_group 2;" ::: "memory");    // this thread's copies of the current tile have landed ...
+      asm volatile("bar.sync 1, %0;" ::"n"(BUILD_THREADS) : "memory");   // ... and everybody else's
       // the MMAs that read this A buffer two tiles ago have retired
       mbar_wait(smem_u32(&bar_a_empty[buf]), ((it >> 1) & 1) ^ 1);
       // work item = (8-column group cg of the 19 real ones, 32-pixel group pg): lane = pixel
@@ -227,7 +240,7 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_const
         const int off[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
         float v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = off[e] >= 0 ? stg[off[e] + r] : 0.f;
+        for (int e = 0; e < 8; ++e) v[e] = off[e] >= 0 ? cur[off[e] + r] : 0.f;
         uint32_t h[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) h[e] = pack_f16x2(v[2 * e], v[2 * e + 1]);
