@@ -19,14 +19,18 @@ __global__ void fold_conv_kernel(const float* __restrict__ w, const float* __res
                                  const float* __restrict__ beta, const float* __restrict__ mean,
                                  const float* __restrict__ var, float eps, __nv_bfloat16* __restrict__ hi,
                                  __nv_bfloat16* __restrict__ lo, float* __restrict__ bias, int Co, int Ci, int KH, int KW,
-                                 int Kpad) {
+                                 int Kpad, int stem_layout) {
   const int co = blockIdx.x;
   const float scale = gamma[co] / sqrtf(var[co] + eps);
   if (threadIdx.x == 0) bias[co] = beta[co] - mean[co] * scale;
   const int K = KH * KW * Ci;
   for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
     float v = 0.f;
-    if (k < K) {
+    if (stem_layout) {  // the fused stem's K order (stem.cuh): k = (ci*KH + kh)*8 + (kw + 1), slot 0 of each group zero
+      const int g = k >> 3, e = k & 7;
+      const int ci = g / KH, kh = g - ci * KH;
+      if (g < Ci * KH && e >= 1 && e <= KW) v = w[((static_cast<int64_t>(co) * Ci + ci) * KH + kh) * KW + (e - 1)] * scale;
+    } else if (k < K) {
       const int tap = k / Ci, ci = k % Ci;
       const int kh = tap / KW, kw = tap % KW;
       v = w[((static_cast<int64_t>(co) * Ci + ci) * KH + kh) * KW + kw] * scale;

@@ -4,19 +4,20 @@
 // 6.3 MB per 256 x 256 patch in fp16: written once, read once, ~12 % of the trunk's time and ~20 % of its DRAM bytes).
 //
 // One persistent CTA per SM (cta_group::1).  A tile = 128 consecutive output pixels of one output row (b, oh):
-//   A [128 pixels x 192]   k = (kh*7 + kw)*3 + c  (147 real columns, zero padded: three 64-wide K blocks)
-//   B [64 channels x 192]  the folded weights as fp16 (hi, lo) planes (toad_resnet_prepare), loaded ONCE by TMA
+//   A [128 pixels x 192]   K order chosen for the gather: column k = (c*7 + kh)*8 + (kw + 1), i.e. one 8-column group
+//                          per (channel, tap row), kw fastest, slot 0 of each group and the groups 21..23 being zero
+//                          padding.  Output pixel r needs input columns 2r - 3 .. 2r + 3 of that image row, so a group
+//                          is EIGHT CONSECUTIVE staged floats starting at 2r: four 64-bit shared loads per lane, and a
+//                          warp's 32 consecutive pixels read 64 consecutive words -- no offset table, no bank conflict.
+//   B [64 channels x 192]  the folded weights in the same K order as fp16 (hi, lo) planes (toad_resnet_prepare with
+//                          the stem layout), loaded ONCE by TMA
 //   D = A.B_hi + A.B_lo    fp32 in TMEM (two 64-column accumulators), fp16 single-plane mode of gemm_tc.cuh
 // Warps: 0 = loads B, 1 = MMA issuer, 2 = TMEM allocator, 4-7 = epilogue (bias + ReLU in the fp16 conversion, 128 B
-// per pixel stored by its own lane), 8-15 = A builders.  They stage the 21 input rows (3 channels x 7 taps) the tile
-// touches with coalesced cp.async copies (zero filled outside the image) into a 3-deep ring -- two tiles ahead of the
-// gather, and the rows of a tile five rounds ahead are pulled into L2 by bulk prefetches, so neither DRAM nor L2
-// latency sits on the loop --, EVEN and ODD input columns in separate arrays: output pixel r needs input column
-// 2r + kw - 3, so for a fixed tap a warp's 32 consecutive pixels read 32 consecutive words -- conflict-free.
-// The gather then writes the swizzled K-major UMMA tile: one work item = (8-column group, 32 pixels), the 8 source
-// offsets of a column group come from a 192-entry table built once per CTA (no div / mod in the loop); the 45 padding
-// columns are zeroed once.  A is double buffered: building tile i+1 overlaps the MMAs of tile i, whose epilogue
-// overlaps the MMAs of tile i+1.
+// per pixel stored by its own lane), 8-15 = A builders: they stage the 21 input rows (3 channels x 7 taps) the tile
+// touches with coalesced 128-bit loads (zero padded; issued one tile ahead into registers, so their latency hides
+// behind the gather of the current tile), then write the swizzled K-major UMMA tile, one work item = (column group,
+// 32 pixels).  A is double buffered: building tile i+1 overlaps the MMAs of tile i, whose epilogue overlaps the MMAs
+// of tile i+1.
 #pragma once
 #include "gemm_tc.cuh"
 
@@ -29,18 +30,15 @@ constexpr int TILE_PIX = 128;
 constexpr int BUILD_WARPS = 8, BUILD_THREADS = BUILD_WARPS * 32;
 constexpr int THREADS = (8 + BUILD_WARPS) * 32;         // 512
 constexpr int STG_W = 2 * TILE_PIX + 8;                 // 264 staged input columns per row ...
-constexpr int STG_HALF_W = STG_W / 2 + 4;               // ... as 132 even + 132 odd ones (pitch 136 floats)
-constexpr int STG_ROWS = 21;                            // (channel, kh)
-constexpr int STG_PARITY = STG_ROWS * STG_HALF_W;       // floats of one parity array
-constexpr int STG_BUFS = 3;                             // staging ring: tiles i, i+1, i+2
-constexpr int REAL_GROUPS = (K_REAL + 7) / 8;           // 19 8-column groups hold real columns
+constexpr int STG_ROWS = 21;                            // (channel, kh) = the 21 real 8-column groups
+constexpr int STG_LOADS = (STG_ROWS * (STG_W / 4) + BUILD_THREADS - 1) / BUILD_THREADS;  // float4 loads per thread and tile
+constexpr int REAL_GROUPS = STG_ROWS;                   // column groups 0..20 are real, 21..23 zero padding
 constexpr int A_KB_BYTES = TILE_PIX * 128;              // 16 KB: one K block of the A tile
 constexpr int A_BUF_BYTES = KBLOCKS * A_KB_BYTES;       // 48 KB
 constexpr int B_KB_BYTES = COUT * 128;                  // 8 KB per plane and K block
 constexpr int B_BYTES = KBLOCKS * 2 * B_KB_BYTES;       // 48 KB
-constexpr int STG_BYTES = 2 * STG_PARITY * 4;           // 22 KB
-constexpr int SMEM_BYTES = B_BYTES + 2 * A_BUF_BYTES + STG_BUFS * STG_BYTES + 1024;
-static_assert(SMEM_BYTES + 2048 <= 227 * 1024, "shared memory");
+constexpr int STG_BYTES = STG_ROWS * STG_W * 4;         // 22 KB
+constexpr int SMEM_BYTES = B_BYTES + 2 * A_BUF_BYTES + STG_BYTES + 1024;
 
 struct StemParams {
   const float* x;        // [B, 3, H, W] fp32 NCHW
@@ -58,7 +56,6 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_const
   __shared__ __align__(8) uint64_t bar_b, bar_a_full[2], bar_a_empty[2], bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_bias[COUT];
-  __shared__ __align__(16) int s_off[K_PAD];   // staging offset of column k for pixel 0 (-1: zero padding column)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sB = base, sA = base + B_BYTES, sStg = sA + 2 * A_BUF_BYTES;
@@ -75,14 +72,6 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_const
     fence_barrier_init();
   }
   if (threadIdx.x < COUT) s_bias[threadIdx.x] = __ldg(p.bias + threadIdx.x);
-  if (threadIdx.x < K_PAD) {
-    // column k = (kh*7 + kw)*3 + c of pixel r reads staged column s = 2r + kw + 1 of row (c, kh):
-    // s even (kw odd) -> even array, index r + (kw + 1)/2;  s odd (kw even) -> odd array, index r + kw/2
-    const int k = threadIdx.x;
-    const int c = k % 3, tap = k / 3;
-    const int kh = tap / 7, kw = tap - kh * 7;
-    s_off[k] = k < K_REAL ? ((kw & 1) ? 0 : STG_PARITY) + (c * 7 + kh) * STG_HALF_W + ((kw + 1) >> 1) : -1;
-  }
   if (warp == 2) tmem_alloc<1>(smem_u32(&tmem_slot), 2 * COUT);
   tc_fence_before();
   __syncthreads();
@@ -178,74 +167,56 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_const
   } else if (warp >= 8) {
     // ---------------------------------------------------------------- A builders (256 threads)
     const int u = threadIdx.x - 8 * 32, bw = warp - 8;
+    const int W4 = p.W >> 2;
     // the padding columns (k >= 152) of both A buffers: zero once, never written again
-    for (int i = u; i < 2 * TILE_PIX * (8 - (REAL_GROUPS - 16)); i += BUILD_THREADS) {
-      const int buf = i / (TILE_PIX * 5), rem = i - buf * (TILE_PIX * 5);
-      const int r = rem / 5, jc = REAL_GROUPS - 16 + (rem - r * 5);
+    constexpr int PAD_GROUPS = 24 - REAL_GROUPS;  // 3
+    for (int i = u; i < 2 * TILE_PIX * PAD_GROUPS; i += BUILD_THREADS) {
+      const int buf = i / (TILE_PIX * PAD_GROUPS), rem = i - buf * (TILE_PIX * PAD_GROUPS);
+      const int r = rem / PAD_GROUPS, jc = REAL_GROUPS - 16 + (rem - r * PAD_GROUPS);
       asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sA + buf * A_BUF_BYTES + 2 * A_KB_BYTES + r * 128 + ((jc ^ (r & 7)) << 4)), "r"(0u) : "memory");
     }
-    // cp.async the 21 x 264 staged words of `tile` into ring slot `slot` (words outside the image: zero fill), one group
-    auto issue_tile = [&](int tile, int slot) {
-      if (tile < p.n_tiles) {
-        const int row_tile = tile / p.tiles_per_row, ow0 = (tile - row_tile * p.tiles_per_row) * TILE_PIX;
-        const int b = row_tile / p.Ho, oh = row_tile - b * p.Ho;
-        const uint32_t dst0 = sStg + slot * STG_BYTES;
-        const float* img = p.x + static_cast<int64_t>(b) * 3 * p.H * p.W;
-        for (int i = u; i < STG_ROWS * STG_W; i += BUILD_THREADS) {
-          const int rr = i / STG_W, sc = i - rr * STG_W;     // staged column sc <-> input column iw = 2*ow0 - 4 + sc
-          const int c = rr / 7, kh = rr - c * 7;
-          const int ih = 2 * oh + kh - 3, iw = 2 * ow0 - 4 + sc;
-          const bool ok = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
-          const float* src = ok ? img + (static_cast<int64_t>(c) * p.H + ih) * p.W + iw : p.x;
-          const uint32_t dst = dst0 + (((sc & 1) ? STG_PARITY : 0) + rr * STG_HALF_W + (sc >> 1)) * 4;
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(ok ? 4 : 0) : "memory");
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");   // (an empty group past the last tile keeps the counting uniform)
-    };
-    // rows of a tile several rounds ahead -> L2 (one 1 KB bulk prefetch per staged row, warp 8 only)
-    auto prefetch_tile_l2 = [&](int tile) {
-      if (bw != 0 || lane >= STG_ROWS || tile >= p.n_tiles) return;
+    float4 pre[STG_LOADS];
+    // float4 i of the tile's staging = input columns 4*(q0 + q) .. +3 of row ih = 2*oh + kh - 3 of channel c
+    auto issue_loads = [&](int tile) {
       const int row_tile = tile / p.tiles_per_row, ow0 = (tile - row_tile * p.tiles_per_row) * TILE_PIX;
       const int b = row_tile / p.Ho, oh = row_tile - b * p.Ho;
-      const int c = lane / 7, kh = lane - c * 7;
-      const int ih = 2 * oh + kh - 3;
-      int w0 = 2 * ow0 - 4, w1 = w0 + STG_W;
-      w0 = w0 < 0 ? 0 : w0;
-      w1 = w1 > p.W ? p.W : w1;
-      if (ih >= 0 && ih < p.H && w1 > w0)
-        prefetch_l2_bulk(p.x + ((static_cast<int64_t>(b) * 3 + c) * p.H + ih) * p.W + w0, static_cast<uint32_t>(w1 - w0) * 4u);
+      const int q0 = (2 * ow0 - 4) >> 2;  // (may be -1)
+#pragma unroll
+      for (int j = 0; j < STG_LOADS; ++j) {
+        const int i = u + j * BUILD_THREADS;
+        const int rr = i / (STG_W / 4), q = i - rr * (STG_W / 4);
+        const int c = rr / 7, kh = rr - c * 7;
+        const int ih = 2 * oh + kh - 3, q4 = q0 + q;
+        pre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rr < STG_ROWS && tile < p.n_tiles && ih >= 0 && ih < p.H && q4 >= 0 && q4 < W4)
+          pre[j] = ld_stream_f4(p.x + ((static_cast<int64_t>(b) * 3 + c) * p.H + ih) * p.W + q4 * 4);
+      }
     };
-    const int G = gridDim.x;
-    issue_tile(blockIdx.x, 0);
-    issue_tile(blockIdx.x + G, 1);
-    for (int a = 2; a < 5; ++a) prefetch_tile_l2(blockIdx.x + a * G);
+    issue_loads(blockIdx.x);
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += G, ++it) {
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
-      const float* const cur = stg + (it % STG_BUFS) * (STG_BYTES / 4);
-      // everybody has finished gathering the previous tile: its ring slot is the one refilled now
+      // everybody has finished gathering the previous tile from the staging rows
       asm volatile("bar.sync 1, %0;" ::"n"(BUILD_THREADS) : "memory");
-      issue_tile(tile + 2 * G, (it + 2) % STG_BUFS);
-      prefetch_tile_l2(tile + 5 * G);
-      asm volatile("cp.async.wait_group 2;" ::: "memory");    // this thread's copies of the current tile have landed ...
-      asm volatile("bar.sync 1, %0;" ::"n"(BUILD_THREADS) : "memory");   // ... and everybody else's
+#pragma unroll
+      for (int j = 0; j < STG_LOADS; ++j) {   // staged column s of row (c, kh) = input column 2*ow0 - 4 + s
+        const int i = u + j * BUILD_THREADS;
+        if (i < STG_ROWS * (STG_W / 4)) reinterpret_cast<float4*>(stg)[i] = pre[j];
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(BUILD_THREADS) : "memory");
+      issue_loads(tile + gridDim.x);   // next tile's rows: in flight during this tile's gather
       // the MMAs that read this A buffer two tiles ago have retired
       mbar_wait(smem_u32(&bar_a_empty[buf]), ((it >> 1) & 1) ^ 1);
-      // work item = (8-column group cg of the 19 real ones, 32-pixel group pg): lane = pixel
+      // work item = (column group cg = (c, kh), 32-pixel group pg): lane = pixel r; the group's 8 columns are the
+      // staged floats 2r .. 2r+7 of row cg (kw = -1 .. 6; the kw = -1 slot meets a zero weight)
       for (int item = bw; item < REAL_GROUPS * 4; item += BUILD_WARPS) {
         const int cg = item >> 2, pg = item & 3;
         const int r = pg * 32 + lane;
-        const int4 o0 = *reinterpret_cast<const int4*>(s_off + cg * 8), o1 = *reinterpret_cast<const int4*>(s_off + cg * 8 + 4);
-        const int off[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
-        float v[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = off[e] >= 0 ? cur[off[e] + r] : 0.f;
-        uint32_t h[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) h[e] = pack_f16x2(v[2 * e], v[2 * e + 1]);
+        const float2* src = reinterpret_cast<const float2*>(stg + cg * STG_W + 2 * r);
+        const float2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3];
+        const uint32_t h0 = pack_f16x2(v0.x, v0.y), h1 = pack_f16x2(v1.x, v1.y), h2 = pack_f16x2(v2.x, v2.y), h3 = pack_f16x2(v3.x, v3.y);
         const uint32_t dst = sA + buf * A_BUF_BYTES + (cg >> 3) * A_KB_BYTES + r * 128 + (((cg & 7) ^ (r & 7)) << 4);  // SWIZZLE_128B
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
       }
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core
       __syncwarp();

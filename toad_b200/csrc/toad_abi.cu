@@ -1149,11 +1149,12 @@ extern "C" int toad_resnet_prepare(const float* const* tensors, int32_t n_tensor
     if (exact)
       resnet::fold_conv_kernel<false><<<specs[i].cout, 256, 0, st>>>(t[0], t[1], t[2], t[3], t[4], 1e-5f, P.conv[i].hi, P.conv[i].lo,
                                                                    P.conv[i].bias, specs[i].cout, specs[i].cin, specs[i].k,
-                                                                   specs[i].k, kpad_of(specs[i]));
+                                                                   specs[i].k, kpad_of(specs[i]), 0);
     else
+      // (conv 0 of the fp16 mode feeds the fused stem kernel: its own K order, see stem.cuh)
       resnet::fold_conv_kernel<true><<<specs[i].cout, 256, 0, st>>>(t[0], t[1], t[2], t[3], t[4], 1e-5f, P.conv[i].hi, P.conv[i].lo,
                                                                   P.conv[i].bias, specs[i].cout, specs[i].cin, specs[i].k,
-                                                                  specs[i].k, kpad_of(specs[i]));
+                                                                  specs[i].k, kpad_of(specs[i]), (i == 0 && !stem_im2col_forced()) ? 1 : 0);
     TOAD_CUDA_TRY(cudaGetLastError());
   }
   return 0;
