@@ -469,10 +469,9 @@ __global__ void __launch_bounds__(cta_threads<A_MODE, EPI>(), 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
-                   const __grid_constant__ CUtensorMap tm_res, const GemmTcParams p) {
+                   const GemmTcParams p) {
   using C = Cfg<BLOCK_N, CG, OUT_BUFS, PREC>;
   static_assert(EPI != EPI_GATE || BLOCK_N <= 256, "the gate epilogue pairs two 128-column halves of a 256-wide tile");
-  static_assert(PREC == PREC_BF16X3 || OUT_BUFS == 2, "fp16 mode: 4 x 2 KB staging slots per epilogue warp (2 output, 2 residual)");
   static_assert(PREC == PREC_BF16X3 || ((A_MODE == A_SPLIT || A_MODE == A_CONV) && EPI == EPI_LINEAR),
                 "the fp16 single-plane mode exists for the plane-fed linear / convolution GEMMs");
   // epilogue warp sets: plane-fed kernels run 8 epilogue warps (two per TMEM lane quarter, each taking one
@@ -490,8 +489,6 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   // fp16 mode: the whole bias vector staged once per CTA (the epilogue reads it with broadcast 128-bit loads)
   constexpr int BIAS_SMEM = PREC == PREC_F16X2 ? 1024 : 1;
   __shared__ __align__(16) float s_bias[BIAS_SMEM];
-  // fp16 mode: the residual operand arrives by TMA, 32 x 32 boxes into per-warp slots (2 per epilogue warp)
-  __shared__ __align__(8) uint64_t bar_res[PREC == PREC_F16X2 ? 8 : 1][2];
   __shared__ uint32_t tmem_slot;
   __shared__ float s_gate[EPI == EPI_GATE ? GATE_SMEM_FLOATS : 1];
 
@@ -518,12 +515,6 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       mbar_init(smem_u32(&bar_full_b[s]), CG);      // producer of each CTA of the pair
       mbar_init(smem_u32(&bar_full_a[s]), 8 * CG);  // one arrive per converter warp (8 per CTA)
       mbar_init(smem_u32(&bar_empty[s]), 1);
-    }
-    if (PREC == PREC_F16X2) {
-      for (int wdx = 0; wdx < 8; ++wdx) {
-        mbar_init(smem_u32(&bar_res[wdx][0]), 1);
-        mbar_init(smem_u32(&bar_res[wdx][1]), 1);
-      }
     }
     for (int a = 0; a < C::ACC_STAGES; ++a) {
       mbar_init(smem_u32(&bar_tmem_full[a]), 1);
@@ -720,7 +711,6 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     const int eh = (warp - 4) >> 2;
     int it = 0;
     uint32_t out_chunk = 0;  // running count of staged chunks (selects the staging buffer)
-    uint32_t res_issued = 0, res_taken = 0;  // fp16 mode: residual chunks requested by / delivered to this warp
     for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
       const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
       const int n_tile = mn % n_tiles;
@@ -752,29 +742,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         for (int q = 0; q < 4; ++q) {
           res_h[q] = make_uint4(0u, 0u, 0u, 0u);
           res_l[q] = make_uint4(0u, 0u, 0u, 0u);
-          if (PREC == PREC_BF16X3 && has_res && row_ok) {
+          if (has_res && row_ok) {
             const int64_t o = row * p.ld_res + n0 + c_ * 32 + q * 8;
             res_h[q] = *reinterpret_cast<const uint4*>(p.res_hi + o);
             if (PREC == PREC_BF16X3) res_l[q] = *reinterpret_cast<const uint4*>(p.res_lo + o);
           }
-        }
-      };
-      // fp16 mode: the residual chunk [32 rows x 32 columns] comes by TMA (the same 64B-swizzled box as the output
-      // store) into one of this warp's two residual slots, requested one chunk ahead: coalesced and asynchronous,
-      // where a per-lane 64-byte row read costs 32 half-used sectors per instruction and a register scoreboard stall.
-      constexpr int RES_SLOT0 = 2;  // slots 0, 1 of the warp's 4 x 2 KB staging: output; 2, 3: residual
-      const uint32_t res_stage = tiles_base + STAGES * C::STAGE_BYTES + (eh * 4 + ew) * ((OUT_BUFS * 2 / EPI_SETS) * 4096) + RES_SLOT0 * 2048;
-      auto request_res = [&](int c_) {
-        if (PREC == PREC_F16X2 && has_res) {
-          const uint32_t slot = res_issued & 1u;
-          __syncwarp();  // every lane has consumed what this slot held two requests ago
-          if (lane == 0) {
-            const uint32_t bar = smem_u32(&bar_res[(eh * 4 + ew) & 7][slot]);
-            fence_proxy_async_smem();
-            mbar_expect_tx(bar, 2048u);
-            tma_load_2d<1>(res_stage + slot * 2048u, &tm_res, bar, n0 + c_ * 32, static_cast<int>(tile_row0) + ew * 32);
-          }
-          ++res_issued;
         }
       };
       // dgrad ReLU mask (the saved activation's bf16 hi plane, 64 B per row and chunk): fetched one chunk ahead too
@@ -806,7 +778,6 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       if (EPI == EPI_LINEAR) {
         bias_nxt = load_bias(eh);
         if (A_MODE != A_F32) load_res(eh);
-        request_res(eh);
       }
       if (EPI == EPI_DGRAD && A_MODE != A_F32) { load_mask(eh); load_pool(eh); }
       mbar_wait(smem_u32(&bar_tmem_full[acc]), (it / C::ACC_STAGES) & 1);
@@ -841,7 +812,6 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             if (EPI == EPI_LINEAR) {
               bias_nxt = load_bias(c + EPI_SETS);
               if (A_MODE != A_F32) load_res(c + EPI_SETS);
-              request_res(c + EPI_SETS);
             } else if (A_MODE != A_F32) {
               load_mask(c + EPI_SETS);
               load_pool(c + EPI_SETS);
@@ -873,14 +843,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
               add_f32x2(r[4 * q + 2], r[4 * q + 3], b4.z, b4.w);
             }
             if (has_res) {
-              const uint32_t slot = res_taken & 1u;
-              mbar_wait(smem_u32(&bar_res[(eh * 4 + ew) & 7][slot]), (res_taken >> 1) & 1u);
-              ++res_taken;
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                uint4 vh;
-                const uint32_t ra = res_stage + slot * 2048u + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4);  // SWIZZLE_64B
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(vh.x), "=r"(vh.y), "=r"(vh.z), "=r"(vh.w) : "r"(ra) : "memory");
+                const uint4 vh = cur_h[q];
                 add_f16x2_to_f32(r[q * 8], r[q * 8 + 1], vh.x);
                 add_f16x2_to_f32(r[q * 8 + 2], r[q * 8 + 3], vh.y);
                 add_f16x2_to_f32(r[q * 8 + 4], r[q * 8 + 5], vh.z);
@@ -948,10 +913,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           }
           if (p.out_hi != nullptr && PREC == PREC_F16X2) {
             // one fp16 plane: 32 rows x 64 B per chunk
-            const uint32_t buf = my_stage + (out_chunk & 1u) * 2048;   // (slots 0, 1; slots 2, 3 hold residual chunks)
+            const uint32_t buf = my_stage + (out_chunk % WARP_BUFS) * 2048;
             ++out_chunk;
             if (use_tma) {  // staging buffer free again?  (this warp's store that last used it must have finished READING it)
-              if (lane == 0) tma_store_wait_read<1>();
+              if (lane == 0) tma_store_wait_read<WARP_BUFS - 1>();
               __syncwarp();
             }
 #pragma unroll
@@ -1252,11 +1217,7 @@ int launch_gemm_maps_b(const GemmTcParams& p, const CUtensorMap& ta_hi, const CU
   if (EPI == EPI_GATE && p.gate_a != nullptr &&
       (((reinterpret_cast<uintptr_t>(p.gate_a) | reinterpret_cast<uintptr_t>(p.gate_b)) & 31) != 0 || p.gate_D % 8 != 0))
     return TOAD_ERR_ARG;
-  CUtensorMap to_hi = tb_hi, to_lo = tb_lo, t_res = tb_hi;
-  if (PREC == PREC_F16X2 && EPI == EPI_LINEAR && p.res_hi != nullptr) {
-    if (p.ld_res % 8 != 0) return TOAD_ERR_ARG;
-    TOAD_TRY(make_bf16_out_tmap(&t_res, p.res_hi, p.M, p.N, p.ld_res));
-  }
+  CUtensorMap to_hi = tb_hi, to_lo = tb_lo;
   if (epi_is_linear(EPI) && p.out_hi != nullptr) {
     if ((PREC == PREC_BF16X3 && p.out_lo == nullptr) || p.ld_split % 8 != 0) return TOAD_ERR_ARG;
     TOAD_TRY(make_bf16_out_tmap(&to_hi, p.out_hi, p.M, p.N, p.ld_split));
@@ -1298,7 +1259,7 @@ int launch_gemm_maps_b(const GemmTcParams& p, const CUtensorMap& ta_hi, const CU
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  TOAD_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, t_res, p));
+  TOAD_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, p));
   TOAD_CUDA_TRY(cudaGetLastError());
   return 0;
 }
