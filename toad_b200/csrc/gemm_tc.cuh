@@ -451,13 +451,16 @@ constexpr int GATE_SMEM_FLOATS = 4 * 1024;  // ba | bb | wc rows (<= 2 tasks sta
 #ifndef TOAD_F32_LINEAR_EPI_SETS
 #define TOAD_F32_LINEAR_EPI_SETS 2
 #endif
-template <int A_MODE, int EPI>
+// The fp16 (ResNet) kernels with tiles of >= 128 columns run FOUR sets (16 epilogue warps, 640 threads): their short-K
+// 1x1 convolutions are paced by the epilogue's instruction stream (ncu profiles/r2o: issue slots 30 % busy with two
+// epilogue warps per scheduler, no memory unit above 50 %), so the cure is more warps in flight, not fewer bytes.
+template <int A_MODE, int EPI, int BLOCK_N = 256, int PREC = PREC_BF16X3>
 __host__ __device__ constexpr int epi_sets() {
-  return A_MODE != A_F32 ? 2 : (epi_is_linear(EPI) ? TOAD_F32_LINEAR_EPI_SETS : 1);
+  return A_MODE != A_F32 ? ((PREC == PREC_F16X2 && BLOCK_N >= 128) ? 4 : 2) : (epi_is_linear(EPI) ? TOAD_F32_LINEAR_EPI_SETS : 1);
 }
-template <int A_MODE, int EPI>
+template <int A_MODE, int EPI, int BLOCK_N = 256, int PREC = PREC_BF16X3>
 __host__ __device__ constexpr int cta_threads() {
-  return A_MODE == A_F32 ? (4 + 4 * epi_sets<A_MODE, EPI>() + 8) * 32 : 384;
+  return A_MODE == A_F32 ? (4 + 4 * epi_sets<A_MODE, EPI>() + 8) * 32 : (4 + 4 * epi_sets<A_MODE, EPI, BLOCK_N, PREC>()) * 32;
 }
 template <int REGS>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
@@ -465,7 +468,7 @@ template <int REGS>
 __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 
 template <int BLOCK_N, int A_MODE, int EPI, int CG, int OUT_BUFS = 1, int PREC = PREC_BF16X3>
-__global__ void __launch_bounds__(cta_threads<A_MODE, EPI>(), 1)
+__global__ void __launch_bounds__(cta_threads<A_MODE, EPI, BLOCK_N, PREC>(), 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
@@ -477,7 +480,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   // epilogue warp sets: plane-fed kernels run 8 epilogue warps (two per TMEM lane quarter, each taking one
   // 32-column half of every 64-column chunk); the fp32-fed kernels keep 4 so that, with their 8 converter
   // warps, the CTA stays at 512 threads / 128 registers.
-  constexpr int EPI_SETS = epi_sets<A_MODE, EPI>();
+  constexpr int EPI_SETS = epi_sets<A_MODE, EPI, BLOCK_N, PREC>();
   constexpr int CONV_WARP0 = 4 + 4 * EPI_SETS;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -791,8 +794,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         // is covered by the others' arithmetic; with WARP_BUFS = 2 a warp's own store overlaps its next chunk.
         constexpr int N_CHUNKS = BLOCK_N / 32;
         // (the fp16 mode stages ONE 2 KB plane per chunk in the same 4 KB slots: twice the buffers)
-        constexpr int WARP_BUFS = (OUT_BUFS * 2 / EPI_SETS) * (PREC == PREC_F16X2 ? 2 : 1);
-        constexpr int WARP_STAGE_BYTES = (OUT_BUFS * 2 / EPI_SETS) * 4096;
+        constexpr int WARP_STAGE_BYTES = OUT_BUFS * 8192 / EPI_SETS;   // OUT_BUFS x 32 KB over 4 * EPI_SETS warps
+        constexpr int WARP_BUFS = WARP_STAGE_BYTES / (PREC == PREC_F16X2 ? 2048 : 4096);
         static_assert(WARP_BUFS >= 1, "staging");
         const uint32_t my_stage = tiles_base + STAGES * C::STAGE_BYTES + (eh * 4 + ew) * WARP_STAGE_BYTES;
         // (fp16 mode: the <= 4 chunks of a warp fully unrolled, so the one-chunk-ahead residual prefetch rotates through
@@ -1240,7 +1243,7 @@ int launch_gemm_maps_b(const GemmTcParams& p, const CUtensorMap& ta_hi, const CU
   const int grid = static_cast<int>(units < max_units ? units : max_units) * CG;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
-  cfg.blockDim = dim3(cta_threads<A_MODE, EPI>());
+  cfg.blockDim = dim3(cta_threads<A_MODE, EPI, BLOCK_N, PREC>());
   cfg.dynamicSmemBytes = kSmem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
