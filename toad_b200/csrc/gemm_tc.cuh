@@ -140,7 +140,6 @@ struct GemmTcParams {
   const __nv_bfloat16* res_hi;
   const __nv_bfloat16* res_lo;
   int64_t ld_res;
-  int32_t res_prefetch;   // set by the launcher: the residual tensor maps are valid, prefetch each tile's box into L2
   // training-mode dropout on the epilogue's activation: EPI_LINEAR uses drop_layer with element index
   // row*N + col; EPI_GATE uses DROP_A / DROP_B with index row*D + gate column.
   DropoutCfg drop;
@@ -271,14 +270,6 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
   }
 }
 
-// `bytes` (multiple of 16) starting at the 16-byte aligned global address p -> L2, no destination
-__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-// the box of `map` at (c0, c1) -> L2, no destination
-__device__ __forceinline__ void prefetch_l2_tensor_2d(const CUtensorMap* map, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
-}
 // packed fp32x2 add (Blackwell FADD2): (a0, a1) += (b0, b1)
 __device__ __forceinline__ void add_f32x2(uint32_t& a0, uint32_t& a1, float b0, float b1) {
   unsigned long long x, y;
@@ -477,7 +468,6 @@ __global__ void __launch_bounds__(cta_threads<A_MODE, EPI, BLOCK_N, PREC>(), 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
-                   const __grid_constant__ CUtensorMap tm_res_hi, const __grid_constant__ CUtensorMap tm_res_lo,
                    const GemmTcParams p) {
   using C = Cfg<BLOCK_N, CG, OUT_BUFS, PREC>;
   static_assert(EPI != EPI_GATE || BLOCK_N <= 256, "the gate epilogue pairs two 128-column halves of a 256-wide tile");
@@ -583,15 +573,6 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         tap_cc = kb0 - tap * p.conv_cchunks;
         tap_kh = tap / p.conv_kw;
         tap_kw = tap - tap_kh * p.conv_kw;
-      }
-      if (EPI == EPI_LINEAR && A_MODE != A_F32 && p.res_hi != nullptr && p.res_prefetch != 0 && lane == 0) {
-        // residual operand of this tile -> L2 now (the producer runs a few tiles ahead of the epilogue, whose
-        // one-chunk-ahead register prefetch then meets L2 latency instead of DRAM latency): ONE tensor-map prefetch of
-        // the [128 rows x BLOCK_N] box per plane -- a bulk prefetch per row kept the TMA unit busy for the whole tile
-        const int r0 = A_MODE == A_CONV ? static_cast<int>(ct.out_row0) : m0;
-        const int c0 = (mn % n_tiles) * BLOCK_N;
-        prefetch_l2_tensor_2d(&tm_res_hi, c0, r0);
-        if (PREC == PREC_BF16X3) prefetch_l2_tensor_2d(&tm_res_lo, c0, r0);
       }
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
@@ -1175,30 +1156,6 @@ inline bool pdl_enabled() {
   return v;
 }
 
-// TOAD_RES_PREFETCH=0 in the environment: no L2 prefetch of the residual operand (A/B aid)
-inline bool res_prefetch_enabled() {
-  static bool v = []() {
-    const char* e = getenv("TOAD_RES_PREFETCH");
-    return !(e != nullptr && e[0] == '0');
-  }();
-  return v;
-}
-
-// Tensor map over a row-major 2-byte matrix [rows, cols] without swizzle: box = box_cols x box_rows (prefetch only).
-inline int make_plain_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int box_cols, int box_rows, int64_t ld) {
-  PFN_encodeTiled enc = get_encode_fn();
-  if (enc == nullptr) return TOAD_ERR_DRIVER;
-  if (ld == 0) ld = cols;
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : TOAD_ERR_DRIVER;
-}
-
 inline int sm_count() {
   static int n = []() {
     int dev = 0, v = 0;
@@ -1247,15 +1204,7 @@ int launch_gemm_maps_b(const GemmTcParams& p, const CUtensorMap& ta_hi, const CU
   if (EPI == EPI_GATE && p.gate_a != nullptr &&
       (((reinterpret_cast<uintptr_t>(p.gate_a) | reinterpret_cast<uintptr_t>(p.gate_b)) & 31) != 0 || p.gate_D % 8 != 0))
     return TOAD_ERR_ARG;
-  CUtensorMap to_hi = tb_hi, to_lo = tb_lo, tr_hi = tb_hi, tr_lo = tb_hi;
-  GemmTcParams pp = p;
-  pp.res_prefetch = 0;
-  if (EPI == EPI_LINEAR && p.res_hi != nullptr && res_prefetch_enabled()) {
-    // [128 rows x BLOCK_N columns] boxes of the residual plane(s), for the producer's L2 prefetch only
-    TOAD_TRY(make_plain_tmap(&tr_hi, p.res_hi, p.M, p.N, BLOCK_N > 256 ? 256 : BLOCK_N, BLOCK_M, p.ld_res));
-    if (PREC == PREC_BF16X3) TOAD_TRY(make_plain_tmap(&tr_lo, p.res_lo, p.M, p.N, BLOCK_N > 256 ? 256 : BLOCK_N, BLOCK_M, p.ld_res));
-    pp.res_prefetch = 1;
-  }
+  CUtensorMap to_hi = tb_hi, to_lo = tb_lo;
   if (epi_is_linear(EPI) && p.out_hi != nullptr) {
     if ((PREC == PREC_BF16X3 && p.out_lo == nullptr) || p.ld_split % 8 != 0) return TOAD_ERR_ARG;
     TOAD_TRY(make_bf16_out_tmap(&to_hi, p.out_hi, p.M, p.N, p.ld_split));
@@ -1297,7 +1246,7 @@ int launch_gemm_maps_b(const GemmTcParams& p, const CUtensorMap& ta_hi, const CU
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  TOAD_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, tr_hi, tr_lo, pp));
+  TOAD_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, p));
   TOAD_CUDA_TRY(cudaGetLastError());
   return 0;
 }
