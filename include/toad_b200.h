@@ -211,11 +211,30 @@ int toad_adam_step(const toad_dims_t* dims, const toad_params_t* params, const f
                    double weight_decay, float grad_scale, toad_stream_t stream);
 
 /* Standalone gated attention head: A[N, n_tasks] = Wc(tanh(Wa x + ba) * sigmoid(Wb x + bb)) + bc. */
+/* Training-side state of the standalone block: the two gate branches as the score contraction saw them (after
+ * dropout when TOAD_FLAG_DROPOUT is set; element i of the tanh / sigmoid branch uses dropout layers 3 / 4 of
+ * toad_dropout_hash, index row*D + column -- the same convention as inside toad_fwd). */
+typedef struct {
+  float* a;              /* [n, D] */
+  float* b;              /* [n, D] */
+  uint64_t dropout_seed;
+  float dropout_p;       /* nn.Dropout(0.25) in the reference (model_toad.py:27-29) */
+} toad_attn_saved_t;
+
 int toad_attn_gated_workspace_bytes(int32_t L, int32_t D, int32_t n_tasks, int64_t n, uint32_t flags, size_t* bytes);
+/* saved: NULL for inference; given, the tensor-core path stores a / b (and applies dropout with TOAD_FLAG_DROPOUT). */
 int toad_attn_gated_fwd(int32_t L, int32_t D, int32_t n_tasks, const float* wa, const float* ba,
                         const float* wb, const float* bb, const float* wc, const float* bc,
-                        const float* x, int64_t n, float* A_out, void* workspace, size_t workspace_bytes,
-                        uint32_t flags, toad_stream_t stream);
+                        const float* x, int64_t n, float* A_out, const toad_attn_saved_t* saved, void* workspace,
+                        size_t workspace_bytes, uint32_t flags, toad_stream_t stream);
+/* Backward of the standalone block (autograd of model_toad.py:36-41): given dA [n, n_tasks] writes the gradients of
+ * the six parameters and, when dx != NULL, of the input x [n, L].  n_tasks <= 2, L % 256 == 0 (tensor-core wgrad /
+ * dgrad tiles).  `saved` is what toad_attn_gated_fwd filled for the same x. */
+int toad_attn_gated_bwd_workspace_bytes(int32_t L, int32_t D, int32_t n_tasks, int64_t n, size_t* bytes);
+int toad_attn_gated_bwd(int32_t L, int32_t D, int32_t n_tasks, const float* wa, const float* wb, const float* wc,
+                        const float* x, int64_t n, const toad_attn_saved_t* saved, const float* dA, float* d_wa,
+                        float* d_ba, float* d_wb, float* d_bb, float* d_wc, float* d_bc, float* dx, void* workspace,
+                        size_t workspace_bytes, toad_stream_t stream);
 
 /* top-k of one score row: values descending, ties -> lower index first (k <= 2048).  One cooperative launch
  * over all SMs; `workspace` (toad_topk_workspace_bytes, 16-byte aligned) holds the radix histograms and is

@@ -67,8 +67,8 @@ def test_attn_net_gated_default_config1():
     assert xx is xd                                    # passthrough is the same object (model_toad.py:41)
     assert tuple(A.shape) == (256, 1)
     np.testing.assert_allclose(to_np(A), g["f64_A"], rtol=1e-3, atol=1e-5)
-    with pytest.raises(NotImplementedError):
-        net(xd)                                        # grad-enabled standalone use is refused, not faked
+    A2, _ = net(xd)                                    # grad-enabled standalone use: same values, with autograd history
+    assert A2.requires_grad and torch.allclose(A2.detach(), A, rtol=0, atol=1e-6)   # (tests/test_gpu_attn_gated_train.py)
 
 
 @pytest.mark.parametrize("n,k", [(5, 1), (5, 5), (1000, 10), (50000, 100), (200000, 1000), (4096, 2048)])

@@ -27,7 +27,7 @@ EXPORTS = [
     "toad_abi_version", "toad_build_id", "toad_error_string", "toad_param_offsets", "toad_dropout_hash",
     "toad_fwd_workspace_bytes", "toad_fwd", "toad_fwd_batch_workspace_bytes", "toad_fwd_batch",
     "toad_bwd_workspace_bytes", "toad_bwd",
-    "toad_attn_gated_workspace_bytes", "toad_attn_gated_fwd",
+    "toad_attn_gated_workspace_bytes", "toad_attn_gated_fwd", "toad_attn_gated_bwd_workspace_bytes", "toad_attn_gated_bwd",
     "toad_topk_workspace_bytes", "toad_topk", "toad_gather_rows",
     "toad_linear_workspace_bytes", "toad_linear_bf16x3",
     "toad_profile_create", "toad_profile_destroy", "toad_profile_read", "toad_fwd_profiled",
@@ -56,6 +56,10 @@ class FwdOut(C.Structure):
 class Saved(C.Structure):
     _fields_ = [(n, _f32p) for n in ("h1", "h", "a", "b")] + [("dropout_seed", C.c_uint64), ("dropout_p", C.c_float)] + \
         [(n, C.c_void_p) for n in ("h1_hi", "h1_lo", "h_hi", "h_lo")]
+
+
+class AttnSaved(C.Structure):
+    _fields_ = [("a", _f32p), ("b", _f32p), ("dropout_seed", C.c_uint64), ("dropout_p", C.c_float)]
 
 
 class ToadError(RuntimeError):
@@ -102,8 +106,11 @@ def load() -> C.CDLL:
                              C.POINTER(Saved), _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
     lib.toad_attn_gated_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_uint32,
                                                     C.POINTER(C.c_size_t)]
-    lib.toad_attn_gated_fwd.argtypes = [C.c_int32, C.c_int32, C.c_int32] + [_f32p] * 7 + [C.c_int64, _f32p,
+    lib.toad_attn_gated_fwd.argtypes = [C.c_int32, C.c_int32, C.c_int32] + [_f32p] * 7 + [C.c_int64, _f32p, C.POINTER(AttnSaved),
                                         C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
+    lib.toad_attn_gated_bwd_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_size_t)]
+    lib.toad_attn_gated_bwd.argtypes = [C.c_int32, C.c_int32, C.c_int32] + [_f32p] * 4 + [C.c_int64, C.POINTER(AttnSaved)] + \
+        [_f32p] * 8 + [C.c_void_p, C.c_size_t, C.c_void_p]
     lib.toad_topk_workspace_bytes.argtypes = [C.c_int64, C.c_int32, C.POINTER(C.c_size_t)]
     lib.toad_topk.argtypes = [_f32p, C.c_int64, C.c_int32, _f32p, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.toad_gather_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]

@@ -817,9 +817,12 @@ extern "C" int toad_attn_gated_workspace_bytes(int32_t L, int32_t D, int32_t nt,
 
 extern "C" int toad_attn_gated_fwd(int32_t L, int32_t D, int32_t nt, const float* wa, const float* ba, const float* wb,
                         const float* bb, const float* wc, const float* bc, const float* x, int64_t n, float* A_out,
-                        void* workspace, size_t workspace_bytes, uint32_t flags, toad_stream_t stream) {
+                        const toad_attn_saved_t* saved, void* workspace, size_t workspace_bytes, uint32_t flags,
+                        toad_stream_t stream) {
   TOAD_TRY(check_ag(L, D, nt, n));
   if (!wa || !ba || !wb || !bb || !wc || !bc || !x || !A_out) return TOAD_ERR_ARG;
+  if (saved != nullptr && (!saved->a || !saved->b || (flags & TOAD_FLAG_SIMT_FP32))) return saved->a && saved->b ? TOAD_ERR_UNSUPPORTED : TOAD_ERR_ARG;
+  if ((flags & TOAD_FLAG_DROPOUT) && (saved == nullptr || saved->dropout_p < 0.f || saved->dropout_p >= 1.f)) return TOAD_ERR_ARG;
   AgWs w = carve_ag(L, D, nt, n, flags, workspace);
   TOAD_TRY(check_ws(workspace, workspace_bytes, w.bytes));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -832,10 +835,108 @@ extern "C" int toad_attn_gated_fwd(int32_t L, int32_t D, int32_t nt, const float
     tc::GemmTcParams g{};
     g.a_f32 = x; g.lda = L; g.M = n; g.N = 2 * D; g.K = L;
     g.gate_ba = ba; g.gate_bb = bb; g.gate_wc = wc; g.gate_D = D; g.gate_ntasks = nt; g.gate_part = w.part;
+    if (saved != nullptr) {
+      g.gate_a = saved->a; g.gate_b = saved->b;
+      if ((flags & TOAD_FLAG_DROPOUT) && saved->dropout_p > 0.f) {
+        g.drop.seed = saved->dropout_seed;
+        const double t = static_cast<double>(saved->dropout_p) * 4294967296.0;
+        g.drop.thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(t);
+        g.drop.scale = 1.0f / (1.0f - saved->dropout_p);
+      }
+    }
     if (flags & TOAD_FLAG_TC_SINGLE_CTA) TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_GATE, 1>(g, nullptr, nullptr, w.w_hi, w.w_lo, st)));
     else TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_GATE, 2>(g, nullptr, nullptr, w.w_hi, w.w_lo, st)));
   }
   return tail::launch_finish_scores(w.part, w.n_parts, bc, A_out, n, nt, st);
+}
+
+namespace {
+struct AgBwdWs {
+  float *dA2, *wc2, *gtmp, *splitk, *gate_part;
+  bf16 *dab_hi, *dab_lo, *xp_hi, *xp_lo, *wabT_hi, *wabT_lo;
+  int gate_blocks;
+  size_t bytes;
+};
+AgBwdWs carve_ag_bwd(int L, int D, int64_t n, void* base) {
+  AgBwdWs w{};
+  Carver c(base);
+  w.dA2 = c.take<float>(n * 2);
+  w.wc2 = c.take<float>(2 * D);
+  w.gtmp = c.take<float>(4 * D + 2);
+  w.dab_hi = c.take<bf16>(n * 2 * D); w.dab_lo = c.take<bf16>(n * 2 * D);
+  w.xp_hi = c.take<bf16>(n * L);      w.xp_lo = c.take<bf16>(n * L);
+  w.wabT_hi = c.take<bf16>(static_cast<size_t>(L) * 2 * D); w.wabT_lo = c.take<bf16>(static_cast<size_t>(L) * 2 * D);
+  const size_t pair_tiles = static_cast<size_t>(kSMs / 2) * 256 * 256, full = static_cast<size_t>(2) * D * L;
+  w.splitk = c.take<float>(pair_tiles > full ? pair_tiles : full);
+  int64_t gb = (n + 127) / 128;
+  if (gb > 2 * kSMs) gb = 2 * kSMs;
+  w.gate_blocks = static_cast<int>(gb);
+  w.gate_part = c.take<float>(static_cast<size_t>(gb) * (4 * D + 2));
+  w.bytes = align_up(c.off, 256);
+  return w;
+}
+// [n, nt] -> [n, 2] (missing task columns zero): the gate backward kernels are written for the two tasks of TOAD
+__global__ void pad_tasks_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n, int nt) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dst[2 * i] = src[i * nt];
+  dst[2 * i + 1] = nt > 1 ? src[i * nt + 1] : 0.f;
+}
+int check_ag_bwd(int L, int D, int nt, int64_t n) {
+  TOAD_TRY(check_ag(L, D, nt, n));
+  if (nt > 2 || L % 256 != 0) return TOAD_ERR_UNSUPPORTED;
+  return 0;
+}
+}  // namespace
+
+extern "C" int toad_attn_gated_bwd_workspace_bytes(int32_t L, int32_t D, int32_t nt, int64_t n, size_t* bytes) {
+  TOAD_TRY(check_ag_bwd(L, D, nt, n));
+  if (bytes == nullptr) return TOAD_ERR_ARG;
+  *bytes = carve_ag_bwd(L, D, n, nullptr).bytes;
+  return 0;
+}
+
+extern "C" int toad_attn_gated_bwd(int32_t L, int32_t D, int32_t nt, const float* wa, const float* wb, const float* wc,
+                                   const float* x, int64_t n, const toad_attn_saved_t* sv, const float* dA, float* d_wa,
+                                   float* d_ba, float* d_wb, float* d_bb, float* d_wc, float* d_bc, float* dx,
+                                   void* workspace, size_t workspace_bytes, toad_stream_t stream) {
+  TOAD_TRY(check_ag_bwd(L, D, nt, n));
+  if (!wa || !wb || !wc || !x || !sv || !sv->a || !sv->b || !dA || !d_wa || !d_ba || !d_wb || !d_bb || !d_wc || !d_bc) return TOAD_ERR_ARG;
+  if (sv->dropout_p < 0.f || sv->dropout_p >= 1.f) return TOAD_ERR_ARG;
+  AgBwdWs w = carve_ag_bwd(L, D, n, workspace);
+  TOAD_TRY(check_ws(workspace, workspace_bytes, w.bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float keep = 1.0f - sv->dropout_p;
+  // two-task views of dA and Wc (zero second task when n_tasks == 1)
+  pad_tasks_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(dA, w.dA2, n, nt);
+  TOAD_CUDA_TRY(cudaGetLastError());
+  TOAD_CUDA_TRY(cudaMemsetAsync(w.wc2, 0, 2 * D * sizeof(float), st));
+  TOAD_CUDA_TRY(cudaMemcpyAsync(w.wc2, wc, static_cast<size_t>(nt) * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // gate derivative: dab = (d tanh-branch pre-activation | d sigmoid-branch pre-activation) as (hi, lo) planes,
+  // per-CTA partial sums of dWc, dba, dbb, dbc
+  {
+    const int rpb = static_cast<int>((n + w.gate_blocks - 1) / w.gate_blocks);
+    bwd::gate_bwd_kernel<true><<<w.gate_blocks, D, bwd::gate_bwd_smem(D), st>>>(sv->a, sv->b, w.dA2, w.wc2, nullptr, w.dab_hi, w.dab_lo,
+                                                                                 w.gate_part, n, D, rpb, keep);
+    TOAD_CUDA_TRY(cudaGetLastError());
+    bwd::ReduceSegs segs{};
+    segs.dst[0] = w.gtmp; segs.dst[1] = d_ba; segs.dst[2] = d_bb; segs.dst[3] = w.gtmp + 2 * D;
+    segs.begin[0] = 0; segs.begin[1] = 2 * D; segs.begin[2] = 3 * D; segs.begin[3] = 4 * D; segs.begin[4] = 4 * D + 2;
+    TOAD_TRY(bwd::launch_reduce_segs(w.gate_part, segs, 4 * D + 2, 4 * D + 2, w.gate_blocks, st));
+    TOAD_CUDA_TRY(cudaMemcpyAsync(d_wc, w.gtmp, static_cast<size_t>(nt) * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    TOAD_CUDA_TRY(cudaMemcpyAsync(d_bc, w.gtmp + 2 * D, static_cast<size_t>(nt) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  // dWa | dWb = dab^T . x   (both operands MN-major from their natural [patch, channel] planes, split-K)
+  TOAD_TRY(tail::launch_split_planes(x, w.xp_hi, w.xp_lo, n * L, st));
+  TOAD_TRY(wgrad_mn(w.dab_hi, w.dab_lo, 2 * D, w.xp_hi, w.xp_lo, L, 2 * D, L, n, w.splitk, d_wa, D, d_wb, st));
+  if (dx != nullptr) {  // dx = dab . [Wa ; Wb]
+    TOAD_TRY(bwd::launch_transpose_split(wa, D, L, L, w.wabT_hi, w.wabT_lo, 2 * D, st));
+    TOAD_TRY(bwd::launch_transpose_split(wb, D, L, L, w.wabT_hi + D, w.wabT_lo + D, 2 * D, st));
+    tc::GemmTcParams g{};
+    g.M = n; g.N = L; g.K = 2 * D; g.out_f32 = dx; g.ld_f32 = L;
+    TOAD_TRY((tc::launch_gemm<256, tc::A_SPLIT, tc::EPI_LINEAR, 2>(g, w.dab_hi, w.dab_lo, w.wabT_hi, w.wabT_lo, st)));
+  }
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------ top-k

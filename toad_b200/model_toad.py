@@ -57,16 +57,53 @@ class Attn_Net_Gated(nn.Module):
         self._ws = ops.Workspace()
 
     def forward(self, x: torch.Tensor):
-        if self.dropout and self.training:
-            raise NotImplementedError("toad_b200: Dropout(0.25) in training mode is not implemented yet; "
-                                      "use dropout=False (the reference default) or .eval()")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("toad_b200: the standalone Attn_Net_Gated has no backward; run it under "
-                                      "torch.no_grad() (inside TOAD_fc_mtl_concat the fused backward is used)")
-        A = ops.attn_gated_fwd(x, self.attention_a[0].weight, self.attention_a[0].bias,
-                               self.attention_b[0].weight, self.attention_b[0].bias,
-                               self.attention_c.weight, self.attention_c.bias, self._ws, _default_flags())
-        return A, x
+        wa, ba = self.attention_a[0].weight, self.attention_a[0].bias
+        wb, bb = self.attention_b[0].weight, self.attention_b[0].bias
+        wc, bc = self.attention_c.weight, self.attention_c.bias
+        drop = self.dropout and self.training
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if not need_grad and not drop:
+            A = ops.attn_gated_fwd(x, wa.detach(), ba.detach(), wb.detach(), bb.detach(), wc.detach(), bc.detach(),
+                                   self._ws, _default_flags())
+            return A, x
+        if _default_flags() & _lib.FLAG_SIMT_FP32:
+            raise NotImplementedError("toad_b200: the standalone Attn_Net_Gated trains on the tensor-core path only "
+                                      "(unset TOAD_B200_SIMT)")
+        return _AttnGatedFunction.apply(self, x, wa, ba, wb, bb, wc, bc), x
+
+
+class _AttnGatedFunction(torch.autograd.Function):
+    """A = Attn_Net_Gated(x) with a hand-written backward (toad_attn_gated_bwd): training-mode dropout (counter-hash
+    masks, like inside TOAD_fc_mtl_concat) and gradients for the six parameters and for x."""
+
+    @staticmethod
+    def forward(ctx, module: "Attn_Net_Gated", x, wa, ba, wb, bb, wc, bc):
+        n, D = x.shape[0], wa.shape[0]
+        f32 = dict(dtype=torch.float32, device=x.device)
+        saved = {"a": torch.empty((n, D), **f32), "b": torch.empty((n, D), **f32)}
+        flags = _default_flags()
+        if module.dropout and module.training:
+            flags |= _lib.FLAG_DROPOUT
+            saved["dropout_seed"] = int(torch.randint(0, 2 ** 62, (1,)).item())   # torch.manual_seed makes runs repeatable
+            saved["dropout_p"] = 0.25
+        A = ops.attn_gated_fwd(x.detach(), wa.detach(), ba.detach(), wb.detach(), bb.detach(), wc.detach(), bc.detach(),
+                               module._ws, flags, saved=saved)
+        ctx.module = module
+        ctx.drop = {k: v for k, v in saved.items() if k.startswith("dropout")}
+        ctx.save_for_backward(x, wa, wb, wc, saved["a"], saved["b"])
+        return A
+
+    @staticmethod
+    def backward(ctx, dA):
+        x, wa, wb, wc, a, b = ctx.saved_tensors
+        saved = dict(ctx.drop, a=a, b=b)
+        ws = ctx.module.__dict__.setdefault("_ws_bwd", ops.Workspace())
+        g = ops.attn_gated_bwd(x, wa.detach(), wb.detach(), wc.detach(), saved, dA, ws, need_dx=ctx.needs_input_grad[1])
+        d_wa, d_ba, d_wb, d_bb, d_wc, d_bc, dx = g
+        need = ctx.needs_input_grad
+        ctx.module = None
+        return (None, dx, d_wa if need[2] else None, d_ba if need[3] else None, d_wb if need[4] else None,
+                d_bb if need[5] else None, d_wc if need[6] else None, d_bc if need[7] else None)
 
 
 class _ToadFunction(torch.autograd.Function):

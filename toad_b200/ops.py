@@ -286,8 +286,18 @@ def adam_step(dims: Dims, params: Sequence[torch.Tensor], grad_flat: torch.Tenso
                                   grad_scale, _stream()), "toad_adam_step")
 
 
-def attn_gated_fwd(x: torch.Tensor, wa, ba, wb, bb, wc, bc, ws: Workspace, flags: int = 0) -> torch.Tensor:
-    """Attn_Net_Gated.forward (models/model_toad.py:36-41): A [N, n_tasks]."""
+def _attn_saved_struct(saved: Dict[str, object]) -> "_lib.AttnSaved":
+    s = _lib.AttnSaved()
+    s.a, s.b = saved["a"].data_ptr(), saved["b"].data_ptr()
+    s.dropout_seed = int(saved.get("dropout_seed", 0))
+    s.dropout_p = float(saved.get("dropout_p", 0.0))
+    return s
+
+
+def attn_gated_fwd(x: torch.Tensor, wa, ba, wb, bb, wc, bc, ws: Workspace, flags: int = 0,
+                   saved: Optional[Dict[str, object]] = None) -> torch.Tensor:
+    """Attn_Net_Gated.forward (models/model_toad.py:36-41): A [N, n_tasks].  `saved` ({"a", "b"} fp32 [N, D] buffers,
+    optionally "dropout_seed" / "dropout_p" with FLAG_DROPOUT in flags): training forward, filled for attn_gated_bwd."""
     lib = _lib.load()
     _check_dev_f32(x, "x")
     if x.dim() != 2:
@@ -303,10 +313,38 @@ def attn_gated_fwd(x: torch.Tensor, wa, ba, wb, bb, wc, bc, ws: Workspace, flags
     nbytes = C.c_size_t()
     _lib.check(lib.toad_attn_gated_workspace_bytes(L, D, nt, n, flags, C.byref(nbytes)), "toad_attn_gated_workspace_bytes")
     wptr, wsize = ws.get(nbytes.value, x.device)
+    sv = None
+    if saved is not None:
+        _check_dev_f32(saved["a"], "saved a", (n, D))
+        _check_dev_f32(saved["b"], "saved b", (n, D))
+        sv = C.byref(_attn_saved_struct(saved))
     _lib.check(lib.toad_attn_gated_fwd(L, D, nt, wa.data_ptr(), ba.data_ptr(), wb.data_ptr(), bb.data_ptr(),
-                                       wc.data_ptr(), bc.data_ptr(), x.data_ptr(), n, A.data_ptr(), wptr, wsize,
+                                       wc.data_ptr(), bc.data_ptr(), x.data_ptr(), n, A.data_ptr(), sv, wptr, wsize,
                                        flags, _stream()), "toad_attn_gated_fwd")
     return A
+
+
+def attn_gated_bwd(x: torch.Tensor, wa, wb, wc, saved: Dict[str, object], dA: torch.Tensor, ws: Workspace,
+                   need_dx: bool = False):
+    """Gradients of Attn_Net_Gated's six parameters (and of x when need_dx) for the upstream gradient dA [N, n_tasks]:
+    (d_wa, d_ba, d_wb, d_bb, d_wc, d_bc, dx or None)."""
+    lib = _lib.load()
+    n, L = x.shape
+    D, nt = wa.shape[0], wc.shape[0]
+    dA = dA.contiguous().float()
+    _check_dev_f32(dA, "dA", (n, nt), align=4)
+    f32 = dict(dtype=torch.float32, device=x.device)
+    g = [torch.empty((D, L), **f32), torch.empty((D,), **f32), torch.empty((D, L), **f32), torch.empty((D,), **f32),
+         torch.empty((nt, D), **f32), torch.empty((nt,), **f32)]
+    dx = torch.empty((n, L), **f32) if need_dx else None
+    nbytes = C.c_size_t()
+    _lib.check(lib.toad_attn_gated_bwd_workspace_bytes(L, D, nt, n, C.byref(nbytes)), "toad_attn_gated_bwd_workspace_bytes")
+    wptr, wsize = ws.get(nbytes.value, x.device)
+    sv = _attn_saved_struct(saved)
+    _lib.check(lib.toad_attn_gated_bwd(L, D, nt, wa.data_ptr(), wb.data_ptr(), wc.data_ptr(), x.data_ptr(), n, C.byref(sv),
+                                       dA.data_ptr(), *[t.data_ptr() for t in g], dx.data_ptr() if need_dx else None,
+                                       wptr, wsize, _stream()), "toad_attn_gated_bwd")
+    return tuple(g) + (dx,)
 
 
 def topk(scores: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
