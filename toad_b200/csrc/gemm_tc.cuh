@@ -145,6 +145,7 @@ struct GemmTcParams {
   DropoutCfg drop;
   uint32_t drop_layer;
   int64_t drop_row0;      // global index of row 0 (a row slice of a bag keeps the bag-wide dropout mask)
+  int32_t pdl;            // launch programmatically dependent on the preceding kernel of the stream (see pdl_enabled)
   // split-K (TMA-fed A only): the K range is cut into k_splits slices of kb_per_split K blocks; slice s
   // writes its fp32 partial tile to out_f32 + s * M * ld_f32 (bias only in slice 0); a reduction follows.
   int32_t k_splits;       // 0 or 1 = no split
@@ -1147,7 +1148,8 @@ inline int make_bf16_out_tmap(CUtensorMap* map, const void* ptr, int64_t rows, i
 // r2h, r2i): on ONE stream it hides the launch gap + prologue of the next kernel (+3 % slides/s at N = 10k, +-0 at
 // 50k); with slides in flight on SEVERAL streams the early-launched CTAs sit on SMs (214 KB of shared memory each)
 // waiting for their predecessor while another stream's runnable kernel needs those SMs: 3-stream throughput fell from
-// ~3500 to 2100 slides/s.  The library cannot know how many streams its caller uses, so the default is off.
+// ~3500 to 2100 slides/s.  The library cannot know how many streams its caller uses, so the default is off for the
+// TOAD head; the ResNet trunk (45 short dependent launches on one stream) sets GemmTcParams::pdl itself.
 inline bool pdl_enabled() {
   static bool v = []() {
     const char* e = getenv("TOAD_B200_PDL");
@@ -1239,7 +1241,7 @@ int launch_gemm_maps_b(const GemmTcParams& p, const CUtensorMap& ta_hi, const CU
     attr[na].val.clusterDim.z = 1;
     ++na;
   }
-  if (pdl_enabled()) {
+  if (pdl_enabled() || p.pdl != 0) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;

@@ -1091,6 +1091,15 @@ bool stem_im2col_forced() {
   return v;
 }
 
+// TOAD_RESNET_PDL=0: the trunk's launches fully serialised (A/B aid)
+bool resnet_pdl() {
+  static bool v = []() {
+    const char* e = getenv("TOAD_RESNET_PDL");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return v;
+}
+
 // exact = (hi, lo) bf16 plane pairs (4 B / element); default = one fp16 plane (2 B / element, lo pointers stay null)
 ResWs carve_resnet(int B, int H, int W, bool exact, void* base) {
   ResWs w{};
@@ -1134,6 +1143,7 @@ int run_conv(const ConvSpec& cs, const PreparedConv& pc, const bf16* in_hi, cons
   g.relu = relu ? 1 : 0;
   g.out_hi = out_hi; g.out_lo = out_lo; g.ld_split = cs.cout;
   g.res_hi = res_hi; g.res_lo = res_lo; g.ld_res = cs.cout;
+  g.pdl = resnet_pdl() ? 1 : 0;   // the next convolution's prologue overlaps this one's last wave
   // OUT_BUFS = 2: the trunk's layers are store-/epilogue-bound (short K, wide outputs), so the TMA-store staging
   // is double buffered at the price of one operand stage.
   if (cs.k == 1 && cs.stride == 1) {  // plain GEMM over the NHWC plane
