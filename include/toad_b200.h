@@ -129,9 +129,6 @@ typedef struct {
   void* h1_lo;
   void* h_hi;
   void* h_lo;
-  void* x_hi; /* optional [N, in_dim] bf16: the (hi, lo) planes of the bag itself.  The forward's fc1 kernel converts */
-  void* x_lo; /* every x row to these planes in shared memory anyway; given the buffers it also stores them, and the
-                 backward's dW1 = dz1^T . x reads them instead of re-reading and re-splitting x (NULL: it does that) */
 } toad_saved_t;
 
 /* The mask hash (host-callable, for tests): high 32 bits of splitmix64(seed, layer, index). */

@@ -55,7 +55,7 @@ class FwdOut(C.Structure):
 
 class Saved(C.Structure):
     _fields_ = [(n, _f32p) for n in ("h1", "h", "a", "b")] + [("dropout_seed", C.c_uint64), ("dropout_p", C.c_float)] + \
-        [(n, C.c_void_p) for n in ("h1_hi", "h1_lo", "h_hi", "h_lo", "x_hi", "x_lo")]
+        [(n, C.c_void_p) for n in ("h1_hi", "h1_lo", "h_hi", "h_lo")]
 
 
 class AttnSaved(C.Structure):

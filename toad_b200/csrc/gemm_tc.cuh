@@ -92,8 +92,6 @@ struct GemmTcParams {
   // A operand when A_MODE == A_F32 (lda = row stride in floats); for plane-fed modes lda / ldb are the
   // row strides of the (hi, lo) planes in elements (0 = K; must be multiples of 8)
   const float* a_f32;
-  __nv_bfloat16* a_store_hi;  // A_F32 only, nullable: also store the converted (hi, lo) planes of A, row stride K
-  __nv_bfloat16* a_store_lo;  //   (the training forward keeps x's planes for the backward's dW1)
   int64_t lda;
   int64_t ldb;
   int64_t M;
@@ -1056,14 +1054,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     };
     int stage = 0;
     uint32_t phase = 0;
-    auto convert = [&](float4(&cur)[8], int64_t g) {
+    auto convert = [&](float4(&cur)[8]) {
       mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
       const uint32_t sa = tiles_base + stage * C::STAGE_BYTES;
-      // (plane store of the converted operand: only the tiles of n_tile 0 -- with one N tile, as fc1 runs, every row once)
-      const int tile_g = unit0 + static_cast<int>(g / num_kb) * unit_stride;
-      const int kb_g = static_cast<int>(g % num_kb);
-      const bool store_planes = p.a_store_hi != nullptr && (tile_g % n_tiles) == 0;
-      const int64_t m0_g = static_cast<int64_t>(tile_g / n_tiles) * (BLOCK_M * CG) + cta_rank * BLOCK_M;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int r = cw * 16 + j * 2 + hw;
@@ -1073,11 +1066,6 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         const uint32_t off = r * 128 + (((l16 >> 1) ^ (r & 7)) << 4) + ((l16 & 1) << 3);
         asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(sa + off), "r"(h0), "r"(h1) : "memory");
         asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(sa + A_TILE_BYTES + off), "r"(l0), "r"(l1) : "memory");
-        if (store_planes && m0_g + r < p.M) {   // a half-warp writes 128 contiguous bytes per plane
-          const int64_t o = (m0_g + r) * p.K + kb_g * BLOCK_K + l16 * 4;
-          *reinterpret_cast<uint2*>(p.a_store_hi + o) = make_uint2(h0, h1);
-          *reinterpret_cast<uint2*>(p.a_store_lo + o) = make_uint2(l0, l1);
-        }
       }
       fence_proxy_async_smem();  // make generic-proxy smem writes visible to the tensor core
       __syncwarp();
@@ -1091,10 +1079,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     if (total > 0) issue(0, buf0);
     for (int64_t g = 0; g < total; g += 2) {
       if (g + 1 < total) issue(g + 1, buf1);
-      convert(buf0, g);
+      convert(buf0);
       if (g + 1 >= total) break;
       if (g + 2 < total) issue(g + 2, buf0);
-      convert(buf1, g + 1);
+      convert(buf1);
     }
   }
 

@@ -249,9 +249,6 @@ static int fwd_impl(const toad_dims_t* d, const toad_params_t* P, const float* x
     g.drop = drop; g.drop_layer = DROP_H1;
     g.out_f32 = save ? saved->h1 : nullptr; g.ld_f32 = Hd;
     g.out_hi = h1_hi; g.out_lo = h1_lo; g.ld_split = Hd;
-    if (save && saved->x_hi != nullptr && saved->x_lo != nullptr && !cg1 && !fc1_pair) {  // (the 512-wide tile: every row converted once)
-      g.a_store_hi = static_cast<bf16*>(saved->x_hi); g.a_store_lo = static_cast<bf16*>(saved->x_lo);
-    }
     if (cg1) TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_LINEAR, 1>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, st)));
     else if (fc1_pair) TOAD_TRY((tc::launch_gemm<256, tc::A_F32, tc::EPI_LINEAR, 2>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, st)));
     else TOAD_TRY((tc::launch_gemm<512, tc::A_F32, tc::EPI_LINEAR, 2>(g, nullptr, nullptr, w.w1_hi, w.w1_lo, st)));
@@ -548,12 +545,8 @@ int bwd_tc(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t
     TOAD_TRY(bwd::launch_reduce_segs(w.gate_part, segs, 4 * D + 2, 4 * D + 2, w.gate_blocks, st));
   }
   // operand preparation: (hi, lo) planes (dab already left gate_bwd as planes)
-  // planes of the bag for dW1: kept by the forward's fc1 converter when the caller provided the buffers
-  const bool have_x_planes = mn && sv->x_hi != nullptr && sv->x_lo != nullptr && !(flags & (TOAD_FLAG_TC_SINGLE_CTA | TOAD_FLAG_TC_PAIR_ALL));
-  const bf16 *xp_hi = have_x_planes ? static_cast<const bf16*>(sv->x_hi) : w.xp_hi;
-  const bf16 *xp_lo = have_x_planes ? static_cast<const bf16*>(sv->x_lo) : w.xp_lo;
   if (mn) {
-    if (!have_x_planes) TOAD_TRY(tail::launch_split_planes(x, w.xp_hi, w.xp_lo, n * L, st));
+    TOAD_TRY(tail::launch_split_planes(x, w.xp_hi, w.xp_lo, n * L, st));
   } else {
     TOAD_TRY(bwd::launch_transpose_planes(w.dab_hi, w.dab_lo, n, 2 * D, w.dabT_hi, w.dabT_lo, w.ldT, st));
     TOAD_TRY(bwd::launch_transpose_planes(sh_hi, sh_lo, n, Hd, w.hT_hi, w.hT_lo, w.ldT, st));
@@ -595,7 +588,7 @@ int bwd_tc(const toad_dims_t* d, const toad_params_t* P, const float* x, int64_t
   TOAD_TRY(bwd::launch_colsum_planes(w.dz1_hi, w.dz1_lo, w.col_part, n, Hd, w.col_blocks, st));
   TOAD_TRY(bwd::launch_reduce_strided(w.col_part, g_b1, Hd, Hd, w.col_blocks, st));
   // dW1 = dz1^T . x
-  if (mn) return wgrad_mn(w.dz1_hi, w.dz1_lo, Hd, xp_hi, xp_lo, L, Hd, L, n, w.splitk, g_w1, 0, nullptr, st);
+  if (mn) return wgrad_mn(w.dz1_hi, w.dz1_lo, Hd, w.xp_hi, w.xp_lo, L, Hd, L, n, w.splitk, g_w1, 0, nullptr, st);
   TOAD_TRY(bwd::launch_transpose_planes(w.dz1_hi, w.dz1_lo, n, Hd, w.dz1T_hi, w.dz1T_lo, w.ldT, st));
   return wgrad_tc(w.dz1T_hi, w.dz1T_lo, w.xT_hi, w.xT_lo, Hd, L, n, w.ldT, w.splitk, g_w1, 0, nullptr, st);
 }

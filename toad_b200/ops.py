@@ -109,10 +109,6 @@ def alloc_saved(dims: Dims, n: int, device: torch.device, flags: int = 0) -> Dic
     else:
         for k in ("h1_hi", "h1_lo", "h_hi", "h_lo"):
             s[k] = torch.empty((n, dims.hid_dim), dtype=torch.bfloat16, device=device)
-        if not (flags & (_lib.FLAG_TC_SINGLE_CTA | _lib.FLAG_TC_PAIR_ALL)):
-            # the bag's own (hi, lo) planes: written by the forward's fc1 converter, read by the backward's dW1
-            for k in ("x_hi", "x_lo"):
-                s[k] = torch.empty((n, dims.in_dim), dtype=torch.bfloat16, device=device)
     return s
 
 
@@ -125,7 +121,7 @@ def _out_struct(out: Dict[str, torch.Tensor]) -> FwdOut:
 
 def _saved_struct(saved: Dict[str, torch.Tensor]) -> Saved:
     s = Saved()
-    for k in ("h1", "h", "a", "b", "h1_hi", "h1_lo", "h_hi", "h_lo", "x_hi", "x_lo"):
+    for k in ("h1", "h", "a", "b", "h1_hi", "h1_lo", "h_hi", "h_lo"):
         setattr(s, k, saved[k].data_ptr() if saved.get(k) is not None else None)
     s.dropout_seed = int(saved.get("dropout_seed", 0))
     s.dropout_p = float(saved.get("dropout_p", 0.0))
