@@ -1,24 +1,26 @@
-// tcgen05 (5th-gen tensor core) GEMM with 3-pass split-bf16 operands, sm_100a.
+// tcgen05 (5th-gen tensor core) GEMM / implicit-GEMM convolution, sm_100a.
 //
-//   D[M,N] = epilogue( A[M,K] . B[N,K]^T ),   A ~= A_hi + A_lo,  B ~= B_hi + B_lo  (bf16 pairs)
-//   A.B^T  ~= A_hi.B_hi + A_hi.B_lo + A_lo.B_hi      (fp32 accumulation in TMEM)
+//   D[M,N] = epilogue( A[M,K] . B[N,K]^T )      fp32 accumulation in TMEM, two operand precisions (PREC):
+//   PREC_BF16X3  A ~= A_hi + A_lo, B ~= B_hi + B_lo (bf16 pairs); A.B^T ~= A_hi.B_hi + A_hi.B_lo + A_lo.B_hi
+//   PREC_F16X2   A = one fp16 plane, B ~= B_hi + B_lo (fp16 pairs);  A.B^T ~= A.B_hi + A.B_lo
 //
-// This is the nn.Linear building block of the TOAD trunk (reference:
-// models/model_toad.py:59,62 fc layers and :37-38 the gated-attention pair), at
-// fp32-class accuracy (dropped terms are O(2^-16) relative per product).
+// PREC_BF16X3 is the nn.Linear building block of the TOAD trunk (reference: models/model_toad.py:59,62 fc layers
+// and :37-38 the gated-attention pair) and of its backward, at fp32-class accuracy (dropped terms are O(2^-16)
+// relative per product); both precisions serve the convolutions of the ResNet trunk (models/resnet_custom.py:35-55).
 //
-// Structure (one persistent CTA per SM, 128 x BLOCK_N output tiles, K in 64-wide blocks):
-//   warp 0      TMA producer: B_hi/B_lo tiles (and A_hi/A_lo when A is already split)
-//   warp 1      MMA issuer: one elected thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16)
+// Structure (one persistent CTA per SM -- or a CTA pair per 256-row tile, cta_group::2 --, K in 64-wide blocks):
+//   warp 0      TMA producer: B_hi/B_lo tiles and the A plane(s): 2-D boxes of a matrix, or 4-D NHWC boxes (A_CONV)
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma (UMMA 128*CG x <=256 x 16)
 //   warp 2      TMEM allocator
-//   warps 4-11  epilogue (4-7 for the fp32-fed gate kernel): tcgen05.ld accumulator -> registers -> bias / residual /
-//               activation (or the dgrad extras) -> the warp's private 64B-swizzled smem staging tile -> the warp's
-//               own TMA stores; no CTA-wide barrier, TMEM handed back right after the warp's last tcgen05.ld
-//   next 8      (A_MODE 0 only) A converter: fp32 rows from global -> (hi,lo) bf16 pairs written
-//               straight into the 128B-swizzled UMMA operand layout, loads one K block ahead
-// Pipelines: smem ring (full/empty mbarriers) between producer/converter and MMA, and a
-// 2-deep TMEM accumulator ring (tmem_full/tmem_empty) between MMA and epilogue, so the
-// epilogue of tile i overlaps the main loop of tile i+1.
+//   warps 4..   epilogue, 4 per set (TMEM lane quarters): 2 sets for plane-fed kernels, 4 for the wide fp16 tiles, 1-2
+//               for fp32-fed ones: tcgen05.ld accumulator -> registers -> bias / residual / activation (or the dgrad
+//               extras, or the gate) -> the warp's private 64B-swizzled smem staging tile -> the warp's own TMA
+//               stores; no CTA-wide barrier, TMEM handed back right after the warp's last tcgen05.ld
+//   last 8      (A_F32 only) A converter: fp32 rows from global -> (hi,lo) bf16 pairs written straight into the
+//               128B-swizzled UMMA operand layout, loads one K block ahead
+// Pipelines: smem ring (full/empty mbarriers) between producer/converter and MMA, and a TMEM accumulator ring over
+// all 512 columns (tmem_full/tmem_empty) between MMA and epilogue, so the epilogue of tile i overlaps the main loop
+// of the following tiles.
 #pragma once
 #include "common.cuh"
 #include <cuda_fp16.h>
