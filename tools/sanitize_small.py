@@ -27,7 +27,16 @@ def main():
     step(x, torch.tensor([3], device="cuda"), torch.tensor([1], device="cuda"), sex)
     ext = resnet50_baseline().cuda().eval()
     with torch.no_grad():
-        ext(torch.randn(2, 3, 64, 64, device="cuda"))
+        for prec in ("f16x2", "bf16x3"):       # both arithmetic modes; shapes whose conv tiles are clipped / hold several images
+            ext.precision = prec
+            for shape in ((2, 3, 64, 64), (3, 3, 96, 160), (1, 3, 224, 224), (1, 3, 32, 512), (5, 3, 16, 16)):
+                ext(torch.randn(*shape, device="cuda"))
+    # standalone gated-attention block: training forward with dropout + backward (parameters and x)
+    from models.model_toad import Attn_Net_Gated
+    blk = Attn_Net_Gated(L=512, D=384, dropout=True, n_tasks=2).cuda().train()
+    xg = torch.randn(300, 512, device="cuda", requires_grad=True)
+    A, _ = blk(xg)
+    A.sum().backward()
     torch.cuda.synchronize()
     print("sanitize workload done")
 
