@@ -519,8 +519,17 @@ def measure_fc1_traffic(n):
            "regex:gemm_bf16x3", "--csv", sys.executable, os.path.join(ROOT, "tools", "profile_fwd.py"), "--n", str(n),
            "--iters", "3"]
     try:
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0")))
-        rows = list(csv.reader(l for l in r.stdout.splitlines() if l.startswith('"')))
+        # own process group: a hung profiler run is killed together with the workload it spawned
+        import signal
+        proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, start_new_session=True,
+                                env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0")))
+        try:
+            stdout, _ = proc.communicate(timeout=180)
+        except subprocess.TimeoutExpired:
+            os.killpg(proc.pid, signal.SIGKILL)
+            proc.communicate()
+            return None
+        rows = list(csv.reader(l for l in stdout.splitlines() if l.startswith('"')))
         hdr = rows[0]
         ki, mi, vi, ii = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
         per = {}
