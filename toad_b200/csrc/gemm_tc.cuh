@@ -562,10 +562,6 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     // ------------------------------------------------------------------ TMA producer (all lanes loop, lane 0 issues)
     int stage = 0;
     uint32_t phase = 0;
-    // One K block and one N tile (the K = 64 1x1 convolutions): every tile needs the SAME weight tile, so each ring
-    // stage's B area is filled the first time the stage is used and kept -- afterwards a stage is one A load.
-    const bool b_resident = A_MODE != A_F32 && A_MODE != A_MN && num_kb == 1 && n_tiles == 1 && k_splits == 1;
-    int stage_uses = 0;
     for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
       const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
       const int kb0 = split * kb_per, kb1 = (kb0 + kb_per) < num_kb ? (kb0 + kb_per) : num_kb;
@@ -589,8 +585,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           // (a convolution's A box holds conv_tile_rows <= 128 pixels; out-of-image parts are zero-filled AND counted)
           const uint32_t a_bytes = A_MODE == A_F32 ? 0u : (A_MODE == A_CONV ? static_cast<uint32_t>(p.conv_tile_rows) * 128u
                                                                             : static_cast<uint32_t>(A_TILE_BYTES));
-          const bool load_b = !b_resident || stage_uses < STAGES;
-          const uint32_t bytes = (load_b ? 2 * C::B_TILE_BYTES : 0) + C::A_PLANES * a_bytes;
+          const uint32_t bytes = 2 * C::B_TILE_BYTES + C::A_PLANES * a_bytes;
           uint32_t fb = fb_local;
           if (CG == 1) {
             mbar_expect_tx(fb_local, bytes);
@@ -620,7 +615,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
               tma_load_2d<CG>(sa + C::B_OFF + j * 8192, &tm_b_hi, fb, n0 + j * 64, kb * BLOCK_K);
               tma_load_2d<CG>(sa + C::B_OFF + C::B_TILE_BYTES + j * 8192, &tm_b_lo, fb, n0 + j * 64, kb * BLOCK_K);
             }
-          } else if (load_b) {
+          } else {
 #pragma unroll
             for (int hs = 0; hs < C::N_SUB; ++hs) {  // sub-tile hs = rows [n0 + hs*UMMA_N, +B_SUB_ROWS) of this CTA's share
               const uint32_t so = hs * (C::B_SUB_ROWS * 128);
@@ -630,7 +625,6 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           }
         }
         __syncwarp();
-        ++stage_uses;
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
         if (A_MODE == A_CONV) {  // next K block = next (tap, channel chunk), all lanes in step
           if (++tap_cc == p.conv_cchunks) {
