@@ -20,6 +20,15 @@ half = len(fw) // 2
 fw = fw[half:]
 tot = sum(d['gpu__time_duration.sum'] for d in fw)
 print('# last forward: %d launches, %.1f us (ncu, serialised)' % (len(fw), tot / 1e3))
+# one forward = from the stem (im2col or fused stem kernel) to the average pool: DRAM bytes per image of that span
+starts = [i for i, d in enumerate(fw) if 'stem' in d['k']]
+if starts:
+    one = fw[starts[-1]:]
+    by = sum(d.get('dram__bytes_read.sum', 0) + d.get('dram__bytes_write.sum', 0) for d in one)
+    t1 = sum(d['gpu__time_duration.sum'] for d in one)
+    batch = int(sys.argv[3]) if len(sys.argv) > 3 else 128
+    print('# one forward (stem .. avgpool): %d launches, %.1f us, %.1f MB of DRAM traffic = %.1f MB per image at batch %d'
+          % (len(one), t1 / 1e3, by / 1e6, by / 1e6 / batch, batch))
 if len(sys.argv) > 2:   # per-launch listing
     for d in fw:
         t = d['gpu__time_duration.sum']
