@@ -76,31 +76,51 @@ def test_widest_supported_patch_two_stem_tiles_per_row():
         assert np.abs(y - ref).max() <= TOL[precision] * scale, (precision, np.abs(y - ref).max() / scale)
 
 
-def test_fused_stem_equals_the_im2col_stem(monkeypatch):
+def _features_in_child(env_extra, shapes):
+    """Features of make_images(8, 3, H, W) for each (H, W), computed in a child process (the stem switches are read once
+    per process)."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    code = ("import sys, numpy as np, torch; sys.path.insert(0, %r); from oracle import resnet_oracle as RO; "
+            "from models.resnet_custom import resnet50_baseline; m = resnet50_baseline(); "
+            "m.load_state_dict({k: torch.from_numpy(np.asarray(v).copy()) for k, v in RO.make_params(1).items()}); m = m.cuda().eval(); "
+            "shapes = %r; "
+            "np.savez(sys.argv[1], *[m(torch.from_numpy(RO.make_images(8, 3, h, w)).cuda()).cpu().numpy() for h, w in shapes])")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.NamedTemporaryFile(suffix=".npz", delete=False) as f:
+        path = f.name
+    r = subprocess.run([sys.executable, "-c", code % (root, list(shapes)), path], env=dict(os.environ, **env_extra),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    with np.load(path) as z:
+        outs = [z["arr_%d" % i] for i in range(len(shapes))]
+    os.remove(path)
+    return outs
+
+
+def test_fused_stem_equals_the_im2col_stem():
     """The implicit-GEMM stem (stem.cuh) and the explicit im2col + GEMM stem contract the same fp16 operands in a
     different K order (kw-fastest vs channel-fastest): their fp32 sums differ in the last bit, which now and then flips
     the fp16 rounding of a stem activation; downstream that stays at the level of the mode's own rounding noise
     (the CPU restatement test allows the same 2e-4 .. 6e-4), far from what a wrong tap / halo / weight would give."""
-    import subprocess
-    import sys
-    code = ("import sys, numpy as np, torch; sys.path.insert(0, %r); from oracle import resnet_oracle as RO; "
-            "from models.resnet_custom import resnet50_baseline; m = resnet50_baseline(); "
-            "m.load_state_dict({k: torch.from_numpy(np.asarray(v).copy()) for k, v in RO.make_params(1).items()}); m = m.cuda().eval(); "
-            "y = m(torch.from_numpy(RO.make_images(8, 3, 96, 160)).cuda()); np.save(sys.argv[1], y.cpu().numpy())")
-    import os
-    import tempfile
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    outs = []
-    for forced in ("0", "1"):      # the switch is read once per process: one child per setting
-        with tempfile.NamedTemporaryFile(suffix=".npy", delete=False) as f:
-            path = f.name
-        env = dict(os.environ, TOAD_RESNET_STEM_IM2COL=forced)
-        r = subprocess.run([sys.executable, "-c", code % root, path], env=env, capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0, r.stderr[-2000:]
-        outs.append(np.load(path))
-        os.remove(path)
-    scale = np.abs(outs[1]).max()
-    assert np.abs(outs[0] - outs[1]).max() <= 5e-4 * scale, np.abs(outs[0] - outs[1]).max() / scale
+    shapes = [(96, 160)]
+    a = _features_in_child({"TOAD_RESNET_STEM_IM2COL": "0"}, shapes)[0]
+    b = _features_in_child({"TOAD_RESNET_STEM_IM2COL": "1"}, shapes)[0]
+    scale = np.abs(b).max()
+    assert np.abs(a - b).max() <= 5e-4 * scale, np.abs(a - b).max() / scale
+
+
+def test_stem_with_fused_maxpool_is_bit_identical():
+    """MaxPool2d(3, 2, 1) folded into the stem's epilogue (stem.cuh, POOL = true) takes the maximum of the same fp16 stem
+    activations the separate pooling kernel reads: the features must agree bit for bit.  Shapes: whole bands, a ragged
+    last band (H/4 = 20 = 8 + 8 + 4), a single half band, one-tile-wide rows (W = 256)."""
+    shapes = [(96, 160), (80, 48), (16, 16), (64, 256)]
+    fused = _features_in_child({"TOAD_RESNET_STEM_POOL": "1"}, shapes)
+    split = _features_in_child({"TOAD_RESNET_STEM_POOL": "0"}, shapes)
+    for shp, a, b in zip(shapes, fused, split):
+        assert np.array_equal(a, b), (shp, np.abs(a - b).max())
 
 
 def test_resnet_shape_contract():

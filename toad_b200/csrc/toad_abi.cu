@@ -1100,6 +1100,15 @@ bool resnet_pdl() {
   return v;
 }
 
+// TOAD_RESNET_STEM_POOL=0: fused stem without the fused max-pool (A/B and cross-check aid)
+bool stem_pool_unfused() {
+  static bool v = []() {
+    const char* e = getenv("TOAD_RESNET_STEM_POOL");
+    return e != nullptr && e[0] == '0';
+  }();
+  return v;
+}
+
 // exact = (hi, lo) bf16 plane pairs (4 B / element); default = one fp16 plane (2 B / element, lo pointers stay null)
 ResWs carve_resnet(int B, int H, int W, bool exact, void* base) {
   ResWs w{};
@@ -1207,9 +1216,12 @@ int resnet_fwd_impl(const Prepared& P, const float* x, int B, int H, int W, floa
   for (int b0 = 0; b0 < B; b0 += w.stem_chunk) {
     const int nb = (B - b0) < w.stem_chunk ? (B - b0) : w.stem_chunk;
     const float* xb = x + static_cast<int64_t>(b0) * 3 * H * W;
+    bool pooled = false;
     if (HALF && !stem_im2col_forced()) {
-      // conv1 + bn1 + relu as one implicit-GEMM kernel (stem.cuh)
-      TOAD_TRY(stem::launch_stem_fused(xb, P.conv[0].hi, P.conv[0].lo, P.conv[0].bias, w.stem_hi, nb, H, W, st));
+      // conv1 + bn1 + relu (+ the 3x3/s2 max-pool where the output rows fit one tile) as one implicit-GEMM kernel (stem.cuh)
+      pooled = stem::stem_can_pool(H, W) && !stem_pool_unfused();
+      TOAD_TRY(stem::launch_stem_fused(xb, P.conv[0].hi, P.conv[0].lo, P.conv[0].bias, pooled ? w.pool_hi : w.stem_hi, nb, H, W,
+                                       pooled, st));
     } else {
       const int64_t rows = static_cast<int64_t>(nb) * H1 * W1;
       TOAD_TRY(resnet::launch_stem_im2col<HALF>(xb, w.col_hi, w.col_lo, nb, H, W, H1, W1, st));
@@ -1218,10 +1230,12 @@ int resnet_fwd_impl(const Prepared& P, const float* x, int B, int H, int W, floa
       g.out_hi = w.stem_hi; g.out_lo = w.stem_lo; g.ld_split = 64;
       TOAD_TRY((tc::launch_gemm<64, tc::A_SPLIT, tc::EPI_LINEAR, 2, kResOutBufs, PREC>(g, w.col_hi, w.col_lo, P.conv[0].hi, P.conv[0].lo, st)));
     }
-    const int64_t threads = static_cast<int64_t>(nb) * H2 * W2 * (64 / 8);
-    resnet::maxpool3x3s2_kernel<HALF><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
-        w.stem_hi, w.stem_lo, w.pool_hi, w.pool_lo, nb, H1, W1, 64);
-    TOAD_CUDA_TRY(cudaGetLastError());
+    if (!pooled) {
+      const int64_t threads = static_cast<int64_t>(nb) * H2 * W2 * (64 / 8);
+      resnet::maxpool3x3s2_kernel<HALF><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
+          w.stem_hi, w.stem_lo, w.pool_hi, w.pool_lo, nb, H1, W1, 64);
+      TOAD_CUDA_TRY(cudaGetLastError());
+    }
     const Planes l1_out = {bufs[4].hi + b0 * l1_img, HALF ? nullptr : bufs[4].lo + b0 * l1_img};
     TOAD_TRY(run_layer(0, 1, nb, H2, W2, Planes{w.pool_hi, w.pool_lo}, bufs, l1_out));
   }
