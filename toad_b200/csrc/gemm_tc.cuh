@@ -160,7 +160,22 @@ struct GemmTcParams {
   const __nv_bfloat16* mask_bf16;  // the same mask given as the hi plane of the activation (hi > 0 <=> value > 0), or nullptr
   int64_t ld_mask;
   float out_scale;        // 0 = 1
+  // fp16 plane output written into a zero-bordered ("padded") plane for conv3x3_halo.cuh: raster row r of the
+  // [B*H*W, N] result lands at position pad_pos(r, H, W) of a [pad_positions(B, H, W), N] plane (W % 32 == 0).  0 = off.
+  int32_t out_pad_H, out_pad_W;
 };
+
+// zero-bordered activation plane of conv3x3_halo.cuh: padded position of raster row r = (b*H + h)*W + w
+__host__ __device__ __forceinline__ int64_t pad_pos(int64_t r, int H, int W) {
+  const int64_t bh = r / W;
+  const int w = static_cast<int>(r - bh * W);
+  const int64_t b = bh / H;
+  const int h = static_cast<int>(bh - b * H);
+  return (b * (H + 1) + h + 1) * (W + 1) + w + 1;
+}
+// positions of a padded plane holding B images (one trailing border row and one more cell: every tap of every pixel
+// stays inside the matrix)
+inline int64_t pad_positions(int64_t B, int H, int W) { return (B * (H + 1) + 1) * (W + 1) + 1; }
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -930,7 +945,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
               fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0) {
-                tma_store_2d(&tm_o_hi, buf, col0, static_cast<int>(tile_row0) + ew * 32);
+                int r0 = static_cast<int>(tile_row0) + ew * 32;
+                bool inside = true;
+                if (p.out_pad_W != 0) {  // 32 rows of one image row -> 32 consecutive padded positions (no hardware clipping)
+                  inside = r0 < p.M;
+                  r0 = static_cast<int>(pad_pos(r0, p.out_pad_H, p.out_pad_W));
+                }
+                if (inside) tma_store_2d(&tm_o_hi, buf, col0, r0);
                 tma_store_commit();
               }
             }
@@ -1211,7 +1232,13 @@ int launch_gemm_maps_b(const GemmTcParams& p, const CUtensorMap& ta_hi, const CU
   CUtensorMap to_hi = tb_hi, to_lo = tb_lo;
   if (epi_is_linear(EPI) && p.out_hi != nullptr) {
     if ((PREC == PREC_BF16X3 && p.out_lo == nullptr) || p.ld_split % 8 != 0) return TOAD_ERR_ARG;
-    TOAD_TRY(make_bf16_out_tmap(&to_hi, p.out_hi, p.M, p.N, p.ld_split));
+    int64_t out_rows = p.M;
+    if (p.out_pad_W != 0) {
+      const int64_t img = static_cast<int64_t>(p.out_pad_H) * p.out_pad_W;
+      if (PREC != PREC_F16X2 || A_MODE == A_CONV || p.out_pad_W % 32 != 0 || p.out_pad_H <= 0 || p.M % img != 0) return TOAD_ERR_ARG;
+      out_rows = pad_positions(p.M / img, p.out_pad_H, p.out_pad_W);
+    }
+    TOAD_TRY(make_bf16_out_tmap(&to_hi, p.out_hi, out_rows, p.N, p.ld_split));
     if (PREC == PREC_BF16X3) TOAD_TRY(make_bf16_out_tmap(&to_lo, p.out_lo, p.M, p.N, p.ld_split));
   }
   constexpr int kSmem = epi_is_linear(EPI) ? C::SMEM_BYTES_LINEAR : C::SMEM_BYTES;

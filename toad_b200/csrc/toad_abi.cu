@@ -7,6 +7,7 @@
 #include "topk.cuh"
 #include "resnet.cuh"
 #include "stem.cuh"
+#include "conv3x3_halo.cuh"
 #include "train.cuh"
 #include <cmath>
 #include <cstdlib>
@@ -1068,6 +1069,7 @@ Prepared carve_prepared(void* base) {
 struct ResWs {
   bf16 *col_hi, *col_lo, *stem_hi, *stem_lo, *pool_hi, *pool_lo;
   bf16 *buf_hi[5], *buf_lo[5];
+  bf16* pad_hi;   // fp16 mode: zero-bordered plane feeding the halo 3x3 convolutions (conv3x3_halo.cuh)
   int stem_chunk;
   size_t bytes;
 };
@@ -1109,6 +1111,15 @@ bool stem_pool_unfused() {
   return v;
 }
 
+// TOAD_RESNET_HALO=0: the 3x3 convolutions of layer1 / layer2 as tap-by-tap implicit GEMMs (A/B and cross-check aid)
+bool resnet_halo() {
+  static bool v = []() {
+    const char* e = getenv("TOAD_RESNET_HALO");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return v;
+}
+
 // exact = (hi, lo) bf16 plane pairs (4 B / element); default = one fp16 plane (2 B / element, lo pointers stay null)
 ResWs carve_resnet(int B, int H, int W, bool exact, void* base) {
   ResWs w{};
@@ -1130,6 +1141,11 @@ ResWs carve_resnet(int B, int H, int W, bool exact, void* base) {
     w.buf_hi[i] = c.take<bf16>(act);
     if (exact) w.buf_lo[i] = c.take<bf16>(act);
   }
+  if (!exact) {  // the larger of layer1's (per chunk, 64 channels) and layer2's (whole batch, 128 channels) padded planes
+    const size_t p1 = static_cast<size_t>(tc::pad_positions(w.stem_chunk, static_cast<int>(H2), static_cast<int>(W2))) * 64;
+    const size_t p2 = static_cast<size_t>(tc::pad_positions(B, static_cast<int>(H2 / 2), static_cast<int>(W2 / 2))) * 128;
+    w.pad_hi = c.take<bf16>(p1 > p2 ? p1 : p2);
+  }
   w.bytes = align_up(c.off, 256);
   return w;
 }
@@ -1145,8 +1161,10 @@ int check_resnet_shape(int B, int H, int W) {
 // out planes [M, Cout] = act(conv(in) + bias (+ residual)); in: NHWC planes [B, H, W, Cin]
 template <int PREC>
 int run_conv(const ConvSpec& cs, const PreparedConv& pc, const bf16* in_hi, const bf16* in_lo, int B, int H, int W,
-             bf16* out_hi, bf16* out_lo, const bf16* res_hi, const bf16* res_lo, bool relu, cudaStream_t st) {
+             bf16* out_hi, bf16* out_lo, const bf16* res_hi, const bf16* res_lo, bool relu, cudaStream_t st,
+             bool out_padded = false) {
   tc::GemmTcParams g{};
+  if (out_padded) { g.out_pad_H = H; g.out_pad_W = W; }   // (1x1 / stride 1 only: checked by launch_gemm)
   g.N = cs.cout;
   g.bias = pc.bias;
   g.relu = relu ? 1 : 0;
@@ -1181,6 +1199,7 @@ int resnet_fwd_impl(const Prepared& P, const float* x, int B, int H, int W, floa
     const int blocks[3] = {3, 4, 6};
     Planes x = in;
     int xs = -1;  // scratch slot holding x (-1: external)
+    bool borders_zeroed = false;
     for (int i = 0; i < blocks[l]; ++i) {
       const ConvSpec &c1 = specs[ci], &c2 = specs[ci + 1], &c3 = specs[ci + 2];
       const bool has_ds = i == 0, is_last = i == blocks[l] - 1;
@@ -1191,8 +1210,23 @@ int resnet_fwd_impl(const Prepared& P, const float* x, int B, int H, int W, floa
       const int ys = free_slots[2];
       const Planes y = is_last ? out : s[ys];
       const int ho = h / c2.stride, wo = wd / c2.stride;
-      TOAD_TRY(run_conv<PREC>(c1, P.conv[ci], x.hi, x.lo, bc, h, wd, t1.hi, t1.lo, nullptr, nullptr, true, st));
-      TOAD_TRY(run_conv<PREC>(c2, P.conv[ci + 1], t1.hi, t1.lo, bc, h, wd, t2.hi, t2.lo, nullptr, nullptr, true, st));
+      // conv2 with halo reuse (conv3x3_halo.cuh) where it applies: conv1 then writes into the zero-bordered plane
+      const int halo_kb = (HALF && resnet_halo() && c2.k == 3 && c2.stride == 1 && c1.k == 1 && c1.stride == 1)
+                              ? (halo::halo_supported<1>(h, wd, c2.cin, c2.cout) ? 1 : (halo::halo_supported<2>(h, wd, c2.cin, c2.cout) ? 2 : 0))
+                              : 0;
+      if (halo_kb != 0) {
+        if (!borders_zeroed) {  // (conv1 only ever writes the interior: once per layer call)
+          TOAD_TRY(halo::launch_zero_borders(w.pad_hi, bc, h, wd, c2.cin, st));
+          borders_zeroed = true;
+        }
+        TOAD_TRY(run_conv<PREC>(c1, P.conv[ci], x.hi, x.lo, bc, h, wd, w.pad_hi, nullptr, nullptr, nullptr, true, st, true));
+        const PreparedConv& pc = P.conv[ci + 1];
+        if (halo_kb == 1) TOAD_TRY(halo::launch_conv3x3_halo<1>(w.pad_hi, pc.hi, pc.lo, pc.bias, t2.hi, bc, h, wd, c2.cout, true, resnet_pdl(), st));
+        else TOAD_TRY(halo::launch_conv3x3_halo<2>(w.pad_hi, pc.hi, pc.lo, pc.bias, t2.hi, bc, h, wd, c2.cout, true, resnet_pdl(), st));
+      } else {
+        TOAD_TRY(run_conv<PREC>(c1, P.conv[ci], x.hi, x.lo, bc, h, wd, t1.hi, t1.lo, nullptr, nullptr, true, st));
+        TOAD_TRY(run_conv<PREC>(c2, P.conv[ci + 1], t1.hi, t1.lo, bc, h, wd, t2.hi, t2.lo, nullptr, nullptr, true, st));
+      }
       Planes res = x;
       if (has_ds) {  // (xs == -1 here: all four scratch slots are free, the fourth holds the shortcut)
         res = s[free_slots[3]];

@@ -15,7 +15,7 @@ for r in rows[1:]:
         d[r[mi]] = float(r[vi].replace(',', ''))
     except ValueError:
         pass
-fw = [d for d in recs.values() if 'gpu__time_duration.sum' in d and ('toad' in d['k'] or 'tc::' in d['k'] or 'resnet::' in d['k'] or 'stem' in d['k'])]
+fw = [d for d in recs.values() if 'gpu__time_duration.sum' in d and ('toad' in d['k'] or 'tc::' in d['k'] or 'resnet::' in d['k'] or 'stem' in d['k'] or 'halo' in d['k'])]
 half = len(fw) // 2
 fw = fw[half:]
 tot = sum(d['gpu__time_duration.sum'] for d in fw)
