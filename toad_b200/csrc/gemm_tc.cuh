@@ -813,7 +813,18 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 #pragma unroll
           for (int q = 0; q < 4; ++q) { cur_h[q] = res_h[q]; cur_l[q] = res_l[q]; cur_m[q] = msk[q]; }
           const float pv0_cur = pv0_nxt, pv1_cur = pv1_nxt;
-          if (!last) {  // next chunk's bias / residual (forward) or mask / pooling vectors (dgrad), in flight below
+          // fp16 mode: the first half of the chunk's bias (4 broadcast 128-bit loads, batched: their shared-memory
+          // latency -- long while the tensor pipe and the TMA own the shared-memory port -- overlaps the TMEM load);
+          // the next chunk's residual is fetched AFTER this chunk's has been consumed (same registers, no copies).
+          uint4 bias_a[4];
+          if (PREC == PREC_F16X2) {
+            const uint32_t sb = smem_u32(s_bias + n0 + c * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(bias_a[q].x), "=r"(bias_a[q].y), "=r"(bias_a[q].z), "=r"(bias_a[q].w)
+                           : "r"(sb + q * 16));
+          }
+          if (!last && PREC != PREC_F16X2) {  // next chunk's bias / residual (forward) or mask / pooling vectors (dgrad), in flight below
             if (EPI == EPI_LINEAR) {
               bias_nxt = load_bias(c + EPI_SETS);
               if (A_MODE != A_F32) load_res(c + EPI_SETS);
@@ -840,23 +851,35 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           if (PREC == PREC_F16X2) {
             // lean fp16-mode arithmetic: bias from shared memory (8 broadcast 128-bit loads) with packed fp32x2 adds,
             // the residual's fp16 halves added straight into the fp32 values (FHADD); ReLU rides on the final conversion
-            const float4* sb = reinterpret_cast<const float4*>(s_bias + col0);
+            uint4 bias_b[4];
+            {
+              const uint32_t sb = smem_u32(s_bias + col0 + 16);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 b4 = sb[q];
-              add_f32x2(r[4 * q], r[4 * q + 1], b4.x, b4.y);
-              add_f32x2(r[4 * q + 2], r[4 * q + 3], b4.z, b4.w);
+              for (int q = 0; q < 4; ++q)
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(bias_b[q].x), "=r"(bias_b[q].y), "=r"(bias_b[q].z), "=r"(bias_b[q].w)
+                             : "r"(sb + q * 16));
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              add_f32x2(r[4 * q], r[4 * q + 1], __uint_as_float(bias_a[q].x), __uint_as_float(bias_a[q].y));
+              add_f32x2(r[4 * q + 2], r[4 * q + 3], __uint_as_float(bias_a[q].z), __uint_as_float(bias_a[q].w));
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              add_f32x2(r[16 + 4 * q], r[16 + 4 * q + 1], __uint_as_float(bias_b[q].x), __uint_as_float(bias_b[q].y));
+              add_f32x2(r[16 + 4 * q + 2], r[16 + 4 * q + 3], __uint_as_float(bias_b[q].z), __uint_as_float(bias_b[q].w));
             }
             if (has_res) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const uint4 vh = cur_h[q];
+                const uint4 vh = res_h[q];
                 add_f16x2_to_f32(r[q * 8], r[q * 8 + 1], vh.x);
                 add_f16x2_to_f32(r[q * 8 + 2], r[q * 8 + 3], vh.y);
                 add_f16x2_to_f32(r[q * 8 + 4], r[q * 8 + 5], vh.z);
                 add_f16x2_to_f32(r[q * 8 + 6], r[q * 8 + 7], vh.w);
               }
             }
+            if (!last) load_res(c + EPI_SETS);   // lands during this chunk's stores and the next chunk's TMEM wait
           }
           if (has_res && PREC == PREC_BF16X3) {
 #pragma unroll
