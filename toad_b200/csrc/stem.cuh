@@ -42,6 +42,7 @@ constexpr int REAL_GROUPS = STG_ROWS;                   // column groups 0..20 a
 constexpr int A_KB_BYTES = TILE_PIX * 128;              // 16 KB: one K block of the A tile
 constexpr int A_BUF_BYTES = KBLOCKS * A_KB_BYTES;       // 48 KB
 constexpr int B_KB_BYTES = COUT * 128;                  // 8 KB per plane and K block
+constexpr int ACC_COLS = 2 * COUT;                      // accumulator columns: [x . w_hi | x . w_lo] (the planes ride in N, see below)
 constexpr int B_BYTES = KBLOCKS * 2 * B_KB_BYTES;       // 48 KB
 constexpr int STG_BYTES = STG_ROWS * STG_W * 4;         // 22 KB
 constexpr int SMEM_BYTES = B_BYTES + 2 * A_BUF_BYTES + STG_BYTES + 1024;
@@ -122,7 +123,7 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_const
     fence_barrier_init();
   }
   if (threadIdx.x < COUT) s_bias[threadIdx.x] = __ldg(p.bias + threadIdx.x);
-  if (warp == 2) tmem_alloc<1>(smem_u32(&tmem_slot), 2 * COUT);
+  if (warp == 2) tmem_alloc<1>(smem_u32(&tmem_slot), 2 * ACC_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -141,7 +142,9 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_const
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
-    constexpr uint32_t idesc = make_idesc_f16(TILE_PIX, COUT);
+    // one 128 x 128 x 16 UMMA per K step: B = the K block's [64 hi rows | 64 lo rows] (contiguous), so A is read from
+    // shared memory once for both weight planes; the epilogue adds the two column halves
+    constexpr uint32_t idesc = make_idesc_f16(TILE_PIX, ACC_COLS);
     mbar_wait(smem_u32(&bar_b), 0);
     int it = 0;
     TileWalk<POOL> tw;
@@ -152,21 +155,15 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_const
       mbar_wait(smem_u32(&bar_a_full[buf]), par);
       tc_fence_after();
       if (lane == 0) {
-        const uint32_t d_tmem = tmem_base + buf * COUT;
+        const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
 #pragma unroll
         for (int kb = 0; kb < KBLOCKS; ++kb) {
           const uint64_t a = make_kmajor_sw128_desc(sA + buf * A_BUF_BYTES + kb * A_KB_BYTES);
-          const uint64_t b_hi = make_kmajor_sw128_desc(sB + kb * 2 * B_KB_BYTES);
-          const uint64_t b_lo = make_kmajor_sw128_desc(sB + kb * 2 * B_KB_BYTES + B_KB_BYTES);
+          const uint64_t b = make_kmajor_sw128_desc(sB + kb * 2 * B_KB_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t koff = static_cast<uint64_t>(k) * ((UMMA_K * 2) >> 4);
-            umma_bf16<1>(d_tmem, a + koff, b_hi + koff, idesc, (kb > 0) || (k != 0));
-          }
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t koff = static_cast<uint64_t>(k) * ((UMMA_K * 2) >> 4);
-            umma_bf16<1>(d_tmem, a + koff, b_lo + koff, idesc, 1);
+            umma_bf16<1>(d_tmem, a + koff, b + koff, idesc, (kb > 0) || (k != 0));
           }
         }
         umma_commit<1>(smem_u32(&bar_a_empty[buf]));   // the A buffer may be rebuilt once these MMAs retire
@@ -187,11 +184,12 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_const
       const uint32_t ring_row = sRing + (POOL ? (tw.sr % 3) : 0) * RING_ROW_BYTES;
       mbar_wait(smem_u32(&bar_acc_full[buf]), (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * COUT;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * ACC_COLS;
 #pragma unroll
       for (int c = 0; c < COUT / 32; ++c) {
-        uint32_t v[32];
+        uint32_t v[32], vl[32];
         tmem_ld32(t_row + c * 32, v);
+        tmem_ld32(t_row + COUT + c * 32, vl);
         tmem_ld_wait();
         if (c == COUT / 32 - 1) {  // accumulator drained by this warp
           tc_fence_before();
@@ -202,8 +200,8 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_const
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float4 b4 = sb[q];
-          add_f32x2(v[4 * q], v[4 * q + 1], b4.x, b4.y);
-          add_f32x2(v[4 * q + 2], v[4 * q + 3], b4.z, b4.w);
+          add_f32x2(v[4 * q], v[4 * q + 1], __uint_as_float(vl[4 * q]) + b4.x, __uint_as_float(vl[4 * q + 1]) + b4.y);
+          add_f32x2(v[4 * q + 2], v[4 * q + 3], __uint_as_float(vl[4 * q + 2]) + b4.z, __uint_as_float(vl[4 * q + 3]) + b4.w);
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -321,7 +319,7 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_const
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<1>(tmem_base, 2 * COUT);
+    tmem_dealloc<1>(tmem_base, 2 * ACC_COLS);
   }
 }
 
