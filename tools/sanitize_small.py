@@ -30,7 +30,7 @@ def main():
         for prec in ("f16x2", "bf16x3"):       # both arithmetic modes; shapes whose conv tiles are clipped / hold several images
             ext.precision = prec
             for shape in ((2, 3, 64, 64), (3, 3, 96, 160), (1, 3, 224, 224), (1, 3, 32, 512), (5, 3, 16, 16),
-                          (3, 3, 128, 128), (2, 3, 64, 256))   # the last two: halo 3x3 convolutions, stem with fused max-pool:
+                          (3, 3, 128, 128), (2, 3, 64, 256)):   # the last two: halo 3x3 convolutions, stem with fused max-pool
                 ext(torch.randn(*shape, device="cuda"))
     # standalone gated-attention block: training forward with dropout + backward (parameters and x)
     from models.model_toad import Attn_Net_Gated
