@@ -72,12 +72,15 @@ def test_halo_convs_equal_the_tap_by_tap_convs():
     """conv3x3_halo.cuh and the A_CONV implicit GEMM contract the same fp16 operands (same K order per tap, same fp32
     accumulator), so the features agree to fp16-rounding noise; the workspace is reused across calls and shapes, so
     the second shape also proves the border cells are re-zeroed."""
-    shapes = [(256, 256), (128, 128), (64, 256)]
+    shapes = [(256, 256), (128, 128), (64, 256), (16, 128), (32, 256)]   # (the last two: image heights of 4 / 8 rows)
     a = _features_in_child({"TOAD_RESNET_HALO": "1"}, shapes)
     b = _features_in_child({"TOAD_RESNET_HALO": "0"}, shapes)
     for shp, ya, yb in zip(shapes, a, b):
         scale = np.abs(yb).max()
-        assert np.abs(ya - yb).max() <= 5e-4 * scale, (shp, np.abs(ya - yb).max() / scale)
+        # (features of the tiny inputs average only 8 / 32 positions: the same fp16 rounding flips weigh more --
+        # measured 5.4e-4 at 16 x 128; a wrong tap, border or image boundary shows at 1e-2 and more)
+        tol = 5e-4 if shp[0] * shp[1] >= 128 * 128 else 1e-3
+        assert np.abs(ya - yb).max() <= tol * scale, (shp, np.abs(ya - yb).max() / scale)
 
 
 def test_widest_supported_patch_two_stem_tiles_per_row():
