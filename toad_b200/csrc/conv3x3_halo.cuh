@@ -2,8 +2,8 @@
 //
 // The bottleneck blocks' conv2 (reference: models/resnet_custom.py:23-24,44-46: conv3x3 -> bn2 -> relu) of layer1
 // (64 -> 64 channels at 64 x 64) and layer2 (128 -> 128 at 32 x 32) are short-N, long-K problems: as a tap-by-tap implicit
-// GEMM (gemm_tc.cuh, A_CONV) they re-fetch the activation nine times and the weights once per tile from L2 and sit at
-// the L2 -> SM ceiling (~43 B/clk/SM: ~1000 cycles per K block, tensor pipe 26 % / 50 % busy, profiles/r2y).  Here
+// GEMM (gemm_tc.cuh, A_CONV) they re-fetch the activation nine times and the weights once per tile from L2 and
+// run two narrow UMMAs per K step (~1000 cycles per K block, tensor pipe 26 % / 50 % busy, profiles/r2y).  Here
 //   * the WEIGHTS of the CTA's 64 output channels stay resident in shared memory for the whole kernel (a CTA pair
 //     splits them: 32 rows x 9*Cin x 2 fp16 planes = 72 KB per CTA for Cin = 64, 144 KB for Cin = 128), and
 //   * the ACTIVATION is read from a zero-bordered ("padded") plane in which a pixel's 3x3 neighbourhood sits at fixed
