@@ -261,21 +261,23 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   if (warp == 2) tmem_dealloc<2>(tmem_base, ACC_STAGES * ACC_COLS);
 }
 
-// zero the border cells of a padded plane [P, C] (the interior is written by the producing convolution)
-__global__ void zero_borders_kernel(__nv_bfloat16* __restrict__ plane, int64_t P, int H, int W, int C) {
-  const int cpr = C / 8;   // 16-byte chunks per position
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int64_t q = i / cpr;
-  if (q >= P) return;
-  const int64_t rr = q / (W + 1);
-  const int cc = static_cast<int>(q - rr * (W + 1));
-  if (cc == 0 || rr % (H + 1) == 0)
-    *reinterpret_cast<uint4*>(plane + q * C + (i - q * cpr) * 8) = make_uint4(0u, 0u, 0u, 0u);
+// zero the border cells of a padded plane [P, C] (the interior is written by the producing convolution): one warp per
+// padded row -- a border row is cleared whole, of an image row only cell 0 (the column shared with the previous row);
+// the last warp also clears the plane's trailing cell
+__global__ void zero_borders_kernel(__nv_bfloat16* __restrict__ plane, int64_t n_rows, int H, int W, int C) {
+  const int64_t rr = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (rr >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const int cpr = C / 8;   // 16-byte chunks per cell
+  const bool border_row = rr % (H + 1) == 0;
+  int cells = border_row ? (W + 1) : 1;
+  if (rr == n_rows - 1) ++cells;   // (the cell after the last row)
+  uint4* row = reinterpret_cast<uint4*>(plane + rr * (W + 1) * C);
+  for (int i = lane; i < cells * cpr; i += 32) row[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 inline int launch_zero_borders(__nv_bfloat16* plane, int B, int H, int W, int C, cudaStream_t stream) {
-  const int64_t P = pad_positions(B, H, W);
-  const int64_t n = P * (C / 8);
-  zero_borders_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(plane, P, H, W, C);
+  const int64_t n_rows = static_cast<int64_t>(B) * (H + 1) + 1;   // pad_positions = n_rows * (W + 1) + 1
+  zero_borders_kernel<<<static_cast<unsigned>((n_rows + 7) / 8), 256, 0, stream>>>(plane, n_rows, H, W, C);
   TOAD_CUDA_TRY(cudaGetLastError());
   return 0;
 }
