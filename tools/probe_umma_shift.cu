@@ -6,7 +6,7 @@
 // field (bits 49..51) for exactly that.  This program measures it: A = a [272 x 64] fp16 matrix in smem (TMA,
 // SWIZZLE_128B), B = the 64 x 64 identity, D = A_view . B^T should equal rows s .. s+127 of A.
 //
-//   nvcc -gencode arch=compute_100a,code=sm_100a -I toad_b200/csrc -o gpurun_out/probe_umma_shift tools/probe_umma_shift.cu -lcuda
+//   nvcc -gencode arch=compute_100a,code=sm_100a -I toad_b200/csrc -std=c++17 -o build_probe/probe_umma_shift tools/probe_umma_shift.cu -lcuda   (build_probe/ is git-ignored but travels with gpurun)
 #include "gemm_tc.cuh"
 #include <cstdio>
 #include <vector>
