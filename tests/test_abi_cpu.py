@@ -119,3 +119,24 @@ def test_dropout_hash_matches_oracle(lib):
         assert O.dropout_hash(seed, layer, idx).tolist() == ours
     m = O.dropout_multipliers(42, 0.25, 64, 512, 256)
     assert abs((m[1] == 0).mean() - 0.25) < 0.02 and set(np.unique(m[3])) == {0.0, 1.0 / 0.75}
+
+
+def test_python_flag_constants_match_the_header():
+    """toad_b200/_lib.py restates the header's flag bits and ABI version: a drifted constant would silently select another
+    code path (or none)."""
+    import re
+    from toad_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "toad_b200.h")).read()
+    defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(TOAD_\w+)\s+(\d+)u?\b", hdr)}
+    assert defs["TOAD_ABI_VERSION"] == _lib.ABI_VERSION
+    seen = 0
+    for name, value in vars(_lib).items():
+        if name.startswith("FLAG_"):
+            assert defs["TOAD_" + name] == value, name
+            seen += 1
+    assert seen >= 8
+    assert defs["TOAD_RESNET_FLAG_EXACT"] == _lib.RESNET_FLAG_EXACT
+    fwd_flags = [v for k, v in defs.items() if k.startswith("TOAD_FLAG_")]
+    assert len(set(fwd_flags)) == len(fwd_flags) and all(v & (v - 1) == 0 for v in fwd_flags)   # distinct single bits
+
